@@ -1,0 +1,126 @@
+/* libtecogan_b200 — C ABI of the B200-native TecoGAN hot path.
+ *
+ * Plain C, raw device/host pointers and sizes, no torch types.  Every entry point
+ *   - returns 0 on success or a negative TG_ERR_* code (never throws, never exits);
+ *     tg_last_error_string() then describes the failure;
+ *   - is asynchronous with respect to the host: work is enqueued on `stream` (a cudaStream_t
+ *     passed as void*), performs no allocation and no synchronisation, and is therefore
+ *     CUDA-graph capturable (exception: the *_host entry points, which stage host buffers);
+ *   - borrows the pointers for the duration of the enqueued work only; the caller (PyTorch's
+ *     caching allocator in the Python mirror) owns all memory.
+ *
+ * Each function names the reference call site(s) it replaces (paths relative to the
+ * reference repo dwight-foster/Pytorch-TecoGAN).  The reference is pure Python over PyTorch
+ * and has no FFI of its own; INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Layout conventions
+ *   "NCHW f32"  : contiguous float tensors exactly as the reference holds them.
+ *   "NHWC bf16" : contiguous __nv_bfloat16 [N][H][W][C], C in {64,128}; the internal activation
+ *                 format of the generator (51 input channels are zero-padded to 64).
+ */
+#ifndef TECOGAN_B200_H
+#define TECOGAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_OK 0
+#define TG_ERR_BAD_ARG (-1)   /* shape / alignment / null pointer */
+#define TG_ERR_CUDA (-2)      /* a CUDA runtime or driver call failed */
+#define TG_ERR_ARCH (-3)      /* device is not sm_100 */
+#define TG_ERR_WORKSPACE (-4) /* workspace too small */
+
+/* A-operand staging of the tensor-core conv kernels (DESIGN.md "A staging modes"). */
+#define TG_AMODE_HALO 0 /* one TMA box with halo per stage; taps are row-shifted descriptors */
+#define TG_AMODE_DX3 1  /* three x-shifted copies per stage; every descriptor 1024B-aligned */
+
+const char* tg_last_error_string(void);
+int tg_version(void);
+/* 0 if the current device can run this library (compute capability 10.x), else TG_ERR_ARCH. */
+int tg_check_device(void);
+
+/* ------------------------------------------------------------------ glue (HBM-bound) ------- */
+
+/* out[n, c*r*r + dy*r + dx, y, x] = in[n, c, r*y+dy, r*x+dx]; bit-exact, any 4-byte element.
+ * Replaces the inline view/permute/reshape at main.py:207-212, code/train.py:102-106. */
+int tg_space_to_depth(const void* in, void* out, int n, int c, int h_out, int w_out, int r,
+                      void* stream);
+/* inverse of tg_space_to_depth (== F.pixel_shuffle); in [n, c*r*r, h, w] -> out [n, c, h*r, w*r]. */
+int tg_depth_to_space(const void* in, void* out, int n, int c, int h_in, int w_in, int r,
+                      void* stream);
+/* F.grid_sample(img, grid.half()) bilinear / zeros / align_corners=False.
+ * img [n,c,h,w] f32, grid [n,ho,wo,2] f32 (rounded to fp16 inside, as the reference does),
+ * out [n,c,ho,wo] f32.  Replaces main.py:203, code/train.py:81,98,165,187. */
+int tg_warp_bilinear(const float* img, const float* grid, float* out, int n, int c, int h, int w,
+                     int ho, int wo, void* stream);
+/* nn.Upsample(scale_factor=4, mode="bilinear") (align_corners=False); out = up4(in * pre_scale).
+ * in [n,c,h,w] f32 -> out [n,c,4h,4w] f32.  Replaces code/ops.py:98-100 as used at main.py:186. */
+int tg_upscale4_bilinear(const float* in, float* out, int n, int c, int h, int w, float pre_scale,
+                         void* stream);
+/* Fused producer of the generator input for frame t (main.py:186-213 in one pass):
+ *   flow  = upscale_four(lr_prev*4)[:,0:2] re-viewed as [n,4h,4w,2]   (computed on the fly)
+ *   x     = cat(lr_t, space_to_depth(deprocess(grid_sample(prev_hr, flow.half()))))
+ * written as NHWC bf16 [n,h,w,64] (channels 51..63 zero).  lr_prev == NULL or prev_hr == NULL
+ * selects the first-frame input cat(lr_t, zeros) (main.py:191-193).
+ * lr_t, lr_prev: [n,3,h,w] f32 with batch stride lr_batch_stride elements;
+ * prev_hr: [n,3,4h,4w] f32 with batch stride hr_batch_stride elements. */
+int tg_fused_warp_s2d_concat(const float* lr_t, const float* lr_prev, const float* prev_hr,
+                             void* x_nhwc, int n, int h, int w, long long lr_batch_stride,
+                             long long hr_batch_stride, void* stream);
+/* NCHW f32 [n,c,h,w] (c <= 64) -> NHWC bf16 [n,h,w,64] zero padded: the boundary conversion of
+ * generator.forward(x) (code/models.py:78). */
+int tg_pack_nchw_to_nhwc64(const float* in, void* out, int n, int c, int h, int w, void* stream);
+
+/* ------------------------------------------------------ tensor-core convolutions (tcgen05) -- */
+
+/* Packed-weight sizes/packers.  `kind`: 0 = Conv2d 3x3 s1 p1 (weight [cout,cin,3,3], code/ops.py:57-63)
+ *                                       1 = ConvTranspose2d 3x3 s2 p1 op1 (weight [cin,cout,3,3], code/ops.py:45-54).
+ * The packed blob holds bf16 weight blocks in MMA issue order followed by the fp32 bias
+ * (zero if bias == NULL), padded to the kernel's channel granularity. */
+size_t tg_packed_conv_bytes(int kind, int cin, int cout);
+int tg_pack_weights(int kind, const float* weight, const float* bias, int cin, int cout,
+                    void* packed, void* stream);
+
+/* y = act(conv3x3(x) + bias) (+ residual).  x NHWC bf16 [n,h,w,cin_pad], y NHWC bf16 [n,h,w,cout].
+ * cin_pad in {64,128} (51 -> 64), cout in {64,128}.  relu: apply ReLU before the residual add is
+ * never needed by the reference; semantics are  y = relu?(conv+bias) + residual?  with at most
+ * one of (relu, residual) set.  Replaces nn.Conv2d calls of code/models.py:55-56,68,75. */
+int tg_conv3x3_fwd(const void* x, const void* packed, const void* residual, void* y, int n, int h,
+                   int w, int cin_pad, int cout, int relu, int amode, void* stream);
+/* y = relu?(convT3x3s2(x) + bias); x [n,h,w,c] -> y [n,2h,2w,cout].  code/models.py:72,74. */
+int tg_convT3x3s2_fwd(const void* x, const void* packed, void* y, int n, int h, int w, int cin,
+                      int cout, int relu, int amode, void* stream);
+/* out = sigmoid(conv3x3(x) + bias), cout = 3, x NHWC bf16 [n,h,w,64] -> out NCHW f32 [n,3,h,w]
+ * (callers .view the result: main.py:196).  logits != NULL additionally stores the pre-sigmoid
+ * values.  code/models.py:76,86. */
+int tg_conv3x3_out_sigmoid(const void* x, const void* packed, float* out, float* logits, int n,
+                           int h, int w, int amode, void* stream);
+
+/* ----------------------------------------------------------------- generator (41 convs) ---- */
+
+/* Parameters are passed as ONE flat f32 device buffer holding the tensors of
+ * generator.state_dict() in its iteration order (conv.0.weight, conv.0.bias, resids.0.0.weight,
+ * ... output.bias), so reference checkpoints map 1:1. */
+size_t tg_gen_param_count(int num_resblock);
+size_t tg_gen_packed_bytes(int num_resblock);
+int tg_gen_pack(const float* flat_params, int num_resblock, void* packed, void* stream);
+size_t tg_gen_workspace_bytes(int n, int h, int w);
+/* generator.forward on an already packed input: x NHWC bf16 [n,h,w,64] -> out NCHW f32
+ * [n,3,4h,4w] (sigmoid applied).  code/models.py:78-86. */
+int tg_gen_forward(const void* packed, int num_resblock, const void* x_nhwc, float* out,
+                   float* logits_or_null, void* workspace, size_t workspace_bytes, int n, int h,
+                   int w, int amode, void* stream);
+/* Whole recurrent clip on device (main.py:173-219): lr [n,t,3,h,w] f32 -> out [n,t,3,4h,4w] f32.
+ * Frames are strictly sequential; the n clips of the batch are independent. */
+int tg_gen_clip_forward(const void* packed, int num_resblock, const float* lr, float* out,
+                        void* workspace, size_t workspace_bytes, int n, int t, int h, int w,
+                        int amode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TECOGAN_B200_H */

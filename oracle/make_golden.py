@@ -1,0 +1,111 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Usage:  python oracle/make_golden.py
+Reads /root/reference (absent on the GPU box — that is why the outputs are committed).
+
+What runs is the reference's own code:
+  * models.generator / models.discriminator / ops.upscale_four imported from
+    /root/reference/code after stubbing the two absent, arithmetic-irrelevant modules
+    (matplotlib, imageio — code/ops.py:9-11,20);
+  * the inference frame loop is script-level code, so lines 173-219 of
+    /root/reference/main.py are read from disk and exec'd with three textual shims:
+    ``.cuda()`` and ``.cpu()`` removed, ``.half()`` -> ``.half().float()`` (CPU grid_sample
+    rejects mixed dtypes).  Nothing is copied into this repository.
+Weights/inputs come from oracle/synth.py so they can be regenerated anywhere.
+"""
+import os
+import sys
+import textwrap
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+
+def import_reference():
+    for name in ["matplotlib", "matplotlib.animation", "matplotlib.pyplot", "imageio"]:
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib.animation"].ArtistAnimation = object
+    sys.modules["matplotlib.animation"].PillowWriter = object
+    sys.path.insert(1, os.path.join(REF, "code"))
+    import models as ref_models  # noqa
+    import ops as ref_ops  # noqa
+    return ref_models, ref_ops
+
+
+def run_reference_loop(ref_models, ref_ops, G, r_inputs, crop):
+    """exec main.py:173-219 (the per-clip body of the inference loop)."""
+    src = open(os.path.join(REF, "main.py")).read().split("\n")
+    body = "\n".join(src[174:219])          # lines 175..219: body of `for batch_idx, r_inputs`
+    body = textwrap.dedent(body)
+    body = body.replace(".cuda()", "").replace(".cpu()", "").replace(".half()", ".half().float()")
+    ns = dict(vars(ref_ops))
+    ns.update(torch=torch, F=torch.nn.functional, generator_F=G, r_inputs=r_inputs,
+              args=types.SimpleNamespace(crop_size=crop, learning_rate=1e-4))
+    with torch.no_grad():
+        exec(compile(body, "reference_main_loop", "exec"), ns)
+    return ns["gen_outputs"]
+
+
+def main():
+    from oracle import synth
+    ref_models, ref_ops = import_reference()
+    torch.set_num_threads(4)
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    args = types.SimpleNamespace(num_resblock=16, discrim_resblocks=4, discrim_channels=128)
+
+    # ---- glue ops, exactly the calls the reference makes -------------------------------
+    F = torch.nn.functional
+    img = torch.from_numpy(synth.det_uniform((2, 3, 16, 24), 11, -1.0, 1.0))
+    grid = torch.from_numpy(synth.det_uniform((2, 16, 24, 2), 12, -1.2, 1.2))
+    lr = torch.from_numpy(synth.det_uniform((2, 3, 6, 10), 13, 0.0, 1.0))
+    np.savez_compressed(
+        os.path.join(out_dir, "glue.npz"),
+        warp=F.grid_sample(img, grid.half().float()).numpy(),                   # main.py:203
+        upscale=ref_ops.upscale_four(lr * 4.0).numpy(),                         # main.py:186
+        s2d=img.view(2, 3, 4, 4, 6, 4).permute(0, 1, 3, 5, 2, 4).reshape(2, 48, 4, 6).numpy(),  # :207-212
+        deprocess=ref_ops.deprocess(img).numpy(), preprocess=ref_ops.preprocess(img).numpy(),
+        torch_version=str(torch.__version__))
+
+    # ---- generator: single forward + the full recurrent loop ---------------------------
+    for tag, gain in (("g1", 1.0), ("g17", 1.7)):
+        G = ref_models.generator(3, args=args).eval()
+        named = synth.fill_state_dict(G.state_dict(), seed=1, gain=gain)
+        G.load_state_dict({k: torch.from_numpy(v) for k, v in named.items()})
+        crop, T = 16, 4
+        r_inputs = torch.from_numpy(synth.clip_inputs(1, T, crop, crop, seed=1234, hi=0.25))
+        outs = run_reference_loop(ref_models, ref_ops, G, r_inputs, crop)        # [T,3,64,64]
+        x51 = torch.from_numpy(synth.det_uniform((1, 51, 12, 20), 21, 0.0, 1.0))
+        with torch.no_grad():
+            y = G(x51)
+        np.savez_compressed(os.path.join(out_dir, f"gen_{tag}.npz"),
+                            loop_out=outs.numpy().astype(np.float32),
+                            fwd_out=y.numpy().astype(np.float32),
+                            gain=np.float32(gain), crop=crop, T=T)
+
+    # ---- discriminator forward (train-mode BN, as the reference always runs it) --------
+    D = ref_models.discriminator(args=args)
+    named = synth.fill_state_dict(D.state_dict(), seed=2, gain=1.0)
+    D.load_state_dict({k: torch.from_numpy(v) for k, v in named.items()})
+    D.train()
+    x = torch.from_numpy(synth.det_uniform((3, 27, 128, 128), 31, -1.0, 1.0))
+    with torch.no_grad():
+        prob, feats = D(x)
+    np.savez_compressed(os.path.join(out_dir, "disc.npz"), prob=prob.numpy(),
+                        f4=feats[3].numpy(),
+                        f_abs_mean=np.array([f.abs().mean().item() for f in feats], np.float64),
+                        f_mean=np.array([f.mean().item() for f in feats], np.float64),
+                        running_mean_block1=D.block1[1].running_mean.numpy())
+    print("golden fixtures written to", out_dir)
+    for f in sorted(os.listdir(out_dir)):
+        print(" ", f, os.path.getsize(os.path.join(out_dir, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()

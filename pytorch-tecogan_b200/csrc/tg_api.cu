@@ -1,0 +1,124 @@
+// Error reporting, device checks and the public conv / pack entry points of libtecogan_b200.
+#include <stdarg.h>
+#include <string.h>
+
+#include "tg_conv_tc.cuh"
+
+static thread_local char g_err[512] = "";
+
+void tg_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int tg_num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+extern "C" const char* tg_last_error_string(void) { return g_err; }
+extern "C" int tg_version(void) { return 100; }
+
+extern "C" int tg_check_device(void) {
+  int dev = 0, major = 0;
+  TG_CUDA(cudaGetDevice(&dev));
+  TG_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    tg_set_error("libtecogan_b200 is built for sm_100a only; device has compute capability %d.x", major);
+    return TG_ERR_ARCH;
+  }
+  return TG_OK;
+}
+
+// ------------------------------------------------------------------------------ weight packing
+// Packed blob = bf16 blocks [cout_chunk][k_chunk][tap][NT rows (out ch)][64 (in ch)] in MMA issue
+// order, followed by the f32 bias padded to cout_pad.  TMA applies the 128B swizzle on load, so
+// the global image is plain row-major.
+namespace tg {
+
+__global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const float* __restrict__ bias,
+                                    int cin, int cout, int cin_pad, int cout_pad, int nt,
+                                    __nv_bfloat16* __restrict__ dst, float* __restrict__ bias_dst) {
+  // conv taps in (ky,kx) raster order; transposed conv in (phase,tap) order, see launch_conv_tc
+  const int ct_ky[9] = {1, 1, 1, 2, 0, 2, 2, 0, 0};
+  const int ct_kx[9] = {1, 2, 0, 1, 1, 2, 0, 2, 0};
+  const int kchunks = cin_pad / 64;
+  const long long total = 9LL * cin_pad * cout_pad;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci_l = static_cast<int>(i % 64);
+    long long r = i / 64;
+    const int co_l = static_cast<int>(r % nt); r /= nt;
+    const int j = static_cast<int>(r % 9); r /= 9;
+    const int kc = static_cast<int>(r % kchunks); r /= kchunks;
+    const int chunk = static_cast<int>(r);
+    const int ci = kc * 64 + ci_l, co = chunk * nt + co_l;
+    float v = 0.f;
+    if (ci < cin && co < cout) {
+      if (kind == kConv3x3) {
+        const int ky = j / 3, kx = j % 3;
+        v = w[((static_cast<long long>(co) * cin + ci) * 3 + ky) * 3 + kx];
+      } else {
+        v = w[((static_cast<long long>(ci) * cout + co) * 3 + ct_ky[j]) * 3 + ct_kx[j]];
+      }
+    }
+    dst[i] = __float2bfloat16_rn(v);
+  }
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < cout_pad; c += blockDim.x) bias_dst[c] = (bias && c < cout) ? bias[c] : 0.f;
+}
+
+}  // namespace tg
+
+extern "C" size_t tg_packed_conv_bytes(int kind, int cin, int cout) {
+  (void)kind;
+  const int cp = tg::cin_padded(cin), op = tg::cout_padded(cout);
+  size_t b = tg::packed_weight_bytes(cp, op) + static_cast<size_t>(op) * 4;
+  return (b + 255) & ~static_cast<size_t>(255);
+}
+
+extern "C" int tg_pack_weights(int kind, const float* weight, const float* bias, int cin, int cout,
+                               void* packed, void* stream) {
+  TG_CHECK_ARG(weight && packed, "pack_weights: null pointer");
+  TG_CHECK_ARG(kind == 0 || kind == 1, "pack_weights: kind must be 0 (conv) or 1 (convT)");
+  TG_CHECK_ARG(cin >= 1 && cin <= 128 && cout >= 1 && cout <= 128, "pack_weights: channels out of range");
+  const int cp = tg::cin_padded(cin), op = tg::cout_padded(cout);
+  const int nt = op == 16 ? 16 : 64;
+  auto* dst = static_cast<__nv_bfloat16*>(packed);
+  auto* bdst = reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + tg::packed_weight_bytes(cp, op));
+  tg::pack_weights_kernel<<<64, 256, 0, static_cast<cudaStream_t>(stream)>>>(kind, weight, bias, cin, cout, cp, op, nt, dst, bdst);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+static const float* packed_bias(const void* packed, int cin_pad, int cout_pad) {
+  return reinterpret_cast<const float*>(static_cast<const uint8_t*>(packed) + tg::packed_weight_bytes(cin_pad, cout_pad));
+}
+
+extern "C" int tg_conv3x3_fwd(const void* x, const void* packed, const void* residual, void* y, int n, int h,
+                              int w, int cin_pad, int cout, int relu, int amode, void* stream) {
+  TG_CHECK_ARG(cout == 64 || cout == 128, "conv3x3_fwd: cout must be 64 or 128 (got %d)", cout);
+  TG_CHECK_ARG(!(relu && residual), "conv3x3_fwd: relu and residual are mutually exclusive");
+  return tg::launch_conv_tc(tg::kConv3x3, tg::kOutNHWCbf16, x, packed, packed_bias(packed, cin_pad, cout), residual, y,
+                            nullptr, n, h, w, cin_pad, cout, relu, amode, 0, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tg_convT3x3s2_fwd(const void* x, const void* packed, void* y, int n, int h, int w, int cin,
+                                 int cout, int relu, int amode, void* stream) {
+  TG_CHECK_ARG(cout == 64 || cout == 128, "convT3x3s2_fwd: cout must be 64 or 128 (got %d)", cout);
+  return tg::launch_conv_tc(tg::kConvT3x3s2, tg::kOutNHWCbf16, x, packed, packed_bias(packed, cin, cout), nullptr, y,
+                            nullptr, n, h, w, cin, cout, relu, amode, 0, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tg_conv3x3_out_sigmoid(const void* x, const void* packed, float* out, float* logits, int n, int h,
+                                      int w, int amode, void* stream) {
+  return tg::launch_conv_tc(tg::kConv3x3, tg::kOutNCHWf32Sigmoid, x, packed, packed_bias(packed, 64, 16), nullptr, out,
+                            logits, n, h, w, 64, 16, 0, amode, 0, static_cast<cudaStream_t>(stream));
+}

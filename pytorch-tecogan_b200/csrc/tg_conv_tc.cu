@@ -1,0 +1,406 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a.
+//
+// Replaces the nn.Conv2d / nn.ConvTranspose2d calls of the generator
+// (reference code/models.py:54-58,68-76 via code/ops.py:45-63).
+//
+// GEMM view (per work item = one 16x8 pixel sub-tile of one image):
+//   D[128 pixels x NT out-channels] += A_tap[128 pixels x 64 in-channels] * W_tap[NT x 64]^T
+// summed over filter taps and 64-channel K chunks.  Activations are NHWC bf16, so one pixel's
+// 64 channels are one 128-byte row == one SWIZZLE_128B row of the UMMA K-major canonical layout.
+//
+//  * A operand: ONE TMA box {64ch, 10, 18} (sub-tile + halo, out-of-bounds zero-filled == the
+//    conv's zero padding) per stage.  The nine taps are nine *views* of that box: the UMMA
+//    descriptor start address is shifted by (dy*10+dx) rows and the 8-row-group stride (SBO) is
+//    the 10-pixel row pitch, so every input byte is fetched from L2 once per item (not 9x).
+//    (TG_AMODE_DX3 is the conservative variant: three x-shifted boxes so that every descriptor
+//    start stays 1024-byte aligned; 3x L2 traffic.)
+//  * B operand: the layer's packed weights for this CTA's 64-wide output-channel chunk stay
+//    resident in shared memory for the lifetime of the persistent CTA.
+//  * Accumulators live in TMEM (ring of 512/64 columns), so the epilogue of item i overlaps the
+//    MMAs of item i+1.  ConvTranspose(k3,s2) runs as 4 output phases = 4 accumulators fed from
+//    the same staged A tile (9 (phase,tap) pairs == 9 MMA groups, same FLOPs as a 3x3 conv).
+//  * Warp roles: warp0 = TMA producer, warp1 = TMEM owner + single-thread MMA issuer,
+//    warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU/residual -> global).
+#include "tg_conv_tc.cuh"
+
+namespace tg {
+
+constexpr int kThreads = 192;
+constexpr uint32_t kSmemLimit = 232448;   // 227 KB opt-in maximum per CTA
+
+struct SmemLayout {
+  uint32_t w_off, a_off, bar_off, tmem_ptr_off, bias_off, total;
+};
+
+__host__ __device__ inline SmemLayout make_layout(uint32_t w_bytes, uint32_t stage_stride,
+                                                  int nstages, int ngroups, int nt) {
+  SmemLayout l;
+  l.w_off = 0;
+  l.a_off = (w_bytes + 1023u) & ~1023u;
+  l.bar_off = l.a_off + stage_stride * nstages;
+  uint32_t nbar = 1 + 2 * nstages + 2 * ngroups;
+  l.tmem_ptr_off = l.bar_off + 8 * nbar;
+  l.bias_off = (l.tmem_ptr_off + 4 + 15u) & ~15u;
+  l.total = l.bias_off + 4 * nt;
+  return l;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+               const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;            // SWIZZLE_128B needs 1024B alignment
+  uint8_t* gbase = smem_raw + (base - raw);
+  const SmemLayout L = make_layout(p.w_bytes, p.stage_stride, p.nstages, p.ngroups, NT);
+
+  const uint32_t s_w = base + L.w_off;
+  const uint32_t s_a = base + L.a_off;
+  const uint32_t bar_w = base + L.bar_off;
+  const uint32_t bar_afull = bar_w + 8;
+  const uint32_t bar_aempty = bar_afull + 8 * p.nstages;
+  const uint32_t bar_cfull = bar_aempty + 8 * p.nstages;
+  const uint32_t bar_cempty = bar_cfull + 8 * p.ngroups;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gbase + L.tmem_ptr_off);
+  float* s_bias = reinterpret_cast<float*>(gbase + L.bias_off);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.y;                             // 64-wide output channel chunk
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_w);
+    mbar_init(bar_w, 1);
+    for (int i = 0; i < p.nstages; ++i) {
+      mbar_init(bar_afull + 8 * i, 1);
+      mbar_init(bar_aempty + 8 * i, 1);
+    }
+    for (int i = 0; i < p.ngroups; ++i) {
+      mbar_init(bar_cfull + 8 * i, 1);
+      mbar_init(bar_cempty + 8 * i, 4);                     // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + NT) {
+    const int c = threadIdx.x - 64;
+    s_bias[c] = p.bias ? p.bias[chunk * NT + c] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int blocks_per_chunk = p.kchunks * p.ntaps;
+  constexpr uint32_t kWBlockBytes = NT * 128;
+
+  if (warp == 0) {
+    // ================================ TMA producer =========================================
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, p.w_bytes);
+      for (int b = 0; b < blocks_per_chunk; ++b)
+        tma_load_2d(s_w + b * kWBlockBytes, &tm_w, bar_w, 0, (chunk * blocks_per_chunk + b) * NT);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+        const int tx = it % p.tiles_x;
+        const int r = it / p.tiles_x;
+        const int ty = r % p.tiles_y;
+        const int n = r / p.tiles_y;
+        const int x0 = tx * kTileW, y0 = ty * kTileH;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(bar_aempty + 8 * s, ph ^ 1);
+          mbar_expect_tx(bar_afull + 8 * s, p.stage_bytes);
+          const uint32_t dst = s_a + s * p.stage_stride;
+          for (int c = 0; c < p.ncopies; ++c)
+            tma_load_4d(dst + c * p.copy_bytes, &tm_a, bar_afull + 8 * s, kc * 64,
+                        x0 + p.copy_dx[c], y0 + p.box_y0, n);
+          if (++s == p.nstages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ===========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, NT);
+      mbar_wait(bar_w, 0);
+      tc_fence_after();
+      int s = 0, g = 0;
+      uint32_t ph = 0, gph = 0;
+      for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+        mbar_wait(bar_cempty + 8 * g, gph ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + static_cast<uint32_t>(g * p.n_acc * kAccCols);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(bar_afull + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t a_base = s_a + s * p.stage_stride;
+          const uint32_t w_base = s_w + kc * p.ntaps * kWBlockBytes;
+          for (int j = 0; j < p.ntaps; ++j) {
+            const TcTap tap = p.taps[j];
+            const uint64_t ad = umma_desc_sw128(a_base + tap.a_off, p.sbo);
+            const uint64_t bd = umma_desc_sw128(w_base + j * kWBlockBytes, 1024);
+            const uint32_t d = d_base + tap.acc * kAccCols;
+            const uint32_t keep = (kc > 0 || !tap.first) ? 1u : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // 4 x (K=16 bf16 = 32 bytes) inside the 128B swizzle row
+              umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
+          }
+          umma_commit(bar_aempty + 8 * s);                 // stage reusable once these MMAs retire
+          if (++s == p.nstages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(bar_cfull + 8 * g);                    // accumulators of this item complete
+        if (++g == p.ngroups) { g = 0; gph ^= 1; }
+      }
+    }
+  } else {
+    // ================================ epilogue (4 warps) ===================================
+    const int q = warp & 3;                                // TMEM lane quarter of this warp
+    const int m = q * 32 + lane;                           // GEMM row == pixel within sub-tile
+    const int pr = m >> 3, pc = m & 7;
+    int g = 0;
+    uint32_t gph = 0;
+    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+      const int tx = it % p.tiles_x;
+      const int r = it / p.tiles_x;
+      const int ty = r % p.tiles_y;
+      const int n = r / p.tiles_y;
+      const int iy = ty * kTileH + pr, ix = tx * kTileW + pc;
+      const bool valid = (iy < p.h) && (ix < p.w);
+      mbar_wait(bar_cfull + 8 * g, gph);
+      tc_fence_after();
+      for (int a = 0; a < p.n_acc; ++a) {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>((g * p.n_acc + a) * kAccCols);
+        const int oy = iy * p.sy + p.acc_oy[a], ox = ix * p.sx + p.acc_ox[a];
+        if constexpr (NT == 64) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(taddr, v0);
+          tmem_ld_32x32(taddr + 32, v1);
+          tmem_ld_wait();
+          if (a == p.n_acc - 1) {                          // TMEM drained -> hand the slot back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
+          }
+          if (valid) {
+            const size_t pix = (static_cast<size_t>(n) * p.oh + oy) * p.ow + ox;
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix * p.oc +
+                                                  chunk * 64);
+            const uint4* res = p.resid ? reinterpret_cast<const uint4*>(
+                                             static_cast<const __nv_bfloat16*>(p.resid) +
+                                             pix * p.oc + chunk * 64)
+                                       : nullptr;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              uint32_t* v = h2 ? v1 : v0;
+#pragma unroll
+              for (int c8 = 0; c8 < 4; ++c8) {             // 8 channels = one 16-byte store
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  f[e] = __uint_as_float(v[c8 * 8 + e]) + s_bias[h2 * 32 + c8 * 8 + e];
+                  if (p.relu) f[e] = fmaxf(f[e], 0.f);
+                }
+                if (res) {
+                  const uint4 rv = __ldg(res + h2 * 4 + c8);
+                  f[0] += bf16_lo(rv.x); f[1] += bf16_hi(rv.x);
+                  f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
+                  f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z);
+                  f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
+                }
+                uint4 o;
+                o.x = pack_bf16x2(f[0], f[1]);
+                o.y = pack_bf16x2(f[2], f[3]);
+                o.z = pack_bf16x2(f[4], f[5]);
+                o.w = pack_bf16x2(f[6], f[7]);
+                dst[h2 * 4 + c8] = o;
+              }
+            }
+          }
+        } else {
+          uint32_t v[16];
+          tmem_ld_32x16(taddr, v);
+          tmem_ld_wait();
+          if (a == p.n_acc - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
+          }
+          if (valid) {
+            const size_t plane = static_cast<size_t>(p.oh) * p.ow;
+            const size_t o0 = static_cast<size_t>(n) * p.out_nstride + static_cast<size_t>(oy) * p.ow + ox;
+            for (int c = 0; c < p.oc; ++c) {
+              const float z = __uint_as_float(v[c]) + s_bias[c];
+              if (p.out2) p.out2[o0 + c * plane] = z;
+              static_cast<float*>(p.out)[o0 + c * plane] = 1.f / (1.f + expf(-z));
+            }
+          }
+        }
+      }
+      if (++g == p.ngroups) { g = 0; gph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int encode_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,
+                       const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    tg_set_error("cuTensorMapEncodeTiled entry point not available");
+    return TG_ERR_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims,
+                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tg_set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return TG_ERR_CUDA;
+  }
+  return TG_OK;
+}
+
+int cin_padded(int cin) { return cin <= 64 ? 64 : 128; }
+int cout_padded(int cout) { return cout <= 16 ? 16 : (cout <= 64 ? 64 : 128); }
+size_t packed_weight_bytes(int cin_pad, int cout_pad) {
+  return static_cast<size_t>(9) * cin_pad * cout_pad * 2;
+}
+
+int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, const float* bias,
+                   const void* resid, void* out, float* out2, int n, int h, int w, int cin_pad,
+                   int cout_pad, int relu, int amode, long long out_nstride, cudaStream_t stream) {
+  TG_CHECK_ARG(x && packed_w && out, "conv: null pointer");
+  TG_CHECK_ARG(n > 0 && h > 0 && w > 0, "conv: bad shape n=%d h=%d w=%d", n, h, w);
+  TG_CHECK_ARG(cin_pad == 64 || cin_pad == 128, "conv: cin_pad must be 64 or 128 (got %d)", cin_pad);
+  TG_CHECK_ARG(cout_pad == 16 || cout_pad == 64 || cout_pad == 128, "conv: cout_pad must be 16/64/128 (got %d)", cout_pad);
+  TG_CHECK_ARG((out_mode == kOutNCHWf32Sigmoid) == (cout_pad == 16), "conv: cout 16 <=> sigmoid NCHW output");
+  TG_CHECK_ARG(amode == TG_AMODE_HALO || amode == TG_AMODE_DX3, "conv: bad amode %d", amode);
+  TG_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed_w) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) & 15) == 0, "conv: pointers must be 16-byte aligned");
+  TG_CHECK_ARG(!(resid && (kind != kConv3x3 || out_mode != kOutNHWCbf16)), "conv: residual only for conv3x3 NHWC");
+
+  const int nt = cout_pad == 16 ? 16 : 64;
+  const int chunks = cout_pad / nt;
+
+  TcParams p{};
+  p.n = n; p.h = h; p.w = w;
+  p.tiles_x = tg_div_up(w, kTileW);
+  p.tiles_y = tg_div_up(h, kTileH);
+  p.num_items = n * p.tiles_x * p.tiles_y;
+  p.kchunks = cin_pad / 64;
+  p.ntaps = 9;
+  const int box_w = (amode == TG_AMODE_HALO) ? kTileW + 2 : kTileW;
+  const int box_h = kTileH + 2;
+  p.copy_bytes = static_cast<uint32_t>(box_w * box_h * 128);
+  const uint32_t row_pitch = static_cast<uint32_t>(box_w * 128);
+  if (amode == TG_AMODE_HALO) {
+    p.ncopies = 1;
+    p.sbo = row_pitch;
+  } else {
+    p.ncopies = (kind == kConv3x3) ? 3 : 2;
+    p.sbo = 1024;
+  }
+  // tap tables: (dy,dx) are offsets inside the staged box, in MMA issue order == packed block order
+  static const int conv_dy[9] = {0, 0, 0, 1, 1, 1, 2, 2, 2};
+  static const int conv_dx[9] = {0, 1, 2, 0, 1, 2, 0, 1, 2};
+  //                              phase:   00 | 01     | 10     | 11
+  static const int ct_dy[9] = {0, 0, 0, 0, 1, 0, 0, 1, 1};
+  static const int ct_dx[9] = {0, 0, 1, 0, 0, 0, 1, 0, 1};
+  static const int ct_acc[9] = {0, 1, 1, 2, 2, 3, 3, 3, 3};
+  static const int ct_first[9] = {1, 1, 0, 1, 0, 1, 0, 0, 0};
+  for (int j = 0; j < 9; ++j) {
+    const int dy = (kind == kConv3x3) ? conv_dy[j] : ct_dy[j];
+    const int dx = (kind == kConv3x3) ? conv_dx[j] : ct_dx[j];
+    p.taps[j].a_off = (amode == TG_AMODE_HALO) ? static_cast<uint32_t>((dy * box_w + dx) * 128)
+                                               : static_cast<uint32_t>(dx * p.copy_bytes + dy * row_pitch);
+    p.taps[j].acc = (kind == kConv3x3) ? 0 : ct_acc[j];
+    p.taps[j].first = (kind == kConv3x3) ? (j == 0) : ct_first[j];
+  }
+  const int origin = (kind == kConv3x3) ? -1 : 0;   // conv: box starts at (x0-1,y0-1); convT: (x0,y0)
+  for (int c = 0; c < 3; ++c) p.copy_dx[c] = origin + ((amode == TG_AMODE_HALO) ? 0 : c);
+  p.box_y0 = origin;
+  p.n_acc = (kind == kConv3x3) ? 1 : 4;
+  p.stage_bytes = p.ncopies * p.copy_bytes;
+  p.stage_stride = (p.stage_bytes + 1023u) & ~1023u;
+  p.ngroups = 8 / p.n_acc;
+  p.w_bytes = static_cast<uint32_t>(p.kchunks * p.ntaps * nt * 128);
+  // A ring depth from what is left of the 227 KB
+  int nstages = 8;
+  while (nstages > 0 && make_layout(p.w_bytes, p.stage_stride, nstages, p.ngroups, nt).total + 1024 > kSmemLimit)
+    --nstages;
+  TG_CHECK_ARG(nstages >= 2 || (nstages >= 1 && p.kchunks == 1),
+               "conv: shared memory too small for cin=%d cout=%d amode=%d (stages=%d)", cin_pad, cout_pad, amode, nstages);
+  p.nstages = nstages;
+  const SmemLayout L = make_layout(p.w_bytes, p.stage_stride, nstages, p.ngroups, nt);
+  // request > half of the SM so that two CTAs never share an SM (each allocates all 512 TMEM cols)
+  uint32_t smem_bytes = L.total + 1024;
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
+
+  p.out_mode = out_mode;
+  p.sy = p.sx = (kind == kConv3x3) ? 1 : 2;
+  p.oh = h * p.sy; p.ow = w * p.sx;
+  p.oc = (out_mode == kOutNCHWf32Sigmoid) ? 3 : cout_pad;
+  for (int a = 0; a < kMaxAcc; ++a) { p.acc_oy[a] = (kind == kConv3x3) ? 0 : (a >> 1); p.acc_ox[a] = (kind == kConv3x3) ? 0 : (a & 1); }
+  p.out_nstride = out_nstride > 0 ? out_nstride : static_cast<long long>(p.oc) * p.oh * p.ow;
+  p.relu = relu;
+  p.out = out; p.out2 = out2; p.resid = resid; p.bias = bias;
+
+  CUtensorMap tm_a, tm_w;
+  {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(cin_pad), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(cin_pad) * 2, static_cast<cuuint64_t>(w) * cin_pad * 2,
+                             static_cast<cuuint64_t>(h) * w * cin_pad * 2};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+    int rc = encode_bf16(&tm_a, x, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const int rows = chunks * p.kchunks * p.ntaps * nt;
+    cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(nt)};
+    int rc = encode_bf16(&tm_w, packed_w, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+
+  int per_chunk = tg_num_sms() / chunks;
+  if (per_chunk < 1) per_chunk = 1;
+  dim3 grid(p.num_items < per_chunk ? p.num_items : per_chunk, chunks);
+  static bool attr_done[2] = {false, false};
+  if (nt == 64) {
+    if (!attr_done[0]) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); attr_done[0] = true; }
+    conv_tc_kernel<64><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_w, p);
+  } else {
+    if (!attr_done[1]) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); attr_done[1] = true; }
+    conv_tc_kernel<16><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_w, p);
+  }
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+}  // namespace tg

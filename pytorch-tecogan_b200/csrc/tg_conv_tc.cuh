@@ -1,0 +1,63 @@
+// Internal interface of the tcgen05 implicit-GEMM convolution kernel (tg_conv_tc.cu).
+#pragma once
+#include "tg_common.cuh"
+
+namespace tg {
+
+constexpr int kTileH = 16;        // output sub-tile: 16 rows x 8 columns = 128 GEMM rows (UMMA M)
+constexpr int kTileW = 8;
+constexpr int kAccCols = 64;      // TMEM columns reserved per accumulator
+constexpr int kMaxTaps = 16;
+constexpr int kMaxAcc = 4;
+
+enum TcKind { kConv3x3 = 0, kConvT3x3s2 = 1 };
+enum TcOut { kOutNHWCbf16 = 0, kOutNCHWf32Sigmoid = 1 };
+
+// One MMA group = one filter tap on one 64-channel K chunk: 4 x tcgen05.mma (K=16 each).
+struct TcTap {
+  uint32_t a_off;   // byte offset of the (shifted) A view inside a stage
+  uint16_t acc;     // accumulator (output phase) it adds into
+  uint16_t first;   // 1 = first tap of this accumulator (clears it on K chunk 0)
+};
+
+struct TcParams {
+  // tile space (the resolution the 16x8 sub-tiles tile: the conv input resolution)
+  int n, h, w, tiles_x, tiles_y, num_items;
+  // K loop
+  int kchunks;           // input channels / 64  (A stages per item)
+  int ntaps;             // MMA groups per K chunk
+  TcTap taps[kMaxTaps];
+  int n_acc;             // accumulators per item (1 conv, 4 transposed-conv phases)
+  // A staging
+  int ncopies;           // TMA boxes per stage (1 HALO, 3 DX3)
+  int copy_dx[3];        // x origin of each copy relative to tile x0
+  int box_y0;            // y origin relative to tile y0
+  uint32_t copy_bytes;   // bytes per copy (box bytes)
+  uint32_t stage_bytes;  // ncopies * copy_bytes (mbarrier expect_tx)
+  uint32_t stage_stride; // smem distance between stages (1024-aligned)
+  uint32_t sbo;          // UMMA stride-byte-offset between 8-row groups of A
+  int nstages, ngroups;  // A ring depth, accumulator ring depth
+  uint32_t w_bytes;      // resident weight bytes for this CTA's output-channel chunk
+  // epilogue
+  int out_mode, oh, ow, oc;   // output tensor dims (NHWC: channels oc; NCHW: oc planes)
+  int sy, sx;                 // output pixel = input pixel * (sy,sx) + acc offset
+  int acc_oy[kMaxAcc], acc_ox[kMaxAcc];
+  int relu;
+  long long out_nstride;      // NCHW output: elements between consecutive images
+  void* out;
+  float* out2;                // optional pre-sigmoid logits (NCHW f32)
+  const void* resid;          // optional residual, same layout as out (NHWC bf16)
+  const float* bias;          // padded bias for the whole layer (chunk offset added in-kernel)
+};
+
+// Launches the kernel for one layer.  x: NHWC bf16 with `cin_pad` channels.
+int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, const float* bias,
+                   const void* resid, void* out, float* out2, int n, int h, int w, int cin_pad,
+                   int cout_pad, int relu, int amode, long long out_nstride, cudaStream_t stream);
+
+// packed layout helpers
+size_t packed_weight_bytes(int cin_pad, int cout_pad);   // bf16 blocks only
+int cin_padded(int cin);
+int cout_padded(int cout);
+
+}  // namespace tg

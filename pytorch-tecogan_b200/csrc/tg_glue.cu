@@ -1,0 +1,366 @@
+// HBM-bound glue of the TecoGAN frame loop: space-to-depth / depth-to-space, bilinear backward
+// warp, bilinear x4 upscale, and the fused producer of the generator input.
+// All kernels are pure streaming / gather kernels: coalesced 128-bit accesses on the contiguous
+// side, shared-memory staging where the two sides disagree, grid-stride over whole rows.
+#include "tg_common.cuh"
+
+namespace tg {
+
+// ---------------------------------------------------------------------------------------------
+// space_to_depth / depth_to_space, r = 4 fast path: one thread moves one 16-byte group
+// in[n,c,4y+dy,4x..4x+3]  <->  out[n, c*16+dy*4+{0..3}, y, x].
+// 4-byte payload, bit-exact (values are only moved).
+// ---------------------------------------------------------------------------------------------
+__global__ void s2d4_kernel(const uint4* __restrict__ in, uint32_t* __restrict__ out, int planes, int ho,
+                            int wo) {
+  // in viewed as [planes][4*ho][wo] uint4 ; out as [planes][16][ho][wo]
+  const long long total = static_cast<long long>(planes) * 4 * ho * wo;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % wo);
+    long long r = i / wo;
+    const int iy = static_cast<int>(r % (4 * ho));
+    const long long pl = r / (4 * ho);
+    const int y = iy >> 2, dy = iy & 3;
+    const uint4 v = __ldg(in + i);
+    uint32_t* o = out + ((pl * 16 + dy * 4) * ho + y) * static_cast<long long>(wo) + x;
+    const long long ps = static_cast<long long>(ho) * wo;
+    o[0] = v.x; o[ps] = v.y; o[2 * ps] = v.z; o[3 * ps] = v.w;
+  }
+}
+
+__global__ void d2s4_kernel(const uint32_t* __restrict__ in, uint4* __restrict__ out, int planes, int hi,
+                            int wi) {
+  const long long total = static_cast<long long>(planes) * 4 * hi * wi;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % wi);
+    long long r = i / wi;
+    const int oy = static_cast<int>(r % (4 * hi));
+    const long long pl = r / (4 * hi);
+    const int y = oy >> 2, dy = oy & 3;
+    const uint32_t* s = in + ((pl * 16 + dy * 4) * hi + y) * static_cast<long long>(wi) + x;
+    const long long ps = static_cast<long long>(hi) * wi;
+    uint4 v;
+    v.x = __ldg(s); v.y = __ldg(s + ps); v.z = __ldg(s + 2 * ps); v.w = __ldg(s + 3 * ps);
+    out[i] = v;
+  }
+}
+
+// generic r (any), one thread per element of the depth-side tensor
+__global__ void s2d_generic_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int planes,
+                                   int ho, int wo, int r, int to_depth) {
+  const long long total = static_cast<long long>(planes) * r * r * ho * wo;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % wo);
+    long long q = i / wo;
+    const int y = static_cast<int>(q % ho); q /= ho;
+    const int dx = static_cast<int>(q % r); q /= r;
+    const int dy = static_cast<int>(q % r); q /= r;
+    const long long pl = q;
+    const long long sp = (pl * (static_cast<long long>(ho) * r) + (static_cast<long long>(y) * r + dy)) *
+                             (static_cast<long long>(wo) * r) + static_cast<long long>(x) * r + dx;
+    if (to_depth) out[i] = __ldg(in + sp);
+    else out[sp] = __ldg(in + i);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bilinear helpers.  ATen semantics, align_corners=False.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float round_fp16(float v) { return __half2float(__float2half_rn(v)); }
+
+// value of upscale_four(src*pre)[row, col] for one plane (nn.Upsample bilinear x4)
+__device__ __forceinline__ float up4_sample(const float* __restrict__ plane, int h, int w, int row, int col,
+                                            float pre) {
+  float sy = (row + 0.5f) * 0.25f - 0.5f;
+  float sx = (col + 0.5f) * 0.25f - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  sx = sx < 0.f ? 0.f : sx;
+  const int y0 = min(static_cast<int>(sy), h - 1), x0 = min(static_cast<int>(sx), w - 1);
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float ly1 = sy - y0, lx1 = sx - x0;
+  const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const float p00 = __ldg(plane + y0 * w + x0) * pre, p01 = __ldg(plane + y0 * w + x1) * pre;
+  const float p10 = __ldg(plane + y1 * w + x0) * pre, p11 = __ldg(plane + y1 * w + x1) * pre;
+  return ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11);
+}
+
+__global__ void upscale4_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int h,
+                                int w, float pre) {
+  const int wo = 4 * w, ho = 4 * h;
+  const long long total = static_cast<long long>(planes) * ho * w;   // one thread = 4 outputs in x
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % w);
+    long long r = i / w;
+    const int oy = static_cast<int>(r % ho);
+    const long long pl = r / ho;
+    const float* plane = in + pl * static_cast<long long>(h) * w;
+    float4 v;
+    v.x = up4_sample(plane, h, w, oy, 4 * x + 0, pre);
+    v.y = up4_sample(plane, h, w, oy, 4 * x + 1, pre);
+    v.z = up4_sample(plane, h, w, oy, 4 * x + 2, pre);
+    v.w = up4_sample(plane, h, w, oy, 4 * x + 3, pre);
+    reinterpret_cast<float4*>(out + (pl * ho + oy) * static_cast<long long>(wo))[x] = v;
+  }
+}
+
+// 4-tap bilinear gather with per-tap zero padding (grid_sampler_2d, align_corners=False)
+struct Taps {
+  int x0, y0;
+  float wnw, wne, wsw, wse;
+  bool ok_nw, ok_ne, ok_sw, ok_se;
+};
+__device__ __forceinline__ Taps make_taps(float gx, float gy, int h, int w) {
+  Taps t;
+  const float ix = ((gx + 1.f) * w - 1.f) / 2.f;
+  const float iy = ((gy + 1.f) * h - 1.f) / 2.f;
+  const float fx = floorf(ix), fy = floorf(iy);
+  const float ax = ix - fx, ay = iy - fy;            // == (ix - ix_nw)
+  const float bx = (fx + 1.f) - ix, by = (fy + 1.f) - iy;
+  t.wnw = bx * by; t.wne = ax * by; t.wsw = bx * ay; t.wse = ax * ay;
+  // clamp before the int conversion: far out-of-range / non-finite coordinates only need to fail
+  // the bounds test
+  const float cx = fminf(fmaxf(fx, -2.f), static_cast<float>(w) + 1.f);
+  const float cy = fminf(fmaxf(fy, -2.f), static_cast<float>(h) + 1.f);
+  t.x0 = static_cast<int>(cx); t.y0 = static_cast<int>(cy);
+  const bool finite = (fx == fx) && (fy == fy);
+  const bool xl = t.x0 >= 0 && t.x0 < w, xr = t.x0 + 1 >= 0 && t.x0 + 1 < w;
+  const bool yt = t.y0 >= 0 && t.y0 < h, yb = t.y0 + 1 >= 0 && t.y0 + 1 < h;
+  t.ok_nw = finite && xl && yt; t.ok_ne = finite && xr && yt;
+  t.ok_sw = finite && xl && yb; t.ok_se = finite && xr && yb;
+  return t;
+}
+__device__ __forceinline__ float gather(const float* __restrict__ plane, int w, const Taps& t) {
+  const float* p = plane + static_cast<long long>(t.y0) * w + t.x0;
+  float acc = 0.f;
+  if (t.ok_nw) acc += __ldg(p) * t.wnw;
+  if (t.ok_ne) acc += __ldg(p + 1) * t.wne;
+  if (t.ok_sw) acc += __ldg(p + w) * t.wsw;
+  if (t.ok_se) acc += __ldg(p + w + 1) * t.wse;
+  return acc;
+}
+
+__global__ void warp_kernel(const float* __restrict__ img, const float2* __restrict__ grid,
+                            float* __restrict__ out, int n, int c, int h, int w, int ho, int wo) {
+  const long long total = static_cast<long long>(n) * ho * wo;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / (static_cast<long long>(ho) * wo);
+    const long long pix = i - b * static_cast<long long>(ho) * wo;
+    const float2 g = __ldg(grid + i);
+    const Taps t = make_taps(round_fp16(g.x), round_fp16(g.y), h, w);
+    for (int ch = 0; ch < c; ++ch) {
+      const float* plane = img + (b * c + ch) * static_cast<long long>(h) * w;
+      out[(b * c + ch) * static_cast<long long>(ho) * wo + pix] = gather(plane, w, t);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused producer of the generator input (reference main.py:186-213 as one pass):
+// one CTA = 8x8 LR pixels = 32x32 HR pixels.  Each thread warps 4 HR pixels (flow computed on the
+// fly from LR_{t-1}, rounded to fp16 as the reference does), applies (v+1)/2, and drops the
+// results at their space-to-depth channel of an smem tile [64 LR px][64 ch] bf16, which is then
+// written out as whole 128-byte NHWC pixel rows.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFT = 8;   // LR tile edge
+
+__global__ void __launch_bounds__(256)
+fused_input_kernel(const float* __restrict__ lr_t, const float* __restrict__ lr_prev,
+                   const float* __restrict__ prev_hr, __nv_bfloat16* __restrict__ x, int n, int h, int w,
+                   long long lr_bs, long long hr_bs) {
+  __shared__ __align__(16) __nv_bfloat16 tile[kFT * kFT][64];
+  const int tiles_x = (w + kFT - 1) / kFT, tiles_y = (h + kFT - 1) / kFT;
+  const int ho = 4 * h, wo = 4 * w;
+  const long long hw_o = static_cast<long long>(ho) * wo;
+  const int ntiles = n * tiles_x * tiles_y;
+  for (int tIdx = blockIdx.x; tIdx < ntiles; tIdx += gridDim.x) {
+    const int tx = tIdx % tiles_x;
+    const int r = tIdx / tiles_x;
+    const int ty = r % tiles_y;
+    const int b = r / tiles_y;
+    const int lx0 = tx * kFT, ly0 = ty * kFT;
+    // channels 0..2 (LR frame t) and 51..63 (zero padding)
+    for (int i = threadIdx.x; i < kFT * kFT * 16; i += blockDim.x) {
+      const int px = i >> 4, k = i & 15;                    // k: 0..2 LR, 3..15 -> zero pad 51..63
+      const int ly = ly0 + px / kFT, lx = lx0 + px % kFT;
+      if (k < 3) {
+        float v = 0.f;
+        if (ly < h && lx < w) v = __ldg(lr_t + b * lr_bs + (static_cast<long long>(k) * h + ly) * w + lx);
+        tile[px][k] = __float2bfloat16_rn(v);
+      } else {
+        tile[px][48 + k] = __float2bfloat16_rn(0.f);
+      }
+    }
+    // channels 3..50: space_to_depth(deprocess(warp(prev_hr)))
+    for (int i = threadIdx.x; i < (4 * kFT) * (4 * kFT); i += blockDim.x) {
+      const int hy = i / (4 * kFT), hx = i % (4 * kFT);
+      const int oy = 4 * ly0 + hy, ox = 4 * lx0 + hx;
+      float v[3] = {0.f, 0.f, 0.f};
+      if (prev_hr != nullptr && oy < ho && ox < wo) {
+        // grid element (oy,ox,:) = two consecutive floats of the [2,Ho,Wo] planar flow buffer
+        const long long f = (static_cast<long long>(oy) * wo + ox) * 2;
+        const int plane = static_cast<int>(f / hw_o);
+        const long long rem = f - plane * hw_o;
+        const int row = static_cast<int>(rem / wo), col = static_cast<int>(rem % wo);
+        const float* fl = lr_prev + b * lr_bs + static_cast<long long>(plane) * h * w;
+        const float gx = round_fp16(up4_sample(fl, h, w, row, col, 4.f));
+        const float gy = round_fp16(up4_sample(fl, h, w, row, col + 1, 4.f));
+        const Taps t = make_taps(gx, gy, ho, wo);
+        const float* img = prev_hr + b * hr_bs;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) v[ch] = (gather(img + ch * hw_o, wo, t) + 1.f) / 2.f;
+      }
+      const int px = (hy >> 2) * kFT + (hx >> 2);
+      const int sub = (hy & 3) * 4 + (hx & 3);
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) tile[px][3 + ch * 16 + sub] = __float2bfloat16_rn(v[ch]);
+    }
+    __syncthreads();
+    // write whole pixels: 64 px x 128 B, 8 x 16B chunks per pixel
+    for (int i = threadIdx.x; i < kFT * kFT * 8; i += blockDim.x) {
+      const int px = i >> 3, ck = i & 7;
+      const int ly = ly0 + px / kFT, lx = lx0 + px % kFT;
+      if (ly < h && lx < w) {
+        const uint4 vv = reinterpret_cast<const uint4*>(&tile[px][0])[ck];
+        reinterpret_cast<uint4*>(x + ((static_cast<long long>(b) * h + ly) * w + lx) * 64)[ck] = vv;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// NCHW f32 [n,c,h,w] -> NHWC bf16 [n,h,w,64] (zero padded).  One CTA = 32 consecutive pixels.
+__global__ void __launch_bounds__(256)
+pack_nhwc64_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int n, int c,
+                   long long hw) {
+  __shared__ __align__(16) __nv_bfloat16 tile[32][64 + 8];
+  const long long groups = (hw + 31) / 32;
+  for (long long gi = blockIdx.x; gi < groups * n; gi += gridDim.x) {
+    const long long b = gi / groups;
+    const long long p0 = (gi % groups) * 32;
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
+      const int ch = i >> 5, px = i & 31;
+      float v = 0.f;
+      if (ch < c && p0 + px < hw) v = __ldg(in + (b * c + ch) * hw + p0 + px);
+      tile[px][ch] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 8; i += blockDim.x) {
+      const int px = i >> 3, ck = i & 7;
+      if (p0 + px < hw) {
+        const uint4 vv = *reinterpret_cast<const uint4*>(&tile[px][ck * 8]);
+        reinterpret_cast<uint4*>(out + (b * hw + p0 + px) * 64)[ck] = vv;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static int grid_for(long long work_items, int threads, int per_sm) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(tg_num_sms()) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace tg
+
+using namespace tg;
+
+extern "C" int tg_space_to_depth(const void* in, void* out, int n, int c, int h_out, int w_out, int r,
+                                 void* stream) {
+  TG_CHECK_ARG(in && out, "space_to_depth: null pointer");
+  TG_CHECK_ARG(n >= 0 && c >= 0 && h_out >= 0 && w_out >= 0 && r >= 1, "space_to_depth: bad shape");
+  const long long planes = static_cast<long long>(n) * c;
+  if (planes == 0 || h_out == 0 || w_out == 0) return TG_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (r == 4 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    const long long work = planes * 4 * h_out * w_out;
+    s2d4_kernel<<<grid_for(work, 256, 16), 256, 0, st>>>(static_cast<const uint4*>(in), static_cast<uint32_t*>(out),
+                                                        static_cast<int>(planes), h_out, w_out);
+  } else {
+    const long long work = planes * r * r * h_out * w_out;
+    s2d_generic_kernel<<<grid_for(work, 256, 16), 256, 0, st>>>(static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out),
+                                                               static_cast<int>(planes), h_out, w_out, r, 1);
+  }
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+extern "C" int tg_depth_to_space(const void* in, void* out, int n, int c, int h_in, int w_in, int r, void* stream) {
+  TG_CHECK_ARG(in && out, "depth_to_space: null pointer");
+  TG_CHECK_ARG(n >= 0 && c >= 0 && h_in >= 0 && w_in >= 0 && r >= 1, "depth_to_space: bad shape");
+  const long long planes = static_cast<long long>(n) * c;
+  if (planes == 0 || h_in == 0 || w_in == 0) return TG_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (r == 4 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const long long work = planes * 4 * h_in * w_in;
+    d2s4_kernel<<<grid_for(work, 256, 16), 256, 0, st>>>(static_cast<const uint32_t*>(in), static_cast<uint4*>(out),
+                                                        static_cast<int>(planes), h_in, w_in);
+  } else {
+    const long long work = planes * r * r * h_in * w_in;
+    s2d_generic_kernel<<<grid_for(work, 256, 16), 256, 0, st>>>(static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out),
+                                                               static_cast<int>(planes), h_in, w_in, r, 0);
+  }
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+extern "C" int tg_warp_bilinear(const float* img, const float* grid, float* out, int n, int c, int h, int w, int ho,
+                                int wo, void* stream) {
+  TG_CHECK_ARG(img && grid && out, "warp_bilinear: null pointer");
+  TG_CHECK_ARG(n >= 0 && c >= 1 && h >= 1 && w >= 1 && ho >= 0 && wo >= 0, "warp_bilinear: bad shape");
+  TG_CHECK_ARG((reinterpret_cast<uintptr_t>(grid) & 7) == 0, "warp_bilinear: grid must be 8-byte aligned");
+  const long long work = static_cast<long long>(n) * ho * wo;
+  if (work == 0) return TG_OK;
+  warp_kernel<<<grid_for(work, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      img, reinterpret_cast<const float2*>(grid), out, n, c, h, w, ho, wo);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+extern "C" int tg_upscale4_bilinear(const float* in, float* out, int n, int c, int h, int w, float pre_scale,
+                                    void* stream) {
+  TG_CHECK_ARG(in && out, "upscale4: null pointer");
+  TG_CHECK_ARG(n >= 0 && c >= 0 && h >= 1 && w >= 1, "upscale4: bad shape");
+  TG_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "upscale4: out must be 16-byte aligned");
+  const long long planes = static_cast<long long>(n) * c;
+  if (planes == 0) return TG_OK;
+  const long long work = planes * 4 * h * w;
+  upscale4_kernel<<<grid_for(work, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, static_cast<int>(planes),
+                                                                                       h, w, pre_scale);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+extern "C" int tg_fused_warp_s2d_concat(const float* lr_t, const float* lr_prev, const float* prev_hr, void* x_nhwc,
+                                        int n, int h, int w, long long lr_batch_stride, long long hr_batch_stride,
+                                        void* stream) {
+  TG_CHECK_ARG(lr_t && x_nhwc, "fused_warp_s2d_concat: null pointer");
+  TG_CHECK_ARG(n >= 1 && h >= 1 && w >= 1, "fused_warp_s2d_concat: bad shape");
+  TG_CHECK_ARG((reinterpret_cast<uintptr_t>(x_nhwc) & 15) == 0, "fused_warp_s2d_concat: x must be 16-byte aligned");
+  if (!lr_prev || !prev_hr) { lr_prev = nullptr; prev_hr = nullptr; }
+  const int tiles = n * tg_div_up(w, kFT) * tg_div_up(h, kFT);
+  int blocks = tiles < tg_num_sms() * 8 ? tiles : tg_num_sms() * 8;
+  fused_input_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      lr_t, lr_prev, prev_hr, static_cast<__nv_bfloat16*>(x_nhwc), n, h, w, lr_batch_stride, hr_batch_stride);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+extern "C" int tg_pack_nchw_to_nhwc64(const float* in, void* out, int n, int c, int h, int w, void* stream) {
+  TG_CHECK_ARG(in && out, "pack_nchw_to_nhwc64: null pointer");
+  TG_CHECK_ARG(n >= 1 && c >= 1 && c <= 64 && h >= 1 && w >= 1, "pack_nchw_to_nhwc64: bad shape (c must be <= 64)");
+  const long long hw = static_cast<long long>(h) * w;
+  const long long groups = (hw + 31) / 32 * n;
+  const long long cap = static_cast<long long>(tg_num_sms()) * 8;
+  pack_nhwc64_kernel<<<static_cast<int>(groups < cap ? groups : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, static_cast<__nv_bfloat16*>(out), n, c, hw);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}

@@ -1,0 +1,154 @@
+"""Host-side mirror of the reference ``code/models.py`` (generator / discriminator interfaces).
+
+``generator(gen_output_channels, args)`` keeps the reference's constructor, attribute tree
+(``conv``, ``resids``, ``conv_trans``, ``output`` — hence identical ``state_dict`` keys,
+shapes and default initialisation; code/models.py:61-76) and ``forward`` contract
+(x [N,51,H,W] -> [N,3,4H,4W], NCHW-contiguous, values in (0,1); code/models.py:78-86), but
+``forward`` runs the 41 convolutions as hand-written tcgen05 kernels through the C ABI.
+The nn.Conv2d children are parameter containers only; they are never called.
+"""
+import torch
+import torch.nn as nn
+
+from . import _native as _nt
+from .ops import *  # noqa: F401,F403  (reference star-import chain: code/models.py:1 -> dataloader -> ops)
+from .ops import conv2, conv2_tran, lrelu, batchnorm, denselayer
+
+
+def residual_block(inputs, output_channel=64, stride=1):
+    """code/models.py:54-58"""
+    return nn.Sequential(conv2(inputs, 3, output_channel, stride, use_bias=True), nn.ReLU(),
+                         conv2(output_channel, 3, output_channel, stride, use_bias=False))
+
+
+class generator(nn.Module):
+    """code/models.py:61-86, B200-native forward."""
+
+    def __init__(self, gen_output_channels, args=None):
+        super().__init__()
+        if args is None:
+            raise ValueError("No args is provided for generator")       # code/models.py:65-66
+        if int(gen_output_channels) != 3:
+            raise ValueError("tecogan_b200 generator supports gen_output_channels == 3 (the reference's only use)")
+        self.conv = nn.Sequential(conv2(51, 3, 64, 1), nn.ReLU())
+        self.num = args.num_resblock
+        self.resids = nn.ModuleList([residual_block(64, 64, 1) for _ in range(int(self.num))])
+        self.conv_trans = nn.Sequential(conv2_tran(64, 3, 64, stride=2, output_padding=1), nn.ReLU(),
+                                        residual_block(64, 64, 1), residual_block(64, 128, 1),
+                                        conv2_tran(128, 3, 128, stride=2, output_padding=1), nn.ReLU(),
+                                        conv2(128, 3, 64, 1), nn.ReLU())
+        self.output = conv2(64, 3, gen_output_channels, 1)
+        self.amode = _nt.AMODE_HALO
+        self._packed = None
+        self._packed_key = None
+        self._ws = None
+
+    # ------------------------------------------------------------------ packed-weight cache
+    def _param_list(self):
+        # state_dict iteration order == the flat layout tg_gen_pack expects
+        return [p for _, p in self.named_parameters()]
+
+    def packed_weights(self):
+        """bf16 MMA-ordered weight blocks + f32 biases; a derived cache, rebuilt whenever a
+        parameter changed (optimizer step, load_state_dict) — tracked by tensor versions."""
+        params = self._param_list()
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or key != self._packed_key:
+            lib = _nt.lib()
+            dev = params[0].device
+            if dev.type != "cuda":
+                raise RuntimeError("generator parameters must live on a CUDA device (call .cuda()); no CPU fallback")
+            nres = int(self.num)
+            flat = torch.cat([p.detach().reshape(-1).float() for p in params])
+            assert flat.numel() == lib.tg_gen_param_count(nres), "parameter layout mismatch"
+            if self._packed is None or self._packed.device != dev:
+                self._packed = torch.empty(lib.tg_gen_packed_bytes(nres), dtype=torch.uint8, device=dev)
+            _nt.check(lib.tg_gen_pack(_nt.ptr(flat), nres, _nt.ptr(self._packed), _nt.stream_ptr()))
+            self._packed_key = key
+        return self._packed
+
+    def _workspace(self, n, h, w, dev):
+        need = _nt.lib().tg_gen_workspace_bytes(n, h, w)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        return self._ws
+
+    # ----------------------------------------------------------------------------- forward
+    def forward(self, x, return_logits=False):
+        if not x.is_cuda:
+            raise RuntimeError("generator.forward: input must be a CUDA tensor (no CPU fallback)")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError(
+                "tecogan_b200 generator: backward kernels are not built yet; call under torch.no_grad()")
+        if x.dim() != 4 or x.shape[1] != 51:
+            raise RuntimeError(f"generator.forward: expected [N,51,H,W], got {tuple(x.shape)}")
+        lib = _nt.lib()
+        x = x.float().contiguous()
+        n, _, h, w = x.shape
+        packed = self.packed_weights()
+        ws = self._workspace(n, h, w, x.device)
+        x_nhwc = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=x.device)
+        _nt.check(lib.tg_pack_nchw_to_nhwc64(_nt.ptr(x), _nt.ptr(x_nhwc), n, 51, h, w, _nt.stream_ptr()))
+        out = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=x.device)
+        logits = torch.empty_like(out) if return_logits else None
+        _nt.check(lib.tg_gen_forward(_nt.ptr(packed), int(self.num), _nt.ptr(x_nhwc), _nt.ptr(out), _nt.ptr(logits),
+                                     _nt.ptr(ws), ws.numel(), n, h, w, int(self.amode), _nt.stream_ptr()))
+        return (out, logits) if return_logits else out
+
+    @torch.no_grad()
+    def infer_clip(self, r_inputs):
+        """The whole recurrent loop of main.py:173-219 on the device:
+        r_inputs [B,T,3,H,W] (CUDA, f32) -> [B,T,3,4H,4W] f32."""
+        lib = _nt.lib()
+        r = _nt.require_cuda_f32(r_inputs, "infer_clip(r_inputs)")
+        b, t, c, h, w = r.shape
+        if c != 3:
+            raise RuntimeError("infer_clip: LR frames must have 3 channels")
+        packed = self.packed_weights()
+        ws = self._workspace(b, h, w, r.device)
+        out = torch.empty((b, t, 3, 4 * h, 4 * w), dtype=torch.float32, device=r.device)
+        _nt.check(lib.tg_gen_clip_forward(_nt.ptr(packed), int(self.num), _nt.ptr(r), _nt.ptr(out), _nt.ptr(ws),
+                                          ws.numel(), b, t, h, w, int(self.amode), _nt.stream_ptr()))
+        return out
+
+
+def discriminator_block(inputs, output_channel, kernel_size, stride):
+    """code/models.py:90-94"""
+    return nn.Sequential(conv2(inputs, kernel_size, output_channel, stride, use_bias=False),
+                         batchnorm(output_channel, is_training=True), lrelu(0.2))
+
+
+class discriminator(nn.Module):
+    """code/models.py:97-146 — interface and state_dict mirror.  The tensor-core forward/backward
+    for the spatio-temporal discriminator is the next hot-path row; until
+    it lands, calling it fails loudly instead of falling back to library kernels."""
+
+    def __init__(self, args=None):
+        super().__init__()
+        if args is None:
+            raise ValueError("No args is provided for discriminator")   # code/models.py:100-101
+        ch = args.discrim_channels
+        nb = int(args.discrim_resblocks)
+        self.conv = nn.Sequential(conv2(27, 3, 64, 1), lrelu(0.2))
+        self.block1 = discriminator_block(64, 64, 4, 2)
+        self.resids1 = nn.ModuleList([nn.Sequential(residual_block(64, 64, 1), batchnorm(64, True)) for _ in range(nb)])
+        self.block2 = discriminator_block(64, ch, 4, 2)
+        self.resids2 = nn.ModuleList([nn.Sequential(residual_block(ch, ch, 1), batchnorm(ch, True)) for _ in range(nb)])
+        self.block3 = discriminator_block(ch, ch, 4, 2)
+        self.resids3 = nn.ModuleList([nn.Sequential(residual_block(ch, ch, 1), batchnorm(ch, True)) for _ in range(nb)])
+        self.block4 = discriminator_block(ch, 64, 4, 2)
+        self.block5 = discriminator_block(64, 3, 4, 2)
+        # 48 = 3*4*4 features of a 128x128 input (32x32 LR crops, code/models.py:123); larger crops
+        # need 48*(crop/32)^2 (colab/README.md:15-22) — derived here, default unchanged.
+        crop = int(getattr(args, "crop_size", 32) or 32)
+        self.fc = denselayer(48 * max(1, crop // 32) ** 2, 1)
+
+    def forward(self, x):
+        raise NotImplementedError(
+            "tecogan_b200 discriminator: sm_100a forward/backward kernels are not built yet (no library fallback)")
+
+
+def f_net():
+    """code/models.py:22-50 is dead code in the reference (never instantiated, main.py:231
+    commented out).  Kept importable for `from models import generator, f_net, discriminator`."""
+    raise NotImplementedError("f_net is unused by the reference hot path and is not provided")

@@ -1,0 +1,84 @@
+"""CPU: pin the oracle (oracle/) to outputs of the unmodified reference (tests/golden/*.npz,
+written by oracle/make_golden.py from /root/reference)."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import glue_np, synth, tecogan_oracle as O
+
+warnings.filterwarnings("ignore", category=UserWarning)
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_glue_numpy_vs_reference(golden_dir):
+    g = _load(golden_dir, "glue.npz")
+    img = synth.det_uniform((2, 3, 16, 24), 11, -1.0, 1.0)
+    grid = synth.det_uniform((2, 16, 24, 2), 12, -1.2, 1.2)
+    lr = synth.det_uniform((2, 3, 6, 10), 13, 0.0, 1.0)
+    assert np.array_equal(glue_np.space_to_depth(img, 4), g["s2d"])                 # bit-exact
+    assert np.array_equal(glue_np.depth_to_space(g["s2d"], 4), img)                 # round trip
+    np.testing.assert_allclose(glue_np.warp(img, grid), g["warp"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(glue_np.upscale_four(lr * np.float32(4.0)), g["upscale"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(glue_np.deprocess(img), g["deprocess"], rtol=0, atol=0)
+    np.testing.assert_allclose(glue_np.preprocess(img), g["preprocess"], rtol=0, atol=0)
+
+
+def test_glue_torch_oracle_vs_reference(golden_dir):
+    g = _load(golden_dir, "glue.npz")
+    img = torch.from_numpy(synth.det_uniform((2, 3, 16, 24), 11, -1.0, 1.0))
+    grid = torch.from_numpy(synth.det_uniform((2, 16, 24, 2), 12, -1.2, 1.2))
+    lr = torch.from_numpy(synth.det_uniform((2, 3, 6, 10), 13, 0.0, 1.0))
+    assert np.array_equal(O.space_to_depth(img, 4).numpy(), g["s2d"])
+    assert np.array_equal(O.depth_to_space(torch.from_numpy(g["s2d"]), 4).numpy(), img.numpy())
+    np.testing.assert_allclose(O.warp(img, grid).numpy(), g["warp"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(O.upscale_four(lr * 4.0).numpy(), g["upscale"], rtol=0, atol=1e-7)
+
+
+def test_frame_input_numpy_vs_torch():
+    lr_t = synth.det_uniform((2, 3, 5, 7), 41, 0, 0.25)
+    lr_p = synth.det_uniform((2, 3, 5, 7), 42, 0, 0.25)
+    hr = synth.det_uniform((2, 3, 20, 28), 43, 0, 1)
+    a = glue_np.frame_input(lr_t, lr_p, hr)
+    b = O.frame_input(torch.from_numpy(lr_t), torch.from_numpy(lr_p), torch.from_numpy(hr)).numpy()
+    # a 1-ulp fp32 difference in the upscale can flip an fp16 grid ulp: allow
+    # a handful of outliers, everything else must agree to 1e-5
+    bad = np.abs(a - b) > 1e-5
+    assert bad.mean() < 2e-3, bad.mean()
+
+
+@pytest.mark.parametrize("tag,gain", [("g1", 1.0), ("g17", 1.7)])
+def test_generator_and_loop_vs_reference(golden_dir, tag, gain):
+    g = _load(golden_dir, f"gen_{tag}.npz")
+    torch.set_num_threads(4)
+    G = O.OracleGenerator(3, 16).eval()
+    O.load_numpy_state(G, synth.fill_state_dict(G.state_dict(), seed=1, gain=gain))
+    x51 = torch.from_numpy(synth.det_uniform((1, 51, 12, 20), 21, 0.0, 1.0))
+    with torch.no_grad():
+        y = G(x51).numpy()
+    np.testing.assert_allclose(y, g["fwd_out"], rtol=0, atol=2e-6)
+    crop, T = int(g["crop"]), int(g["T"])
+    r = torch.from_numpy(synth.clip_inputs(1, T, crop, crop, seed=1234, hi=0.25))
+    out = O.infer_clip(G, r)[0].numpy()
+    assert out.shape == g["loop_out"].shape
+    np.testing.assert_allclose(out, g["loop_out"], rtol=0, atol=5e-6)
+
+
+def test_discriminator_vs_reference(golden_dir):
+    g = _load(golden_dir, "disc.npz")
+    torch.set_num_threads(4)
+    D = O.OracleDiscriminator(4, 128, 48)
+    O.load_numpy_state(D, synth.fill_state_dict(D.state_dict(), seed=2, gain=1.0))
+    D.train()
+    x = torch.from_numpy(synth.det_uniform((3, 27, 128, 128), 31, -1.0, 1.0))
+    with torch.no_grad():
+        prob, feats = D(x)
+    np.testing.assert_allclose(prob.numpy(), g["prob"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(feats[3].numpy(), g["f4"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose([f.abs().mean().item() for f in feats], g["f_abs_mean"], rtol=1e-5)
+    np.testing.assert_allclose(D.block1[1].running_mean.numpy(), g["running_mean_block1"], rtol=0, atol=1e-6)
