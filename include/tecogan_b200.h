@@ -43,6 +43,15 @@ int tg_version(void);
 /* 0 if the current device can run this library (compute capability 10.x), else TG_ERR_ARCH. */
 int tg_check_device(void);
 
+/* Measurement hooks (bench.py): number of kernels this library launched since load, and optional
+ * per-launch CUDA-event timing.  Between tg_profile_begin() and tg_profile_end() every launch is
+ * bracketed by events on its stream; tg_profile_end synchronises and returns up to max_entries
+ * records (kernel id: 0 conv_tc<64>, 1 output conv, 2 fused frame input, 3 other glue, 4 pack;
+ * duration in ms; algorithmic work = FLOPs for convs, bytes for glue).  Not graph-capturable. */
+long long tg_launch_count(void);
+int tg_profile_begin(void);
+int tg_profile_end(int max_entries, int* kernel_ids, float* ms, double* work);
+
 /* ------------------------------------------------------------------ glue (HBM-bound) ------- */
 
 /* out[n, c*r*r + dy*r + dx, y, x] = in[n, c, r*y+dy, r*x+dx]; bit-exact, any 4-byte element.

@@ -2,6 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+#include <vector>
+
 #include "tg_conv_tc.cuh"
 
 static thread_local char g_err[512] = "";
@@ -21,6 +24,46 @@ int tg_num_sms() {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
   return sms;
+}
+
+// ------------------------------------------------------------------- launch accounting / profiling
+struct ProfEntry { cudaEvent_t a, b; int kid; double work; };
+static std::atomic<long long> g_launches{0};
+static bool g_prof_on = false;
+static std::vector<ProfEntry> g_prof;
+
+void tg_prof_pre(int kernel_id, double work, cudaStream_t stream) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on) return;
+  ProfEntry e{nullptr, nullptr, kernel_id, work};
+  cudaEventCreate(&e.a);
+  cudaEventCreate(&e.b);
+  cudaEventRecord(e.a, stream);
+  g_prof.push_back(e);
+}
+void tg_prof_post(cudaStream_t stream) {
+  if (g_prof_on && !g_prof.empty()) cudaEventRecord(g_prof.back().b, stream);
+}
+
+extern "C" long long tg_launch_count(void) { return g_launches.load(); }
+extern "C" int tg_profile_begin(void) {
+  for (auto& e : g_prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  g_prof.clear();
+  g_prof_on = true;
+  return TG_OK;
+}
+extern "C" int tg_profile_end(int max_entries, int* kernel_ids, float* ms, double* work) {
+  g_prof_on = false;
+  int n = 0;
+  for (auto& e : g_prof) {
+    float t = 0.f;
+    cudaEventSynchronize(e.b);
+    cudaEventElapsedTime(&t, e.a, e.b);
+    if (n < max_entries) { kernel_ids[n] = e.kid; ms[n] = t; work[n] = e.work; ++n; }
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+  }
+  g_prof.clear();
+  return n;
 }
 
 extern "C" const char* tg_last_error_string(void) { return g_err; }
@@ -93,7 +136,9 @@ extern "C" int tg_pack_weights(int kind, const float* weight, const float* bias,
   const int nt = op == 16 ? 16 : 64;
   auto* dst = static_cast<__nv_bfloat16*>(packed);
   auto* bdst = reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + tg::packed_weight_bytes(cp, op));
+  tg_prof_pre(TG_K_PACK, 0.0, static_cast<cudaStream_t>(stream));
   tg::pack_weights_kernel<<<64, 256, 0, static_cast<cudaStream_t>(stream)>>>(kind, weight, bias, cin, cout, cp, op, nt, dst, bdst);
+  tg_prof_post(static_cast<cudaStream_t>(stream));
   TG_CUDA(cudaGetLastError());
   return TG_OK;
 }

@@ -392,6 +392,8 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   if (per_chunk < 1) per_chunk = 1;
   dim3 grid(p.num_items < per_chunk ? p.num_items : per_chunk, chunks);
   static bool attr_done[2] = {false, false};
+  // algorithmic FLOPs (MAC = 2, real channels of the padded tensors are not known here: padded dims)
+  tg_prof_pre(nt == 64 ? TG_K_CONV64 : TG_K_CONV16, 2.0 * 9.0 * cin_pad * (nt == 64 ? cout_pad : 3) * n * h * w, stream);
   if (nt == 64) {
     if (!attr_done[0]) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); attr_done[0] = true; }
     conv_tc_kernel<64><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_w, p);
@@ -399,6 +401,7 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
     if (!attr_done[1]) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); attr_done[1] = true; }
     conv_tc_kernel<16><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_w, p);
   }
+  tg_prof_post(stream);
   TG_CUDA(cudaGetLastError());
   return TG_OK;
 }

@@ -279,6 +279,7 @@ extern "C" int tg_space_to_depth(const void* in, void* out, int n, int c, int h_
   const long long planes = static_cast<long long>(n) * c;
   if (planes == 0 || h_out == 0 || w_out == 0) return TG_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  tg_prof_pre(TG_K_GLUE, 8.0 * planes * r * r * h_out * w_out, st);   // bytes: 4 in + 4 out per element
   if (r == 4 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
     const long long work = planes * 4 * h_out * w_out;
     s2d4_kernel<<<grid_for(work, 256, 16), 256, 0, st>>>(static_cast<const uint4*>(in), static_cast<uint32_t*>(out),
@@ -288,6 +289,7 @@ extern "C" int tg_space_to_depth(const void* in, void* out, int n, int c, int h_
     s2d_generic_kernel<<<grid_for(work, 256, 16), 256, 0, st>>>(static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out),
                                                                static_cast<int>(planes), h_out, w_out, r, 1);
   }
+  tg_prof_post(static_cast<cudaStream_t>(stream));
   TG_CUDA(cudaGetLastError());
   return TG_OK;
 }
@@ -298,6 +300,7 @@ extern "C" int tg_depth_to_space(const void* in, void* out, int n, int c, int h_
   const long long planes = static_cast<long long>(n) * c;
   if (planes == 0 || h_in == 0 || w_in == 0) return TG_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  tg_prof_pre(TG_K_GLUE, 8.0 * planes * r * r * h_in * w_in, st);
   if (r == 4 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     const long long work = planes * 4 * h_in * w_in;
     d2s4_kernel<<<grid_for(work, 256, 16), 256, 0, st>>>(static_cast<const uint32_t*>(in), static_cast<uint4*>(out),
@@ -307,6 +310,7 @@ extern "C" int tg_depth_to_space(const void* in, void* out, int n, int c, int h_
     s2d_generic_kernel<<<grid_for(work, 256, 16), 256, 0, st>>>(static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out),
                                                                static_cast<int>(planes), h_in, w_in, r, 0);
   }
+  tg_prof_post(static_cast<cudaStream_t>(stream));
   TG_CUDA(cudaGetLastError());
   return TG_OK;
 }
@@ -318,8 +322,10 @@ extern "C" int tg_warp_bilinear(const float* img, const float* grid, float* out,
   TG_CHECK_ARG((reinterpret_cast<uintptr_t>(grid) & 7) == 0, "warp_bilinear: grid must be 8-byte aligned");
   const long long work = static_cast<long long>(n) * ho * wo;
   if (work == 0) return TG_OK;
+  tg_prof_pre(TG_K_GLUE, (8.0 * c + 4.0) * n * ho * wo, static_cast<cudaStream_t>(stream));   // f32 img in/out + fp16 grid
   warp_kernel<<<grid_for(work, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       img, reinterpret_cast<const float2*>(grid), out, n, c, h, w, ho, wo);
+  tg_prof_post(static_cast<cudaStream_t>(stream));
   TG_CUDA(cudaGetLastError());
   return TG_OK;
 }
@@ -332,8 +338,10 @@ extern "C" int tg_upscale4_bilinear(const float* in, float* out, int n, int c, i
   const long long planes = static_cast<long long>(n) * c;
   if (planes == 0) return TG_OK;
   const long long work = planes * 4 * h * w;
+  tg_prof_pre(TG_K_GLUE, 4.0 * planes * h * w * 17.0, static_cast<cudaStream_t>(stream));
   upscale4_kernel<<<grid_for(work, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, static_cast<int>(planes),
                                                                                        h, w, pre_scale);
+  tg_prof_post(static_cast<cudaStream_t>(stream));
   TG_CUDA(cudaGetLastError());
   return TG_OK;
 }
@@ -347,8 +355,10 @@ extern "C" int tg_fused_warp_s2d_concat(const float* lr_t, const float* lr_prev,
   if (!lr_prev || !prev_hr) { lr_prev = nullptr; prev_hr = nullptr; }
   const int tiles = n * tg_div_up(w, kFT) * tg_div_up(h, kFT);
   int blocks = tiles < tg_num_sms() * 8 ? tiles : tg_num_sms() * 8;
+  tg_prof_pre(TG_K_FUSED_INPUT, 18.4 * 16.0 * n * h * w, static_cast<cudaStream_t>(stream));      // 12+4+6.4 B/HR px... minus grid (on the fly)
   fused_input_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       lr_t, lr_prev, prev_hr, static_cast<__nv_bfloat16*>(x_nhwc), n, h, w, lr_batch_stride, hr_batch_stride);
+  tg_prof_post(static_cast<cudaStream_t>(stream));
   TG_CUDA(cudaGetLastError());
   return TG_OK;
 }
@@ -359,8 +369,10 @@ extern "C" int tg_pack_nchw_to_nhwc64(const float* in, void* out, int n, int c, 
   const long long hw = static_cast<long long>(h) * w;
   const long long groups = (hw + 31) / 32 * n;
   const long long cap = static_cast<long long>(tg_num_sms()) * 8;
+  tg_prof_pre(TG_K_GLUE, (4.0 * c + 128.0) * n * hw, static_cast<cudaStream_t>(stream));
   pack_nhwc64_kernel<<<static_cast<int>(groups < cap ? groups : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       in, static_cast<__nv_bfloat16*>(out), n, c, hw);
+  tg_prof_post(static_cast<cudaStream_t>(stream));
   TG_CUDA(cudaGetLastError());
   return TG_OK;
 }

@@ -25,6 +25,9 @@ SIGNATURES = {
     "tg_last_error_string": (ctypes.c_char_p, []),
     "tg_version": (_c_int, []),
     "tg_check_device": (_c_int, []),
+    "tg_launch_count": (_c_ll, []),
+    "tg_profile_begin": (_c_int, []),
+    "tg_profile_end": (_c_int, [_c_int, _c_void_p, _c_void_p, _c_void_p]),
     "tg_space_to_depth": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "tg_depth_to_space": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "tg_warp_bilinear": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
