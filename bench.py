@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py — TecoGAN x4 VSR inference throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): generator inference 320x180 -> 1280x720, 100-frame synthetic
+clips, bf16 tensor-core convolutions, sharded by clip across GPUs (no data-path collective).
+One "step" = one batch of B independent 100-frame clips per GPU through the recurrent frame loop.
+
+  value      frames/s, whole job, LR clips already resident in HBM
+  e2e        frames/s through ClipPipeline.run_host: pinned host LR in, every HR frame copied
+             back to pinned host memory, copies inside the timed region
+  roofline   dominant kernel (tcgen05 conv, conv_tc_kernel<64>) timed per launch with CUDA events
+  cpu_baseline / --impl reference: the CPU oracle port (torch fp32 on the host cores) on a
+             bounded sample of the same workload.  Only these legs import oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "pytorch-tecogan_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+H, W, T = 180, 320, 100
+FLOP_PER_LR_PIXEL = 8445312           # whole generator, MAC=2, padding not counted
+FLOP_PER_LR_PIXEL_OUTCONV = 2 * 9 * 64 * 3 * 16
+METRIC = "720p output frames/s (x4 VSR inference)"
+WORKLOAD = "cfg2: generator inference 320x180 -> 1280x720, 100-frame synthetic clips, sharded by clip"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=int(os.environ.get("TG_BENCH_CLIPS", "2")),
+                    help="independent clips per GPU per step")
+    ap.add_argument("--frames", type=int, default=T)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            for i, nm in enumerate(names):
+                if len(r) > 4 + i and r[4 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        # median over samples taken under load (upper half of the sorted clocks: idle samples at start/stop)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": (max(mx) if mx else None),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def cpu_oracle_fps(n_frames, steps, warmup):
+    """frames/s of the CPU oracle port (oracle/tecogan_oracle.py, torch fp32 on the host cores) on an
+    n_frames-long 320x180 clip.  This is the reference's CPU path timed on this box."""
+    import torch
+    from oracle import synth, tecogan_oracle as O
+    torch.manual_seed(1)
+    G = O.OracleGenerator(3, 16).eval()
+    r = torch.from_numpy(synth.clip_inputs(1, n_frames, H, W, seed=1234, hi=0.25))
+    for _ in range(warmup):
+        O.infer_clip(G, r[:, :1])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.infer_clip(G, r)
+    dt = time.perf_counter() - t0
+    return n_frames * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_frames = 2
+    fps, step_s, cores = cpu_oracle_fps(n_frames, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "arm": "reference CPU path (oracle port of models.py + main.py:173-219, "
+                   "torch fp32 on the host cores)",
+                   "sample": f"{n_frames}-frame clip per step (bounded sample of the 100-frame clip)"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_frames} frames of a 320x180 clip per step, {args.steps} steps"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------- ours
+def run_ours(args):
+    import types
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from tecogan_b200 import _native as nt, models
+    from tecogan_b200.pipeline import ClipPipeline
+    lib = nt.lib()
+
+    B, K, Wm = args.clips, args.steps, max(args.warmup, 3)
+    frames = args.frames
+    torch.manual_seed(1)                                   # reference default --rand_seed 1 (main.py:34)
+    G = models.generator(3, types.SimpleNamespace(num_resblock=16)).to(dev).eval()   # random init
+    pipe = ClipPipeline(G, B, frames, H, W, dev)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    lr = torch.rand((B, frames, 3, H, W), device=dev, generator=gen) * 0.25
+    out = torch.empty((B, frames, 3, 4 * H, 4 * W), dtype=torch.float32, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    # ---------------- device-resident throughput (value) ----------------
+    for _ in range(Wm):
+        pipe.run_device(lr, out)
+    barrier()
+    sampler.start()
+    launches0 = lib.tg_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        pipe.run_device(lr, out)
+    e1.record()
+    barrier()
+    launches = lib.tg_launch_count() - launches0
+    dev_s = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    clocks = sampler.stop()
+    value = world * B * frames * K / dev_s
+    finite = bool(torch.isfinite(out[:, -1]).all().item())
+
+    # ---------------- end to end with host buffers (e2e) ----------------
+    e2e = None
+    if not args.no_e2e:
+        lr_host = torch.empty((B, frames, 3, H, W), dtype=torch.float32).pin_memory()
+        lr_host.copy_(lr.cpu())
+        out_host = torch.empty((frames, B, 3, 4 * H, 4 * W), dtype=torch.float32).pin_memory()
+        for _ in range(Wm):
+            pipe.run_host(lr_host, out_host)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(K):
+            pipe.run_host(lr_host, out_host)               # returns with every frame in host memory
+        e1.record()
+        barrier()
+        host_s = max_over_ranks(max(e0.elapsed_time(e1) * 1e-3, 0.0))
+        wall_s = max_over_ranks(time.perf_counter() - t0)
+        bi, bo = pipe.bytes_per_run()
+        e2e = {"value": world * B * frames * K / max(host_s, wall_s), "unit": "frames/s",
+               "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
+               "api": "tecogan_b200.pipeline.ClipPipeline.run_host (pinned host in/out, D2H overlapped)",
+               "result_mean": float(out_host[-1].mean())}
+        del lr_host, out_host
+
+    # ---------------- roofline of the dominant kernel, per-launch CUDA events ----------------
+    roof = None
+    if rank == 0:
+        import ctypes
+        pf = min(frames, 5)
+        pipe_p = ClipPipeline(G, B, pf, H, W, dev)
+        lr_p = lr[:, :pf].contiguous()
+        pipe_p.run_device(lr_p)
+        torch.cuda.synchronize()
+        nt.check(lib.tg_profile_begin())
+        pipe_p.run_device(lr_p)
+        cap = 64 * pf + 64
+        ids = (ctypes.c_int * cap)()
+        ms = (ctypes.c_float * cap)()
+        work = (ctypes.c_double * cap)()
+        n = lib.tg_profile_end(cap, ids, ms, work)
+        conv_ms = sum(ms[i] for i in range(n) if ids[i] == 0)
+        conv_n = sum(1 for i in range(n) if ids[i] == 0)
+        all_ms = sum(ms[i] for i in range(n))
+        flops = float(pf) * B * (FLOP_PER_LR_PIXEL - FLOP_PER_LR_PIXEL_OUTCONV) * H * W
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained")
+        src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+        if not peak:
+            peak, src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+        achieved = flops / (conv_ms * 1e-3) / 1e12
+        roof = {"kernel": "tg::conv_tc_kernel<64> (tcgen05 implicit-GEMM conv, 40 launches/frame)",
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": src, "traffic": None,
+                "launches_timed": conv_n, "avg_launch_us": conv_ms * 1e3 / max(conv_n, 1),
+                "algorithmic_flops_per_launch": flops / max(conv_n, 1),
+                "kernel_share_of_step": conv_ms / all_ms if all_ms else None}
+        del pipe_p
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        fps, step_s, cores = cpu_oracle_fps(3, 1, 1)
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "one 3-frame 320x180 clip through oracle.infer_clip (torch CPU fp32)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD,
+                       "clips_per_gpu_per_step": B, "frames_per_clip": frames, "lr_dist": "U[0,0.25) (all warp taps "
+                       "in bounds)", "weights": "random init, seed 1", "parallelism": f"clip-sharded x{world}, no collective",
+                       "l2": "no explicit flush: every frame streams ~0.56 GB of activations per clip through the "
+                             "126 MB L2, far larger than L2"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "outputs_finite": finite,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -21,6 +21,8 @@
 //    the same staged A tile (9 (phase,tap) pairs == 9 MMA groups, same FLOPs as a 3x3 conv).
 //  * Warp roles: warp0 = TMA producer, warp1 = TMEM owner + single-thread MMA issuer,
 //    warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU/residual -> global).
+#include <stdlib.h>
+
 #include "tg_conv_tc.cuh"
 
 namespace tg {
@@ -92,50 +94,61 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Programmatic dependent launch: the next layer's CTAs may start their prologue (barrier init,
+  // TMEM alloc, weight TMA) as soon as SMs free up; they block in griddepcontrol.wait until this
+  // grid has completed and flushed, before touching any activation.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int blocks_per_chunk = p.kchunks * p.ntaps;
   constexpr uint32_t kWBlockBytes = NT * 128;
 
   if (warp == 0) {
     // ================================ TMA producer =========================================
-    if (lane == 0) {
+    // Whole warp runs the (uniform) loop; one elected lane issues.  Keeps TMA operands in uniform
+    // registers (no per-lane waterfall loops around UTMALDG).
+    if (elect_one()) {
       mbar_expect_tx(bar_w, p.w_bytes);
       for (int b = 0; b < blocks_per_chunk; ++b)
         tma_load_2d(s_w + b * kWBlockBytes, &tm_w, bar_w, 0, (chunk * blocks_per_chunk + b) * NT);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
-        const int tx = it % p.tiles_x;
-        const int r = it / p.tiles_x;
-        const int ty = r % p.tiles_y;
-        const int n = r / p.tiles_y;
-        const int x0 = tx * kTileW, y0 = ty * kTileH;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(bar_aempty + 8 * s, ph ^ 1);
+    }
+    __syncwarp();
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // weights are constants; activations are not
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+      const int tx = it % p.tiles_x;
+      const int r = it / p.tiles_x;
+      const int ty = r % p.tiles_y;
+      const int n = r / p.tiles_y;
+      const int x0 = tx * kTileW, y0 = ty * kTileH;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(bar_aempty + 8 * s, ph ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(bar_afull + 8 * s, p.stage_bytes);
           const uint32_t dst = s_a + s * p.stage_stride;
           for (int c = 0; c < p.ncopies; ++c)
             tma_load_4d(dst + c * p.copy_bytes, &tm_a, bar_afull + 8 * s, kc * 64,
                         x0 + p.copy_dx[c], y0 + p.box_y0, n);
-          if (++s == p.nstages) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == p.nstages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ===========================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, NT);
-      mbar_wait(bar_w, 0);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, NT);
+    mbar_wait(bar_w, 0);
+    tc_fence_after();
+    int s = 0, g = 0;
+    uint32_t ph = 0, gph = 0;
+    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+      mbar_wait(bar_cempty + 8 * g, gph ^ 1);
       tc_fence_after();
-      int s = 0, g = 0;
-      uint32_t ph = 0, gph = 0;
-      for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
-        mbar_wait(bar_cempty + 8 * g, gph ^ 1);
+      const uint32_t d_base = tmem_base + static_cast<uint32_t>(g * p.n_acc * kAccCols);
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(bar_afull + 8 * s, ph);
         tc_fence_after();
-        const uint32_t d_base = tmem_base + static_cast<uint32_t>(g * p.n_acc * kAccCols);
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(bar_afull + 8 * s, ph);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t a_base = s_a + s * p.stage_stride;
           const uint32_t w_base = s_w + kc * p.ntaps * kWBlockBytes;
           for (int j = 0; j < p.ntaps; ++j) {
@@ -149,17 +162,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
           }
           umma_commit(bar_aempty + 8 * s);                 // stage reusable once these MMAs retire
-          if (++s == p.nstages) { s = 0; ph ^= 1; }
+          if (kc == p.kchunks - 1) umma_commit(bar_cfull + 8 * g);   // accumulators of this item complete
         }
-        umma_commit(bar_cfull + 8 * g);                    // accumulators of this item complete
-        if (++g == p.ngroups) { g = 0; gph ^= 1; }
+        __syncwarp();
+        if (++s == p.nstages) { s = 0; ph ^= 1; }
       }
+      if (++g == p.ngroups) { g = 0; gph ^= 1; }
     }
   } else {
     // ================================ epilogue (4 warps) ===================================
     const int q = warp & 3;                                // TMEM lane quarter of this warp
     const int m = q * 32 + lane;                           // GEMM row == pixel within sub-tile
     const int pr = m >> 3, pc = m & 7;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     int g = 0;
     uint32_t gph = 0;
     for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
@@ -392,14 +407,25 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   if (per_chunk < 1) per_chunk = 1;
   dim3 grid(p.num_items < per_chunk ? p.num_items : per_chunk, chunks);
   static bool attr_done[2] = {false, false};
-  // algorithmic FLOPs (MAC = 2, real channels of the padded tensors are not known here: padded dims)
+  // algorithmic FLOPs (MAC = 2) on the padded channel counts; bench.py uses SURVEY.md's unpadded figure
   tg_prof_pre(nt == 64 ? TG_K_CONV64 : TG_K_CONV16, 2.0 * 9.0 * cin_pad * (nt == 64 ? cout_pad : 3) * n * h * w, stream);
+  static const bool use_pdl = []() { const char* e = getenv("TG_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
   if (nt == 64) {
     if (!attr_done[0]) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); attr_done[0] = true; }
-    conv_tc_kernel<64><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_w, p);
+    TG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64>, tm_a, tm_w, p));
   } else {
     if (!attr_done[1]) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); attr_done[1] = true; }
-    conv_tc_kernel<16><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_w, p);
+    TG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<16>, tm_a, tm_w, p));
   }
   tg_prof_post(stream);
   TG_CUDA(cudaGetLastError());

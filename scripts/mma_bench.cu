@@ -1,0 +1,110 @@
+// Microbenchmark: issue-to-retire cost of tcgen05.mma (M=128, K=16, bf16, SS operands) as a
+// function of N and of the A descriptor (aligned SBO=1024 vs row-shifted SBO=1280).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_bench scripts/mma_bench.cu
+#include <cstdio>
+#include <cstdlib>
+
+#include "../pytorch-tecogan_b200/csrc/tg_common.cuh"
+
+void tg_set_error(const char*, ...) {}
+int tg_num_sms() { return 148; }
+
+using namespace tg;
+
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+// mode 0: A from smem aligned; 1: A from smem row-shifted (SBO 1280); 2: A from TMEM
+// nacc: consecutive MMAs rotate over this many accumulators (1 = one dependent accumulate chain)
+template <int NACC>
+__global__ void __launch_bounds__(128, 1) k(int n, int mode, int reps, long long* out) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  __shared__ uint32_t tptr;
+  __shared__ __align__(8) uint64_t bar;
+  if (threadIdx.x < 32) tmem_alloc(smem_u32(&tptr), 512);
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(raw + (base - smem_u32(raw)))[i] = 0x3c003c00u;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tptr;
+  if (threadIdx.x < 32) {
+    const uint32_t idesc = umma_idesc_bf16(128, n);
+    const uint32_t a0 = base, b0 = base + 96 * 1024;
+    const uint32_t sbo = mode == 1 ? 1280 : 1024;
+    uint64_t ad[36], bd[4];
+#pragma unroll
+    for (int v = 0; v < 36; ++v) {
+      const uint32_t aoff = (mode == 1 ? (uint32_t)((v / 4) * 128 * 11) : (uint32_t)((v / 4) * 16384 % 65536)) + (v & 3) * 32;
+      ad[v] = umma_desc_sw128(a0 + aoff, sbo);
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) bd[v] = umma_desc_sw128(b0 + v * 32, 1024);
+    const uint32_t dstride = (n <= 128) ? 128 : 256;      // accumulator spacing in TMEM columns
+    uint32_t ph = 0;
+    long long best = 1ll << 60;
+    for (int trial = 0; trial < 5; ++trial) {
+      const long long t0 = clock64();
+      for (int r = 0; r < reps / 36; ++r) {
+        if (elect_one()) {
+#pragma unroll
+          for (int v = 0; v < 36; ++v) {
+            const uint32_t d = tm + (uint32_t)(v % NACC) * dstride % 512;
+            if (mode == 2) umma_ts(d, tm + 480 + (v & 3) * 8, bd[v & 3], idesc, 1);
+            else umma_bf16(d, ad[v], bd[v & 3], idesc, 1);
+          }
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(smem_u32(&bar));
+      __syncwarp();
+      mbar_wait(smem_u32(&bar), ph);
+      ph ^= 1;
+      const long long t1 = clock64();
+      if (t1 - t0 < best) best = t1 - t0;
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = best;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tm, 512);
+}
+
+template <int NACC>
+void run(int n, int mode, int reps, long long* d) {
+  cudaFuncSetAttribute(k<NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  k<NACC><<<148, 128, 200 * 1024>>>(n, mode, reps, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("mode %d n %d: %s\n", mode, n, cudaGetErrorString(e)); exit(1); }
+  long long h[148];
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  long long mx = 0, mn = 1ll << 60;
+  for (int i = 0; i < 148; ++i) { if (h[i] > mx) mx = h[i]; if (h[i] < mn) mn = h[i]; }
+  const int r = reps / 36 * 36;
+  printf("mode %d (%-18s) nacc %d N %3d : %6.1f cycles/MMA (min %6.1f)  -> %3.0f%% of N/2 floor\n", mode,
+         mode == 0 ? "A smem aligned" : mode == 1 ? "A smem row-shifted" : "A tmem", NACC, n, (double)mx / r,
+         (double)mn / r, 100.0 * (n / 2.0) / ((double)mx / r));
+}
+
+int main() {
+  long long* d;
+  cudaMalloc(&d, 148 * sizeof(long long));
+  const int reps = 36 * 64;
+  const int ns[] = {16, 32, 64, 128, 256};
+  for (int mode = 0; mode < 3; ++mode)
+    for (int n : ns) {
+      run<1>(n, mode, reps, d);
+      run<2>(n, mode, reps, d);
+      if (n <= 128) run<4>(n, mode, reps, d);
+    }
+  return 0;
+}
