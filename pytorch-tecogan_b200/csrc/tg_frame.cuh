@@ -1,0 +1,57 @@
+// Persistent whole-generator kernel ("frame kernel"): all 41 convolutions of one generator forward
+// (reference code/models.py:78-86) as ONE launch.  See tg_frame.cu for the design.
+#pragma once
+#include "tg_conv_tc.cuh"
+
+namespace tg {
+
+constexpr int kFrMaxSegs = 56;     // 41 layers + one extra segment per 128-wide layer
+constexpr int kFrMaxMaps = 44;     // [0] packed weights, [1 + layer] input activation of the layer
+
+// One segment = one (layer, 64-wide output-channel chunk) pass over all 16x8 tiles of the layer.
+struct FrSeg {
+  int item_begin, item_end;   // global item range [begin, end)
+  int tiles_x, tiles_y;       // tiles per image in the layer's input resolution
+  int h, w;                   // input resolution
+  int map_a;                  // index of the input-activation tensor map
+  int kchunks;                // input channels / 64
+  int kind;                   // kConv3x3 / kConvT3x3s2
+  int nt;                     // UMMA N: 64, or 16 for the 3-channel output conv
+  uint32_t w_row0[2];         // first 128-byte row of the weight block of K chunk 0/1 in the packed blob
+  uint32_t w_rows;            // rows per weight block (9 taps * nt)
+  // epilogue
+  int out_mode, relu, oh, ow, oc, ch0;   // ch0 = first output channel of this chunk
+  long long out_nstride;
+  void* out;
+  float* out2;
+  const void* resid;
+  const float* bias;          // already offset to ch0
+  // tile-level dependencies: the producer layer's segments
+  int dep_seg0, dep_nseg;     // first producer segment, count (0 = input comes from a previous kernel)
+  int dep_tiles_x, dep_tiles_y, dep_shift_y, dep_shift_x;   // producer tile = (y >> shift_y, x >> shift_x)
+  uint32_t flag_off;          // offset of this segment's per-item completion counters
+};
+
+struct FrProgram {
+  CUtensorMap maps[kFrMaxMaps];
+  FrSeg segs[kFrMaxSegs];
+  int nseg, total_items;
+  uint32_t* flags;            // zeroed before the launch; one counter per item (4 = complete)
+};
+
+struct FrLayer {              // host-side description of one conv layer of the frame
+  int kind, cin_pad, cout_pad, out_mode, relu, h, w;
+  const void* in;
+  void* out;
+  const void* resid;
+  float* out2;
+  size_t blob_off;            // byte offset of the layer's packed blob
+  long long out_nstride;
+};
+
+size_t frame_flag_count(const FrLayer* layers, int nlayers, int n);
+// Builds the program and launches the frame kernel.  `flags` must hold frame_flag_count() uint32.
+int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t packed_bytes, int n,
+                 uint32_t* flags, cudaStream_t stream);
+
+}  // namespace tg
