@@ -37,6 +37,9 @@ extern "C" {
 /* A-operand staging of the tensor-core conv kernels (DESIGN.md "A staging modes"). */
 #define TG_AMODE_HALO 0 /* one TMA box with halo per stage; taps are row-shifted descriptors */
 #define TG_AMODE_DX3 1  /* three x-shifted copies per stage; every descriptor 1024B-aligned */
+/* tg_gen_forward / tg_gen_clip_forward only: all 41 layers as ONE persistent kernel chained by
+ * per-tile completion counters (HALO staging inside); the default of the Python mirror. */
+#define TG_AMODE_FRAME 2
 
 const char* tg_last_error_string(void);
 int tg_version(void);
@@ -46,11 +49,17 @@ int tg_check_device(void);
 /* Measurement hooks (bench.py): number of kernels this library launched since load, and optional
  * per-launch CUDA-event timing.  Between tg_profile_begin() and tg_profile_end() every launch is
  * bracketed by events on its stream; tg_profile_end synchronises and returns up to max_entries
- * records (kernel id: 0 conv_tc<64>, 1 output conv, 2 fused frame input, 3 other glue, 4 pack;
+ * records (kernel id: 0 conv_tc<64>, 1 output conv, 2 fused frame input, 3 other glue, 4 pack, 5 frame kernel;
  * duration in ms; algorithmic work = FLOPs for convs, bytes for glue).  Not graph-capturable. */
 long long tg_launch_count(void);
 int tg_profile_begin(void);
 int tg_profile_end(int max_entries, int* kernel_ids, float* ms, double* work);
+
+/* Measurement hook for the frame kernel (TG_AMODE_FRAME): while buf != NULL every frame launch writes
+ * %globaltimer stamps [segment][cta] (first item of each (layer, Cout chunk) segment per CTA, plus the
+ * kernel end in row nseg) into the device buffer; scripts/frame_trace.py turns them into a per-layer
+ * timeline.  buf == NULL switches it off. */
+int tg_frame_set_trace(void* buf, size_t bytes);
 
 /* ------------------------------------------------------------------ glue (HBM-bound) ------- */
 

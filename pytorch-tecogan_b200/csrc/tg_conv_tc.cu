@@ -282,8 +282,8 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int encode_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,
-                       const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+int encode_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,
+                const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     tg_set_error("cuTensorMapEncodeTiled entry point not available");

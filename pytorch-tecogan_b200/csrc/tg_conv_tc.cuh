@@ -55,6 +55,10 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
                    const void* resid, void* out, float* out2, int n, int h, int w, int cin_pad,
                    int cout_pad, int relu, int amode, long long out_nstride, cudaStream_t stream);
 
+// SWIZZLE_128B bf16 tiled tensor map (cuTensorMapEncodeTiled through the runtime's driver entry point)
+int encode_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,
+                const cuuint64_t* strides_bytes, const cuuint32_t* box);
+
 // packed layout helpers
 size_t packed_weight_bytes(int cin_pad, int cout_pad);   // bf16 blocks only
 int cin_padded(int cin);

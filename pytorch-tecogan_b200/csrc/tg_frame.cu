@@ -1,0 +1,520 @@
+// Persistent whole-generator kernel for sm_100a: the 41 convolutions of generator.forward
+// (reference code/models.py:78-86) as ONE launch of one CTA per SM.
+//
+// Why: at 320x180 the 33 trunk layers are 3.6 us of tensor work each; as separate launches they
+// cost 13-18 us (launch, prologue, weight fetch, pipeline fill/drain, 3.04-wave quantisation; see
+// profiles/r01_summary_v1_perlayer.md).  Here the whole frame is one ordered queue of work items
+//     item = (segment = layer x 64-wide Cout chunk, image, 16x8 pixel tile)
+// statically dealt round-robin to the CTAs, and layers are chained by per-tile completion counters
+// in global memory instead of kernel boundaries:
+//   * an item's TMA producer waits (ld.acquire.gpu) until the <= 3x3 producer tiles of the previous
+//     layer that its halo box touches have been published (one red.release.gpu per tile by a publisher warp,
+//     after the 128 epilogue threads arrived on a CTA-local mbarrier),
+//     then issues the box load; MMAs and epilogues of earlier items never wait on later ones, all
+//     CTAs are co-resident (1 per SM) and every dependency points to an earlier item of the queue,
+//     so the schedule cannot deadlock;
+//   * weights live in two 72 KB shared-memory slots managed as an LRU pair: a layer with one K chunk
+//     prefetches the next layer's block into the idle slot while it computes; a layer with two K
+//     chunks keeps both blocks resident.  A block is released (tcgen05.commit -> mbarrier) after the
+//     CTA's last item of the segment;
+//   * the tensor pipe therefore never drains between layers; TMEM, barriers and tensor maps are
+//     set up once per frame.
+// The GEMM core is the one of tg_conv_tc.cu (A = activation halo box, nine row-shifted descriptor
+// views; B = weights; accumulators in TMEM; UMMA M=128, N=64, K=16).
+#include <stdlib.h>
+#include <string.h>
+
+#include "tg_frame.cuh"
+
+namespace tg {
+
+constexpr int kFrThreads = 224;                        // producer, MMA, 4 epilogue warps, publisher
+constexpr uint32_t kFrSmemLimit = 232448;
+constexpr uint32_t kWSlotBytes = 73728;               // 9 taps x 64 x 64 bf16
+constexpr uint32_t kABoxBytes = 18 * 10 * 128;        // {64ch, 10, 18} halo box
+constexpr uint32_t kAStride = 23552;                  // 1024-aligned
+constexpr int kFrStages = 3;
+constexpr int kWBoxRows = 48;                         // weight TMA box: 48 rows x 128 B
+constexpr int kGroupCols = 256;                       // TMEM columns per accumulator group (2 groups)
+constexpr uint32_t kItemDone = 128;                   // counter value of a published tile
+
+// tap tables: [kind][j] ; A view offset inside the staged box, accumulator, "first tap of accumulator"
+__constant__ uint32_t c_aoff[2][9] = {
+    {0 * 128, 1 * 128, 2 * 128, 10 * 128, 11 * 128, 12 * 128, 20 * 128, 21 * 128, 22 * 128},
+    //  phase:   00 | 01        | 10         | 11
+    {0 * 128, 0 * 128, 1 * 128, 0 * 128, 10 * 128, 0 * 128, 1 * 128, 10 * 128, 11 * 128}};
+__constant__ uint8_t c_acc[2][9] = {{0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 1, 1, 2, 2, 3, 3, 3, 3}};
+__constant__ uint8_t c_first[2][9] = {{1, 0, 0, 0, 0, 0, 0, 0, 0}, {1, 1, 0, 1, 0, 1, 0, 0, 0}};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// L2-only load: the residual buffer is rewritten every third layer, L1 must not serve a stale line
+__device__ __forceinline__ void ld_global_cg_v8(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.cg.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p)
+               : "memory");
+}
+
+// Weight-slot LRU pair.  Producer and MMA warps run the same deterministic state machine over the
+// same item sequence, so they agree on slot and load parity without communicating.
+struct WSlots {
+  int blk0, blk1, mru;
+  uint32_t loads0, loads1;
+  __device__ __forceinline__ void init() { blk0 = blk1 = -1; mru = 1; loads0 = loads1 = 0; }
+  // returns slot; *is_load = block had to be (re)loaded; *nth = number of earlier loads into the slot
+  __device__ __forceinline__ int use(int b, bool* is_load, uint32_t* nth) {
+    int s;
+    if (blk0 == b) { s = 0; *is_load = false; }
+    else if (blk1 == b) { s = 1; *is_load = false; }
+    else {
+      s = 1 - mru;
+      if (s == 0) blk0 = b; else blk1 = b;
+      *is_load = true;
+    }
+    *nth = s ? loads1 : loads0;
+    if (*is_load) { if (s == 0) ++loads0; else ++loads1; }
+    mru = s;
+    return s;
+  }
+};
+
+__global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_constant__ FrProgram P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+
+  const uint32_t s_w = base;
+  const uint32_t s_a = base + 2 * kWSlotBytes;
+  const uint32_t bar0 = s_a + kFrStages * kAStride;
+  const uint32_t bar_wfull = bar0, bar_wempty = bar0 + 16;
+  const uint32_t bar_afull = bar0 + 32, bar_aempty = bar_afull + 8 * kFrStages;
+  const uint32_t bar_cfull = bar_aempty + 8 * kFrStages, bar_cempty = bar_cfull + 16;
+  const uint32_t bar_pfull = bar_cempty + 16, bar_pempty = bar_pfull + 16;
+  const uint32_t off_misc = (bar_pempty + 16) - base;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gbase + off_misc);
+  float* s_bias_all = reinterpret_cast<float*>(gbase + off_misc + 16);   // [4 warps][64]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_wfull + 8 * i, 1);
+      mbar_init(bar_wempty + 8 * i, 1);
+      mbar_init(bar_cfull + 8 * i, 1);
+      mbar_init(bar_cempty + 8 * i, 4);
+      mbar_init(bar_pfull + 8 * i, 128);
+      mbar_init(bar_pempty + 8 * i, 1);
+    }
+    for (int i = 0; i < kFrStages; ++i) {
+      mbar_init(bar_afull + 8 * i, 1);
+      mbar_init(bar_aempty + 8 * i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const int G = gridDim.x;
+
+  if (warp == 0) {
+    // ================================ TMA producer =========================================
+    if (lane < P.nseg) tma_prefetch_desc(&P.maps[P.segs[lane].map_a]);
+    if (lane == 0) tma_prefetch_desc(&P.maps[0]);
+    WSlots ws;
+    ws.init();
+    int si = 0, st = 0;
+    uint32_t ph = 0;
+    bool grid_waited = false;
+    for (int it = blockIdx.x; it < P.total_items; it += G) {
+      while (it >= P.segs[si].item_end) ++si;
+      const FrSeg& S = P.segs[si];
+      const int local = it - S.item_begin;
+      const int tx = local % S.tiles_x;
+      const int r = local / S.tiles_x;
+      const int ty = r % S.tiles_y;
+      const int n = r / S.tiles_y;
+      const int origin = (S.kind == kConv3x3) ? -1 : 0;
+      const int bx0 = tx * kTileW + origin, by0 = ty * kTileH + origin;
+      for (int kc = 0; kc < S.kchunks; ++kc) {
+        bool is_load;
+        uint32_t nth;
+        const int slot = ws.use(si * 2 + kc, &is_load, &nth);
+        if (is_load) {
+          mbar_wait(bar_wempty + 8 * slot, (nth & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(bar_wfull + 8 * slot, S.w_rows * 128);
+            for (uint32_t r0 = 0; r0 < S.w_rows; r0 += kWBoxRows)
+              tma_load_2d(s_w + slot * kWSlotBytes + r0 * 128, &P.maps[0], bar_wfull + 8 * slot, 0,
+                          static_cast<int>(S.w_row0[kc] + r0));
+          }
+          __syncwarp();
+        }
+        if (!grid_waited) {   // weights are constants; activations of a previous kernel are not
+          asm volatile("griddepcontrol.wait;" ::: "memory");
+          grid_waited = true;
+        }
+        if (kc == 0 && S.dep_nseg > 0 && !(P.dbg & 1)) {
+          // producer tiles of the previous layer touched by the halo box (clipped to the image)
+          const int ya = max(by0, 0), yb = min(by0 + kTileH + 1, S.h - 1);
+          const int xa = max(bx0, 0), xb = min(bx0 + kTileW + 1, S.w - 1);
+          const int tya = (ya >> S.dep_shift_y), tyb = (yb >> S.dep_shift_y);
+          const int txa = (xa >> S.dep_shift_x), txb = (xb >> S.dep_shift_x);
+          const int nx = txb - txa + 1, ny = tyb - tya + 1;
+          const int cnt = nx * ny * S.dep_nseg;
+          if (lane < cnt) {
+            const int ds = lane / (nx * ny);
+            const int q = lane - ds * (nx * ny);
+            const int dty = tya + q / nx, dtx = txa + q % nx;
+            const uint32_t* f = P.flags + P.segs[S.dep_seg0 + ds].flag_off +
+                                (static_cast<uint32_t>(n) * S.dep_tiles_y + dty) * S.dep_tiles_x + dtx;
+            if (ld_acquire_gpu(f) < kItemDone) {
+              const uint64_t t0 = global_ns();
+              uint32_t spins = 0;
+              while (ld_acquire_gpu(f) < kItemDone) {
+                __nanosleep(64);
+                if ((++spins & 0x3FFu) == 0 && global_ns() - t0 > 4000000000ull) {
+                  printf("tg: frame dependency timeout seg=%d item=%d block=%d\n", si, it, blockIdx.x);
+                  __trap();
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+        mbar_wait(bar_aempty + 8 * st, ph ^ 1);
+        if (elect_one()) {
+          fence_proxy_async_global();   // generic-proxy writes of other CTAs (acquired above) -> async-proxy read
+          mbar_expect_tx(bar_afull + 8 * st, kABoxBytes);
+          tma_load_4d(s_a + st * kAStride, &P.maps[S.map_a], bar_afull + 8 * st, kc * 64, bx0, by0, n);
+        }
+        __syncwarp();
+        if (++st == kFrStages) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ===========================================
+    WSlots ws;
+    ws.init();
+    int si = 0, st = 0, g = 0;
+    uint32_t ph = 0, gph = 0;
+    int traced_si = -1;
+    for (int it = blockIdx.x; it < P.total_items; it += G) {
+      while (it >= P.segs[si].item_end) ++si;
+      const FrSeg& S = P.segs[si];
+      if (P.trace && si != traced_si) {
+        if (lane == 0) P.trace[static_cast<size_t>(si) * G + blockIdx.x] = global_ns();
+        traced_si = si;
+      }
+      const bool last_in_seg = (it + G >= S.item_end);
+      const uint32_t idesc = umma_idesc_bf16(128, S.nt);
+      const uint32_t wtap_bytes = static_cast<uint32_t>(S.nt) * 128;
+      const int kind = S.kind;
+      mbar_wait(bar_cempty + 8 * g, gph ^ 1);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + static_cast<uint32_t>(g * kGroupCols);
+      for (int kc = 0; kc < S.kchunks; ++kc) {
+        bool is_load;
+        uint32_t nth;
+        const int slot = ws.use(si * 2 + kc, &is_load, &nth);
+        if (is_load) mbar_wait(bar_wfull + 8 * slot, nth & 1);
+        mbar_wait(bar_afull + 8 * st, ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_base = s_a + st * kAStride;
+          const uint32_t w_base = s_w + slot * kWSlotBytes;
+#pragma unroll 1
+          for (int j = 0; j < 9; ++j) {
+            const uint64_t ad = umma_desc_sw128(a_base + c_aoff[kind][j], 10 * 128);
+            const uint64_t bd = umma_desc_sw128(w_base + j * wtap_bytes, 1024);
+            const uint32_t d = d_base + c_acc[kind][j] * kAccCols;
+            const uint32_t keep = (kc > 0 || !c_first[kind][j]) ? 1u : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
+          }
+          umma_commit(bar_aempty + 8 * st);
+          if (last_in_seg) umma_commit(bar_wempty + 8 * slot);
+          if (kc == S.kchunks - 1) umma_commit(bar_cfull + 8 * g);
+        }
+        __syncwarp();
+        if (++st == kFrStages) { st = 0; ph ^= 1; }
+      }
+      g ^= 1;
+      if (g == 0) gph ^= 1;
+    }
+  } else if (warp < 6) {
+    // ================================ epilogue (4 warps) ===================================
+    const int q = warp & 3;                                // TMEM lane quarter of this warp
+    const int m = q * 32 + lane;
+    const int pr = m >> 3, pc = m & 7;
+    float* s_bias = s_bias_all + q * 64;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    int si = 0, cur_si = -1, g = 0;
+    uint32_t gph = 0;
+    // Publishing a tile: every epilogue thread arrives (release.cta) on a CTA-local mbarrier after its stores;
+    // the publisher warp then performs ONE gpu-scope release (MEMBAR.GPU + RED) for the whole tile, so the
+    // fence latency never stalls the epilogue.
+    uint32_t pk = 0;
+    for (int it = blockIdx.x; it < P.total_items; it += G) {
+      while (it >= P.segs[si].item_end) ++si;
+      const FrSeg& S = P.segs[si];
+      if (si != cur_si) {                                  // warp-private bias copy of this segment
+        __syncwarp();
+        for (int c = lane; c < S.nt; c += 32) s_bias[c] = S.bias[c];
+        __syncwarp();
+        cur_si = si;
+      }
+      const int local = it - S.item_begin;
+      const int tx = local % S.tiles_x;
+      const int r = local / S.tiles_x;
+      const int ty = r % S.tiles_y;
+      const int n = r / S.tiles_y;
+      const int iy = ty * kTileH + pr, ix = tx * kTileW + pc;
+      const bool valid = (iy < S.h) && (ix < S.w);
+      const int n_acc = (S.kind == kConv3x3) ? 1 : 4;
+      const int sc = (S.kind == kConv3x3) ? 1 : 2;
+      mbar_wait(bar_cfull + 8 * g, gph);
+      tc_fence_after();
+      for (int a = 0; a < n_acc; ++a) {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(g * kGroupCols + a * kAccCols);
+        const int oy = iy * sc + (a >> 1), ox = ix * sc + (a & 1);
+        if (S.out_mode == kOutNHWCbf16) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(taddr, v0);
+          tmem_ld_32x32(taddr + 32, v1);
+          tmem_ld_wait();
+          if (a == n_acc - 1) {                            // TMEM drained -> hand the group back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
+          }
+          if (valid) {
+            const size_t pix = (static_cast<size_t>(n) * S.oh + oy) * S.ow + ox;
+            uint8_t* dst = static_cast<uint8_t*>(S.out) + (pix * S.oc + S.ch0) * 2;
+            const uint8_t* res = S.resid ? static_cast<const uint8_t*>(S.resid) + (pix * S.oc + S.ch0) * 2 : nullptr;
+            const bool relu = S.relu != 0;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              uint32_t* v = h2 ? v1 : v0;
+#pragma unroll
+              for (int c16 = 0; c16 < 2; ++c16) {          // 16 channels = one 32-byte store
+                float f[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  f[e] = __uint_as_float(v[c16 * 16 + e]) + s_bias[h2 * 32 + c16 * 16 + e];
+                  if (relu) f[e] = fmaxf(f[e], 0.f);
+                }
+                if (res) {
+                  uint32_t rv[8];
+                  ld_global_cg_v8(res + h2 * 64 + c16 * 32, rv);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) { f[2 * e] += bf16_lo(rv[e]); f[2 * e + 1] += bf16_hi(rv[e]); }
+                }
+                uint32_t o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+                st_global_v8(dst + h2 * 64 + c16 * 32, o);
+              }
+            }
+          }
+        } else {
+          uint32_t v[16];
+          tmem_ld_32x16(taddr, v);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
+          if (valid) {
+            const size_t plane = static_cast<size_t>(S.oh) * S.ow;
+            const size_t o0 = static_cast<size_t>(n) * S.out_nstride + static_cast<size_t>(oy) * S.ow + ox;
+            for (int c = 0; c < S.oc; ++c) {
+              const float z = __uint_as_float(v[c]) + s_bias[c];
+              if (S.out2) S.out2[o0 + c * plane] = z;
+              static_cast<float*>(S.out)[o0 + c * plane] = 1.f / (1.f + expf(-z));
+            }
+          }
+        }
+      }
+      // the network output has no consumer inside the kernel: nothing to publish
+      if (S.out_mode == kOutNHWCbf16 && !(P.dbg & 2)) {
+        const uint32_t pg = pk & 1u, pph = (pk >> 1) & 1u;
+        mbar_wait(bar_pempty + 8 * pg, pph ^ 1);             // publisher at most 2 tiles behind
+        mbar_arrive(bar_pfull + 8 * pg);
+        ++pk;
+      }
+      g ^= 1;
+      if (g == 0) gph ^= 1;
+    }
+  } else {
+    // ================================ publisher ============================================
+    int si = 0;
+    uint32_t pk = 0;
+    for (int it = blockIdx.x; it < P.total_items; it += G) {
+      while (it >= P.segs[si].item_end) ++si;
+      const FrSeg& S = P.segs[si];
+      if (S.out_mode == kOutNHWCbf16 && !(P.dbg & 2)) {
+        const uint32_t pg = pk & 1u, pph = (pk >> 1) & 1u;
+        mbar_wait(bar_pfull + 8 * pg, pph);                  // all 128 epilogue threads stored (acquire.cta)
+        if (lane == 0) {
+          red_release_gpu_add(P.flags + S.flag_off + (it - S.item_begin), kItemDone);   // cumulative gpu-scope release
+          mbar_arrive(bar_pempty + 8 * pg);
+        }
+        __syncwarp();
+        ++pk;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (P.trace && threadIdx.x == 0) P.trace[static_cast<size_t>(P.nseg) * G + blockIdx.x] = global_ns();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------ host
+static unsigned long long* g_trace = nullptr;
+static size_t g_trace_words = 0;
+void frame_set_trace(unsigned long long* buf, size_t words) { g_trace = buf; g_trace_words = words; }
+
+static int layer_nt(const FrLayer& l) { return l.cout_pad == 16 ? 16 : 64; }
+
+size_t frame_flag_count(const FrLayer* layers, int nlayers, int n) {
+  size_t total = 0;
+  for (int i = 0; i < nlayers; ++i) {
+    const size_t tiles = static_cast<size_t>(n) * tg_div_up(layers[i].w, kTileW) * tg_div_up(layers[i].h, kTileH);
+    total += tiles * (layers[i].cout_pad / layer_nt(layers[i]));
+  }
+  return total;
+}
+
+int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t packed_bytes, int n,
+                 uint32_t* flags, size_t flag_capacity, bool flags_zeroed, cudaStream_t stream) {
+  TG_CHECK_ARG(nlayers >= 1 && nlayers + 1 <= kFrMaxMaps, "frame: too many layers (%d)", nlayers);
+  TG_CHECK_ARG(packed && flags && (packed_bytes % 128) == 0, "frame: bad packed blob");
+  static thread_local FrProgram P;   // 13 KB: keep it off the stack
+  memset(&P, 0, sizeof(P));
+  {
+    cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(packed_bytes / 128)};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, kWBoxRows};
+    int rc = encode_bf16(&P.maps[0], packed, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  int nseg = 0, items = 0;
+  int first_seg[kFrMaxMaps], nchunks[kFrMaxMaps];
+  double flops = 0.0;
+  for (int li = 0; li < nlayers; ++li) {
+    const FrLayer& l = layers[li];
+    TG_CHECK_ARG(l.cin_pad == 64 || l.cin_pad == 128, "frame: cin_pad must be 64 or 128");
+    TG_CHECK_ARG(l.cout_pad == 16 || l.cout_pad == 64 || l.cout_pad == 128, "frame: cout_pad must be 16/64/128");
+    TG_CHECK_ARG((l.blob_off % 128) == 0, "frame: packed blob offsets must be 128-byte aligned");
+    {
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(l.cin_pad), static_cast<cuuint64_t>(l.w),
+                            static_cast<cuuint64_t>(l.h), static_cast<cuuint64_t>(n)};
+      cuuint64_t strides[3] = {static_cast<cuuint64_t>(l.cin_pad) * 2, static_cast<cuuint64_t>(l.w) * l.cin_pad * 2,
+                               static_cast<cuuint64_t>(l.h) * l.w * l.cin_pad * 2};
+      cuuint32_t box[4] = {64, kTileW + 2, kTileH + 2, 1};
+      int rc = encode_bf16(&P.maps[1 + li], l.in, 4, dims, strides, box);
+      if (rc) return rc;
+    }
+    const int nt = layer_nt(l);
+    const int chunks = l.cout_pad / nt;
+    const int kchunks = l.cin_pad / 64;
+    const int tiles_x = tg_div_up(l.w, kTileW), tiles_y = tg_div_up(l.h, kTileH);
+    const int sc = (l.kind == kConv3x3) ? 1 : 2;
+    first_seg[li] = nseg;
+    nchunks[li] = chunks;
+    flops += 2.0 * 9.0 * l.cin_pad * (nt == 64 ? l.cout_pad : 3) * n * l.h * l.w;
+    for (int c = 0; c < chunks; ++c) {
+      TG_CHECK_ARG(nseg < kFrMaxSegs, "frame: too many segments");
+      FrSeg& S = P.segs[nseg];
+      S.item_begin = items;
+      items += n * tiles_x * tiles_y;
+      S.item_end = items;
+      S.tiles_x = tiles_x; S.tiles_y = tiles_y; S.h = l.h; S.w = l.w;
+      S.map_a = 1 + li;
+      S.kchunks = kchunks; S.kind = l.kind; S.nt = nt;
+      S.w_rows = 9u * nt;
+      for (int kc = 0; kc < kchunks; ++kc)
+        S.w_row0[kc] = static_cast<uint32_t>(l.blob_off / 128) + static_cast<uint32_t>(c * kchunks + kc) * S.w_rows;
+      S.out_mode = l.out_mode; S.relu = l.relu;
+      S.oh = l.h * sc; S.ow = l.w * sc;
+      S.oc = (l.out_mode == kOutNCHWf32Sigmoid) ? 3 : l.cout_pad;
+      S.ch0 = c * 64;
+      S.out_nstride = l.out_nstride > 0 ? l.out_nstride : static_cast<long long>(S.oc) * S.oh * S.ow;
+      S.out = l.out; S.out2 = l.out2; S.resid = l.resid;
+      S.bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(packed) + l.blob_off +
+                                              packed_weight_bytes(l.cin_pad, l.cout_pad)) + c * 64;
+      if (li == 0) {
+        S.dep_seg0 = 0; S.dep_nseg = 0;
+      } else {
+        const FrLayer& pl = layers[li - 1];
+        const int psc = (pl.kind == kConv3x3) ? 1 : 2;
+        TG_CHECK_ARG(pl.h * psc == l.h && pl.w * psc == l.w && pl.out == l.in, "frame: layer %d does not consume layer %d", li, li - 1);
+        S.dep_seg0 = first_seg[li - 1]; S.dep_nseg = nchunks[li - 1];
+        S.dep_tiles_x = tg_div_up(pl.w, kTileW); S.dep_tiles_y = tg_div_up(pl.h, kTileH);
+        S.dep_shift_y = (psc == 1) ? 4 : 5;   // producer tile = 16 (32) output rows
+        S.dep_shift_x = (psc == 1) ? 3 : 4;   //                  8 (16) output columns
+      }
+      S.flag_off = static_cast<uint32_t>(S.item_begin);
+      ++nseg;
+    }
+  }
+  P.nseg = nseg;
+  P.total_items = items;
+  P.flags = flags;
+  {
+    static const int dbg = []() { const char* e = getenv("TG_FRAME_DBG"); return e ? atoi(e) : 0; }();
+    P.dbg = dbg;
+    const int grid = items < tg_num_sms() ? items : tg_num_sms();
+    P.trace = (g_trace && g_trace_words >= static_cast<size_t>(nseg + 1) * grid) ? g_trace : nullptr;
+  }
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    TG_CUDA(cudaFuncSetAttribute(frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrSmemLimit));
+    attr_done = true;
+  }
+  TG_CHECK_ARG(static_cast<size_t>(items) <= flag_capacity, "frame: %d items exceed the flag capacity %zu", items, flag_capacity);
+  if (!flags_zeroed) TG_CUDA(cudaMemsetAsync(flags, 0, static_cast<size_t>(items) * sizeof(uint32_t), stream));
+  const uint32_t smem_bytes = 2 * kWSlotBytes + kFrStages * kAStride + 256 + 4 * 64 * 4 + 1024;
+  static_assert(2 * kWSlotBytes + kFrStages * kAStride + 256 + 4 * 64 * 4 + 1024 <= kFrSmemLimit, "smem budget");
+  cudaLaunchConfig_t cfg{};
+  const int sms = tg_num_sms();
+  cfg.gridDim = dim3(items < sms ? items : sms);
+  cfg.blockDim = dim3(kFrThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  tg_prof_pre(TG_K_FRAME, flops, stream);
+  TG_CUDA(cudaLaunchKernelEx(&cfg, frame_kernel, P));
+  tg_prof_post(stream);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+}  // namespace tg

@@ -36,7 +36,9 @@ struct FrProgram {
   CUtensorMap maps[kFrMaxMaps];
   FrSeg segs[kFrMaxSegs];
   int nseg, total_items;
-  uint32_t* flags;            // zeroed before the launch; one counter per item (4 = complete)
+  uint32_t* flags;            // zeroed before the launch; one counter per item (128 = complete)
+  unsigned long long* trace;  // optional [nseg+1][grid] globaltimer stamps (tg_frame_set_trace), else null
+  int dbg;                    // measurement-only knobs (TG_FRAME_DBG): 1 no dependency wait, 2 no publish
 };
 
 struct FrLayer {              // host-side description of one conv layer of the frame
@@ -50,8 +52,17 @@ struct FrLayer {              // host-side description of one conv layer of the 
 };
 
 size_t frame_flag_count(const FrLayer* layers, int nlayers, int n);
-// Builds the program and launches the frame kernel.  `flags` must hold frame_flag_count() uint32.
+// Builds the program and launches the frame kernel.  `flags` holds `flag_capacity` uint32 counters
+// (>= frame_flag_count()); flags_zeroed = an earlier kernel of the stream already cleared them.
 int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t packed_bytes, int n,
-                 uint32_t* flags, cudaStream_t stream);
+                 uint32_t* flags, size_t flag_capacity, bool flags_zeroed, cudaStream_t stream);
+
+// measurement hook: subsequent frame launches stamp [nseg+1][grid] globaltimer values into buf (null = off)
+void frame_set_trace(unsigned long long* buf, size_t words);
+
+// tg_glue.cu: the fused frame-input producer, optionally clearing `zero_count` uint32 at `zero`.
+int fused_input_launch(const float* lr_t, const float* lr_prev, const float* prev_hr, void* x_nhwc, int n, int h,
+                       int w, long long lr_bs, long long hr_bs, uint32_t* zero, size_t zero_count,
+                       cudaStream_t stream);
 
 }  // namespace tg

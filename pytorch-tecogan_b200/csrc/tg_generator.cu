@@ -2,7 +2,7 @@
 // the recurrent clip loop (reference main.py:173-219) kept entirely on the device.
 #include <vector>
 
-#include "tg_conv_tc.cuh"
+#include "tg_frame.cuh"
 
 namespace tg {
 
@@ -46,7 +46,7 @@ static std::vector<GenLayer> gen_layers(int nres, size_t* n_params, size_t* pack
 static inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
 struct GenWorkspace {
-  size_t x0, a[3], b[2], c[2], d, e, total;
+  size_t x0, a[3], b[2], c[2], d, e, flags, flag_count, total;
 };
 static GenWorkspace gen_ws(int n, int h, int w) {
   GenWorkspace ws;
@@ -59,44 +59,79 @@ static GenWorkspace gen_ws(int n, int h, int w) {
   for (int i = 0; i < 2; ++i) ws.c[i] = take(px * 4 * 128 * 2);
   ws.d = take(px * 16 * 128 * 2);
   ws.e = take(px * 16 * 64 * 2);
+  // per-item completion counters of the frame kernel: trunk/convT64 items at 1x, 2x items, 4x items
+  auto tiles = [&](int s) { return static_cast<size_t>(n) * tg_div_up(w * s, kTileW) * tg_div_up(h * s, kTileH); };
+  ws.flag_count = 132 * tiles(1) + 16 * tiles(2) + 4 * tiles(4);   // covers num_resblock <= 64
+  ws.flags = take(ws.flag_count * 4);
   ws.total = o;
   return ws;
 }
 
-static int gen_forward_impl(const std::vector<GenLayer>& L, const uint8_t* packed, int nres, const void* x,
-                            float* out, float* logits, uint8_t* wsp, int n, int h, int w, int amode,
-                            long long out_nstride, cudaStream_t st) {
+// The 41 layers of one forward as a list (input/output/residual buffers inside the workspace).
+static std::vector<FrLayer> gen_plan(const std::vector<GenLayer>& L, int nres, const void* x, float* out,
+                                     float* logits, uint8_t* wsp, int n, int h, int w, long long out_nstride) {
   const GenWorkspace ws = gen_ws(n, h, w);
-  auto blob = [&](int i) { return packed + L[i].p_off; };
-  auto bias = [&](int i) {
-    return reinterpret_cast<const float*>(blob(i) + packed_weight_bytes(cin_padded(L[i].cin), cout_padded(L[i].cout)));
+  std::vector<FrLayer> P;
+  int li = 0;
+  auto add = [&](const void* in, void* o, const void* resid, int relu, int hh, int ww) {
+    FrLayer f{};
+    f.kind = L[li].kind;
+    f.cin_pad = cin_padded(L[li].cin);
+    f.cout_pad = cout_padded(L[li].cout);
+    f.out_mode = kOutNHWCbf16;
+    f.relu = relu; f.h = hh; f.w = ww;
+    f.in = in; f.out = o; f.resid = resid; f.out2 = nullptr;
+    f.blob_off = L[li].p_off;
+    f.out_nstride = 0;
+    P.push_back(f);
+    ++li;
   };
-  auto conv = [&](int i, const void* in, void* o, const void* resid, int relu, int hh, int ww) {
-    return launch_conv_tc(L[i].kind, kOutNHWCbf16, in, blob(i), bias(i), resid, o, nullptr, n, hh, ww,
-                          cin_padded(L[i].cin), cout_padded(L[i].cout), relu, amode, 0, st);
-  };
-  int rc, li = 0;
   void* a[3] = {wsp + ws.a[0], wsp + ws.a[1], wsp + ws.a[2]};
-  if ((rc = conv(li++, x, a[0], nullptr, 1, h, w))) return rc;               // conv.0 + ReLU
+  add(x, a[0], nullptr, 1, h, w);                                            // conv.0 + ReLU
   int cur = 0;
   for (int i = 0; i < nres; ++i) {                                           // net = block(net) + net
     const int t = (cur + 1) % 3, nx = (cur + 2) % 3;
-    if ((rc = conv(li++, a[cur], a[t], nullptr, 1, h, w))) return rc;
-    if ((rc = conv(li++, a[t], a[nx], a[cur], 0, h, w))) return rc;
+    add(a[cur], a[t], nullptr, 1, h, w);
+    add(a[t], a[nx], a[cur], 0, h, w);
     cur = nx;
   }
   void* b0 = wsp + ws.b[0]; void* b1 = wsp + ws.b[1];
   void* c0 = wsp + ws.c[0]; void* c1 = wsp + ws.c[1];
   void* d = wsp + ws.d; void* e = wsp + ws.e;
-  if ((rc = conv(li++, a[cur], b0, nullptr, 1, h, w))) return rc;            // conv_trans.0 (x2) + ReLU
-  if ((rc = conv(li++, b0, b1, nullptr, 1, 2 * h, 2 * w))) return rc;        // conv_trans.2.0 + ReLU
-  if ((rc = conv(li++, b1, b0, nullptr, 0, 2 * h, 2 * w))) return rc;        // conv_trans.2.2 (no skip)
-  if ((rc = conv(li++, b0, c0, nullptr, 1, 2 * h, 2 * w))) return rc;        // conv_trans.3.0 + ReLU
-  if ((rc = conv(li++, c0, c1, nullptr, 0, 2 * h, 2 * w))) return rc;        // conv_trans.3.2
-  if ((rc = conv(li++, c1, d, nullptr, 1, 2 * h, 2 * w))) return rc;         // conv_trans.4 (x2) + ReLU
-  if ((rc = conv(li++, d, e, nullptr, 1, 4 * h, 4 * w))) return rc;          // conv_trans.6 + ReLU
-  return launch_conv_tc(kConv3x3, kOutNCHWf32Sigmoid, e, blob(li), bias(li), nullptr, out, logits, n, 4 * h, 4 * w,
-                        64, 16, 0, amode, out_nstride, st);                  // output + sigmoid
+  add(a[cur], b0, nullptr, 1, h, w);                                         // conv_trans.0 (x2) + ReLU
+  add(b0, b1, nullptr, 1, 2 * h, 2 * w);                                     // conv_trans.2.0 + ReLU
+  add(b1, b0, nullptr, 0, 2 * h, 2 * w);                                     // conv_trans.2.2 (no skip)
+  add(b0, c0, nullptr, 1, 2 * h, 2 * w);                                     // conv_trans.3.0 + ReLU
+  add(c0, c1, nullptr, 0, 2 * h, 2 * w);                                     // conv_trans.3.2
+  add(c1, d, nullptr, 1, 2 * h, 2 * w);                                      // conv_trans.4 (x2) + ReLU
+  add(d, e, nullptr, 1, 4 * h, 4 * w);                                       // conv_trans.6 + ReLU
+  add(e, out, nullptr, 0, 4 * h, 4 * w);                                     // output + sigmoid
+  P.back().out_mode = kOutNCHWf32Sigmoid;
+  P.back().out2 = logits;
+  P.back().out_nstride = out_nstride;
+  return P;
+}
+
+// flags_zeroed: the per-item completion counters were already cleared by an earlier kernel of the stream
+static int gen_forward_impl(const std::vector<GenLayer>& L, const uint8_t* packed, int nres, const void* x,
+                            float* out, float* logits, uint8_t* wsp, int n, int h, int w, int amode,
+                            long long out_nstride, bool flags_zeroed, cudaStream_t st) {
+  const std::vector<FrLayer> P = gen_plan(L, nres, x, out, logits, wsp, n, h, w, out_nstride);
+  if (amode == TG_AMODE_FRAME) {
+    size_t pb = 0;
+    for (auto& l : L) pb += tg_packed_conv_bytes(l.kind, l.cin, l.cout);
+    return launch_frame(P.data(), static_cast<int>(P.size()), packed, pb, n,
+                        reinterpret_cast<uint32_t*>(wsp + gen_ws(n, h, w).flags), gen_ws(n, h, w).flag_count,
+                        flags_zeroed, st);
+  }
+  for (const FrLayer& f : P) {
+    const uint8_t* blob = packed + f.blob_off;
+    const float* bias = reinterpret_cast<const float*>(blob + packed_weight_bytes(f.cin_pad, f.cout_pad));
+    int rc = launch_conv_tc(f.kind, f.out_mode, f.in, blob, bias, f.resid, f.out, f.out2, n, f.h, f.w, f.cin_pad,
+                            f.cout_pad, f.relu, amode, f.out_nstride, st);
+    if (rc) return rc;
+  }
+  return TG_OK;
 }
 
 }  // namespace tg
@@ -141,8 +176,9 @@ extern "C" int tg_gen_forward(const void* packed, int num_resblock, const void* 
     return TG_ERR_WORKSPACE;
   }
   auto L = gen_layers(num_resblock, nullptr, nullptr);
+  TG_CHECK_ARG(amode == TG_AMODE_HALO || amode == TG_AMODE_DX3 || amode == TG_AMODE_FRAME, "gen_forward: bad amode %d", amode);
   return gen_forward_impl(L, static_cast<const uint8_t*>(packed), num_resblock, x_nhwc, out, logits_or_null,
-                          static_cast<uint8_t*>(workspace), n, h, w, amode, 0, static_cast<cudaStream_t>(stream));
+                          static_cast<uint8_t*>(workspace), n, h, w, amode, 0, false, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tg_gen_clip_forward(const void* packed, int num_resblock, const float* lr, float* out, void* workspace,
@@ -160,15 +196,25 @@ extern "C" int tg_gen_clip_forward(const void* packed, int num_resblock, const f
   void* x0 = wsp + ws.x0;
   const long long lr_frame = 3LL * h * w, hr_frame = 48LL * h * w;
   const long long lr_bs = lr_frame * t, hr_bs = hr_frame * t;
+  const bool frame_mode = (amode == TG_AMODE_FRAME);
   for (int f = 0; f < t; ++f) {
     const float* lr_t = lr + f * lr_frame;
     const float* lr_prev = f ? lr + (f - 1) * lr_frame : nullptr;
     const float* prev_hr = f ? out + (f - 1) * hr_frame : nullptr;
-    int rc = tg_fused_warp_s2d_concat(lr_t, lr_prev, prev_hr, x0, n, h, w, lr_bs, hr_bs, stream);
+    // the frame-input kernel also clears the frame kernel's completion counters (it runs strictly
+    // after the previous frame kernel and strictly before the next one)
+    int rc = fused_input_launch(lr_t, lr_prev, prev_hr, x0, n, h, w, lr_bs, hr_bs,
+                                frame_mode ? reinterpret_cast<uint32_t*>(wsp + ws.flags) : nullptr,
+                                frame_mode ? ws.flag_count : 0, static_cast<cudaStream_t>(stream));
     if (rc) return rc;
     rc = gen_forward_impl(L, static_cast<const uint8_t*>(packed), num_resblock, x0, out + f * hr_frame, nullptr, wsp, n,
-                          h, w, amode, hr_bs, static_cast<cudaStream_t>(stream));
+                          h, w, amode, hr_bs, frame_mode, static_cast<cudaStream_t>(stream));
     if (rc) return rc;
   }
+  return TG_OK;
+}
+
+extern "C" int tg_frame_set_trace(void* buf, size_t bytes) {
+  tg::frame_set_trace(static_cast<unsigned long long*>(buf), buf ? bytes / 8 : 0);
   return TG_OK;
 }

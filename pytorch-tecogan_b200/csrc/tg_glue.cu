@@ -2,7 +2,7 @@
 // warp, bilinear x4 upscale, and the fused producer of the generator input.
 // All kernels are pure streaming / gather kernels: coalesced 128-bit accesses on the contiguous
 // side, shared-memory staging where the two sides disagree, grid-stride over whole rows.
-#include "tg_common.cuh"
+#include "tg_frame.cuh"
 
 namespace tg {
 
@@ -171,8 +171,12 @@ constexpr int kFT = 8;   // LR tile edge
 __global__ void __launch_bounds__(256)
 fused_input_kernel(const float* __restrict__ lr_t, const float* __restrict__ lr_prev,
                    const float* __restrict__ prev_hr, __nv_bfloat16* __restrict__ x, int n, int h, int w,
-                   long long lr_bs, long long hr_bs) {
+                   long long lr_bs, long long hr_bs, uint32_t* __restrict__ zero, size_t zero_count) {
   __shared__ __align__(16) __nv_bfloat16 tile[kFT * kFT][64];
+  // clear the frame kernel's per-item completion counters (this kernel runs between two frame kernels)
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < zero_count;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    zero[i] = 0u;
   const int tiles_x = (w + kFT - 1) / kFT, tiles_y = (h + kFT - 1) / kFT;
   const int ho = 4 * h, wo = 4 * w;
   const long long hw_o = static_cast<long long>(ho) * wo;
@@ -346,21 +350,30 @@ extern "C" int tg_upscale4_bilinear(const float* in, float* out, int n, int c, i
   return TG_OK;
 }
 
-extern "C" int tg_fused_warp_s2d_concat(const float* lr_t, const float* lr_prev, const float* prev_hr, void* x_nhwc,
-                                        int n, int h, int w, long long lr_batch_stride, long long hr_batch_stride,
-                                        void* stream) {
+int tg::fused_input_launch(const float* lr_t, const float* lr_prev, const float* prev_hr, void* x_nhwc, int n, int h,
+                           int w, long long lr_batch_stride, long long hr_batch_stride, uint32_t* zero,
+                           size_t zero_count, cudaStream_t stream) {
   TG_CHECK_ARG(lr_t && x_nhwc, "fused_warp_s2d_concat: null pointer");
   TG_CHECK_ARG(n >= 1 && h >= 1 && w >= 1, "fused_warp_s2d_concat: bad shape");
   TG_CHECK_ARG((reinterpret_cast<uintptr_t>(x_nhwc) & 15) == 0, "fused_warp_s2d_concat: x must be 16-byte aligned");
   if (!lr_prev || !prev_hr) { lr_prev = nullptr; prev_hr = nullptr; }
   const int tiles = n * tg_div_up(w, kFT) * tg_div_up(h, kFT);
   int blocks = tiles < tg_num_sms() * 8 ? tiles : tg_num_sms() * 8;
-  tg_prof_pre(TG_K_FUSED_INPUT, 18.4 * 16.0 * n * h * w, static_cast<cudaStream_t>(stream));      // 12+4+6.4 B/HR px... minus grid (on the fly)
-  fused_input_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      lr_t, lr_prev, prev_hr, static_cast<__nv_bfloat16*>(x_nhwc), n, h, w, lr_batch_stride, hr_batch_stride);
-  tg_prof_post(static_cast<cudaStream_t>(stream));
+  // algorithmic bytes, SURVEY.md 8(d): 12 B (prev HR f32) + 6.4 B (51 bf16 channels / 16) per HR pixel; the flow
+  // is computed on the fly from the LR frame, so the 4 B/px grid read does not exist
+  tg_prof_pre(TG_K_FUSED_INPUT, 18.4 * 16.0 * n * h * w, stream);
+  fused_input_kernel<<<blocks, 256, 0, stream>>>(lr_t, lr_prev, prev_hr, static_cast<__nv_bfloat16*>(x_nhwc), n, h, w,
+                                                 lr_batch_stride, hr_batch_stride, zero, zero_count);
+  tg_prof_post(stream);
   TG_CUDA(cudaGetLastError());
   return TG_OK;
+}
+
+extern "C" int tg_fused_warp_s2d_concat(const float* lr_t, const float* lr_prev, const float* prev_hr, void* x_nhwc,
+                                        int n, int h, int w, long long lr_batch_stride, long long hr_batch_stride,
+                                        void* stream) {
+  return tg::fused_input_launch(lr_t, lr_prev, prev_hr, x_nhwc, n, h, w, lr_batch_stride, hr_batch_stride, nullptr, 0,
+                                static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tg_pack_nchw_to_nhwc64(const float* in, void* out, int n, int c, int h, int w, void* stream) {

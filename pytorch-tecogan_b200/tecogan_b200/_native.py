@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libtecogan_b200.so")
 
 AMODE_HALO = 0
 AMODE_DX3 = 1
+AMODE_FRAME = 2     # whole generator forward as one persistent kernel (tg_gen_forward / tg_gen_clip_forward)
 
 _c_void_p = ctypes.c_void_p
 _c_int = ctypes.c_int
@@ -28,6 +29,7 @@ SIGNATURES = {
     "tg_launch_count": (_c_ll, []),
     "tg_profile_begin": (_c_int, []),
     "tg_profile_end": (_c_int, [_c_int, _c_void_p, _c_void_p, _c_void_p]),
+    "tg_frame_set_trace": (_c_int, [_c_void_p, _c_size_t]),
     "tg_space_to_depth": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "tg_depth_to_space": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "tg_warp_bilinear": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,

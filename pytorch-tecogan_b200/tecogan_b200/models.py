@@ -38,7 +38,7 @@ class generator(nn.Module):
                                         conv2_tran(128, 3, 128, stride=2, output_padding=1), nn.ReLU(),
                                         conv2(128, 3, 64, 1), nn.ReLU())
         self.output = conv2(64, 3, gen_output_channels, 1)
-        self.amode = _nt.AMODE_HALO
+        self.amode = _nt.AMODE_FRAME
         self._packed = None
         self._packed_key = None
         self._ws = None

@@ -73,8 +73,9 @@ if __name__ == "__main__":
     nt.check(lib.tg_gen_pack(nt.ptr(flat), nres, nt.ptr(packed), nt.stream_ptr()))
     ws = torch.empty(lib.tg_gen_workspace_bytes(N, H, W), dtype=torch.uint8, device="cuda")
     x0 = torch.rand(N, H, W, 64, device="cuda").to(torch.bfloat16)
-    t = timeit(lambda: nt.check(lib.tg_gen_forward(nt.ptr(packed), nres, nt.ptr(x0), nt.ptr(out), None, nt.ptr(ws), ws.numel(), N, H, W, AMODE, nt.stream_ptr())), iters=10)
-    print(f"generator frame 720p: {t*1e3:.3f} ms  -> {N/t:.1f} frames/s  {N*486.45e9/t/1e12:.1f} TFLOP/s")
+    for am, nm in ((AMODE, "per-layer launches"), (2, "frame kernel")):
+        t = timeit(lambda: nt.check(lib.tg_gen_forward(nt.ptr(packed), nres, nt.ptr(x0), nt.ptr(out), None, nt.ptr(ws), ws.numel(), N, H, W, am, nt.stream_ptr())), iters=10)
+        print(f"generator frame 720p ({nm}): {t*1e3:.3f} ms  -> {N/t:.1f} frames/s  {N*486.45e9/t/1e12:.1f} TFLOP/s", flush=True)
     lr = torch.rand(N, 3, H, W, device="cuda")
     hr = torch.rand(N, 3, 4 * H, 4 * W, device="cuda")
     t = timeit(lambda: nt.check(lib.tg_fused_warp_s2d_concat(nt.ptr(lr), nt.ptr(lr), nt.ptr(hr), nt.ptr(x0), N, H, W, 3 * H * W, 48 * H * W, nt.stream_ptr())))

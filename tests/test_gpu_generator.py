@@ -19,7 +19,10 @@ def _psnr(a, b):
     return 99.0 if mse == 0 else 10.0 * math.log10(1.0 / mse)
 
 
-def _make(gain, nres=16, amode=0):
+PER_LAYER, FRAME = 0, 2      # one launch per conv layer (HALO staging) / one persistent kernel per frame
+
+
+def _make(gain, nres=16, amode=FRAME):
     from tecogan_b200 import models
     ref = O.OracleGenerator(3, nres).eval()
     named = synth.fill_state_dict(ref.state_dict(), seed=1, gain=gain)
@@ -31,7 +34,7 @@ def _make(gain, nres=16, amode=0):
     return ref, G
 
 
-@pytest.mark.parametrize("amode", [0])
+@pytest.mark.parametrize("amode", [PER_LAYER, FRAME], ids=["perlayer", "frame"])
 @pytest.mark.parametrize("gain,shape", [(1.0, (1, 51, 12, 20)), (1.7, (1, 51, 12, 20)), (1.7, (2, 51, 33, 17)),
                                         (1.0, (1, 51, 64, 64))])
 def test_forward_vs_oracle(amode, gain, shape):
@@ -50,10 +53,11 @@ def test_forward_vs_oracle(amode, gain, shape):
     assert _psnr(got, want) >= 50.0
 
 
+@pytest.mark.parametrize("amode", [PER_LAYER, FRAME], ids=["perlayer", "frame"])
 @pytest.mark.parametrize("tag,gain", [("g1", 1.0), ("g17", 1.7)])
-def test_forward_and_loop_vs_golden(golden_dir, tag, gain):
+def test_forward_and_loop_vs_golden(golden_dir, tag, gain, amode):
     g = np.load(os.path.join(golden_dir, f"gen_{tag}.npz"))
-    _, G = _make(gain)
+    _, G = _make(gain, amode=amode)
     x = torch.from_numpy(synth.det_uniform((1, 51, 12, 20), 21, 0.0, 1.0)).cuda()
     with torch.no_grad():
         y = G(x).cpu()
@@ -67,10 +71,11 @@ def test_forward_and_loop_vs_golden(golden_dir, tag, gain):
     assert _psnr(out, want) >= 50.0
 
 
-def test_cfg1_loop_vs_oracle():
+@pytest.mark.parametrize("amode", [PER_LAYER, FRAME], ids=["perlayer", "frame"])
+def test_cfg1_loop_vs_oracle(amode):
     """BASELINE config 1: 10-frame 64x64 LR clip -> 256x256, recurrent loop on device."""
     torch.set_num_threads(8)
-    ref, G = _make(1.0)
+    ref, G = _make(1.0, amode=amode)
     for hi in (1.0, 0.25):
         r = torch.from_numpy(synth.clip_inputs(1, 10, 64, 64, seed=1234, hi=hi))
         want = O.infer_clip(ref, r)
@@ -103,3 +108,34 @@ def test_weight_cache_tracks_updates():
         G.output.bias.add_(1.0)
         b = G(x)
     assert (b - a).abs().min().item() > 0.1
+
+
+@pytest.mark.parametrize("shape", [(1, 51, 12, 20), (2, 51, 33, 17), (1, 51, 180, 320), (3, 51, 90, 100)])
+def test_frame_kernel_is_bit_identical_to_per_layer_path(shape):
+    """Size-independent property used at the full BASELINE cfg2 size: the persistent frame kernel chains the
+    41 layers through per-tile counters instead of kernel boundaries but issues the same MMAs in the same order,
+    so its output must equal the per-layer path bit for bit (any missed dependency or stale read breaks this)."""
+    _, G = _make(1.7)
+    x = torch.from_numpy(synth.det_uniform(shape, 33, 0.0, 1.0)).cuda()
+    outs = {}
+    with torch.no_grad():
+        for amode in (PER_LAYER, FRAME):
+            G.amode = amode
+            for rep in range(3):                       # repeated launches reuse the workspace and its counters
+                y, lg = G(x, return_logits=True)
+                outs[(amode, rep)] = (y.clone(), lg.clone())
+    for rep in range(3):
+        assert torch.equal(outs[(PER_LAYER, 0)][1], outs[(FRAME, rep)][1])
+        assert torch.equal(outs[(PER_LAYER, 0)][0], outs[(FRAME, rep)][0])
+
+
+def test_frame_clip_is_bit_identical_to_per_layer_clip():
+    """Recurrent loop at cfg2 frame size (2 clips x 4 frames of 320x180): frame kernel == per-layer path."""
+    _, G = _make(1.0)
+    r = torch.from_numpy(synth.clip_inputs(2, 4, 180, 320, seed=7, hi=0.25)).cuda()
+    G.amode = PER_LAYER
+    a = G.infer_clip(r)
+    G.amode = FRAME
+    b = G.infer_clip(r)
+    assert torch.equal(a, b)
+    assert torch.isfinite(b).all()
