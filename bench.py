@@ -11,7 +11,7 @@ One "step" = one batch of B independent 100-frame clips per GPU through the recu
   value      frames/s, whole job, LR clips already resident in HBM
   e2e        frames/s through ClipPipeline.run_host: pinned host LR in, every HR frame copied
              back to pinned host memory, copies inside the timed region
-  roofline   dominant kernel (tcgen05 conv, conv_tc_kernel<64>) timed per launch with CUDA events
+  roofline   dominant kernel (tg::frame_kernel: all 41 tcgen05 conv layers of a frame) timed per launch with CUDA events
   cpu_baseline / --impl reference: the CPU oracle port (torch fp32 on the host cores) on a
              bounded sample of the same workload.  Only these legs import oracle/.
 """
@@ -31,6 +31,7 @@ for p in (ROOT, os.path.join(ROOT, "pytorch-tecogan_b200")):
 H, W, T = 180, 320, 100
 FLOP_PER_LR_PIXEL = 8445312           # whole generator, MAC=2, padding not counted
 FLOP_PER_LR_PIXEL_OUTCONV = 2 * 9 * 64 * 3 * 16
+TRAFFIC_BYTES_PER_LAUNCH = 2.527e9     # ncu --set full, frame_kernel, 2 clips/launch: dram read 1.344 GB + write 1.183 GB (profiles/r01_summary_v2_frame.md)
 METRIC = "720p output frames/s (x4 VSR inference)"
 WORKLOAD = "cfg2: generator inference 320x180 -> 1280x720, 100-frame synthetic clips, sharded by clip"
 
@@ -220,7 +221,7 @@ def run_ours(args):
     roof = None
     if rank == 0:
         import ctypes
-        pf = min(frames, 5)
+        pf = min(frames, 20)
         pipe_p = ClipPipeline(G, B, pf, H, W, dev)
         lr_p = lr[:, :pf].contiguous()
         pipe_p.run_device(lr_p)
@@ -232,10 +233,7 @@ def run_ours(args):
         ms = (ctypes.c_float * cap)()
         work = (ctypes.c_double * cap)()
         n = lib.tg_profile_end(cap, ids, ms, work)
-        conv_ms = sum(ms[i] for i in range(n) if ids[i] == 0)
-        conv_n = sum(1 for i in range(n) if ids[i] == 0)
         all_ms = sum(ms[i] for i in range(n))
-        flops = float(pf) * B * (FLOP_PER_LR_PIXEL - FLOP_PER_LR_PIXEL_OUTCONV) * H * W
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -245,13 +243,26 @@ def run_ours(args):
         src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
         if not peak:
             peak, src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
-        achieved = flops / (conv_ms * 1e-3) / 1e12
-        roof = {"kernel": "tg::conv_tc_kernel<64> (tcgen05 implicit-GEMM conv, 40 launches/frame)",
-                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": src, "traffic": None,
-                "launches_timed": conv_n, "avg_launch_us": conv_ms * 1e3 / max(conv_n, 1),
-                "algorithmic_flops_per_launch": flops / max(conv_n, 1),
-                "kernel_share_of_step": conv_ms / all_ms if all_ms else None}
+        fr = [i for i in range(n) if ids[i] == 5]
+        if fr:      # frame kernel: one launch = all 41 conv layers of one generator forward for B clips
+            k_ms = sum(ms[i] for i in fr)
+            k_n = len(fr)
+            flops = float(k_n) * B * FLOP_PER_LR_PIXEL * H * W
+            kname = "tg::frame_kernel (persistent tcgen05 implicit-GEMM generator forward, 1 launch/frame)"
+        else:       # per-layer path: 40 conv_tc_kernel<64> launches per frame
+            k_ms = sum(ms[i] for i in range(n) if ids[i] == 0)
+            k_n = sum(1 for i in range(n) if ids[i] == 0)
+            flops = float(pf) * B * (FLOP_PER_LR_PIXEL - FLOP_PER_LR_PIXEL_OUTCONV) * H * W
+            kname = "tg::conv_tc_kernel<64> (tcgen05 implicit-GEMM conv, 40 launches/frame)"
+        achieved = flops / (k_ms * 1e-3) / 1e12
+        roof = {"kernel": kname, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "peak_source": src,
+                "traffic": TRAFFIC_BYTES_PER_LAUNCH if (fr and B == 2) else None,
+                "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, one frame_kernel launch at "
+                                  "2 clips/launch (profiles/)" if (fr and B == 2 and TRAFFIC_BYTES_PER_LAUNCH) else None,
+                "launches_timed": k_n, "avg_launch_us": k_ms * 1e3 / max(k_n, 1),
+                "algorithmic_flops_per_launch": flops / max(k_n, 1),
+                "kernel_share_of_step": k_ms / all_ms if all_ms else None}
         del pipe_p
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
@@ -268,7 +279,9 @@ def run_ours(args):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "clips_per_gpu_per_step": B, "frames_per_clip": frames, "lr_dist": "U[0,0.25) (all warp taps "
-                       "in bounds)", "weights": "random init, seed 1", "parallelism": f"clip-sharded x{world}, no collective",
+                       "in bounds)", "weights": "random init, seed 1",
+                       "generator_mode": {0: "one launch per conv layer", 2: "persistent frame kernel"}.get(int(G.amode), str(G.amode)),
+                       "parallelism": f"clip-sharded x{world}, no collective",
                        "l2": "no explicit flush: every frame streams ~0.56 GB of activations per clip through the "
                              "126 MB L2, far larger than L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,

@@ -138,6 +138,15 @@ int tg_gen_clip_forward(const void* packed, int num_resblock, const float* lr, f
                         void* workspace, size_t workspace_bytes, int n, int t, int h, int w,
                         int amode, void* stream);
 
+/* One step of that loop (main.py:199-216): x_t = cat(lr_t, s2d(deprocess(warp(prev_hr, flow(lr_prev))))),
+ * out_t = generator(x_t).  lr_prev == prev_hr == NULL selects the first-frame input (main.py:191-195).
+ * lr_t/lr_prev [n,3,h,w], prev_hr/out_t [n,3,4h,4w], all f32 with the given batch strides (elements), so a
+ * caller can keep frames clip-major ([n,t,...]) or frame-major ([t,n,...]). */
+int tg_gen_clip_step(const void* packed, int num_resblock, const float* lr_t, const float* lr_prev,
+                     const float* prev_hr, float* out_t, void* workspace, size_t workspace_bytes, int n,
+                     int h, int w, long long lr_batch_stride, long long prev_batch_stride,
+                     long long out_batch_stride, int amode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,9 +7,11 @@
 //     item = (segment = layer x 64-wide Cout chunk, image, 16x8 pixel tile)
 // statically dealt round-robin to the CTAs, and layers are chained by per-tile completion counters
 // in global memory instead of kernel boundaries:
+//   * warp roles: TMA producer, single-thread MMA issuer, 8 epilogue warps (two per TMEM lane quarter, 32
+//     accumulator columns each), one publisher warp;
 //   * an item's TMA producer waits (ld.acquire.gpu) until the <= 3x3 producer tiles of the previous
 //     layer that its halo box touches have been published (one red.release.gpu per tile by a publisher warp,
-//     after the 128 epilogue threads arrived on a CTA-local mbarrier),
+//     after the 256 epilogue threads arrived on a CTA-local mbarrier),
 //     then issues the box load; MMAs and epilogues of earlier items never wait on later ones, all
 //     CTAs are co-resident (1 per SM) and every dependency points to an earlier item of the queue,
 //     so the schedule cannot deadlock;
@@ -28,7 +30,8 @@
 
 namespace tg {
 
-constexpr int kFrThreads = 224;                        // producer, MMA, 4 epilogue warps, publisher
+constexpr int kFrThreads = 352;                        // producer, MMA, 8 epilogue warps, publisher
+constexpr int kEpiWarps = 8;                           // 2 per TMEM lane quarter: channels 0-31 / 32-63
 constexpr uint32_t kFrSmemLimit = 232448;
 constexpr uint32_t kWSlotBytes = 73728;               // 9 taps x 64 x 64 bf16
 constexpr uint32_t kABoxBytes = 18 * 10 * 128;        // {64ch, 10, 18} halo box
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
   const uint32_t bar_pfull = bar_cempty + 16, bar_pempty = bar_pfull + 16;
   const uint32_t off_misc = (bar_pempty + 16) - base;
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gbase + off_misc);
-  float* s_bias_all = reinterpret_cast<float*>(gbase + off_misc + 16);   // [4 warps][64]
+  float* s_bias_all = reinterpret_cast<float*>(gbase + off_misc + 16);   // [8 warps][64]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,8 +120,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       mbar_init(bar_wfull + 8 * i, 1);
       mbar_init(bar_wempty + 8 * i, 1);
       mbar_init(bar_cfull + 8 * i, 1);
-      mbar_init(bar_cempty + 8 * i, 4);
-      mbar_init(bar_pfull + 8 * i, 128);
+      mbar_init(bar_cempty + 8 * i, kEpiWarps);
+      mbar_init(bar_pfull + 8 * i, kEpiWarps * 32);
       mbar_init(bar_pempty + 8 * i, 1);
     }
     for (int i = 0; i < kFrStages; ++i) {
@@ -261,12 +264,13 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       g ^= 1;
       if (g == 0) gph ^= 1;
     }
-  } else if (warp < 6) {
-    // ================================ epilogue (4 warps) ===================================
+  } else if (warp < 2 + kEpiWarps) {
+    // ================================ epilogue (8 warps) ===================================
     const int q = warp & 3;                                // TMEM lane quarter of this warp
+    const int half = (warp - 2) >> 2;                      // which 32 of the 64 accumulator columns
     const int m = q * 32 + lane;
     const int pr = m >> 3, pc = m & 7;
-    float* s_bias = s_bias_all + q * 64;
+    float* s_bias = s_bias_all + (warp - 2) * 64;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     int si = 0, cur_si = -1, g = 0;
     uint32_t gph = 0;
@@ -299,9 +303,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
                                static_cast<uint32_t>(g * kGroupCols + a * kAccCols);
         const int oy = iy * sc + (a >> 1), ox = ix * sc + (a & 1);
         if (S.out_mode == kOutNHWCbf16) {
-          uint32_t v0[32], v1[32];
-          tmem_ld_32x32(taddr, v0);
-          tmem_ld_32x32(taddr + 32, v1);
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + half * 32, v);
           tmem_ld_wait();
           if (a == n_acc - 1) {                            // TMEM drained -> hand the group back
             tc_fence_before();
@@ -310,31 +313,28 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           }
           if (valid) {
             const size_t pix = (static_cast<size_t>(n) * S.oh + oy) * S.ow + ox;
-            uint8_t* dst = static_cast<uint8_t*>(S.out) + (pix * S.oc + S.ch0) * 2;
-            const uint8_t* res = S.resid ? static_cast<const uint8_t*>(S.resid) + (pix * S.oc + S.ch0) * 2 : nullptr;
+            const size_t off = (pix * S.oc + S.ch0) * 2 + half * 64;
+            uint8_t* dst = static_cast<uint8_t*>(S.out) + off;
+            const uint8_t* res = S.resid ? static_cast<const uint8_t*>(S.resid) + off : nullptr;
             const bool relu = S.relu != 0;
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              uint32_t* v = h2 ? v1 : v0;
+            for (int c16 = 0; c16 < 2; ++c16) {            // 16 channels = one 32-byte store
+              float f[16];
 #pragma unroll
-              for (int c16 = 0; c16 < 2; ++c16) {          // 16 channels = one 32-byte store
-                float f[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  f[e] = __uint_as_float(v[c16 * 16 + e]) + s_bias[h2 * 32 + c16 * 16 + e];
-                  if (relu) f[e] = fmaxf(f[e], 0.f);
-                }
-                if (res) {
-                  uint32_t rv[8];
-                  ld_global_cg_v8(res + h2 * 64 + c16 * 32, rv);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) { f[2 * e] += bf16_lo(rv[e]); f[2 * e + 1] += bf16_hi(rv[e]); }
-                }
-                uint32_t o[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
-                st_global_v8(dst + h2 * 64 + c16 * 32, o);
+              for (int e = 0; e < 16; ++e) {
+                f[e] = __uint_as_float(v[c16 * 16 + e]) + s_bias[half * 32 + c16 * 16 + e];
+                if (relu) f[e] = fmaxf(f[e], 0.f);
               }
+              if (res) {
+                uint32_t rv[8];
+                ld_global_cg_v8(res + c16 * 32, rv);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { f[2 * e] += bf16_lo(rv[e]); f[2 * e + 1] += bf16_hi(rv[e]); }
+              }
+              uint32_t o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+              st_global_v8(dst + c16 * 32, o);
             }
           }
         } else {
@@ -347,7 +347,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           if (valid) {
             const size_t plane = static_cast<size_t>(S.oh) * S.ow;
             const size_t o0 = static_cast<size_t>(n) * S.out_nstride + static_cast<size_t>(oy) * S.ow + ox;
-            for (int c = 0; c < S.oc; ++c) {
+            // 3 output planes: warps of half 0 store planes 0 and 1, warps of half 1 store plane 2
+            for (int c = half * 2; c < min(S.oc, half * 2 + 2); ++c) {
               const float z = __uint_as_float(v[c]) + s_bias[c];
               if (S.out2) S.out2[o0 + c * plane] = z;
               static_cast<float*>(S.out)[o0 + c * plane] = 1.f / (1.f + expf(-z));
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       g ^= 1;
       if (g == 0) gph ^= 1;
     }
-  } else {
+  } else if (warp == 2 + kEpiWarps) {
     // ================================ publisher ============================================
     int si = 0;
     uint32_t pk = 0;
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       const FrSeg& S = P.segs[si];
       if (S.out_mode == kOutNHWCbf16 && !(P.dbg & 2)) {
         const uint32_t pg = pk & 1u, pph = (pk >> 1) & 1u;
-        mbar_wait(bar_pfull + 8 * pg, pph);                  // all 128 epilogue threads stored (acquire.cta)
+        mbar_wait(bar_pfull + 8 * pg, pph);                  // all 256 epilogue threads stored (acquire.cta)
         if (lane == 0) {
           red_release_gpu_add(P.flags + S.flag_off + (it - S.item_begin), kItemDone);   // cumulative gpu-scope release
           mbar_arrive(bar_pempty + 8 * pg);
@@ -497,8 +498,8 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
   }
   TG_CHECK_ARG(static_cast<size_t>(items) <= flag_capacity, "frame: %d items exceed the flag capacity %zu", items, flag_capacity);
   if (!flags_zeroed) TG_CUDA(cudaMemsetAsync(flags, 0, static_cast<size_t>(items) * sizeof(uint32_t), stream));
-  const uint32_t smem_bytes = 2 * kWSlotBytes + kFrStages * kAStride + 256 + 4 * 64 * 4 + 1024;
-  static_assert(2 * kWSlotBytes + kFrStages * kAStride + 256 + 4 * 64 * 4 + 1024 <= kFrSmemLimit, "smem budget");
+  const uint32_t smem_bytes = 2 * kWSlotBytes + kFrStages * kAStride + 256 + kEpiWarps * 64 * 4 + 1024;
+  static_assert(2 * kWSlotBytes + kFrStages * kAStride + 256 + kEpiWarps * 64 * 4 + 1024 <= kFrSmemLimit, "smem budget");
   cudaLaunchConfig_t cfg{};
   const int sms = tg_num_sms();
   cfg.gridDim = dim3(items < sms ? items : sms);

@@ -181,34 +181,65 @@ extern "C" int tg_gen_forward(const void* packed, int num_resblock, const void* 
                           static_cast<uint8_t*>(workspace), n, h, w, amode, 0, false, static_cast<cudaStream_t>(stream));
 }
 
+// One recurrent step: frame input (warp of the previous HR estimate + space-to-depth + concat) and
+// generator forward.  Batch strides are in elements.
+static int gen_clip_step_impl(const std::vector<GenLayer>& L, const uint8_t* packed, int nres, const float* lr_t,
+                              const float* lr_prev, const float* prev_hr, float* out_t, uint8_t* wsp, int n, int h,
+                              int w, long long lr_bs, long long prev_bs, long long out_bs, int amode, cudaStream_t st) {
+  const GenWorkspace ws = gen_ws(n, h, w);
+  void* x0 = wsp + ws.x0;
+  const bool frame_mode = (amode == TG_AMODE_FRAME);
+  size_t nflags = 0;
+  if (frame_mode) {
+    const std::vector<FrLayer> P = gen_plan(L, nres, x0, out_t, nullptr, wsp, n, h, w, out_bs);
+    nflags = frame_flag_count(P.data(), static_cast<int>(P.size()), n);
+  }
+  // the frame-input kernel also clears the frame kernel's completion counters (it runs strictly
+  // after the previous frame kernel and strictly before the next one)
+  int rc = fused_input_launch(lr_t, lr_prev, prev_hr, x0, n, h, w, lr_bs, prev_bs,
+                              frame_mode ? reinterpret_cast<uint32_t*>(wsp + ws.flags) : nullptr, nflags, st);
+  if (rc) return rc;
+  return gen_forward_impl(L, packed, nres, x0, out_t, nullptr, wsp, n, h, w, amode, out_bs, frame_mode, st);
+}
+
+static int check_ws(const char* who, const void* workspace, size_t workspace_bytes, int n, int h, int w) {
+  TG_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "%s: workspace must be 256-byte aligned", who);
+  if (workspace_bytes < gen_ws(n, h, w).total) {
+    tg_set_error("%s: workspace too small (%zu < %zu)", who, workspace_bytes, gen_ws(n, h, w).total);
+    return TG_ERR_WORKSPACE;
+  }
+  return TG_OK;
+}
+
+extern "C" int tg_gen_clip_step(const void* packed, int num_resblock, const float* lr_t, const float* lr_prev,
+                                const float* prev_hr, float* out_t, void* workspace, size_t workspace_bytes, int n,
+                                int h, int w, long long lr_batch_stride, long long prev_batch_stride,
+                                long long out_batch_stride, int amode, void* stream) {
+  TG_CHECK_ARG(packed && lr_t && out_t && workspace, "gen_clip_step: null pointer");
+  TG_CHECK_ARG(n >= 1 && h >= 1 && w >= 1, "gen_clip_step: bad shape");
+  TG_CHECK_ARG(amode == TG_AMODE_HALO || amode == TG_AMODE_DX3 || amode == TG_AMODE_FRAME, "gen_clip_step: bad amode %d", amode);
+  TG_CHECK_ARG((lr_prev == nullptr) == (prev_hr == nullptr), "gen_clip_step: lr_prev and prev_hr go together");
+  if (int rc = check_ws("gen_clip_step", workspace, workspace_bytes, n, h, w)) return rc;
+  auto L = gen_layers(num_resblock, nullptr, nullptr);
+  return gen_clip_step_impl(L, static_cast<const uint8_t*>(packed), num_resblock, lr_t, lr_prev, prev_hr, out_t,
+                            static_cast<uint8_t*>(workspace), n, h, w, lr_batch_stride, prev_batch_stride,
+                            out_batch_stride, amode, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int tg_gen_clip_forward(const void* packed, int num_resblock, const float* lr, float* out, void* workspace,
                                    size_t workspace_bytes, int n, int t, int h, int w, int amode, void* stream) {
   TG_CHECK_ARG(packed && lr && out && workspace, "gen_clip_forward: null pointer");
   TG_CHECK_ARG(n >= 1 && t >= 1 && h >= 1 && w >= 1, "gen_clip_forward: bad shape");
-  TG_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "gen_clip_forward: workspace must be 256-byte aligned");
-  const GenWorkspace ws = gen_ws(n, h, w);
-  if (workspace_bytes < ws.total) {
-    tg_set_error("gen_clip_forward: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
-    return TG_ERR_WORKSPACE;
-  }
+  TG_CHECK_ARG(amode == TG_AMODE_HALO || amode == TG_AMODE_DX3 || amode == TG_AMODE_FRAME, "gen_clip_forward: bad amode %d", amode);
+  if (int rc = check_ws("gen_clip_forward", workspace, workspace_bytes, n, h, w)) return rc;
   auto L = gen_layers(num_resblock, nullptr, nullptr);
-  uint8_t* wsp = static_cast<uint8_t*>(workspace);
-  void* x0 = wsp + ws.x0;
   const long long lr_frame = 3LL * h * w, hr_frame = 48LL * h * w;
   const long long lr_bs = lr_frame * t, hr_bs = hr_frame * t;
-  const bool frame_mode = (amode == TG_AMODE_FRAME);
   for (int f = 0; f < t; ++f) {
-    const float* lr_t = lr + f * lr_frame;
-    const float* lr_prev = f ? lr + (f - 1) * lr_frame : nullptr;
-    const float* prev_hr = f ? out + (f - 1) * hr_frame : nullptr;
-    // the frame-input kernel also clears the frame kernel's completion counters (it runs strictly
-    // after the previous frame kernel and strictly before the next one)
-    int rc = fused_input_launch(lr_t, lr_prev, prev_hr, x0, n, h, w, lr_bs, hr_bs,
-                                frame_mode ? reinterpret_cast<uint32_t*>(wsp + ws.flags) : nullptr,
-                                frame_mode ? ws.flag_count : 0, static_cast<cudaStream_t>(stream));
-    if (rc) return rc;
-    rc = gen_forward_impl(L, static_cast<const uint8_t*>(packed), num_resblock, x0, out + f * hr_frame, nullptr, wsp, n,
-                          h, w, amode, hr_bs, frame_mode, static_cast<cudaStream_t>(stream));
+    int rc = gen_clip_step_impl(L, static_cast<const uint8_t*>(packed), num_resblock, lr + f * lr_frame,
+                                f ? lr + (f - 1) * lr_frame : nullptr, f ? out + (f - 1) * hr_frame : nullptr,
+                                out + f * hr_frame, static_cast<uint8_t*>(workspace), n, h, w, lr_bs, hr_bs, hr_bs, amode,
+                                static_cast<cudaStream_t>(stream));
     if (rc) return rc;
   }
   return TG_OK;

@@ -22,7 +22,6 @@ class ClipPipeline:
         lib = _nt.lib()
         self.nres = int(gen.num)
         self.ws = torch.empty(lib.tg_gen_workspace_bytes(self.b, self.h, self.w), dtype=torch.uint8, device=self.dev)
-        self.x0 = torch.empty((self.b, self.h, self.w, 64), dtype=torch.bfloat16, device=self.dev)
         self._frames_tb = None          # [T,B,3,4h,4w] device staging for run_host
         self._lr_dev = None
         self._copy_stream = None
@@ -68,10 +67,9 @@ class ClipPipeline:
             lr_prev = vp(lr_ptr + 4 * (f - 1) * lr_frame) if f else vp(0)
             prev_hr = vp(fr_ptr + 4 * (f - 1) * b * hr_frame) if f else vp(0)
             cur_hr = vp(fr_ptr + 4 * f * b * hr_frame)
-            _nt.check(lib.tg_fused_warp_s2d_concat(lr_t, lr_prev, prev_hr, _nt.ptr(self.x0), b, h, w, t * lr_frame,
-                                                   hr_frame, _nt.stream_ptr()))
-            _nt.check(lib.tg_gen_forward(_nt.ptr(packed), self.nres, _nt.ptr(self.x0), cur_hr, vp(0), _nt.ptr(self.ws),
-                                         self.ws.numel(), b, h, w, int(self.gen.amode), _nt.stream_ptr()))
+            _nt.check(lib.tg_gen_clip_step(_nt.ptr(packed), self.nres, lr_t, lr_prev, prev_hr, cur_hr, _nt.ptr(self.ws),
+                                           self.ws.numel(), b, h, w, t * lr_frame, hr_frame, hr_frame,
+                                           int(self.gen.amode), _nt.stream_ptr()))
             ev = torch.cuda.Event()
             ev.record(main)
             self._copy_stream.wait_event(ev)
