@@ -101,6 +101,8 @@ def cpu_oracle_fps(n_frames, steps, warmup):
     n_frames-long 320x180 clip.  This is the reference's CPU path timed on this box."""
     import torch
     from oracle import synth, tecogan_oracle as O
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it may run on
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     torch.manual_seed(1)
     G = O.OracleGenerator(3, 16).eval()
     r = torch.from_numpy(synth.clip_inputs(1, n_frames, H, W, seed=1234, hi=0.25))

@@ -96,7 +96,8 @@ int tg_pack_nchw_to_nhwc64(const float* in, void* out, int n, int c, int h, int 
 /* ------------------------------------------------------ tensor-core convolutions (tcgen05) -- */
 
 /* Packed-weight sizes/packers.  `kind`: 0 = Conv2d 3x3 s1 p1 (weight [cout,cin,3,3], code/ops.py:57-63)
- *                                       1 = ConvTranspose2d 3x3 s2 p1 op1 (weight [cin,cout,3,3], code/ops.py:45-54).
+ *                                       1 = ConvTranspose2d 3x3 s2 p1 op1 (weight [cin,cout,3,3], code/ops.py:45-54)
+ *                                       2 = Conv2d 4x4 s2 p1 (weight [cout,cin,4,4]; discriminator blocks, code/models.py:90-94).
  * The packed blob holds bf16 weight blocks in MMA issue order followed by the fp32 bias
  * (zero if bias == NULL), padded to the kernel's channel granularity. */
 size_t tg_packed_conv_bytes(int kind, int cin, int cout);
@@ -109,6 +110,12 @@ int tg_pack_weights(int kind, const float* weight, const float* bias, int cin, i
  * one of (relu, residual) set.  Replaces nn.Conv2d calls of code/models.py:55-56,68,75. */
 int tg_conv3x3_fwd(const void* x, const void* packed, const void* residual, void* y, int n, int h,
                    int w, int cin_pad, int cout, int relu, int amode, void* stream);
+/* `relu` of the conv entry points is an activation code: 0 none, 1 ReLU, 2 LeakyReLU(0.2) (code/ops.py:71-72). */
+/* y = act(conv4x4s2(x) + bias): x NHWC bf16 [n,h,w,cin_pad] (h, w even) -> y NHWC bf16 [n,h/2,w/2,cout] for
+ * cout in {64,128}; for cout == 3 (discriminator block5) y is the raw f32 NCHW [n,3,h/2,w/2] conv output.
+ * Replaces the k4 s2 nn.Conv2d of discriminator_block (code/models.py:90-94,104,109,114,119,121). */
+int tg_conv4x4s2_fwd(const void* x, const void* packed, void* y, int n, int h, int w, int cin_pad,
+                     int cout, int act, void* stream);
 /* y = relu?(convT3x3s2(x) + bias); x [n,h,w,c] -> y [n,2h,2w,cout].  code/models.py:72,74. */
 int tg_convT3x3s2_fwd(const void* x, const void* packed, void* y, int n, int h, int w, int cin,
                       int cout, int relu, int amode, void* stream);

@@ -93,13 +93,14 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
   const int ct_ky[9] = {1, 1, 1, 2, 0, 2, 2, 0, 0};
   const int ct_kx[9] = {1, 2, 0, 1, 1, 2, 0, 2, 0};
   const int kchunks = cin_pad / 64;
-  const long long total = 9LL * cin_pad * cout_pad;
+  const int ntap = (kind == kConv4x4s2) ? 16 : 9;
+  const long long total = static_cast<long long>(ntap) * cin_pad * cout_pad;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int ci_l = static_cast<int>(i % 64);
     long long r = i / 64;
     const int co_l = static_cast<int>(r % nt); r /= nt;
-    const int j = static_cast<int>(r % 9); r /= 9;
+    const int j = static_cast<int>(r % ntap); r /= ntap;
     const int kc = static_cast<int>(r % kchunks); r /= kchunks;
     const int chunk = static_cast<int>(r);
     const int ci = kc * 64 + ci_l, co = chunk * nt + co_l;
@@ -108,6 +109,11 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
       if (kind == kConv3x3) {
         const int ky = j / 3, kx = j % 3;
         v = w[((static_cast<long long>(co) * cin + ci) * 3 + ky) * 3 + kx];
+      } else if (kind == kConv4x4s2) {
+        // j = phase * 4 + tap: phase = (py,px) input parity, tap = (dy,dx) offset inside the phase box
+        const int ph = j >> 2, t = j & 3;
+        const int ky = 2 * (t >> 1) + (ph >> 1), kx = 2 * (t & 1) + (ph & 1);
+        v = w[((static_cast<long long>(co) * cin + ci) * 4 + ky) * 4 + kx];
       } else {
         v = w[((static_cast<long long>(ci) * cout + co) * 3 + ct_ky[j]) * 3 + ct_kx[j]];
       }
@@ -121,21 +127,20 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
 }  // namespace tg
 
 extern "C" size_t tg_packed_conv_bytes(int kind, int cin, int cout) {
-  (void)kind;
   const int cp = tg::cin_padded(cin), op = tg::cout_padded(cout);
-  size_t b = tg::packed_weight_bytes(cp, op) + static_cast<size_t>(op) * 4;
+  size_t b = tg::packed_weight_bytes_k(kind, cp, op) + static_cast<size_t>(op) * 4;
   return (b + 255) & ~static_cast<size_t>(255);
 }
 
 extern "C" int tg_pack_weights(int kind, const float* weight, const float* bias, int cin, int cout,
                                void* packed, void* stream) {
   TG_CHECK_ARG(weight && packed, "pack_weights: null pointer");
-  TG_CHECK_ARG(kind == 0 || kind == 1, "pack_weights: kind must be 0 (conv) or 1 (convT)");
+  TG_CHECK_ARG(kind == 0 || kind == 1 || kind == 2, "pack_weights: kind must be 0 (conv3x3), 1 (convT3x3s2) or 2 (conv4x4s2)");
   TG_CHECK_ARG(cin >= 1 && cin <= 128 && cout >= 1 && cout <= 128, "pack_weights: channels out of range");
   const int cp = tg::cin_padded(cin), op = tg::cout_padded(cout);
   const int nt = op == 16 ? 16 : 64;
   auto* dst = static_cast<__nv_bfloat16*>(packed);
-  auto* bdst = reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + tg::packed_weight_bytes(cp, op));
+  auto* bdst = reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + tg::packed_weight_bytes_k(kind, cp, op));
   tg_prof_pre(TG_K_PACK, 0.0, static_cast<cudaStream_t>(stream));
   tg::pack_weights_kernel<<<64, 256, 0, static_cast<cudaStream_t>(stream)>>>(kind, weight, bias, cin, cout, cp, op, nt, dst, bdst);
   tg_prof_post(static_cast<cudaStream_t>(stream));
@@ -147,10 +152,21 @@ static const float* packed_bias(const void* packed, int cin_pad, int cout_pad) {
   return reinterpret_cast<const float*>(static_cast<const uint8_t*>(packed) + tg::packed_weight_bytes(cin_pad, cout_pad));
 }
 
+extern "C" int tg_conv4x4s2_fwd(const void* x, const void* packed, void* y, int n, int h, int w, int cin_pad,
+                                int cout, int act, void* stream) {
+  TG_CHECK_ARG(cout == 3 || cout == 64 || cout == 128, "conv4x4s2_fwd: cout must be 3, 64 or 128 (got %d)", cout);
+  const int op = tg::cout_padded(cout);
+  const float* bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(packed) +
+                                                     tg::packed_weight_bytes_k(tg::kConv4x4s2, cin_pad, op));
+  TG_CHECK_ARG(!(cout == 3 && act != 0), "conv4x4s2_fwd: the 3-channel f32 output is raw (act must be 0)");
+  return tg::launch_conv_tc(tg::kConv4x4s2, cout == 3 ? tg::kOutNCHWf32Raw : tg::kOutNHWCbf16, x, packed, bias, nullptr, y,
+                            nullptr, n, h, w, cin_pad, op, act, TG_AMODE_HALO, 0, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int tg_conv3x3_fwd(const void* x, const void* packed, const void* residual, void* y, int n, int h,
                               int w, int cin_pad, int cout, int relu, int amode, void* stream) {
   TG_CHECK_ARG(cout == 64 || cout == 128, "conv3x3_fwd: cout must be 64 or 128 (got %d)", cout);
-  TG_CHECK_ARG(!(relu && residual), "conv3x3_fwd: relu and residual are mutually exclusive");
+  TG_CHECK_ARG(!(relu && residual), "conv3x3_fwd: activation and residual are mutually exclusive");
   return tg::launch_conv_tc(tg::kConv3x3, tg::kOutNHWCbf16, x, packed, packed_bias(packed, cin_pad, cout), residual, y,
                             nullptr, n, h, w, cin_pad, cout, relu, amode, 0, static_cast<cudaStream_t>(stream));
 }

@@ -99,14 +99,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   // grid has completed and flushed, before touching any activation.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  const int blocks_per_chunk = p.kchunks * p.ntaps;
+  const int blocks_per_chunk = p.stages_per_item * p.ntaps;
   constexpr uint32_t kWBlockBytes = NT * 128;
 
   if (warp == 0) {
     // ================================ TMA producer =========================================
     // Whole warp runs the (uniform) loop; one elected lane issues.  Keeps TMA operands in uniform
     // registers (no per-lane waterfall loops around UTMALDG).
-    if (elect_one()) {
+    if (!p.w_stage_bytes && elect_one()) {
       mbar_expect_tx(bar_w, p.w_bytes);
       for (int b = 0; b < blocks_per_chunk; ++b)
         tma_load_2d(s_w + b * kWBlockBytes, &tm_w, bar_w, 0, (chunk * blocks_per_chunk + b) * NT);
@@ -121,14 +121,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int ty = r % p.tiles_y;
       const int n = r / p.tiles_y;
       const int x0 = tx * kTileW, y0 = ty * kTileH;
-      for (int kc = 0; kc < p.kchunks; ++kc) {
+      for (int sidx = 0; sidx < p.stages_per_item; ++sidx) {
+        const int kc = sidx / p.nphase, phs = sidx - kc * p.nphase;
         mbar_wait(bar_aempty + 8 * s, ph ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(bar_afull + 8 * s, p.stage_bytes);
+          mbar_expect_tx(bar_afull + 8 * s, p.stage_bytes + p.w_stage_bytes);
           const uint32_t dst = s_a + s * p.stage_stride;
           for (int c = 0; c < p.ncopies; ++c)
             tma_load_4d(dst + c * p.copy_bytes, &tm_a, bar_afull + 8 * s, kc * 64,
-                        x0 + p.copy_dx[c], y0 + p.box_y0, n);
+                        x0 * p.in_scale + p.copy_dx[c] + (phs & 1), y0 * p.in_scale + p.box_y0 + (phs >> 1), n);
+          if (p.w_stage_bytes)                               // weights of this (K chunk, phase) ride in the stage
+            for (int j = 0; j < p.ntaps; ++j)
+              tma_load_2d(dst + p.a_region + j * kWBlockBytes, &tm_w, bar_afull + 8 * s, 0,
+                          ((chunk * p.stages_per_item + sidx) * p.ntaps + j) * NT);
         }
         __syncwarp();
         if (++s == p.nstages) { s = 0; ph ^= 1; }
@@ -137,7 +142,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   } else if (warp == 1) {
     // ================================ MMA issuer ===========================================
     constexpr uint32_t idesc = umma_idesc_bf16(128, NT);
-    mbar_wait(bar_w, 0);
+    if (!p.w_stage_bytes) mbar_wait(bar_w, 0);
     tc_fence_after();
     int s = 0, g = 0;
     uint32_t ph = 0, gph = 0;
@@ -145,24 +150,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       mbar_wait(bar_cempty + 8 * g, gph ^ 1);
       tc_fence_after();
       const uint32_t d_base = tmem_base + static_cast<uint32_t>(g * p.n_acc * kAccCols);
-      for (int kc = 0; kc < p.kchunks; ++kc) {
+      for (int sidx = 0; sidx < p.stages_per_item; ++sidx) {
         mbar_wait(bar_afull + 8 * s, ph);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_base = s_a + s * p.stage_stride;
-          const uint32_t w_base = s_w + kc * p.ntaps * kWBlockBytes;
+          const uint32_t w_base = p.w_stage_bytes ? a_base + p.a_region : s_w + sidx * p.ntaps * kWBlockBytes;
           for (int j = 0; j < p.ntaps; ++j) {
             const TcTap tap = p.taps[j];
             const uint64_t ad = umma_desc_sw128(a_base + tap.a_off, p.sbo);
             const uint64_t bd = umma_desc_sw128(w_base + j * kWBlockBytes, 1024);
             const uint32_t d = d_base + tap.acc * kAccCols;
-            const uint32_t keep = (kc > 0 || !tap.first) ? 1u : 0u;
+            const uint32_t keep = (sidx > 0 || !tap.first) ? 1u : 0u;
 #pragma unroll
             for (int k = 0; k < 4; ++k)   // 4 x (K=16 bf16 = 32 bytes) inside the 128B swizzle row
               umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
           }
           umma_commit(bar_aempty + 8 * s);                 // stage reusable once these MMAs retire
-          if (kc == p.kchunks - 1) umma_commit(bar_cfull + 8 * g);   // accumulators of this item complete
+          if (sidx == p.stages_per_item - 1) umma_commit(bar_cfull + 8 * g);   // accumulators of this item complete
         }
         __syncwarp();
         if (++s == p.nstages) { s = 0; ph ^= 1; }
@@ -217,7 +222,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                   f[e] = __uint_as_float(v[c8 * 8 + e]) + s_bias[h2 * 32 + c8 * 8 + e];
-                  if (p.relu) f[e] = fmaxf(f[e], 0.f);
+                  if (p.relu == kActRelu) f[e] = fmaxf(f[e], 0.f);
+                  else if (p.relu == kActLrelu02) f[e] = f[e] > 0.f ? f[e] : 0.2f * f[e];
                 }
                 if (res) {
                   const uint4 rv = __ldg(res + h2 * 4 + c8);
@@ -250,7 +256,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             for (int c = 0; c < p.oc; ++c) {
               const float z = __uint_as_float(v[c]) + s_bias[c];
               if (p.out2) p.out2[o0 + c * plane] = z;
-              static_cast<float*>(p.out)[o0 + c * plane] = 1.f / (1.f + expf(-z));
+              static_cast<float*>(p.out)[o0 + c * plane] = (p.out_mode == kOutNCHWf32Sigmoid) ? 1.f / (1.f + expf(-z)) : z;
             }
           }
         }
@@ -283,13 +289,14 @@ static EncodeTiledFn get_encode() {
 }
 
 int encode_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,
-                const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+                const cuuint64_t* strides_bytes, const cuuint32_t* box, const cuuint32_t* elem_strides) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     tg_set_error("cuTensorMapEncodeTiled entry point not available");
     return TG_ERR_CUDA;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (elem_strides) for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims,
                    strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -311,26 +318,37 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
                    int cout_pad, int relu, int amode, long long out_nstride, cudaStream_t stream) {
   TG_CHECK_ARG(x && packed_w && out, "conv: null pointer");
   TG_CHECK_ARG(n > 0 && h > 0 && w > 0, "conv: bad shape n=%d h=%d w=%d", n, h, w);
+  TG_CHECK_ARG(kind == kConv3x3 || kind == kConvT3x3s2 || kind == kConv4x4s2, "conv: bad kind %d", kind);
   TG_CHECK_ARG(cin_pad == 64 || cin_pad == 128, "conv: cin_pad must be 64 or 128 (got %d)", cin_pad);
   TG_CHECK_ARG(cout_pad == 16 || cout_pad == 64 || cout_pad == 128, "conv: cout_pad must be 16/64/128 (got %d)", cout_pad);
-  TG_CHECK_ARG((out_mode == kOutNCHWf32Sigmoid) == (cout_pad == 16), "conv: cout 16 <=> sigmoid NCHW output");
+  TG_CHECK_ARG((out_mode != kOutNHWCbf16) == (cout_pad == 16), "conv: cout 16 <=> NCHW f32 output");
   TG_CHECK_ARG(amode == TG_AMODE_HALO || amode == TG_AMODE_DX3, "conv: bad amode %d", amode);
+  TG_CHECK_ARG(relu == kActNone || relu == kActRelu || relu == kActLrelu02, "conv: bad activation %d", relu);
   TG_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed_w) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(out) & 15) == 0, "conv: pointers must be 16-byte aligned");
   TG_CHECK_ARG(!(resid && (kind != kConv3x3 || out_mode != kOutNHWCbf16)), "conv: residual only for conv3x3 NHWC");
+  const bool s2 = (kind == kConv4x4s2);
+  TG_CHECK_ARG(!s2 || ((h % 2) == 0 && (w % 2) == 0), "conv4x4s2: input size %dx%d must be even", h, w);
+  if (s2) amode = TG_AMODE_HALO;
 
   const int nt = cout_pad == 16 ? 16 : 64;
   const int chunks = cout_pad / nt;
+  // tile space: the output resolution for the stride-2 conv, the input resolution otherwise
+  const int th = s2 ? h / 2 : h, tw = s2 ? w / 2 : w;
 
   TcParams p{};
-  p.n = n; p.h = h; p.w = w;
-  p.tiles_x = tg_div_up(w, kTileW);
-  p.tiles_y = tg_div_up(h, kTileH);
+  p.n = n; p.h = th; p.w = tw;
+  p.tiles_x = tg_div_up(tw, kTileW);
+  p.tiles_y = tg_div_up(th, kTileH);
   p.num_items = n * p.tiles_x * p.tiles_y;
   p.kchunks = cin_pad / 64;
-  p.ntaps = 9;
-  const int box_w = (amode == TG_AMODE_HALO) ? kTileW + 2 : kTileW;
-  const int box_h = kTileH + 2;
+  p.nphase = s2 ? 4 : 1;
+  p.stages_per_item = p.kchunks * p.nphase;
+  p.in_scale = s2 ? 2 : 1;
+  p.ntaps = s2 ? 4 : 9;
+  // staged box in pixels: tile + halo; the stride-2 conv stages one input-parity phase (every 2nd pixel)
+  const int box_w = s2 ? kTileW + 1 : ((amode == TG_AMODE_HALO) ? kTileW + 2 : kTileW);
+  const int box_h = s2 ? kTileH + 1 : kTileH + 2;
   p.copy_bytes = static_cast<uint32_t>(box_w * box_h * 128);
   const uint32_t row_pitch = static_cast<uint32_t>(box_w * 128);
   if (amode == TG_AMODE_HALO) {
@@ -348,27 +366,32 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   static const int ct_dx[9] = {0, 0, 1, 0, 0, 0, 1, 0, 1};
   static const int ct_acc[9] = {0, 1, 1, 2, 2, 3, 3, 3, 3};
   static const int ct_first[9] = {1, 1, 0, 1, 0, 1, 0, 0, 0};
-  for (int j = 0; j < 9; ++j) {
-    const int dy = (kind == kConv3x3) ? conv_dy[j] : ct_dy[j];
-    const int dx = (kind == kConv3x3) ? conv_dx[j] : ct_dx[j];
+  for (int j = 0; j < p.ntaps; ++j) {
+    int dy, dx;
+    if (s2) { dy = j >> 1; dx = j & 1; }                    // kernel tap (2*dy + phase_y, 2*dx + phase_x)
+    else if (kind == kConv3x3) { dy = conv_dy[j]; dx = conv_dx[j]; }
+    else { dy = ct_dy[j]; dx = ct_dx[j]; }
     p.taps[j].a_off = (amode == TG_AMODE_HALO) ? static_cast<uint32_t>((dy * box_w + dx) * 128)
                                                : static_cast<uint32_t>(dx * p.copy_bytes + dy * row_pitch);
-    p.taps[j].acc = (kind == kConv3x3) ? 0 : ct_acc[j];
-    p.taps[j].first = (kind == kConv3x3) ? (j == 0) : ct_first[j];
+    p.taps[j].acc = (kind == kConvT3x3s2) ? ct_acc[j] : 0;
+    p.taps[j].first = (kind == kConvT3x3s2) ? ct_first[j] : (j == 0);
   }
-  const int origin = (kind == kConv3x3) ? -1 : 0;   // conv: box starts at (x0-1,y0-1); convT: (x0,y0)
+  const int origin = (kind == kConvT3x3s2) ? 0 : -1;   // conv: box starts at (x0-1,y0-1) (padding 1); convT: (x0,y0)
   for (int c = 0; c < 3; ++c) p.copy_dx[c] = origin + ((amode == TG_AMODE_HALO) ? 0 : c);
   p.box_y0 = origin;
-  p.n_acc = (kind == kConv3x3) ? 1 : 4;
+  p.n_acc = (kind == kConvT3x3s2) ? 4 : 1;
   p.stage_bytes = p.ncopies * p.copy_bytes;
-  p.stage_stride = (p.stage_bytes + 1023u) & ~1023u;
+  p.a_region = (p.stage_bytes + 1023u) & ~1023u;
+  // 4x4 weights (16 taps x Cin x 64) do not fit next to the A ring: stream the block of each (K chunk, phase)
+  p.w_stage_bytes = s2 ? static_cast<uint32_t>(p.ntaps * nt * 128) : 0u;
+  p.stage_stride = p.a_region + p.w_stage_bytes;
   p.ngroups = 8 / p.n_acc;
-  p.w_bytes = static_cast<uint32_t>(p.kchunks * p.ntaps * nt * 128);
+  p.w_bytes = s2 ? 0u : static_cast<uint32_t>(p.stages_per_item * p.ntaps * nt * 128);
   // A ring depth from what is left of the 227 KB
   int nstages = 8;
   while (nstages > 0 && make_layout(p.w_bytes, p.stage_stride, nstages, p.ngroups, nt).total + 1024 > kSmemLimit)
     --nstages;
-  TG_CHECK_ARG(nstages >= 2 || (nstages >= 1 && p.kchunks == 1),
+  TG_CHECK_ARG(nstages >= 2 || (nstages >= 1 && p.stages_per_item == 1),
                "conv: shared memory too small for cin=%d cout=%d amode=%d (stages=%d)", cin_pad, cout_pad, amode, nstages);
   p.nstages = nstages;
   const SmemLayout L = make_layout(p.w_bytes, p.stage_stride, nstages, p.ngroups, nt);
@@ -377,10 +400,10 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
 
   p.out_mode = out_mode;
-  p.sy = p.sx = (kind == kConv3x3) ? 1 : 2;
-  p.oh = h * p.sy; p.ow = w * p.sx;
-  p.oc = (out_mode == kOutNCHWf32Sigmoid) ? 3 : cout_pad;
-  for (int a = 0; a < kMaxAcc; ++a) { p.acc_oy[a] = (kind == kConv3x3) ? 0 : (a >> 1); p.acc_ox[a] = (kind == kConv3x3) ? 0 : (a & 1); }
+  p.sy = p.sx = (kind == kConvT3x3s2) ? 2 : 1;
+  p.oh = th * p.sy; p.ow = tw * p.sx;
+  p.oc = (out_mode != kOutNHWCbf16) ? 3 : cout_pad;
+  for (int a = 0; a < kMaxAcc; ++a) { p.acc_oy[a] = (kind == kConvT3x3s2) ? (a >> 1) : 0; p.acc_ox[a] = (kind == kConvT3x3s2) ? (a & 1) : 0; }
   p.out_nstride = out_nstride > 0 ? out_nstride : static_cast<long long>(p.oc) * p.oh * p.ow;
   p.relu = relu;
   p.out = out; p.out2 = out2; p.resid = resid; p.bias = bias;
@@ -390,12 +413,14 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(cin_pad), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(cin_pad) * 2, static_cast<cuuint64_t>(w) * cin_pad * 2,
                              static_cast<cuuint64_t>(h) * w * cin_pad * 2};
-    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
-    int rc = encode_bf16(&tm_a, x, 4, dims, strides, box);
+    // stride-2 conv: boxDim = pixels * elementStride; every 2nd pixel is loaded -> box_w x box_h pixels land in smem
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_w * p.in_scale), static_cast<cuuint32_t>(box_h * p.in_scale), 1};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(p.in_scale), static_cast<cuuint32_t>(p.in_scale), 1};
+    int rc = encode_bf16(&tm_a, x, 4, dims, strides, box, estr);
     if (rc) return rc;
   }
   {
-    const int rows = chunks * p.kchunks * p.ntaps * nt;
+    const int rows = chunks * p.stages_per_item * p.ntaps * nt;
     cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(rows)};
     cuuint64_t strides[1] = {128};
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(nt)};
@@ -408,7 +433,8 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   dim3 grid(p.num_items < per_chunk ? p.num_items : per_chunk, chunks);
   static bool attr_done[2] = {false, false};
   // algorithmic FLOPs (MAC = 2) on the padded channel counts; bench.py uses SURVEY.md's unpadded figure
-  tg_prof_pre(nt == 64 ? TG_K_CONV64 : TG_K_CONV16, 2.0 * 9.0 * cin_pad * (nt == 64 ? cout_pad : 3) * n * h * w, stream);
+  tg_prof_pre(nt == 64 ? TG_K_CONV64 : TG_K_CONV16,
+              2.0 * (s2 ? 16.0 : 9.0) * cin_pad * (nt == 64 ? cout_pad : 3) * n * th * tw, stream);
   static const bool use_pdl = []() { const char* e = getenv("TG_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
@@ -430,6 +456,10 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   tg_prof_post(stream);
   TG_CUDA(cudaGetLastError());
   return TG_OK;
+}
+
+size_t packed_weight_bytes_k(int kind, int cin_pad, int cout_pad) {
+  return static_cast<size_t>(kind == kConv4x4s2 ? 16 : 9) * cin_pad * cout_pad * 2;
 }
 
 }  // namespace tg

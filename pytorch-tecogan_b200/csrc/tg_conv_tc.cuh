@@ -10,8 +10,9 @@ constexpr int kAccCols = 64;      // TMEM columns reserved per accumulator
 constexpr int kMaxTaps = 16;
 constexpr int kMaxAcc = 4;
 
-enum TcKind { kConv3x3 = 0, kConvT3x3s2 = 1 };
-enum TcOut { kOutNHWCbf16 = 0, kOutNCHWf32Sigmoid = 1 };
+enum TcKind { kConv3x3 = 0, kConvT3x3s2 = 1, kConv4x4s2 = 2 };
+enum TcOut { kOutNHWCbf16 = 0, kOutNCHWf32Sigmoid = 1, kOutNCHWf32Raw = 2 };
+enum TcAct { kActNone = 0, kActRelu = 1, kActLrelu02 = 2 };   // LeakyReLU(0.2): code/ops.py:71-72
 
 // One MMA group = one filter tap on one 64-channel K chunk: 4 x tcgen05.mma (K=16 each).
 struct TcTap {
@@ -23,9 +24,12 @@ struct TcTap {
 struct TcParams {
   // tile space (the resolution the 16x8 sub-tiles tile: the conv input resolution)
   int n, h, w, tiles_x, tiles_y, num_items;
-  // K loop
-  int kchunks;           // input channels / 64  (A stages per item)
-  int ntaps;             // MMA groups per K chunk
+  // K loop: an item consumes stages_per_item pipeline stages = kchunks x nphase
+  int kchunks;           // input channels / 64
+  int nphase;            // 1, or 4 input-parity phases of a stride-2 conv (one strided TMA box each)
+  int stages_per_item;
+  int in_scale;          // input coordinate = tile coordinate * in_scale (2 for the stride-2 conv)
+  int ntaps;             // MMA groups per stage
   TcTap taps[kMaxTaps];
   int n_acc;             // accumulators per item (1 conv, 4 transposed-conv phases)
   // A staging
@@ -34,6 +38,8 @@ struct TcParams {
   int box_y0;            // y origin relative to tile y0
   uint32_t copy_bytes;   // bytes per copy (box bytes)
   uint32_t stage_bytes;  // ncopies * copy_bytes (mbarrier expect_tx)
+  uint32_t a_region;     // stage_bytes rounded up to 1024: offset of the streamed weight block in a stage
+  uint32_t w_stage_bytes;// 0 = weights resident for the CTA's lifetime; else bytes of weights streamed per stage
   uint32_t stage_stride; // smem distance between stages (1024-aligned)
   uint32_t sbo;          // UMMA stride-byte-offset between 8-row groups of A
   int nstages, ngroups;  // A ring depth, accumulator ring depth
@@ -42,7 +48,7 @@ struct TcParams {
   int out_mode, oh, ow, oc;   // output tensor dims (NHWC: channels oc; NCHW: oc planes)
   int sy, sx;                 // output pixel = input pixel * (sy,sx) + acc offset
   int acc_oy[kMaxAcc], acc_ox[kMaxAcc];
-  int relu;
+  int relu;                   // TcAct
   long long out_nstride;      // NCHW output: elements between consecutive images
   void* out;
   float* out2;                // optional pre-sigmoid logits (NCHW f32)
@@ -57,10 +63,11 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
 
 // SWIZZLE_128B bf16 tiled tensor map (cuTensorMapEncodeTiled through the runtime's driver entry point)
 int encode_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,
-                const cuuint64_t* strides_bytes, const cuuint32_t* box);
+                const cuuint64_t* strides_bytes, const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr);
 
 // packed layout helpers
-size_t packed_weight_bytes(int cin_pad, int cout_pad);   // bf16 blocks only
+size_t packed_weight_bytes(int cin_pad, int cout_pad);   // bf16 blocks only, 3x3 kernels
+size_t packed_weight_bytes_k(int kind, int cin_pad, int cout_pad);   // ... 16 taps for kConv4x4s2
 int cin_padded(int cin);
 int cout_padded(int cout);
 

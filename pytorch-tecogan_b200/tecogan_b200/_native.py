@@ -42,6 +42,7 @@ SIGNATURES = {
     "tg_pack_weights": (_c_int, [_c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
     "tg_conv3x3_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
                                 _c_int, _c_int, _c_void_p]),
+    "tg_conv4x4s2_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "tg_convT3x3s2_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                    _c_int, _c_void_p]),
     "tg_conv3x3_out_sigmoid": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,

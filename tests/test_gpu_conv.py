@@ -137,3 +137,65 @@ def test_conv_full_size_windows():
         ref = ref[:, :, oy:oy + 24, ox:ox + 24]
         got = y[:, y0:y0 + 24, x0:x0 + 24].float().cpu().permute(0, 3, 1, 2)
         assert _rel(got, ref) <= 6e-3
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,act", [
+    (1, 32, 16, 64, 64, 0),        # exactly one output tile
+    (2, 38, 26, 64, 64, 2),        # ragged edges, LeakyReLU(0.2)
+    (1, 64, 64, 64, 128, 0),       # block2: two output chunks
+    (3, 32, 32, 128, 128, 0),      # block3: two K chunks
+    (2, 16, 16, 128, 64, 1),       # block4
+    (12, 128, 128, 64, 64, 0),     # block1 at the cfg4 size
+])
+def test_conv4x4s2(n, h, w, cin, cout, act):
+    """Conv2d(k=4, s=2, p=1, bias=False) of discriminator_block (code/models.py:90-94): strided TMA phase boxes."""
+    from tecogan_b200 import _native as nt
+    lib = nt.lib()
+    x = _bf(torch.from_numpy(synth.det_uniform((n, cin, h, w), 1, -1, 1)))
+    wt = _bf(torch.from_numpy(synth.det_uniform((cout, cin, 4, 4), 2, -0.1, 0.1)))
+    want = F.conv2d(x, wt, None, stride=2, padding=1)
+    if act == 1:
+        want = want.relu()
+    elif act == 2:
+        want = F.leaky_relu(want, 0.2)
+    packed = _pack(2, wt, None, cin, cout)
+    xd = _nhwc_bf16(x, cin)
+    y = torch.empty(n, h // 2, w // 2, cout, dtype=torch.bfloat16, device="cuda")
+    nt.check(lib.tg_conv4x4s2_fwd(nt.ptr(xd), nt.ptr(packed), nt.ptr(y), n, h, w, cin, cout, act, nt.stream_ptr()))
+    torch.cuda.synchronize()
+    got = y.float().cpu().permute(0, 3, 1, 2)
+    assert got.shape == want.shape
+    assert _rel(got, want) <= 6e-3, _rel(got, want)
+
+
+@pytest.mark.parametrize("n,h,w", [(3, 8, 8), (2, 16, 16), (1, 34, 18)])
+def test_conv4x4s2_three_channels_raw_nchw(n, h, w):
+    """discriminator block5 (64 -> 3): raw f32 NCHW output feeding BatchNorm + flatten (code/models.py:121,141-142)."""
+    from tecogan_b200 import _native as nt
+    lib = nt.lib()
+    x = _bf(torch.from_numpy(synth.det_uniform((n, 64, h, w), 5, -1, 1)))
+    wt = _bf(torch.from_numpy(synth.det_uniform((3, 64, 4, 4), 6, -0.1, 0.1)))
+    want = F.conv2d(x, wt, None, stride=2, padding=1)
+    packed = _pack(2, wt, None, 64, 3)
+    xd = _nhwc_bf16(x, 64)
+    y = torch.empty(n, 3, h // 2, w // 2, dtype=torch.float32, device="cuda")
+    nt.check(lib.tg_conv4x4s2_fwd(nt.ptr(xd), nt.ptr(packed), nt.ptr(y), n, h, w, 64, 3, 0, nt.stream_ptr()))
+    torch.cuda.synchronize()
+    assert (y.cpu() - want).abs().max().item() <= 1e-4
+
+
+def test_conv3x3_leaky_relu():
+    """discriminator first conv: conv3x3(27 -> 64) + bias + LeakyReLU(0.2) (code/models.py:102)."""
+    from tecogan_b200 import _native as nt
+    lib = nt.lib()
+    n, h, w, cin, cout = 2, 24, 40, 27, 64
+    x = _bf(torch.from_numpy(synth.det_uniform((n, cin, h, w), 1, -1, 1)))
+    wt = _bf(torch.from_numpy(synth.det_uniform((cout, cin, 3, 3), 2, -0.1, 0.1)))
+    b = torch.from_numpy(synth.det_uniform((cout,), 3, -0.5, 0.5))
+    want = F.leaky_relu(F.conv2d(x, wt, b, padding=1), 0.2)
+    packed = _pack(0, wt, b, cin, cout)
+    xd = _nhwc_bf16(x, 64)
+    y = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
+    nt.check(lib.tg_conv3x3_fwd(nt.ptr(xd), nt.ptr(packed), None, nt.ptr(y), n, h, w, 64, cout, 2, HALO, nt.stream_ptr()))
+    torch.cuda.synchronize()
+    assert _rel(y.float().cpu().permute(0, 3, 1, 2), want) <= 6e-3
