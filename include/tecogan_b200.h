@@ -154,6 +154,28 @@ int tg_gen_clip_step(const void* packed, int num_resblock, const float* lr_t, co
                      int h, int w, long long lr_batch_stride, long long prev_batch_stride,
                      long long out_batch_stride, int amode, void* stream);
 
+/* -------------------------------------------------- spatio-temporal discriminator (forward) ---- */
+
+/* discriminator(args) of code/models.py:97-146 with nb = args.discrim_resblocks, ch = args.discrim_channels
+ * (64 or 128), fc_in = in-features of fc (48 in the reference = 128x128 inputs; 3*(h/32)*(w/32) in general).
+ * Parameters: ONE flat f32 device buffer in named_parameters() order (conv.0.{weight,bias}, block1.0.weight,
+ * block1.1.{weight,bias}, resids1.i.0.0.{weight,bias}, resids1.i.0.2.weight, resids1.i.1.{weight,bias}, ...,
+ * block5.1.{weight,bias}, fc.{weight,bias}); tg_disc_pack derives the bf16 MMA-ordered conv blocks from it. */
+size_t tg_disc_param_count(int nb, int ch, int fc_in);
+size_t tg_disc_packed_bytes(int nb, int ch);
+int tg_disc_pack(const float* flat_params, int nb, int ch, void* packed, void* stream);
+size_t tg_disc_workspace_bytes(int n, int h, int w, int nb, int ch);
+/* discriminator.forward (code/models.py:125-146): x NCHW f32 [n,27,h,w] -> prob [n] (sigmoid applied) and, for
+ * every non-NULL feats[i] (host array of 4 device pointers), the layer_list feature map i as NCHW f32
+ * ([n,64,h/2,w/2], [n,ch,h/4,w/4], [n,ch,h/8,w/8], [n,64,h/16,w/16]).  BatchNorm2d(eps=1e-3) uses batch statistics
+ * when training != 0 (the reference never leaves train mode) and then updates the running statistics in place:
+ * bn_running is a host array of 3 device pointers per BatchNorm layer {running_mean, running_var,
+ * num_batches_tracked (int64)} in module order (block1, resids1.*, block2, resids2.*, block3, resids3.*, block4,
+ * block5), or NULL to skip the update.  All activations stay in the workspace for a backward pass. */
+int tg_disc_forward(const float* flat_params, const void* packed, int nb, int ch, int fc_in, const float* x,
+                    float* prob, float* const* feats, void* const* bn_running, int training,
+                    void* workspace, size_t workspace_bytes, int n, int h, int w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,285 @@
+// BatchNorm2d(eps=1e-3) in training mode (reference code/ops.py:75-77, used by discriminator_block and the
+// discriminator's residual blocks, code/models.py:90-94,106,130) on NHWC bf16 activations, plus the
+// discriminator head (block5 BatchNorm + LeakyReLU + flatten + Linear + sigmoid, code/models.py:121,141-145).
+// HBM/latency-bound elementwise + reduction kernels: 128-bit vector access, fp32 statistics.
+#include "tg_disc.cuh"
+
+namespace tg {
+
+constexpr int kBnThreads = 256;
+constexpr int kBnMaxBlocks = 64;
+
+// ---------------------------------------------------------------------------------------------
+// Batch statistics of x [P pixels][C] f32 (raw conv outputs are kept in f32: normalisation amplifies rounding).  Every block reduces a strided slice of the pixels to
+// per-channel (sum, sum of squares) partials; the last block to finish (atomic ticket) reduces the
+// partials in a fixed order (deterministic), writes {mean, rstd, a, b} with y = a*x + b the folded
+// normalise+affine, and applies the running-statistics update of nn.BatchNorm2d (momentum 0.1,
+// unbiased variance).  The ticket is reset for the next use.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBnThreads)
+bn_stats_nhwc_kernel(const float* __restrict__ x, long long pixels, int c, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, float momentum, float* __restrict__ partial,
+                     unsigned int* __restrict__ ticket, float* __restrict__ stats, float* running_mean,
+                     float* running_var, long long* num_batches_tracked) {
+  __shared__ float s_sum[kBnThreads][9];      // +1 padding
+  __shared__ float s_sq[kBnThreads][9];
+  __shared__ bool s_last;
+  const int groups = c / 8;                                   // 16-byte groups per pixel
+  const int pix_per_iter = kBnThreads / groups;
+  const int gi = threadIdx.x % groups, pl = threadIdx.x / groups;
+  float sum[8], sq[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sum[e] = sq[e] = 0.f;
+  for (long long p = static_cast<long long>(blockIdx.x) * pix_per_iter + pl; p < pixels;
+       p += static_cast<long long>(gridDim.x) * pix_per_iter) {
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(x + p * c) + 2 * gi);
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(x + p * c) + 2 * gi + 1);
+    const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sum[e] += f[e]; sq[e] += f[e] * f[e]; }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s_sum[threadIdx.x][e] = sum[e]; s_sq[threadIdx.x][e] = sq[e]; }
+  __syncthreads();
+  // one thread per channel sums the pix_per_iter rows that hold it
+  if (threadIdx.x < c) {
+    const int g = threadIdx.x / 8, e = threadIdx.x % 8;
+    float a = 0.f, b = 0.f;
+    for (int r = 0; r < pix_per_iter; ++r) { a += s_sum[r * groups + g][e]; b += s_sq[r * groups + g][e]; }
+    partial[(static_cast<size_t>(blockIdx.x) * c + threadIdx.x) * 2 + 0] = a;
+    partial[(static_cast<size_t>(blockIdx.x) * c + threadIdx.x) * 2 + 1] = b;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < c) {
+    double a = 0.0, b = 0.0;
+    for (unsigned int k = 0; k < gridDim.x; ++k) {
+      a += static_cast<double>(__ldcg(partial + (static_cast<size_t>(k) * c + threadIdx.x) * 2 + 0));
+      b += static_cast<double>(__ldcg(partial + (static_cast<size_t>(k) * c + threadIdx.x) * 2 + 1));
+    }
+    const double mean = a / static_cast<double>(pixels);
+    double var = b / static_cast<double>(pixels) - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float ga = gamma[threadIdx.x] * rstd;
+    stats[threadIdx.x * 4 + 0] = static_cast<float>(mean);
+    stats[threadIdx.x * 4 + 1] = rstd;
+    stats[threadIdx.x * 4 + 2] = ga;
+    stats[threadIdx.x * 4 + 3] = beta[threadIdx.x] - static_cast<float>(mean) * ga;
+    if (running_mean) {
+      const double unbiased = pixels > 1 ? var * static_cast<double>(pixels) / static_cast<double>(pixels - 1) : var;
+      running_mean[threadIdx.x] = (1.f - momentum) * running_mean[threadIdx.x] + momentum * static_cast<float>(mean);
+      running_var[threadIdx.x] = (1.f - momentum) * running_var[threadIdx.x] + momentum * static_cast<float>(unbiased);
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (num_batches_tracked) *num_batches_tracked += 1;
+    *ticket = 0u;
+  }
+}
+
+// eval mode: fold the running statistics into {mean, rstd, a, b}
+__global__ void bn_fold_running_kernel(int c, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float eps, const float* __restrict__ running_mean,
+                                       const float* __restrict__ running_var, float* __restrict__ stats) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const float rstd = rsqrtf(running_var[ch] + eps);
+  const float ga = gamma[ch] * rstd;
+  stats[ch * 4 + 0] = running_mean[ch];
+  stats[ch * 4 + 1] = rstd;
+  stats[ch * 4 + 2] = ga;
+  stats[ch * 4 + 3] = beta[ch] - running_mean[ch] * ga;
+}
+
+// y = act(a*x + b) (+ skip); x, skip: [P][C] f32; written twice: y32 (f32: the residual stream / feature maps) and
+// y16 (bf16: the next convolution's operand).  act 0 none / 2 LeakyReLU(0.2)
+__global__ void __launch_bounds__(kBnThreads)
+bn_apply_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ skip, float* __restrict__ y32,
+                     __nv_bfloat16* __restrict__ y16, long long pixels, int c, const float* __restrict__ stats, int act) {
+  __shared__ float s_a[128], s_b[128];
+  for (int i = threadIdx.x; i < c; i += blockDim.x) { s_a[i] = stats[i * 4 + 2]; s_b[i] = stats[i * 4 + 3]; }
+  __syncthreads();
+  const int groups = c / 4;
+  const long long total = pixels * groups;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      f[e] = s_a[g * 4 + e] * f[e] + s_b[g * 4 + e];
+      if (act == kActLrelu02) f[e] = f[e] > 0.f ? f[e] : 0.2f * f[e];
+    }
+    if (skip) {
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(skip) + i);
+      f[0] += s4.x; f[1] += s4.y; f[2] += s4.z; f[3] += s4.w;
+    }
+    reinterpret_cast<float4*>(y32)[i] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<uint2*>(y16)[i] = make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
+  }
+}
+
+// NHWC f32 [n][hw][c] -> NCHW f32 [n][c][hw] (the feature maps returned in layer_list, code/models.py:131,135,139,141)
+__global__ void __launch_bounds__(256)
+nhwc_f32_to_nchw_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int c, long long hw) {
+  __shared__ float tile[32][129];
+  const long long groups = (hw + 31) / 32;
+  for (long long gi = blockIdx.x; gi < groups * n; gi += gridDim.x) {
+    const long long b = gi / groups, p0 = (gi % groups) * 32;
+    for (int i = threadIdx.x; i < 32 * c; i += blockDim.x) {
+      const int px = i / c, ch = i % c;
+      tile[px][ch] = (p0 + px < hw) ? in[(b * hw + p0 + px) * c + ch] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * c; i += blockDim.x) {
+      const int ch = i / 32, px = i % 32;
+      if (p0 + px < hw) out[(b * c + ch) * hw + p0 + px] = tile[px][ch];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Discriminator head, one block: raw block5 conv output r [n][3][hw] f32 -> BatchNorm (batch stats, 3 channels)
+// -> LeakyReLU(0.2) -> flatten (NCHW order) -> Linear(3*hw, 1) -> sigmoid.   code/models.py:121,141-145.
+// Saves y (post-LeakyReLU, the fc input) and {mean, rstd, a, b} for the backward pass.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+disc_head_kernel(const float* __restrict__ r, int n, int hw, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 float eps, float momentum, int training, float* running_mean, float* running_var,
+                 long long* num_batches_tracked, const float* __restrict__ fc_w, const float* __restrict__ fc_b,
+                 float* __restrict__ y, float* __restrict__ stats, float* __restrict__ logit, float* __restrict__ prob) {
+  __shared__ double s_red[2][256];
+  __shared__ float s_ab[3][2];
+  const int per = n * hw;
+  for (int ch = 0; ch < 3; ++ch) {
+    double a = 0.0, b = 0.0;
+    if (training) {
+      for (int i = threadIdx.x; i < per; i += blockDim.x) {
+        const float v = r[(static_cast<long long>(i / hw) * 3 + ch) * hw + i % hw];
+        a += v; b += static_cast<double>(v) * v;
+      }
+    }
+    s_red[0][threadIdx.x] = a; s_red[1][threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) { s_red[0][threadIdx.x] += s_red[0][threadIdx.x + s]; s_red[1][threadIdx.x] += s_red[1][threadIdx.x + s]; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      double mean, var;
+      if (training) {
+        mean = s_red[0][0] / per;
+        var = s_red[1][0] / per - mean * mean;
+        if (var < 0.0) var = 0.0;
+        if (running_mean) {
+          const double unbiased = per > 1 ? var * per / (per - 1) : var;
+          running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * static_cast<float>(mean);
+          running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * static_cast<float>(unbiased);
+        }
+      } else {
+        mean = running_mean[ch]; var = running_var[ch];
+      }
+      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      const float ga = gamma[ch] * rstd;
+      stats[ch * 4 + 0] = static_cast<float>(mean); stats[ch * 4 + 1] = rstd;
+      stats[ch * 4 + 2] = ga; stats[ch * 4 + 3] = beta[ch] - static_cast<float>(mean) * ga;
+      s_ab[ch][0] = ga; s_ab[ch][1] = stats[ch * 4 + 3];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
+  const int feat = 3 * hw;
+  for (int i = threadIdx.x; i < n * feat; i += blockDim.x) {
+    const int ch = (i % feat) / hw;
+    float v = s_ab[ch][0] * r[i] + s_ab[ch][1];
+    y[i] = v > 0.f ? v : 0.2f * v;
+  }
+  __syncthreads();
+  // one warp per sample: dot(y[s], fc_w) + b
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int s = warp; s < n; s += blockDim.x / 32) {
+    float acc = 0.f;
+    for (int k = lane; k < feat; k += 32) acc += y[s * feat + k] * fc_w[k];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const float z = acc + fc_b[0];
+      if (logit) logit[s] = z;
+      prob[s] = 1.f / (1.f + expf(-z));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ launchers
+int bn_stats_launch(const void* x, long long pixels, int c, const float* gamma, const float* beta, float* partial,
+                    unsigned int* ticket, float* stats, float* running_mean, float* running_var,
+                    long long* nbt, cudaStream_t st) {
+  TG_CHECK_ARG(c == 64 || c == 128, "bn_stats: channels must be 64 or 128 (got %d)", c);
+  TG_CHECK_ARG(pixels >= 1, "bn_stats: empty batch");
+  const int pix_per_iter = kBnThreads / (c / 8);
+  long long blocks = (pixels + pix_per_iter * 4 - 1) / (pix_per_iter * 4);
+  if (blocks > kBnMaxBlocks) blocks = kBnMaxBlocks;
+  if (blocks < 1) blocks = 1;
+  tg_prof_pre(TG_K_GLUE, 4.0 * pixels * c, st);
+  bn_stats_nhwc_kernel<<<static_cast<int>(blocks), kBnThreads, 0, st>>>(
+      static_cast<const float*>(x), pixels, c, gamma, beta, 1e-3f, 0.1f, partial, ticket, stats, running_mean,
+      running_var, nbt);
+  tg_prof_post(st);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+size_t bn_partial_floats() { return static_cast<size_t>(kBnMaxBlocks) * 128 * 2; }
+
+int bn_fold_running_launch(int c, const float* gamma, const float* beta, const float* running_mean,
+                           const float* running_var, float* stats, cudaStream_t st) {
+  bn_fold_running_kernel<<<1, 128, 0, st>>>(c, gamma, beta, 1e-3f, running_mean, running_var, stats);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+int bn_apply_launch(const void* x, const void* skip, void* y32, void* y16, long long pixels, int c, const float* stats,
+                    int act, cudaStream_t st) {
+  TG_CHECK_ARG(c == 64 || c == 128, "bn_apply: channels must be 64 or 128 (got %d)", c);
+  const long long total = pixels * (c / 4);
+  long long blocks = (total + kBnThreads - 1) / kBnThreads;
+  const long long cap = static_cast<long long>(tg_num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  tg_prof_pre(TG_K_GLUE, (skip ? 14.0 : 10.0) * pixels * c, st);
+  bn_apply_nhwc_kernel<<<static_cast<int>(blocks), kBnThreads, 0, st>>>(
+      static_cast<const float*>(x), static_cast<const float*>(skip), static_cast<float*>(y32),
+      static_cast<__nv_bfloat16*>(y16), pixels, c, stats, act);
+  tg_prof_post(st);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+int nhwc_to_nchw_f32_launch(const void* in, float* out, int n, int c, long long hw, cudaStream_t st) {
+  TG_CHECK_ARG(c <= 128, "nhwc_to_nchw: at most 128 channels");
+  const long long groups = (hw + 31) / 32 * n;
+  const long long cap = static_cast<long long>(tg_num_sms()) * 8;
+  tg_prof_pre(TG_K_GLUE, 8.0 * n * c * hw, st);
+  nhwc_f32_to_nchw_f32_kernel<<<static_cast<int>(groups < cap ? groups : cap), 256, 0, st>>>(
+      static_cast<const float*>(in), out, n, c, hw);
+  tg_prof_post(st);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+int disc_head_launch(const float* r, int n, int hw, const float* gamma, const float* beta, int training,
+                     float* running_mean, float* running_var, long long* nbt, const float* fc_w, const float* fc_b,
+                     float* y, float* stats, float* logit, float* prob, cudaStream_t st) {
+  tg_prof_pre(TG_K_GLUE, 8.0 * n * 3 * hw, st);
+  disc_head_kernel<<<1, 256, 0, st>>>(r, n, hw, gamma, beta, 1e-3f, 0.1f, training, running_mean, running_var, nbt, fc_w,
+                                      fc_b, y, stats, logit, prob);
+  tg_prof_post(st);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+}  // namespace tg

@@ -205,7 +205,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
           }
-          if (valid) {
+          if (valid && p.out_mode == kOutNHWCf32) {          // raw f32 (bias, no activation): BatchNorm input
+            const size_t pix = (static_cast<size_t>(n) * p.oh + oy) * p.ow + ox;
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + pix * p.oc + chunk * 64);
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              uint32_t* v = h2 ? v1 : v0;
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4)
+                dst[h2 * 8 + c4] = make_float4(__uint_as_float(v[c4 * 4 + 0]) + s_bias[h2 * 32 + c4 * 4 + 0],
+                                               __uint_as_float(v[c4 * 4 + 1]) + s_bias[h2 * 32 + c4 * 4 + 1],
+                                               __uint_as_float(v[c4 * 4 + 2]) + s_bias[h2 * 32 + c4 * 4 + 2],
+                                               __uint_as_float(v[c4 * 4 + 3]) + s_bias[h2 * 32 + c4 * 4 + 3]);
+            }
+          } else if (valid) {
             const size_t pix = (static_cast<size_t>(n) * p.oh + oy) * p.ow + ox;
             uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix * p.oc +
                                                   chunk * 64);
@@ -321,7 +334,9 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   TG_CHECK_ARG(kind == kConv3x3 || kind == kConvT3x3s2 || kind == kConv4x4s2, "conv: bad kind %d", kind);
   TG_CHECK_ARG(cin_pad == 64 || cin_pad == 128, "conv: cin_pad must be 64 or 128 (got %d)", cin_pad);
   TG_CHECK_ARG(cout_pad == 16 || cout_pad == 64 || cout_pad == 128, "conv: cout_pad must be 16/64/128 (got %d)", cout_pad);
-  TG_CHECK_ARG((out_mode != kOutNHWCbf16) == (cout_pad == 16), "conv: cout 16 <=> NCHW f32 output");
+  const bool nchw_out = (out_mode == kOutNCHWf32Sigmoid || out_mode == kOutNCHWf32Raw);
+  TG_CHECK_ARG(nchw_out == (cout_pad == 16), "conv: cout 16 <=> NCHW f32 output");
+  TG_CHECK_ARG(!(out_mode == kOutNHWCf32 && (relu != kActNone || resid)), "conv: the f32 NHWC output is raw (no activation / residual)");
   TG_CHECK_ARG(amode == TG_AMODE_HALO || amode == TG_AMODE_DX3, "conv: bad amode %d", amode);
   TG_CHECK_ARG(relu == kActNone || relu == kActRelu || relu == kActLrelu02, "conv: bad activation %d", relu);
   TG_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed_w) & 15) == 0 &&
@@ -402,7 +417,7 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   p.out_mode = out_mode;
   p.sy = p.sx = (kind == kConvT3x3s2) ? 2 : 1;
   p.oh = th * p.sy; p.ow = tw * p.sx;
-  p.oc = (out_mode != kOutNHWCbf16) ? 3 : cout_pad;
+  p.oc = nchw_out ? 3 : cout_pad;
   for (int a = 0; a < kMaxAcc; ++a) { p.acc_oy[a] = (kind == kConvT3x3s2) ? (a >> 1) : 0; p.acc_ox[a] = (kind == kConvT3x3s2) ? (a & 1) : 0; }
   p.out_nstride = out_nstride > 0 ? out_nstride : static_cast<long long>(p.oc) * p.oh * p.ow;
   p.relu = relu;

@@ -11,7 +11,7 @@ constexpr int kMaxTaps = 16;
 constexpr int kMaxAcc = 4;
 
 enum TcKind { kConv3x3 = 0, kConvT3x3s2 = 1, kConv4x4s2 = 2 };
-enum TcOut { kOutNHWCbf16 = 0, kOutNCHWf32Sigmoid = 1, kOutNCHWf32Raw = 2 };
+enum TcOut { kOutNHWCbf16 = 0, kOutNCHWf32Sigmoid = 1, kOutNCHWf32Raw = 2, kOutNHWCf32 = 3 };   // 3: pre-BatchNorm conv outputs
 enum TcAct { kActNone = 0, kActRelu = 1, kActLrelu02 = 2 };   // LeakyReLU(0.2): code/ops.py:71-72
 
 // One MMA group = one filter tap on one 64-channel K chunk: 4 x tcgen05.mma (K=16 each).

@@ -1,0 +1,21 @@
+// Internal interface of the discriminator building blocks (tg_bn.cu) used by tg_discriminator.cu.
+#pragma once
+#include "tg_conv_tc.cuh"
+
+namespace tg {
+
+// stats layout per BN layer: [c][4] = {mean, rstd, a = gamma*rstd, b = beta - mean*a}
+int bn_stats_launch(const void* x, long long pixels, int c, const float* gamma, const float* beta, float* partial,
+                    unsigned int* ticket, float* stats, float* running_mean, float* running_var,
+                    long long* num_batches_tracked, cudaStream_t st);
+size_t bn_partial_floats();
+int bn_fold_running_launch(int c, const float* gamma, const float* beta, const float* running_mean,
+                           const float* running_var, float* stats, cudaStream_t st);
+int bn_apply_launch(const void* x, const void* skip, void* y32, void* y16, long long pixels, int c, const float* stats,
+                    int act, cudaStream_t st);
+int nhwc_to_nchw_f32_launch(const void* in, float* out, int n, int c, long long hw, cudaStream_t st);
+int disc_head_launch(const float* r, int n, int hw, const float* gamma, const float* beta, int training,
+                     float* running_mean, float* running_var, long long* nbt, const float* fc_w, const float* fc_b,
+                     float* y, float* stats, float* logit, float* prob, cudaStream_t st);
+
+}  // namespace tg

@@ -1,0 +1,227 @@
+// The spatio-temporal discriminator forward (reference code/models.py:97-146) as a sequence of tensor-core
+// conv launches (3x3 s1 and 4x4 s2), BatchNorm (batch statistics) + LeakyReLU / skip passes and the head.
+// All intermediates that a backward pass needs stay in the caller's workspace.
+#include <vector>
+
+#include "tg_disc.cuh"
+
+namespace tg {
+
+struct DConv {
+  int kind, cin, cout, has_bias;
+  size_t w_off, b_off;     // element offsets in the flat parameter buffer
+  size_t p_off;            // byte offset in the packed blob
+};
+struct DBn { int c; size_t g_off, b_off; };   // gamma / beta element offsets in the flat parameter buffer
+
+struct DLayout {
+  std::vector<DConv> convs;   // conv.0, block1, [res.0, res.2]*nb, block2, ..., block4, block5
+  std::vector<DBn> bns;       // block1, res*nb, block2, res*nb, block3, res*nb, block4, block5
+  size_t fc_w, fc_b, n_params, packed_bytes;
+};
+
+// state_dict / named_parameters order: conv.0.{w,b}, block1.0.w, block1.1.{w,b},
+// resids1.i.0.0.{w,b}, resids1.i.0.2.w, resids1.i.1.{w,b}, block2..., block5.1.{w,b}, fc.{w,b}
+static DLayout disc_layout(int nb, int ch, int fc_in) {
+  DLayout L;
+  size_t po = 0, bo = 0;
+  auto conv = [&](int kind, int cin, int cout, int has_bias) {
+    DConv c{kind, cin, cout, has_bias, po, 0, bo};
+    po += static_cast<size_t>(cin) * cout * (kind == kConv4x4s2 ? 16 : 9);
+    if (has_bias) { c.b_off = po; po += cout; }
+    bo += tg_packed_conv_bytes(kind, cin, cout);
+    L.convs.push_back(c);
+  };
+  auto bn = [&](int c) {
+    DBn b{c, po, po + static_cast<size_t>(c)};
+    po += 2 * static_cast<size_t>(c);
+    L.bns.push_back(b);
+  };
+  auto stage = [&](int cin, int cout) {
+    conv(kConv4x4s2, cin, cout, 0); bn(cout);
+  };
+  auto resids = [&](int c) {
+    for (int i = 0; i < nb; ++i) { conv(kConv3x3, c, c, 1); conv(kConv3x3, c, c, 0); bn(c); }
+  };
+  conv(kConv3x3, 27, 64, 1);
+  stage(64, 64); resids(64);
+  stage(64, ch); resids(ch);
+  stage(ch, ch); resids(ch);
+  stage(ch, 64);
+  stage(64, 3);
+  L.fc_w = po; po += fc_in;
+  L.fc_b = po; po += 1;
+  L.n_params = po;
+  L.packed_bytes = bo;
+  return L;
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+// Workspace: every activation of the forward pass is kept (the backward pass reads them).
+struct DWorkspace {
+  size_t x_in, a0;                    // packed input, conv.0 output
+  // per BN layer: raw conv output (f32), BN(+act/skip) output as f32 (residual stream, features) and as bf16
+  // (conv operand); per resblock: relu(conv1) (bf16)
+  std::vector<size_t> raw, act, act16, mid;
+  size_t r5, y5;                      // block5 raw conv [n,3,hw] f32, head fc input [n,3*hw] f32
+  size_t stats, partial, tickets, logit, total;
+};
+static DWorkspace disc_ws(int n, int h, int w, int nb, int ch) {
+  DWorkspace ws;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align256(bytes); return r; };
+  const size_t px = static_cast<size_t>(n) * h * w;
+  ws.x_in = take(px * 64 * 2);
+  ws.a0 = take(px * 64 * 2);
+  const int cs[4] = {64, ch, ch, 64};
+  for (int s = 0; s < 4; ++s) {
+    const size_t p = px >> (2 * (s + 1));
+    const int reps = (s < 3) ? 1 + nb : 1;
+    for (int i = 0; i < reps; ++i) {
+      ws.raw.push_back(take(p * cs[s] * 4));
+      ws.act.push_back(take(p * cs[s] * 4));
+      ws.act16.push_back(take(p * cs[s] * 2));
+      if (i > 0) ws.mid.push_back(take(p * cs[s] * 2));
+    }
+  }
+  const size_t p5 = px >> 10;
+  ws.r5 = take(p5 * 3 * 4);
+  ws.y5 = take(p5 * 3 * 4);
+  ws.stats = take(static_cast<size_t>(5 + 3 * nb) * 128 * 4 * 4);
+  ws.partial = take(bn_partial_floats() * 4);
+  ws.tickets = take(256);
+  ws.logit = take(static_cast<size_t>(n) * 4);
+  ws.total = o;
+  return ws;
+}
+
+}  // namespace tg
+
+using namespace tg;
+
+static int check_cfg(int nb, int ch) {
+  TG_CHECK_ARG(nb >= 0 && nb <= 16, "discriminator: discrim_resblocks %d out of range", nb);
+  TG_CHECK_ARG(ch == 64 || ch == 128, "discriminator: discrim_channels must be 64 or 128 (got %d)", ch);
+  return TG_OK;
+}
+
+extern "C" size_t tg_disc_param_count(int nb, int ch, int fc_in) {
+  if (check_cfg(nb, ch)) return 0;
+  return disc_layout(nb, ch, fc_in).n_params;
+}
+extern "C" size_t tg_disc_packed_bytes(int nb, int ch) {
+  if (check_cfg(nb, ch)) return 0;
+  return disc_layout(nb, ch, 48).packed_bytes;
+}
+extern "C" int tg_disc_pack(const float* flat_params, int nb, int ch, void* packed, void* stream) {
+  TG_CHECK_ARG(flat_params && packed, "disc_pack: null pointer");
+  if (int rc = check_cfg(nb, ch)) return rc;
+  TG_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 255) == 0, "disc_pack: packed must be 256-byte aligned");
+  const DLayout L = disc_layout(nb, ch, 48);
+  for (auto& c : L.convs) {
+    int rc = tg_pack_weights(c.kind, flat_params + c.w_off, c.has_bias ? flat_params + c.b_off : nullptr, c.cin, c.cout,
+                             static_cast<uint8_t*>(packed) + c.p_off, stream);
+    if (rc) return rc;
+  }
+  return TG_OK;
+}
+extern "C" size_t tg_disc_workspace_bytes(int n, int h, int w, int nb, int ch) {
+  if (n <= 0 || h <= 0 || w <= 0 || check_cfg(nb, ch)) return 0;
+  return disc_ws(n, h, w, nb, ch).total;
+}
+
+extern "C" int tg_disc_forward(const float* flat_params, const void* packed, int nb, int ch, int fc_in, const float* x,
+                               float* prob, float* const* feats, void* const* bn_running, int training,
+                               void* workspace, size_t workspace_bytes, int n, int h, int w, void* stream) {
+  TG_CHECK_ARG(flat_params && packed && x && prob && workspace, "disc_forward: null pointer");
+  if (int rc = check_cfg(nb, ch)) return rc;
+  TG_CHECK_ARG(n >= 1 && h >= 32 && w >= 32 && (h % 32) == 0 && (w % 32) == 0,
+               "disc_forward: input must be [n,27,h,w] with h, w multiples of 32 (got %dx%d)", h, w);
+  TG_CHECK_ARG(fc_in == 3 * (h / 32) * (w / 32), "disc_forward: fc in-features %d do not match 3*(h/32)*(w/32) = %d "
+               "(code/models.py:123 hard-codes 48 = 128x128 inputs)", fc_in, 3 * (h / 32) * (w / 32));
+  TG_CHECK_ARG(training || bn_running, "disc_forward: eval mode needs the running statistics");
+  TG_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "disc_forward: workspace must be 256-byte aligned");
+  const DWorkspace ws = disc_ws(n, h, w, nb, ch);
+  if (workspace_bytes < ws.total) {
+    tg_set_error("disc_forward: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+    return TG_ERR_WORKSPACE;
+  }
+  const DLayout L = disc_layout(nb, ch, fc_in);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* wsp = static_cast<uint8_t*>(workspace);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  float* stats_all = reinterpret_cast<float*>(wsp + ws.stats);
+  float* partial = reinterpret_cast<float*>(wsp + ws.partial);
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(wsp + ws.tickets);
+  TG_CUDA(cudaMemsetAsync(tickets, 0, 256, st));
+
+  int ci = 0, bi = 0;
+  // raw = pre-BatchNorm output, kept in f32
+  auto conv = [&](const void* in, void* out, int hh, int ww, int act, bool raw) {
+    const DConv& c = L.convs[ci++];
+    const int cp = cin_padded(c.cin), op = cout_padded(c.cout);
+    const uint8_t* blob = pk + c.p_off;
+    const float* bias = reinterpret_cast<const float*>(blob + packed_weight_bytes_k(c.kind, cp, op));
+    const int mode = c.cout == 3 ? kOutNCHWf32Raw : (raw ? kOutNHWCf32 : kOutNHWCbf16);
+    return launch_conv_tc(c.kind, mode, in, blob, bias, nullptr, out, nullptr, n, hh, ww, cp, op, act, TG_AMODE_HALO, 0, st);
+  };
+  // BatchNorm (+ LeakyReLU or + skip) of the raw conv output of BN layer `bi`
+  auto bn = [&](const void* raw, const void* skip, void* out32, void* out16, long long pixels, int act) {
+    const DBn& b = L.bns[bi];
+    float* stats = stats_all + static_cast<size_t>(bi) * 128 * 4;
+    float* rm = bn_running ? static_cast<float*>(bn_running[3 * bi + 0]) : nullptr;
+    float* rv = bn_running ? static_cast<float*>(bn_running[3 * bi + 1]) : nullptr;
+    long long* nbt = bn_running ? static_cast<long long*>(bn_running[3 * bi + 2]) : nullptr;
+    int rc;
+    if (training) rc = bn_stats_launch(raw, pixels, b.c, flat_params + b.g_off, flat_params + b.b_off, partial, tickets, stats,
+                                       rm, rv, nbt, st);
+    else rc = bn_fold_running_launch(b.c, flat_params + b.g_off, flat_params + b.b_off, rm, rv, stats, st);
+    if (rc) return rc;
+    ++bi;
+    return bn_apply_launch(raw, skip, out32, out16, pixels, b.c, stats, act, st);
+  };
+
+  int rc;
+  if ((rc = tg_pack_nchw_to_nhwc64(x, wsp + ws.x_in, n, 27, h, w, stream))) return rc;
+  if ((rc = conv(wsp + ws.x_in, wsp + ws.a0, h, w, kActLrelu02, false))) return rc;      // conv + lrelu  (:102,127)
+  const void* cur16 = wsp + ws.a0;     // bf16 copy: conv operand
+  const void* cur32 = nullptr;         // f32 copy: residual stream
+  int hh = h, ww = w, li = 0, mi = 0;
+  const int cs[4] = {64, ch, ch, 64};
+  for (int s = 0; s < 4; ++s) {
+    // discriminator_block: conv k4 s2 (no bias) -> BN -> LeakyReLU   (:90-94)
+    if ((rc = conv(cur16, wsp + ws.raw[li], hh, ww, kActNone, true))) return rc;
+    hh /= 2; ww /= 2;
+    const long long pixels = static_cast<long long>(n) * hh * ww;
+    if ((rc = bn(wsp + ws.raw[li], nullptr, wsp + ws.act[li], wsp + ws.act16[li], pixels, kActLrelu02))) return rc;
+    cur32 = wsp + ws.act[li]; cur16 = wsp + ws.act16[li];
+    ++li;
+    if (s < 3) {
+      for (int i = 0; i < nb; ++i) {                                                    // net = block(net) + net  (:128-130)
+        if ((rc = conv(cur16, wsp + ws.mid[mi], hh, ww, kActRelu, false))) return rc;   // conv + bias + ReLU
+        if ((rc = conv(wsp + ws.mid[mi], wsp + ws.raw[li], hh, ww, kActNone, true))) return rc;   // conv (no bias)
+        if ((rc = bn(wsp + ws.raw[li], cur32, wsp + ws.act[li], wsp + ws.act16[li], pixels, kActNone))) return rc;   // BN, + skip
+        cur32 = wsp + ws.act[li]; cur16 = wsp + ws.act16[li];
+        ++li; ++mi;
+      }
+    }
+    if (feats && feats[s]) {                                                            // layer_list (:131,135,139,141)
+      if ((rc = nhwc_to_nchw_f32_launch(cur32, feats[s], n, cs[s], static_cast<long long>(hh) * ww, st))) return rc;
+    }
+  }
+  // block5 conv (64 -> 3) raw, then BN + LeakyReLU + flatten + fc + sigmoid in the head kernel  (:121,141-145)
+  if ((rc = conv(cur16, wsp + ws.r5, hh, ww, kActNone, false))) return rc;
+  hh /= 2; ww /= 2;
+  {
+    const DBn& b = L.bns[bi];
+    float* rm = bn_running ? static_cast<float*>(bn_running[3 * bi + 0]) : nullptr;
+    float* rv = bn_running ? static_cast<float*>(bn_running[3 * bi + 1]) : nullptr;
+    long long* nbt = bn_running ? static_cast<long long*>(bn_running[3 * bi + 2]) : nullptr;
+    rc = disc_head_launch(reinterpret_cast<const float*>(wsp + ws.r5), n, hh * ww, flat_params + b.g_off, flat_params + b.b_off,
+                          training, rm, rv, nbt, flat_params + L.fc_w, flat_params + L.fc_b,
+                          reinterpret_cast<float*>(wsp + ws.y5), stats_all + static_cast<size_t>(bi) * 128 * 4,
+                          reinterpret_cast<float*>(wsp + ws.logit), prob, st);
+  }
+  return rc;
+}

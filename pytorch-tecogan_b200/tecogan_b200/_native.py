@@ -57,6 +57,12 @@ SIGNATURES = {
                                   _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_int, _c_void_p]),
     "tg_gen_clip_forward": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_int, _c_int,
                                      _c_int, _c_int, _c_int, _c_void_p]),
+    "tg_disc_param_count": (_c_size_t, [_c_int, _c_int, _c_int]),
+    "tg_disc_packed_bytes": (_c_size_t, [_c_int, _c_int]),
+    "tg_disc_pack": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
+    "tg_disc_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int, _c_int]),
+    "tg_disc_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                 _c_int, _c_void_p, _c_size_t, _c_int, _c_int, _c_int, _c_void_p]),
 }
 
 _lib = None

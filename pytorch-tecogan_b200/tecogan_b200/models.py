@@ -119,15 +119,16 @@ def discriminator_block(inputs, output_channel, kernel_size, stride):
 
 
 class discriminator(nn.Module):
-    """code/models.py:97-146 — interface and state_dict mirror.  The tensor-core forward/backward
-    for the spatio-temporal discriminator is the next hot-path row; until
-    it lands, calling it fails loudly instead of falling back to library kernels."""
+    """code/models.py:97-146, B200-native forward: tcgen05 3x3 / 4x4-stride-2 convolutions, BatchNorm (batch
+    statistics, always train mode in the reference) + LeakyReLU / skip passes and the fc + sigmoid head run as
+    hand-written kernels through the C ABI (tg_disc_forward).  The nn.Module children are parameter / buffer
+    containers (identical state_dict keys, shapes and default initialisation); they are never called."""
 
     def __init__(self, args=None):
         super().__init__()
         if args is None:
             raise ValueError("No args is provided for discriminator")   # code/models.py:100-101
-        ch = args.discrim_channels
+        ch = int(args.discrim_channels)
         nb = int(args.discrim_resblocks)
         self.conv = nn.Sequential(conv2(27, 3, 64, 1), lrelu(0.2))
         self.block1 = discriminator_block(64, 64, 4, 2)
@@ -142,10 +143,64 @@ class discriminator(nn.Module):
         # need 48*(crop/32)^2 (colab/README.md:15-22) — derived here, default unchanged.
         crop = int(getattr(args, "crop_size", 32) or 32)
         self.fc = denselayer(48 * max(1, crop // 32) ** 2, 1)
+        self.nb, self.ch = nb, ch
+        self._packed = None
+        self._flat = None
+        self._key = None
+        self._ws = None
+
+    def _bn_modules(self):
+        mods = [self.block1[1]] + [r[1] for r in self.resids1] + [self.block2[1]] + [r[1] for r in self.resids2]
+        mods += [self.block3[1]] + [r[1] for r in self.resids3] + [self.block4[1], self.block5[1]]
+        return mods
+
+    def _weights(self):
+        """(flat f32 parameters in named_parameters order, packed bf16 conv blocks) — a derived cache rebuilt
+        whenever a parameter changed (tensor versions)."""
+        params = [p for _, p in self.named_parameters()]
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or key != self._key:
+            lib = _nt.lib()
+            dev = params[0].device
+            if dev.type != "cuda":
+                raise RuntimeError("discriminator parameters must live on a CUDA device (call .cuda()); no CPU fallback")
+            flat = torch.cat([p.detach().reshape(-1).float() for p in params])
+            assert flat.numel() == lib.tg_disc_param_count(self.nb, self.ch, self.fc.in_features), "parameter layout mismatch"
+            packed = torch.empty(lib.tg_disc_packed_bytes(self.nb, self.ch), dtype=torch.uint8, device=dev)
+            _nt.check(lib.tg_disc_pack(_nt.ptr(flat), self.nb, self.ch, _nt.ptr(packed), _nt.stream_ptr()))
+            self._flat, self._packed, self._key = flat, packed, key
+        return self._flat, self._packed
 
     def forward(self, x):
-        raise NotImplementedError(
-            "tecogan_b200 discriminator: sm_100a forward/backward kernels are not built yet (no library fallback)")
+        import ctypes
+        if not x.is_cuda:
+            raise RuntimeError("discriminator.forward: input must be a CUDA tensor (no CPU fallback)")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError(
+                "tecogan_b200 discriminator: backward kernels are not built yet; call under torch.no_grad()")
+        if x.dim() != 4 or x.shape[1] != 27:
+            raise RuntimeError(f"discriminator.forward: expected [N,27,H,W], got {tuple(x.shape)}")
+        lib = _nt.lib()
+        x = x.float().contiguous()
+        n, _, h, w = x.shape
+        flat, packed = self._weights()
+        need = lib.tg_disc_workspace_bytes(n, h, w, self.nb, self.ch)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        prob = torch.empty((n, 1), dtype=torch.float32, device=x.device)
+        shapes = [(n, 64, h // 2, w // 2), (n, self.ch, h // 4, w // 4), (n, self.ch, h // 8, w // 8), (n, 64, h // 16, w // 16)]
+        feats = [torch.empty(s, dtype=torch.float32, device=x.device) for s in shapes]
+        feat_ptrs = (ctypes.c_void_p * 4)(*[f.data_ptr() for f in feats])
+        bns = self._bn_modules()
+        run = (ctypes.c_void_p * (3 * len(bns)))()
+        for i, m in enumerate(bns):
+            run[3 * i + 0] = m.running_mean.data_ptr()
+            run[3 * i + 1] = m.running_var.data_ptr()
+            run[3 * i + 2] = m.num_batches_tracked.data_ptr()
+        _nt.check(lib.tg_disc_forward(_nt.ptr(flat), _nt.ptr(packed), self.nb, self.ch, self.fc.in_features, _nt.ptr(x),
+                                      _nt.ptr(prob), feat_ptrs, run, 1 if self.training else 0, _nt.ptr(self._ws),
+                                      self._ws.numel(), n, h, w, _nt.stream_ptr()))
+        return prob, feats
 
 
 def f_net():
