@@ -125,6 +125,15 @@ int tg_convT3x3s2_fwd(const void* x, const void* packed, void* y, int n, int h, 
 int tg_conv3x3_out_sigmoid(const void* x, const void* packed, float* out, float* logits, int n,
                            int h, int w, int amode, void* stream);
 
+/* ------------------------------------------------------ backward kernels (training, code/train.py:336,340) -- */
+
+/* Weight gradient of Conv2d 3x3 s1 p1: dw[cout][cin][3][3] (f32, PyTorch layout) += sum over pixels of
+ * dy[n,y,x,co] * x[n,y+ky-1,x+kx-1,ci].  x NHWC bf16 [n,h,w,pad64(cin)], dy NHWC bf16 [n,h,w,pad64(cout)]
+ * (channels beyond cin / cout are ignored).  The result is ACCUMULATED with f32 atomics: zero dw first for a
+ * plain gradient.  tcgen05 kernel with the pixel index as the GEMM reduction dimension (MN-major operands). */
+int tg_conv3x3_wgrad(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
+                     void* stream);
+
 /* ----------------------------------------------------------------- generator (41 convs) ---- */
 
 /* Parameters are passed as ONE flat f32 device buffer holding the tensors of

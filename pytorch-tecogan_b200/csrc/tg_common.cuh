@@ -34,8 +34,8 @@ int tg_num_sms();
 
 // Launch accounting + optional per-launch CUDA-event timing (tg_profile_begin / tg_profile_end).
 // kernel ids: 0 conv_tc<64>, 1 conv_tc<16> (output conv), 2 fused frame input, 3 other glue, 4 pack,
-// 5 frame kernel (whole generator forward).
-enum { TG_K_CONV64 = 0, TG_K_CONV16 = 1, TG_K_FUSED_INPUT = 2, TG_K_GLUE = 3, TG_K_PACK = 4, TG_K_FRAME = 5 };
+// 5 frame kernel (whole generator forward), 6 weight-gradient kernels.
+enum { TG_K_CONV64 = 0, TG_K_CONV16 = 1, TG_K_FUSED_INPUT = 2, TG_K_GLUE = 3, TG_K_PACK = 4, TG_K_FRAME = 5, TG_K_WGRAD = 6 };
 void tg_prof_pre(int kernel_id, double work, cudaStream_t stream);   // call right before a launch
 void tg_prof_post(cudaStream_t stream);                              // call right after it
 

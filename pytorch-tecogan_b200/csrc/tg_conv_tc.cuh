@@ -65,6 +65,10 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
 int encode_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,
                 const cuuint64_t* strides_bytes, const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr);
 
+// tg_wgrad.cu: dW[cout][cin][3][3] += sum_pixels dY (x) X (f32 atomics); x NHWC bf16 [n,h,w,cin_pad], dy [n,h,w,cout_pad]
+int launch_wgrad3x3(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout, int cin_pad,
+                    int cout_pad, cudaStream_t stream);
+
 // packed layout helpers
 size_t packed_weight_bytes(int cin_pad, int cout_pad);   // bf16 blocks only, 3x3 kernels
 size_t packed_weight_bytes_k(int kind, int cin_pad, int cout_pad);   // ... 16 taps for kConv4x4s2
