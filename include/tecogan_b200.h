@@ -133,6 +133,16 @@ int tg_conv3x3_out_sigmoid(const void* x, const void* packed, float* out, float*
  * plain gradient.  tcgen05 kernel with the pixel index as the GEMM reduction dimension (MN-major operands). */
 int tg_conv3x3_wgrad(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
                      void* stream);
+/* Data gradients.  tg_pack_weights kinds 3 / 4 take the FORWARD layer's weight (and its cin, cout) and pack the
+ * weights of the convolution that computes dX from dY (kind 3: conv3x3 with the kernel rotated by 180 degrees and
+ * channels transposed; kind 4: the stride-2 3x3 convolution that is the adjoint of ConvTranspose2d(k3,s2,p1,op1)).
+ * dx = (conv(dy) + residual?) zeroed where mask == 0 (ReLU backward with the saved post-ReLU activation); all
+ * tensors NHWC bf16 padded to 64/128 channels.  tg_conv3x3_dgrad: dy [n,h,w,cout] -> dx [n,h,w,cin].
+ * tg_convT3x3s2_dgrad: dy [n,2h,2w,cout] -> dx [n,h,w,cin] (h, w = the forward layer's INPUT size). */
+int tg_conv3x3_dgrad(const void* dy, const void* packed_dgrad, const void* residual, const void* mask,
+                     void* dx, int n, int h, int w, int cin, int cout, void* stream);
+int tg_convT3x3s2_dgrad(const void* dy, const void* packed_dgrad, const void* mask, void* dx, int n, int h,
+                        int w, int cin, int cout, void* stream);
 
 /* ----------------------------------------------------------------- generator (41 convs) ---- */
 

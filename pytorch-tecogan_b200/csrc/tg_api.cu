@@ -93,7 +93,7 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
   const int ct_ky[9] = {1, 1, 1, 2, 0, 2, 2, 0, 0};
   const int ct_kx[9] = {1, 2, 0, 1, 1, 2, 0, 2, 0};
   const int kchunks = cin_pad / 64;
-  const int ntap = (kind == kConv4x4s2) ? 16 : 9;
+  const int ntap = (kind == kConv4x4s2 || kind == kPackConvT3x3s2Dgrad) ? 16 : 9;
   const long long total = static_cast<long long>(ntap) * cin_pad * cout_pad;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -114,6 +114,16 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
         const int ph = j >> 2, t = j & 3;
         const int ky = 2 * (t >> 1) + (ph >> 1), kx = 2 * (t & 1) + (ph & 1);
         v = w[((static_cast<long long>(co) * cin + ci) * 4 + ky) * 4 + kx];
+      } else if (kind == kPackConv3x3Dgrad) {
+        // dX = conv3x3(dY, W'), W'[ci_f][co_f][ky][kx] = W[co_f][ci_f][2-ky][2-kx]; here ci = co_f, co = ci_f, cout = cin_f
+        const int ky = j / 3, kx = j % 3;
+        v = w[((static_cast<long long>(ci) * cout + co) * 3 + (2 - ky)) * 3 + (2 - kx)];
+      } else if (kind == kPackConvT3x3s2Dgrad) {
+        // dX[ci_f] = conv k3 s2 p1 (dY[co_f], Wt[ci_f][co_f]) == conv k4 s2 p1 with a zero 4th row / column;
+        // here ci = co_f, co = ci_f, cin = cout_f.  Tap order as kConv4x4s2.
+        const int ph = j >> 2, t = j & 3;
+        const int ky = 2 * (t >> 1) + (ph >> 1), kx = 2 * (t & 1) + (ph & 1);
+        v = (ky < 3 && kx < 3) ? w[((static_cast<long long>(co) * cin + ci) * 3 + ky) * 3 + kx] : 0.f;
       } else {
         v = w[((static_cast<long long>(ci) * cout + co) * 3 + ct_ky[j]) * 3 + ct_kx[j]];
       }
@@ -126,21 +136,36 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
 
 }  // namespace tg
 
+// kinds 3 / 4 derive the data-gradient convolution of a forward layer: its input channels are the forward
+// layer's output channels and vice versa
+static void derived_channels(int kind, int cin, int cout, int* dcin, int* dcout, int* launch_kind) {
+  const bool dgrad = (kind == tg::kPackConv3x3Dgrad || kind == tg::kPackConvT3x3s2Dgrad);
+  *dcin = dgrad ? cout : cin;
+  *dcout = dgrad ? cin : cout;
+  *launch_kind = kind == tg::kPackConv3x3Dgrad ? tg::kConv3x3 : (kind == tg::kPackConvT3x3s2Dgrad ? tg::kConv4x4s2 : kind);
+}
+
 extern "C" size_t tg_packed_conv_bytes(int kind, int cin, int cout) {
-  const int cp = tg::cin_padded(cin), op = tg::cout_padded(cout);
-  size_t b = tg::packed_weight_bytes_k(kind, cp, op) + static_cast<size_t>(op) * 4;
+  int dci, dco, lk;
+  derived_channels(kind, cin, cout, &dci, &dco, &lk);
+  const int cp = tg::cin_padded(dci), op = tg::cout_padded(dco);
+  size_t b = tg::packed_weight_bytes_k(lk, cp, op) + static_cast<size_t>(op) * 4;
   return (b + 255) & ~static_cast<size_t>(255);
 }
 
 extern "C" int tg_pack_weights(int kind, const float* weight, const float* bias, int cin, int cout,
                                void* packed, void* stream) {
   TG_CHECK_ARG(weight && packed, "pack_weights: null pointer");
-  TG_CHECK_ARG(kind == 0 || kind == 1 || kind == 2, "pack_weights: kind must be 0 (conv3x3), 1 (convT3x3s2) or 2 (conv4x4s2)");
+  TG_CHECK_ARG(kind >= 0 && kind <= 4, "pack_weights: kind must be 0 (conv3x3), 1 (convT3x3s2), 2 (conv4x4s2), "
+               "3 (dgrad of conv3x3) or 4 (dgrad of convT3x3s2)");
   TG_CHECK_ARG(cin >= 1 && cin <= 128 && cout >= 1 && cout <= 128, "pack_weights: channels out of range");
+  TG_CHECK_ARG(!(kind >= 3 && bias), "pack_weights: data-gradient convolutions have no bias");
+  int lk;
+  { int a, b; derived_channels(kind, cin, cout, &a, &b, &lk); cin = a; cout = b; }   // from here: the derived conv's channels
   const int cp = tg::cin_padded(cin), op = tg::cout_padded(cout);
   const int nt = op == 16 ? 16 : 64;
   auto* dst = static_cast<__nv_bfloat16*>(packed);
-  auto* bdst = reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + tg::packed_weight_bytes_k(kind, cp, op));
+  auto* bdst = reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + tg::packed_weight_bytes_k(lk, cp, op));
   tg_prof_pre(TG_K_PACK, 0.0, static_cast<cudaStream_t>(stream));
   tg::pack_weights_kernel<<<64, 256, 0, static_cast<cudaStream_t>(stream)>>>(kind, weight, bias, cin, cout, cp, op, nt, dst, bdst);
   tg_prof_post(static_cast<cudaStream_t>(stream));
@@ -182,4 +207,23 @@ extern "C" int tg_conv3x3_out_sigmoid(const void* x, const void* packed, float* 
                                       int w, int amode, void* stream) {
   return tg::launch_conv_tc(tg::kConv3x3, tg::kOutNCHWf32Sigmoid, x, packed, packed_bias(packed, 64, 16), nullptr, out,
                             logits, n, h, w, 64, 16, 0, amode, 0, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------ data gradients
+extern "C" int tg_conv3x3_dgrad(const void* dy, const void* packed_dgrad, const void* residual, const void* mask,
+                                void* dx, int n, int h, int w, int cin, int cout, void* stream) {
+  // dX = conv3x3(dY, rotated/transposed W) (+ residual), zeroed where mask == 0 (ReLU backward)
+  const int dci = cout <= 64 ? 64 : 128, dco = cin <= 64 ? 64 : 128;
+  return tg::launch_conv_tc(tg::kConv3x3, tg::kOutNHWCbf16, dy, packed_dgrad, packed_bias(packed_dgrad, dci, dco), residual,
+                            dx, nullptr, n, h, w, dci, dco, 0, TG_AMODE_HALO, 0, static_cast<cudaStream_t>(stream), mask);
+}
+
+extern "C" int tg_convT3x3s2_dgrad(const void* dy, const void* packed_dgrad, const void* mask, void* dx, int n, int h,
+                                   int w, int cin, int cout, void* stream) {
+  // forward: x [n,h,w,cin] -> y [n,2h,2w,cout]; dX = conv k3 s2 p1 over dY, run as the 4x4 stride-2 kernel
+  const int dci = cout <= 64 ? 64 : 128, dco = cin <= 64 ? 64 : 128;
+  const float* bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(packed_dgrad) +
+                                                     tg::packed_weight_bytes_k(tg::kConv4x4s2, dci, dco));
+  return tg::launch_conv_tc(tg::kConv4x4s2, tg::kOutNHWCbf16, dy, packed_dgrad, bias, nullptr, dx, nullptr, n, 2 * h, 2 * w,
+                            dci, dco, 0, TG_AMODE_HALO, 0, static_cast<cudaStream_t>(stream), mask);
 }

@@ -226,6 +226,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                                              static_cast<const __nv_bfloat16*>(p.resid) +
                                              pix * p.oc + chunk * 64)
                                        : nullptr;
+            const uint4* msk = p.mask ? reinterpret_cast<const uint4*>(
+                                            static_cast<const __nv_bfloat16*>(p.mask) + pix * p.oc + chunk * 64)
+                                      : nullptr;
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
               uint32_t* v = h2 ? v1 : v0;
@@ -244,6 +247,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                   f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
                   f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z);
                   f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
+                }
+                if (msk) {                                   // ReLU backward: gradient flows where the saved output > 0
+                  const uint4 mv = __ldg(msk + h2 * 4 + c8);
+                  const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    if ((mw[e] & 0x7FFFu) == 0u) f[2 * e] = 0.f;
+                    if ((mw[e] & 0x7FFF0000u) == 0u) f[2 * e + 1] = 0.f;
+                  }
                 }
                 uint4 o;
                 o.x = pack_bf16x2(f[0], f[1]);
@@ -328,8 +340,9 @@ size_t packed_weight_bytes(int cin_pad, int cout_pad) {
 
 int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, const float* bias,
                    const void* resid, void* out, float* out2, int n, int h, int w, int cin_pad,
-                   int cout_pad, int relu, int amode, long long out_nstride, cudaStream_t stream) {
+                   int cout_pad, int relu, int amode, long long out_nstride, cudaStream_t stream, const void* mask) {
   TG_CHECK_ARG(x && packed_w && out, "conv: null pointer");
+  TG_CHECK_ARG(!(mask && out_mode != kOutNHWCbf16), "conv: mask only for the NHWC bf16 output");
   TG_CHECK_ARG(n > 0 && h > 0 && w > 0, "conv: bad shape n=%d h=%d w=%d", n, h, w);
   TG_CHECK_ARG(kind == kConv3x3 || kind == kConvT3x3s2 || kind == kConv4x4s2, "conv: bad kind %d", kind);
   TG_CHECK_ARG(cin_pad == 64 || cin_pad == 128, "conv: cin_pad must be 64 or 128 (got %d)", cin_pad);
@@ -421,7 +434,7 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   for (int a = 0; a < kMaxAcc; ++a) { p.acc_oy[a] = (kind == kConvT3x3s2) ? (a >> 1) : 0; p.acc_ox[a] = (kind == kConvT3x3s2) ? (a & 1) : 0; }
   p.out_nstride = out_nstride > 0 ? out_nstride : static_cast<long long>(p.oc) * p.oh * p.ow;
   p.relu = relu;
-  p.out = out; p.out2 = out2; p.resid = resid; p.bias = bias;
+  p.out = out; p.out2 = out2; p.resid = resid; p.bias = bias; p.mask = mask;
 
   CUtensorMap tm_a, tm_w;
   {

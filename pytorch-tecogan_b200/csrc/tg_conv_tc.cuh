@@ -12,6 +12,8 @@ constexpr int kMaxAcc = 4;
 
 enum TcKind { kConv3x3 = 0, kConvT3x3s2 = 1, kConv4x4s2 = 2 };
 enum TcOut { kOutNHWCbf16 = 0, kOutNCHWf32Sigmoid = 1, kOutNCHWf32Raw = 2, kOutNHWCf32 = 3 };   // 3: pre-BatchNorm conv outputs
+// tg_pack_weights kinds beyond TcKind: data-gradient convolutions derived from a forward layer's weights
+enum TcPackKind { kPackConv3x3Dgrad = 3, kPackConvT3x3s2Dgrad = 4 };
 enum TcAct { kActNone = 0, kActRelu = 1, kActLrelu02 = 2 };   // LeakyReLU(0.2): code/ops.py:71-72
 
 // One MMA group = one filter tap on one 64-channel K chunk: 4 x tcgen05.mma (K=16 each).
@@ -53,13 +55,15 @@ struct TcParams {
   void* out;
   float* out2;                // optional pre-sigmoid logits (NCHW f32)
   const void* resid;          // optional residual, same layout as out (NHWC bf16)
+  const void* mask;           // optional ReLU-backward mask, same layout as out: result zeroed where mask == 0
   const float* bias;          // padded bias for the whole layer (chunk offset added in-kernel)
 };
 
 // Launches the kernel for one layer.  x: NHWC bf16 with `cin_pad` channels.
 int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, const float* bias,
                    const void* resid, void* out, float* out2, int n, int h, int w, int cin_pad,
-                   int cout_pad, int relu, int amode, long long out_nstride, cudaStream_t stream);
+                   int cout_pad, int relu, int amode, long long out_nstride, cudaStream_t stream,
+                   const void* mask = nullptr);
 
 // SWIZZLE_128B bf16 tiled tensor map (cuTensorMapEncodeTiled through the runtime's driver entry point)
 int encode_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,

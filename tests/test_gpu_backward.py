@@ -51,3 +51,69 @@ def test_conv3x3_wgrad(n, h, w, cin, cout):
     nt.check(lib.tg_conv3x3_wgrad(nt.ptr(xd), nt.ptr(dyd), nt.ptr(dw), n, h, w, cin, cout, nt.stream_ptr()))
     torch.cuda.synchronize()
     assert _rel(dw.cpu(), 2 * want) <= 1e-4
+
+
+def _pack(kind, w, cin, cout):
+    from tecogan_b200 import _native as nt
+    lib = nt.lib()
+    packed = torch.zeros(lib.tg_packed_conv_bytes(kind, cin, cout), dtype=torch.uint8, device="cuda")
+    wd = w.contiguous().cuda()
+    nt.check(lib.tg_pack_weights(kind, nt.ptr(wd), None, cin, cout, nt.ptr(packed), nt.stream_ptr()))
+    torch.cuda.synchronize()
+    return packed
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,use_mask,use_resid", [
+    (1, 16, 8, 64, 64, 0, 0),
+    (2, 20, 13, 64, 64, 1, 0),     # ReLU backward mask
+    (1, 24, 24, 64, 128, 0, 1),    # + gradient of the skip connection
+    (1, 24, 24, 128, 64, 1, 1),
+    (2, 17, 9, 128, 128, 0, 0),
+    (1, 40, 40, 64, 3, 1, 0),      # output conv: dY has 3 real channels
+])
+def test_conv3x3_dgrad(n, h, w, cin, cout, use_mask, use_resid):
+    from tecogan_b200 import _native as nt
+    lib = nt.lib()
+    x = torch.zeros(n, cin, h, w, requires_grad=True)
+    wt = _bf(torch.from_numpy(synth.det_uniform((cout, cin, 3, 3), 2, -0.1, 0.1)))
+    dy = _bf(torch.from_numpy(synth.det_uniform((n, cout, h, w), 3, -1, 1)))
+    F.conv2d(x, wt, None, padding=1).backward(dy)
+    want = x.grad
+    m = _bf(torch.from_numpy(synth.det_uniform((n, cin, h, w), 4, -1, 1))).relu() if use_mask else None
+    r = _bf(torch.from_numpy(synth.det_uniform((n, cin, h, w), 5, -1, 1))) if use_resid else None
+    if use_resid:
+        want = want + r
+    if use_mask:
+        want = want * (m > 0)
+    packed = _pack(3, wt, cin, cout)
+    dyd = _nhwc_bf16(dy, 64 if cout <= 64 else 128)
+    dx = torch.empty(n, h, w, cin, dtype=torch.bfloat16, device="cuda")
+    rd = _nhwc_bf16(r, cin) if use_resid else None          # keep the device tensors alive across the launch
+    md = _nhwc_bf16(m, cin) if use_mask else None
+    nt.check(lib.tg_conv3x3_dgrad(nt.ptr(dyd), nt.ptr(packed), nt.ptr(rd), nt.ptr(md), nt.ptr(dx), n, h, w, cin, cout,
+                                  nt.stream_ptr()))
+    torch.cuda.synchronize()
+    got = dx.float().cpu().permute(0, 3, 1, 2)
+    assert _rel(got, want) <= 6e-3, _rel(got, want)
+
+
+@pytest.mark.parametrize("n,h,w,c,use_mask", [(1, 16, 8, 64, 0), (2, 19, 21, 64, 1), (1, 12, 20, 128, 1)])
+def test_conv_transpose_dgrad(n, h, w, c, use_mask):
+    from tecogan_b200 import _native as nt
+    lib = nt.lib()
+    x = torch.zeros(n, c, h, w, requires_grad=True)
+    wt = _bf(torch.from_numpy(synth.det_uniform((c, c, 3, 3), 2, -0.1, 0.1)))          # [cin,cout,3,3]
+    dy = _bf(torch.from_numpy(synth.det_uniform((n, c, 2 * h, 2 * w), 3, -1, 1)))
+    F.conv_transpose2d(x, wt, None, stride=2, padding=1, output_padding=1).backward(dy)
+    want = x.grad
+    m = _bf(torch.from_numpy(synth.det_uniform((n, c, h, w), 4, -1, 1))).relu() if use_mask else None
+    if use_mask:
+        want = want * (m > 0)
+    packed = _pack(4, wt, c, c)
+    dyd = _nhwc_bf16(dy, c)
+    dx = torch.empty(n, h, w, c, dtype=torch.bfloat16, device="cuda")
+    md = _nhwc_bf16(m, c) if use_mask else None
+    nt.check(lib.tg_convT3x3s2_dgrad(nt.ptr(dyd), nt.ptr(packed), nt.ptr(md), nt.ptr(dx), n, h, w, c, c, nt.stream_ptr()))
+    torch.cuda.synchronize()
+    got = dx.float().cpu().permute(0, 3, 1, 2)
+    assert _rel(got, want) <= 6e-3, _rel(got, want)
