@@ -133,6 +133,15 @@ int tg_conv3x3_out_sigmoid(const void* x, const void* packed, float* out, float*
  * plain gradient.  tcgen05 kernel with the pixel index as the GEMM reduction dimension (MN-major operands). */
 int tg_conv3x3_wgrad(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
                      void* stream);
+/* Same for ConvTranspose2d(k3,s2,p1,op1): x [n,h,w,pad64(cin)], dy [n,2h,2w,pad64(cout)] -> dw [cin][cout][3][3];
+ * and for Conv2d(k4,s2,p1): x [n,2h,2w,pad64(cin)], dy [n,h,w,pad64(cout)] -> dw [cout][cin][4][4].  The operand at
+ * twice the resolution is staged per parity phase with stride-2 TMA boxes. */
+int tg_convT3x3s2_wgrad(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
+                        void* stream);
+int tg_conv4x4s2_wgrad(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
+                       void* stream);
+/* db[c] += sum over pixels of dy[p][c] (bias gradient); dy NHWC bf16 [pixels][pad64(c)]. */
+int tg_bias_grad(const void* dy, float* db, long long pixels, int c, void* stream);
 /* Data gradients.  tg_pack_weights kinds 3 / 4 take the FORWARD layer's weight (and its cin, cout) and pack the
  * weights of the convolution that computes dX from dY (kind 3: conv3x3 with the kernel rotated by 180 degrees and
  * channels transposed; kind 4: the stride-2 3x3 convolution that is the adjoint of ConvTranspose2d(k3,s2,p1,op1)).

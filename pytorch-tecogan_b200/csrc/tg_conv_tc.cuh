@@ -72,6 +72,13 @@ int encode_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* di
 // tg_wgrad.cu: dW[cout][cin][3][3] += sum_pixels dY (x) X (f32 atomics); x NHWC bf16 [n,h,w,cin_pad], dy [n,h,w,cout_pad]
 int launch_wgrad3x3(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout, int cin_pad,
                     int cout_pad, cudaStream_t stream);
+// ConvTranspose2d(k3,s2,p1,op1): x [n,h,w,cin_pad], dy [n,2h,2w,cout_pad] -> dw [cin][cout][3][3]
+int launch_wgrad_convT3x3s2(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
+                            int cin_pad, int cout_pad, cudaStream_t stream);
+// Conv2d(k4,s2,p1): x [n,2h,2w,cin_pad], dy [n,h,w,cout_pad] -> dw [cout][cin][4][4]
+int launch_wgrad_conv4x4s2(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
+                           int cin_pad, int cout_pad, cudaStream_t stream);
+int launch_bias_grad(const void* dy, long long pixels, int cpad, int c, float* db, cudaStream_t stream);
 
 // packed layout helpers
 size_t packed_weight_bytes(int cin_pad, int cout_pad);   // bf16 blocks only, 3x3 kernels

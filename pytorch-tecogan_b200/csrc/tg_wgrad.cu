@@ -20,13 +20,23 @@ namespace tg {
 constexpr int kWgThreads = 192;
 constexpr uint32_t kWgSmemLimit = 232448;
 
+struct WgTap { uint32_t b_off; int ky, kx; };   // B view offset inside the staged box; filter tap it belongs to
+struct WgGroup {                                // one blockIdx.y: the taps that share one staged B box
+  int b_ox, b_oy;                               // box origin relative to (in_scale*x0, in_scale*y0)
+  int ntaps;
+  WgTap taps[4];
+};
 struct WgParams {
-  int n, h, w, tiles_x, tiles_y, num_items;
-  int cin, cout, cin_pad, cout_pad;   // real / padded channel counts
-  int a_boxes, b_boxes;               // cout_pad / 64, cin_pad / 64
-  uint32_t a_bytes, b_bytes, stage_stride;
+  int n, h, w, tiles_x, tiles_y, num_items;   // tile space = the resolution of the A operand
+  int rows_real, cols_real;           // real channel counts of the A (GEMM M) and B (GEMM N) tensors
+  int ks;                             // filter size (3 or 4): dw index = ((m * cols_real + c) * ks + ky) * ks + kx
+  int a_boxes, b_boxes;               // padded channels / 64
+  int b_in_scale;                     // 1, or 2: B lives at twice the resolution and is staged with element stride 2
+  int stack3;                         // conv3x3 with 64 B channels: the three kx taps as one N = 192 MMA
+  uint32_t a_bytes, b_bytes, b_pitch, stage_stride;
   int nstages;
-  float* dw;                          // [cout][cin][3][3] f32, accumulated into
+  WgGroup groups[4];
+  float* dw;                          // f32 weight gradient in PyTorch layout, accumulated into
 };
 
 // MN-major SWIZZLE_128B descriptor: [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | version 1 | layout 2
@@ -59,7 +69,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gbase + (bar_done + 8 - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ky = blockIdx.y;
+  const WgGroup& grp = p.groups[blockIdx.y];
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_dy);
@@ -91,15 +101,17 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
         for (int c = 0; c < p.a_boxes; ++c)
           tma_load_4d(dst + c * p.a_bytes, &tm_dy, bar_full + 8 * s, c * 64, x0, y0, n);
         for (int c = 0; c < p.b_boxes; ++c)
-          tma_load_4d(dst + p.a_boxes * p.a_bytes + c * p.b_bytes, &tm_x, bar_full + 8 * s, c * 64, x0 - 1, y0 + ky - 1, n);
+          tma_load_4d(dst + p.a_boxes * p.a_bytes + c * p.b_bytes, &tm_x, bar_full + 8 * s, c * 64,
+                      x0 * p.b_in_scale + grp.b_ox, y0 * p.b_in_scale + grp.b_oy, n);
       }
       __syncwarp();
       if (++s == p.nstages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer: D[co][(kx, ci)] += dY^T[co][pixels] * X[pixels][(kx, ci)]
-    const bool ci64 = (p.b_boxes == 1);
-    const uint32_t idesc = ci64 ? umma_idesc_bf16_mn(128, 192) : umma_idesc_bf16_mn(128, 128);
+    const bool stack3 = p.stack3 != 0;
+    const int ncols = 64 * p.b_boxes;                        // GEMM N of one tap
+    const uint32_t idesc = stack3 ? umma_idesc_bf16_mn(128, 192) : umma_idesc_bf16_mn(128, ncols);
     const uint32_t a_lbo = (p.a_boxes == 2) ? p.a_bytes : 0u;     // 64 output channels: rows 64..127 mirror rows 0..63
     int s = 0;
     uint32_t ph = 0, first = 1;
@@ -112,14 +124,13 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {                         // 16 pixels = tile rows 2j, 2j+1
           const uint64_t ad = umma_desc_mn_sw128(a_base + j * 2048, a_lbo, 1024);
-          if (ci64) {
-            const uint64_t bd = umma_desc_mn_sw128(b_base + (2 * j * 10) * 128, 128, 1280);
+          if (stack3) {
+            const uint64_t bd = umma_desc_mn_sw128(b_base + 2 * j * p.b_pitch, 128, p.b_pitch);
             umma_bf16(tmem_base, ad, bd, idesc, (first && j == 0) ? 0u : 1u);
           } else {
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const uint64_t bd = umma_desc_mn_sw128(b_base + (2 * j * 10 + kx) * 128, p.b_bytes, 1280);
-              umma_bf16(tmem_base + kx * 128, ad, bd, idesc, (first && j == 0) ? 0u : 1u);
+            for (int t = 0; t < grp.ntaps; ++t) {
+              const uint64_t bd = umma_desc_mn_sw128(b_base + 2 * j * p.b_pitch + grp.taps[t].b_off, p.b_bytes, p.b_pitch);
+              umma_bf16(tmem_base + t * ncols, ad, bd, idesc, (first && j == 0) ? 0u : 1u);
             }
           }
         }
@@ -134,24 +145,25 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
   } else {
     // ---------------- epilogue: TMEM -> fp32 atomics into dW[co][ci][ky][kx]
     const int q = warp & 3;
-    const int co = q * 32 + lane;
+    const int m = q * 32 + lane;                             // accumulator row = channel of the A tensor
     const bool have_work = blockIdx.x < p.num_items;
     if (have_work) {
       mbar_wait(bar_done, 0);
       tc_fence_after();
-      const int ncol = (p.b_boxes == 1) ? 192 : 384;
-      const int cstride = (p.b_boxes == 1) ? 64 : 128;      // columns per kx tap
+      const int cstride = 64 * p.b_boxes;                    // columns per tap
+      const int ncol = grp.ntaps * cstride;
       for (int c0 = 0; c0 < ncol; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
         tmem_ld_wait();
-        if (co < p.cout) {
+        if (m < p.rows_real) {
+          const int t = c0 / cstride;
+          const int ky = grp.taps[t].ky, kx = grp.taps[t].kx;
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            const int col = c0 + e;
-            const int kx = col / cstride, ci = col - kx * cstride;
-            if (ci < p.cin)
-              atomicAdd(p.dw + ((static_cast<size_t>(co) * p.cin + ci) * 3 + ky) * 3 + kx, __uint_as_float(v[e]));
+            const int c = c0 - t * cstride + e;
+            if (c < p.cols_real)
+              atomicAdd(p.dw + ((static_cast<size_t>(m) * p.cols_real + c) * p.ks + ky) * p.ks + kx, __uint_as_float(v[e]));
           }
         }
       }
@@ -162,6 +174,56 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+static int wgrad_launch_common(WgParams& p, const void* a, int a_pad, const void* b, int b_pad, int bh, int bw,
+                               int b_box_w, int b_box_h, int ngroups, double flops, cudaStream_t stream) {
+  p.tiles_x = tg_div_up(p.w, kTileW); p.tiles_y = tg_div_up(p.h, kTileH);
+  p.num_items = p.n * p.tiles_x * p.tiles_y;
+  p.a_boxes = a_pad / 64; p.b_boxes = b_pad / 64;
+  p.a_bytes = kTileH * kTileW * 128;                         // 16 KB
+  p.b_bytes = static_cast<uint32_t>(b_box_w * b_box_h * 128);
+  p.b_pitch = static_cast<uint32_t>(b_box_w * 128);
+  p.stage_stride = (p.a_boxes * p.a_bytes + p.b_boxes * p.b_bytes + 1023u) & ~1023u;
+  int nstages = 6;
+  while (nstages > 1 && nstages * p.stage_stride + 16 * nstages + 64 + 1024 > kWgSmemLimit) --nstages;
+  p.nstages = nstages;
+  uint32_t smem_bytes = nstages * p.stage_stride + 16 * nstages + 64 + 1024;
+  TG_CHECK_ARG(smem_bytes <= kWgSmemLimit, "wgrad: stage does not fit in shared memory");
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;     // one CTA per SM (each allocates all of TMEM)
+
+  CUtensorMap tm_a, tm_b;
+  {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(a_pad), static_cast<cuuint64_t>(p.w), static_cast<cuuint64_t>(p.h), static_cast<cuuint64_t>(p.n)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(a_pad) * 2, static_cast<cuuint64_t>(p.w) * a_pad * 2,
+                             static_cast<cuuint64_t>(p.h) * p.w * a_pad * 2};
+    cuuint32_t box[4] = {64, kTileW, kTileH, 1};
+    if (int rc = encode_bf16(&tm_a, a, 4, dims, strides, box)) return rc;
+  }
+  {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(b_pad), static_cast<cuuint64_t>(bw), static_cast<cuuint64_t>(bh), static_cast<cuuint64_t>(p.n)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(b_pad) * 2, static_cast<cuuint64_t>(bw) * b_pad * 2,
+                             static_cast<cuuint64_t>(bh) * bw * b_pad * 2};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(b_box_w * p.b_in_scale), static_cast<cuuint32_t>(b_box_h * p.b_in_scale), 1};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(p.b_in_scale), static_cast<cuuint32_t>(p.b_in_scale), 1};
+    if (int rc = encode_bf16(&tm_b, b, 4, dims, strides, box, estr)) return rc;
+  }
+  // split-K over pixel slabs: enough CTAs to fill the machine on big layers, few on tiny ones (every CTA pays
+  // rows x taps x cols atomics at the end)
+  int slabs = p.num_items / 8;
+  const int max_slabs = tg_num_sms() / ngroups;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TG_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemLimit));
+    attr_done = true;
+  }
+  tg_prof_pre(TG_K_WGRAD, flops, stream);
+  wgrad3x3_kernel<<<dim3(slabs, ngroups), kWgThreads, smem_bytes, stream>>>(tm_a, tm_b, p);
+  tg_prof_post(stream);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
 int launch_wgrad3x3(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout, int cin_pad,
                     int cout_pad, cudaStream_t stream) {
   TG_CHECK_ARG(x && dy && dw, "wgrad3x3: null pointer");
@@ -170,48 +232,112 @@ int launch_wgrad3x3(const void* x, const void* dy, float* dw, int n, int h, int 
   TG_CHECK_ARG(cin >= 1 && cin <= cin_pad && cout >= 1 && cout <= cout_pad, "wgrad3x3: bad channel counts");
   WgParams p{};
   p.n = n; p.h = h; p.w = w;
-  p.tiles_x = tg_div_up(w, kTileW); p.tiles_y = tg_div_up(h, kTileH);
-  p.num_items = n * p.tiles_x * p.tiles_y;
-  p.cin = cin; p.cout = cout; p.cin_pad = cin_pad; p.cout_pad = cout_pad;
-  p.a_boxes = cout_pad / 64; p.b_boxes = cin_pad / 64;
-  p.a_bytes = kTileH * kTileW * 128;            // 16 KB, 1024-aligned
-  p.b_bytes = kTileH * (kTileW + 2) * 128;      // 20 KB, 1024-aligned
-  p.stage_stride = p.a_boxes * p.a_bytes + p.b_boxes * p.b_bytes;
-  int nstages = 6;
-  while (nstages > 1 && nstages * p.stage_stride + 16 * nstages + 64 + 1024 > kWgSmemLimit) --nstages;
-  p.nstages = nstages;
+  p.rows_real = cout; p.cols_real = cin; p.ks = 3;           // A = dY (M = co), B = X (N = ci)
+  p.b_in_scale = 1;
+  p.stack3 = (cin_pad == 64) ? 1 : 0;
+  for (int ky = 0; ky < 3; ++ky) {                           // group = filter row: X rows shifted by ky-1, 1-pixel halo in x
+    p.groups[ky].b_ox = -1; p.groups[ky].b_oy = ky - 1; p.groups[ky].ntaps = 3;
+    for (int kx = 0; kx < 3; ++kx) p.groups[ky].taps[kx] = WgTap{static_cast<uint32_t>(kx * 128), ky, kx};
+  }
   p.dw = dw;
-  uint32_t smem_bytes = nstages * p.stage_stride + 16 * nstages + 64 + 1024;
-  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM (each allocates all of TMEM)
+  return wgrad_launch_common(p, dy, cout_pad, x, cin_pad, h, w, kTileW + 2, kTileH, 3,
+                             2.0 * 9.0 * cin_pad * cout_pad * n * h * w, stream);
+}
 
-  CUtensorMap tm_dy, tm_x;
-  {
-    cuuint64_t dims[4] = {static_cast<cuuint64_t>(cout_pad), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
-    cuuint64_t strides[3] = {static_cast<cuuint64_t>(cout_pad) * 2, static_cast<cuuint64_t>(w) * cout_pad * 2,
-                             static_cast<cuuint64_t>(h) * w * cout_pad * 2};
-    cuuint32_t box[4] = {64, kTileW, kTileH, 1};
-    if (int rc = encode_bf16(&tm_dy, dy, 4, dims, strides, box)) return rc;
+// ConvTranspose2d(k3, s2, p1, op1): y[2iy+ky-1, 2ix+kx-1, co] += x[iy, ix, ci] * Wt[ci][co][ky][kx]
+//   dWt[ci][co][ky][kx] = sum over (n, iy, ix) of x[n, iy, ix, ci] * dY[n, 2iy-1+ky, 2ix-1+kx, co]
+// A = x tile (M = ci), B = dY staged per parity phase with element stride 2 (N = co).  Odd rows 2s+1 hold taps
+// ky = 0 (s = iy-1) and ky = 2 (s = iy); even rows hold ky = 1.  h, w = size of x.
+int launch_wgrad_convT3x3s2(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
+                            int cin_pad, int cout_pad, cudaStream_t stream) {
+  TG_CHECK_ARG(x && dy && dw, "wgrad_convT: null pointer");
+  TG_CHECK_ARG(n > 0 && h > 0 && w > 0, "wgrad_convT: bad shape");
+  TG_CHECK_ARG((cin_pad == 64 || cin_pad == 128) && (cout_pad == 64 || cout_pad == 128), "wgrad_convT: padded channels must be 64 or 128");
+  WgParams p{};
+  p.n = n; p.h = h; p.w = w;
+  p.rows_real = cin; p.cols_real = cout; p.ks = 3;
+  p.b_in_scale = 2;
+  p.stack3 = 0;
+  const int bw = kTileW + 1;                                 // 9 x 17 samples per phase box
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      WgGroup& g = p.groups[py * 2 + px];
+      g.b_ox = px ? -1 : 0; g.b_oy = py ? -1 : 0;            // odd phase: first sample is row/col 2*(t0-1)+1
+      g.ntaps = 0;
+      for (int ty = 0; ty <= py; ++ty)
+        for (int tx = 0; tx <= px; ++tx) {
+          const int ky = py ? 2 * ty : 1, kx = px ? 2 * tx : 1;
+          g.taps[g.ntaps++] = WgTap{static_cast<uint32_t>((ty * bw + tx) * 128), ky, kx};
+        }
+    }
+  p.dw = dw;
+  return wgrad_launch_common(p, x, cin_pad, dy, cout_pad, 2 * h, 2 * w, bw, kTileH + 1, 4,
+                             2.0 * 9.0 * cin_pad * cout_pad * n * h * w, stream);
+}
+
+// Conv2d(k4, s2, p1): dW[co][ci][ky][kx] = sum over (n, oy, ox) of dY[n, oy, ox, co] * X[n, 2oy-1+ky, 2ox-1+kx, ci]
+// A = dY tile (M = co), B = X staged per parity phase (N = ci).  h, w = size of dY (the conv output).
+int launch_wgrad_conv4x4s2(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
+                           int cin_pad, int cout_pad, cudaStream_t stream) {
+  TG_CHECK_ARG(x && dy && dw, "wgrad_conv4x4s2: null pointer");
+  TG_CHECK_ARG(n > 0 && h > 0 && w > 0, "wgrad_conv4x4s2: bad shape");
+  TG_CHECK_ARG((cin_pad == 64 || cin_pad == 128) && (cout_pad == 64 || cout_pad == 128), "wgrad_conv4x4s2: padded channels must be 64 or 128");
+  WgParams p{};
+  p.n = n; p.h = h; p.w = w;
+  p.rows_real = cout; p.cols_real = cin; p.ks = 4;
+  p.b_in_scale = 2;
+  p.stack3 = 0;
+  const int bw = kTileW + 1;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      WgGroup& g = p.groups[py * 2 + px];
+      // input row 2oy-1+ky: ky odd -> even rows (samples oy, oy+1), ky even -> odd rows 2s+1 (samples oy-1, oy)
+      g.b_ox = px ? 0 : -1; g.b_oy = py ? 0 : -1;
+      g.ntaps = 0;
+      for (int ty = 0; ty < 2; ++ty)
+        for (int tx = 0; tx < 2; ++tx)
+          g.taps[g.ntaps++] = WgTap{static_cast<uint32_t>((ty * bw + tx) * 128), 2 * ty + py, 2 * tx + px};
+    }
+  p.dw = dw;
+  return wgrad_launch_common(p, dy, cout_pad, x, cin_pad, 2 * h, 2 * w, bw, kTileH + 1, 4,
+                             2.0 * 16.0 * cin_pad * cout_pad * n * h * w, stream);
+}
+
+// db[c] += sum over pixels of dy[p][c]; dy NHWC bf16 [pixels][cpad]
+__global__ void __launch_bounds__(256)
+bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, long long pixels, int cpad, int c, float* __restrict__ db) {
+  __shared__ float s_sum[256][9];
+  const int groups = cpad / 8, pix_per_iter = 256 / groups;
+  const int gi = threadIdx.x % groups, pl = threadIdx.x / groups;
+  float sum[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sum[e] = 0.f;
+  for (long long px = static_cast<long long>(blockIdx.x) * pix_per_iter + pl; px < pixels;
+       px += static_cast<long long>(gridDim.x) * pix_per_iter) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy + px * cpad) + gi);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { sum[2 * e] += bf16_lo(u[e]); sum[2 * e + 1] += bf16_hi(u[e]); }
   }
-  {
-    cuuint64_t dims[4] = {static_cast<cuuint64_t>(cin_pad), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
-    cuuint64_t strides[3] = {static_cast<cuuint64_t>(cin_pad) * 2, static_cast<cuuint64_t>(w) * cin_pad * 2,
-                             static_cast<cuuint64_t>(h) * w * cin_pad * 2};
-    cuuint32_t box[4] = {64, kTileW + 2, kTileH, 1};
-    if (int rc = encode_bf16(&tm_x, x, 4, dims, strides, box)) return rc;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s_sum[threadIdx.x][e] = sum[e];
+  __syncthreads();
+  if (threadIdx.x < c) {
+    const int g = threadIdx.x / 8, e = threadIdx.x % 8;
+    float a = 0.f;
+    for (int r = 0; r < pix_per_iter; ++r) a += s_sum[r * groups + g][e];
+    atomicAdd(db + threadIdx.x, a);
   }
-  // split-K over pixel slabs: enough CTAs to fill the machine on big layers, few on tiny ones (every CTA pays
-  // cout x 3 x cin atomics at the end)
-  int slabs = p.num_items / 8;
-  const int max_slabs = tg_num_sms() / 3;
-  if (slabs > max_slabs) slabs = max_slabs;
-  if (slabs < 1) slabs = 1;
-  static bool attr_done = false;
-  if (!attr_done) {
-    TG_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemLimit));
-    attr_done = true;
-  }
-  tg_prof_pre(TG_K_WGRAD, 2.0 * 9.0 * cin_pad * cout_pad * n * h * w, stream);
-  wgrad3x3_kernel<<<dim3(slabs, 3), kWgThreads, smem_bytes, stream>>>(tm_dy, tm_x, p);
+}
+
+int launch_bias_grad(const void* dy, long long pixels, int cpad, int c, float* db, cudaStream_t stream) {
+  TG_CHECK_ARG(dy && db && (cpad == 64 || cpad == 128) && c >= 1 && c <= cpad, "bias_grad: bad arguments");
+  const int pix_per_iter = 256 / (cpad / 8);
+  long long blocks = (pixels + pix_per_iter * 8 - 1) / (pix_per_iter * 8);
+  if (blocks > 64) blocks = 64;
+  if (blocks < 1) blocks = 1;
+  tg_prof_pre(TG_K_GLUE, 2.0 * pixels * cpad, stream);
+  bias_grad_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), pixels, cpad, c, db);
   tg_prof_post(stream);
   TG_CUDA(cudaGetLastError());
   return TG_OK;
@@ -219,8 +345,20 @@ int launch_wgrad3x3(const void* x, const void* dy, float* dw, int n, int h, int 
 
 }  // namespace tg
 
+static int pad64(int c) { return c <= 64 ? 64 : 128; }
+
 extern "C" int tg_conv3x3_wgrad(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
                                 void* stream) {
-  return tg::launch_wgrad3x3(x, dy, dw, n, h, w, cin, cout, tg::cin_padded(cin), cout <= 64 ? 64 : 128,
-                             static_cast<cudaStream_t>(stream));
+  return tg::launch_wgrad3x3(x, dy, dw, n, h, w, cin, cout, pad64(cin), pad64(cout), static_cast<cudaStream_t>(stream));
+}
+extern "C" int tg_convT3x3s2_wgrad(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
+                                   void* stream) {
+  return tg::launch_wgrad_convT3x3s2(x, dy, dw, n, h, w, cin, cout, pad64(cin), pad64(cout), static_cast<cudaStream_t>(stream));
+}
+extern "C" int tg_conv4x4s2_wgrad(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
+                                  void* stream) {
+  return tg::launch_wgrad_conv4x4s2(x, dy, dw, n, h, w, cin, cout, pad64(cin), pad64(cout), static_cast<cudaStream_t>(stream));
+}
+extern "C" int tg_bias_grad(const void* dy, float* db, long long pixels, int c, void* stream) {
+  return tg::launch_bias_grad(dy, pixels, pad64(c), c, db, static_cast<cudaStream_t>(stream));
 }

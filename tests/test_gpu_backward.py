@@ -117,3 +117,51 @@ def test_conv_transpose_dgrad(n, h, w, c, use_mask):
     torch.cuda.synchronize()
     got = dx.float().cpu().permute(0, 3, 1, 2)
     assert _rel(got, want) <= 6e-3, _rel(got, want)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 16, 8, 64, 64), (2, 19, 21, 64, 64), (1, 12, 20, 128, 128), (2, 32, 32, 64, 64)])
+def test_conv_transpose_wgrad(n, h, w, cin, cout):
+    from tecogan_b200 import _native as nt
+    lib = nt.lib()
+    x = _bf(torch.from_numpy(synth.det_uniform((n, cin, h, w), 1, -1, 1)))
+    dy = _bf(torch.from_numpy(synth.det_uniform((n, cout, 2 * h, 2 * w), 2, -1, 1)))
+    wt = torch.zeros(cin, cout, 3, 3, requires_grad=True)
+    F.conv_transpose2d(x, wt, None, stride=2, padding=1, output_padding=1).backward(dy)
+    want = wt.grad
+    xd, dyd = _nhwc_bf16(x, cin), _nhwc_bf16(dy, cout)
+    dw = torch.zeros(cin, cout, 3, 3, device="cuda")
+    nt.check(lib.tg_convT3x3s2_wgrad(nt.ptr(xd), nt.ptr(dyd), nt.ptr(dw), n, h, w, cin, cout, nt.stream_ptr()))
+    torch.cuda.synchronize()
+    assert _rel(dw.cpu(), want) <= 1e-4, _rel(dw.cpu(), want)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 16, 8, 64, 64), (2, 19, 13, 64, 128), (3, 16, 16, 128, 128), (2, 8, 8, 128, 64),
+                                            (2, 4, 4, 64, 3), (12, 64, 64, 64, 64)])
+def test_conv4x4s2_wgrad(n, h, w, cin, cout):
+    """h, w = output size of the stride-2 conv; x is [n,cin,2h,2w]."""
+    from tecogan_b200 import _native as nt
+    lib = nt.lib()
+    x = _bf(torch.from_numpy(synth.det_uniform((n, cin, 2 * h, 2 * w), 1, -1, 1)))
+    dy = _bf(torch.from_numpy(synth.det_uniform((n, cout, h, w), 2, -1, 1)))
+    wt = torch.zeros(cout, cin, 4, 4, requires_grad=True)
+    F.conv2d(x, wt, None, stride=2, padding=1).backward(dy)
+    want = wt.grad
+    xd, dyd = _nhwc_bf16(x, cin), _nhwc_bf16(dy, 64 if cout <= 64 else 128)
+    dw = torch.zeros(cout, cin, 4, 4, device="cuda")
+    nt.check(lib.tg_conv4x4s2_wgrad(nt.ptr(xd), nt.ptr(dyd), nt.ptr(dw), n, h, w, cin, cout, nt.stream_ptr()))
+    torch.cuda.synchronize()
+    assert _rel(dw.cpu(), want) <= 1e-4, _rel(dw.cpu(), want)
+
+
+@pytest.mark.parametrize("pixels,c", [(100, 64), (4096, 128), (777, 3)])
+def test_bias_grad(pixels, c):
+    from tecogan_b200 import _native as nt
+    lib = nt.lib()
+    cpad = 64 if c <= 64 else 128
+    dy = torch.zeros(pixels, cpad)
+    dy[:, :c] = _bf(torch.from_numpy(synth.det_uniform((pixels, c), 7, -1, 1)))
+    db = torch.zeros(c, device="cuda")
+    dyd = dy.to(torch.bfloat16).cuda()
+    nt.check(lib.tg_bias_grad(nt.ptr(dyd), nt.ptr(db), pixels, c, nt.stream_ptr()))
+    torch.cuda.synchronize()
+    assert (db.cpu() - dy[:, :c].sum(0)).abs().max().item() <= 1e-3 * max(1.0, pixels ** 0.5)
