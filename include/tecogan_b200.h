@@ -182,6 +182,22 @@ int tg_gen_clip_step(const void* packed, int num_resblock, const float* lr_t, co
                      int h, int w, long long lr_batch_stride, long long prev_batch_stride,
                      long long out_batch_stride, int amode, void* stream);
 
+/* Generator training (code/train.py:86-111,336): a forward that keeps every activation in the workspace and the
+ * backward pass through all 41 layers.  The generator's inputs are detached in the reference (code/train.py:90,108),
+ * so no input gradient is produced.
+ *   tg_gen_forward_train: x NCHW f32 [n,51,h,w] -> out NCHW f32 [n,3,4h,4w] (one frame-kernel launch).
+ *   tg_gen_pack_dgrad   : packs the data-gradient convolutions of every layer from the flat f32 parameters.
+ *   tg_gen_backward     : dout = dL/dout [n,3,4h,4w] f32, out = the forward result; ADDS the parameter gradients into
+ *                         flat_grad (f32, same flat layout as the parameters; zero it for a plain gradient).
+ *                         Uses the workspace of the matching tg_gen_forward_train call. */
+size_t tg_gen_train_workspace_bytes(int n, int h, int w, int num_resblock);
+size_t tg_gen_packed_dgrad_bytes(int num_resblock);
+int tg_gen_pack_dgrad(const float* flat_params, int num_resblock, void* packed_dgrad, void* stream);
+int tg_gen_forward_train(const void* packed, int num_resblock, const float* x_nchw, float* out, void* workspace,
+                         size_t workspace_bytes, int n, int h, int w, void* stream);
+int tg_gen_backward(const void* packed_dgrad, int num_resblock, const float* dout, const float* out,
+                    float* flat_grad, void* workspace, size_t workspace_bytes, int n, int h, int w, void* stream);
+
 /* -------------------------------------------------- spatio-temporal discriminator (forward) ---- */
 
 /* discriminator(args) of code/models.py:97-146 with nb = args.discrim_resblocks, ch = args.discrim_channels

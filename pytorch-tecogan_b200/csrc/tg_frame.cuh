@@ -65,4 +65,8 @@ int fused_input_launch(const float* lr_t, const float* lr_prev, const float* pre
                        int w, long long lr_bs, long long hr_bs, uint32_t* zero, size_t zero_count,
                        cudaStream_t stream);
 
+// tg_glue.cu: dz = dout * out * (1 - out) as NHWC bf16 [n,hw,64] (backward of the final sigmoid)
+int sigmoid_bwd_pack_launch(const float* dout, const float* out, void* dz, int n, long long hw, long long dout_nstride,
+                            long long out_nstride, cudaStream_t st);
+
 }  // namespace tg

@@ -249,3 +249,220 @@ extern "C" int tg_frame_set_trace(void* buf, size_t bytes) {
   tg::frame_set_trace(static_cast<unsigned long long*>(buf), buf ? bytes / 8 : 0);
   return TG_OK;
 }
+
+// =====================================================================================================
+// Training: forward that keeps every activation, and the backward pass (reference code/train.py:336:
+// scaler.scale(gen_loss).backward() through generator.forward; inputs are detached, code/train.py:90,108).
+// =====================================================================================================
+namespace tg {
+
+struct GenTrainWs {
+  size_t x_in;
+  std::vector<size_t> net, t;          // net[0..nres] (64ch @1x), t[0..nres-1] = relu(conv1)
+  size_t b0, b1, b2, c0, c1, d, e;     // upsampling stack activations
+  size_t g_z, g_e, g_d, g_c1, g_c0, g_b[2], g_net[2], g_t;   // gradient buffers
+  size_t flags, flag_count, total;
+};
+static GenTrainWs gen_train_ws(int n, int h, int w, int nres) {
+  GenTrainWs ws;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align256(bytes); return r; };
+  const size_t px = static_cast<size_t>(n) * h * w;
+  ws.x_in = take(px * 128);
+  for (int i = 0; i <= nres; ++i) ws.net.push_back(take(px * 128));
+  for (int i = 0; i < nres; ++i) ws.t.push_back(take(px * 128));
+  ws.b0 = take(px * 4 * 128); ws.b1 = take(px * 4 * 128); ws.b2 = take(px * 4 * 128);
+  ws.c0 = take(px * 4 * 256); ws.c1 = take(px * 4 * 256);
+  ws.d = take(px * 16 * 256); ws.e = take(px * 16 * 128);
+  ws.g_z = take(px * 16 * 128); ws.g_e = take(px * 16 * 128); ws.g_d = take(px * 16 * 256);
+  ws.g_c1 = take(px * 4 * 256); ws.g_c0 = take(px * 4 * 256);
+  ws.g_b[0] = take(px * 4 * 128); ws.g_b[1] = take(px * 4 * 128);
+  ws.g_net[0] = take(px * 128); ws.g_net[1] = take(px * 128); ws.g_t = take(px * 128);
+  auto tiles = [&](int s) { return static_cast<size_t>(n) * tg_div_up(w * s, kTileW) * tg_div_up(h * s, kTileH); };
+  ws.flag_count = static_cast<size_t>(2 * nres + 2) * tiles(1) + 8 * tiles(2) + 2 * tiles(4);
+  ws.flags = take(ws.flag_count * 4);
+  ws.total = o;
+  return ws;
+}
+
+// forward plan with one buffer per activation (nothing is overwritten)
+static std::vector<FrLayer> gen_plan_train(const std::vector<GenLayer>& L, int nres, float* out, uint8_t* wsp, int n, int h,
+                                           int w) {
+  const GenTrainWs ws = gen_train_ws(n, h, w, nres);
+  std::vector<FrLayer> P;
+  int li = 0;
+  auto add = [&](size_t in, void* o, const void* resid, int relu, int hh, int ww) {
+    FrLayer f{};
+    f.kind = L[li].kind; f.cin_pad = cin_padded(L[li].cin); f.cout_pad = cout_padded(L[li].cout);
+    f.out_mode = kOutNHWCbf16; f.relu = relu; f.h = hh; f.w = ww;
+    f.in = wsp + in; f.out = o; f.resid = resid; f.out2 = nullptr; f.blob_off = L[li].p_off; f.out_nstride = 0;
+    P.push_back(f);
+    ++li;
+  };
+  add(ws.x_in, wsp + ws.net[0], nullptr, 1, h, w);
+  for (int k = 0; k < nres; ++k) {
+    add(ws.net[k], wsp + ws.t[k], nullptr, 1, h, w);
+    add(ws.t[k], wsp + ws.net[k + 1], wsp + ws.net[k], 0, h, w);
+  }
+  add(ws.net[nres], wsp + ws.b0, nullptr, 1, h, w);
+  add(ws.b0, wsp + ws.b1, nullptr, 1, 2 * h, 2 * w);
+  add(ws.b1, wsp + ws.b2, nullptr, 0, 2 * h, 2 * w);
+  add(ws.b2, wsp + ws.c0, nullptr, 1, 2 * h, 2 * w);
+  add(ws.c0, wsp + ws.c1, nullptr, 0, 2 * h, 2 * w);
+  add(ws.c1, wsp + ws.d, nullptr, 1, 2 * h, 2 * w);
+  add(ws.d, wsp + ws.e, nullptr, 1, 4 * h, 4 * w);
+  add(ws.e, out, nullptr, 0, 4 * h, 4 * w);
+  P.back().out_mode = kOutNCHWf32Sigmoid;
+  return P;
+}
+
+// packed data-gradient weights: one blob per layer except conv.0 (its input needs no gradient)
+static std::vector<size_t> gen_dgrad_offsets(const std::vector<GenLayer>& L, size_t* total) {
+  std::vector<size_t> off(L.size(), 0);
+  size_t o = 0;
+  for (size_t i = 1; i < L.size(); ++i) {
+    off[i] = o;
+    o += tg_packed_conv_bytes(L[i].kind == kConv3x3 ? kPackConv3x3Dgrad : kPackConvT3x3s2Dgrad, L[i].cin, L[i].cout);
+  }
+  if (total) *total = o;
+  return off;
+}
+
+}  // namespace tg
+
+extern "C" size_t tg_gen_train_workspace_bytes(int n, int h, int w, int num_resblock) {
+  if (n <= 0 || h <= 0 || w <= 0 || num_resblock < 0 || num_resblock > 64) return 0;
+  return gen_train_ws(n, h, w, num_resblock).total;
+}
+extern "C" size_t tg_gen_packed_dgrad_bytes(int num_resblock) {
+  size_t t = 0;
+  gen_dgrad_offsets(gen_layers(num_resblock, nullptr, nullptr), &t);
+  return t;
+}
+extern "C" int tg_gen_pack_dgrad(const float* flat_params, int num_resblock, void* packed_dgrad, void* stream) {
+  TG_CHECK_ARG(flat_params && packed_dgrad, "gen_pack_dgrad: null pointer");
+  TG_CHECK_ARG(num_resblock >= 0 && num_resblock <= 64, "gen_pack_dgrad: bad num_resblock %d", num_resblock);
+  auto L = gen_layers(num_resblock, nullptr, nullptr);
+  const std::vector<size_t> off = gen_dgrad_offsets(L, nullptr);
+  for (size_t i = 1; i < L.size(); ++i) {
+    int rc = tg_pack_weights(L[i].kind == kConv3x3 ? kPackConv3x3Dgrad : kPackConvT3x3s2Dgrad, flat_params + L[i].w_off, nullptr,
+                             L[i].cin, L[i].cout, static_cast<uint8_t*>(packed_dgrad) + off[i], stream);
+    if (rc) return rc;
+  }
+  return TG_OK;
+}
+
+extern "C" int tg_gen_forward_train(const void* packed, int num_resblock, const float* x_nchw, float* out, void* workspace,
+                                    size_t workspace_bytes, int n, int h, int w, void* stream) {
+  TG_CHECK_ARG(packed && x_nchw && out && workspace, "gen_forward_train: null pointer");
+  TG_CHECK_ARG(n >= 1 && h >= 1 && w >= 1, "gen_forward_train: bad shape");
+  TG_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "gen_forward_train: workspace must be 256-byte aligned");
+  const GenTrainWs ws = gen_train_ws(n, h, w, num_resblock);
+  if (workspace_bytes < ws.total) {
+    tg_set_error("gen_forward_train: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+    return TG_ERR_WORKSPACE;
+  }
+  auto L = gen_layers(num_resblock, nullptr, nullptr);
+  uint8_t* wsp = static_cast<uint8_t*>(workspace);
+  int rc = tg_pack_nchw_to_nhwc64(x_nchw, wsp + ws.x_in, n, 51, h, w, stream);
+  if (rc) return rc;
+  const std::vector<FrLayer> P = gen_plan_train(L, num_resblock, out, wsp, n, h, w);
+  size_t pb = 0;
+  for (auto& l : L) pb += tg_packed_conv_bytes(l.kind, l.cin, l.cout);
+  return launch_frame(P.data(), static_cast<int>(P.size()), packed, pb, n, reinterpret_cast<uint32_t*>(wsp + ws.flags),
+                      ws.flag_count, false, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tg_gen_backward(const void* packed_dgrad, int num_resblock, const float* dout, const float* out,
+                               float* flat_grad, void* workspace, size_t workspace_bytes, int n, int h, int w,
+                               void* stream) {
+  TG_CHECK_ARG(packed_dgrad && dout && out && flat_grad && workspace, "gen_backward: null pointer");
+  TG_CHECK_ARG(n >= 1 && h >= 1 && w >= 1, "gen_backward: bad shape");
+  const int nres = num_resblock;
+  const GenTrainWs ws = gen_train_ws(n, h, w, nres);
+  if (workspace_bytes < ws.total) {
+    tg_set_error("gen_backward: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+    return TG_ERR_WORKSPACE;
+  }
+  auto L = gen_layers(nres, nullptr, nullptr);
+  const std::vector<size_t> doff = gen_dgrad_offsets(L, nullptr);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* wsp = static_cast<uint8_t*>(workspace);
+  const uint8_t* pd = static_cast<const uint8_t*>(packed_dgrad);
+  const long long px1 = static_cast<long long>(n) * h * w;
+  int rc;
+  // weight / bias gradient of layer li given its input x and output gradient dy (sizes of the layer's INPUT)
+  auto wgrad = [&](int li, const void* x, const void* dy, int hh, int ww) {
+    const GenLayer& l = L[li];
+    const int cp = cin_padded(l.cin), op = l.cout <= 64 ? 64 : 128;
+    int r = (l.kind == kConv3x3) ? launch_wgrad3x3(x, dy, flat_grad + l.w_off, n, hh, ww, l.cin, l.cout, cp, op, st)
+                                 : launch_wgrad_convT3x3s2(x, dy, flat_grad + l.w_off, n, hh, ww, l.cin, l.cout, cp, op, st);
+    if (r || !l.has_bias) return r;
+    const long long opx = static_cast<long long>(n) * hh * ww * (l.kind == kConv3x3 ? 1 : 4);
+    return launch_bias_grad(dy, opx, op, l.cout, flat_grad + l.b_off, st);
+  };
+  // dx = dgrad(dy) (+ resid) masked by the saved post-ReLU activation; (hh, ww) = size of the layer's INPUT
+  auto dgrad = [&](int li, const void* dy, const void* resid, const void* mask, void* dx, int hh, int ww) {
+    const GenLayer& l = L[li];
+    const int dci = l.cout <= 64 ? 64 : 128, dco = cin_padded(l.cin);
+    const uint8_t* blob = pd + doff[li];
+    if (l.kind == kConv3x3) {
+      const float* bias = reinterpret_cast<const float*>(blob + packed_weight_bytes(dci, dco));
+      return launch_conv_tc(kConv3x3, kOutNHWCbf16, dy, blob, bias, resid, dx, nullptr, n, hh, ww, dci, dco, 0, TG_AMODE_HALO, 0,
+                            st, mask);
+    }
+    const float* bias = reinterpret_cast<const float*>(blob + packed_weight_bytes_k(kConv4x4s2, dci, dco));
+    return launch_conv_tc(kConv4x4s2, kOutNHWCbf16, dy, blob, bias, nullptr, dx, nullptr, n, 2 * hh, 2 * ww, dci, dco, 0,
+                          TG_AMODE_HALO, 0, st, mask);
+  };
+  auto B = [&](size_t off) { return static_cast<void*>(wsp + off); };
+  const int iOut = 2 * nres + 8, iCt6 = iOut - 1, iCt4 = iOut - 2, iC32 = iOut - 3, iC30 = iOut - 4, iC22 = iOut - 5,
+            iC20 = iOut - 6, iCt0 = iOut - 7;
+
+  // final sigmoid
+  if ((rc = sigmoid_bwd_pack_launch(dout, out, B(ws.g_z), n, 16LL * h * w, 48LL * h * w, 48LL * h * w, st))) return rc;
+  // output conv 64 -> 3
+  if ((rc = wgrad(iOut, B(ws.e), B(ws.g_z), 4 * h, 4 * w))) return rc;
+  if ((rc = dgrad(iOut, B(ws.g_z), nullptr, B(ws.e), B(ws.g_e), 4 * h, 4 * w))) return rc;
+  // conv_trans.6: 128 -> 64 @4x
+  if ((rc = wgrad(iCt6, B(ws.d), B(ws.g_e), 4 * h, 4 * w))) return rc;
+  if ((rc = dgrad(iCt6, B(ws.g_e), nullptr, B(ws.d), B(ws.g_d), 4 * h, 4 * w))) return rc;
+  // conv_trans.4: ConvT 128 -> 128, 2x -> 4x
+  if ((rc = wgrad(iCt4, B(ws.c1), B(ws.g_d), 2 * h, 2 * w))) return rc;
+  if ((rc = dgrad(iCt4, B(ws.g_d), nullptr, nullptr, B(ws.g_c1), 2 * h, 2 * w))) return rc;
+  // conv_trans.3.2: 128 -> 128 (no bias, no activation after it)
+  if ((rc = wgrad(iC32, B(ws.c0), B(ws.g_c1), 2 * h, 2 * w))) return rc;
+  if ((rc = dgrad(iC32, B(ws.g_c1), nullptr, B(ws.c0), B(ws.g_c0), 2 * h, 2 * w))) return rc;
+  // conv_trans.3.0: 64 -> 128 + ReLU
+  if ((rc = wgrad(iC30, B(ws.b2), B(ws.g_c0), 2 * h, 2 * w))) return rc;
+  if ((rc = dgrad(iC30, B(ws.g_c0), nullptr, nullptr, B(ws.g_b[0]), 2 * h, 2 * w))) return rc;       // b2 has no activation
+  // conv_trans.2.2: 64 -> 64 (no bias)
+  if ((rc = wgrad(iC22, B(ws.b1), B(ws.g_b[0]), 2 * h, 2 * w))) return rc;
+  if ((rc = dgrad(iC22, B(ws.g_b[0]), nullptr, B(ws.b1), B(ws.g_b[1]), 2 * h, 2 * w))) return rc;
+  // conv_trans.2.0: 64 -> 64 + ReLU
+  if ((rc = wgrad(iC20, B(ws.b0), B(ws.g_b[1]), 2 * h, 2 * w))) return rc;
+  if ((rc = dgrad(iC20, B(ws.g_b[1]), nullptr, B(ws.b0), B(ws.g_b[0]), 2 * h, 2 * w))) return rc;
+  // conv_trans.0: ConvT 64 -> 64, 1x -> 2x
+  if ((rc = wgrad(iCt0, B(ws.net[nres]), B(ws.g_b[0]), h, w))) return rc;
+  int cur = 0;
+  if ((rc = dgrad(iCt0, B(ws.g_b[0]), nullptr, nullptr, B(ws.g_net[cur]), h, w))) return rc;
+  // residual trunk, last block first: net[k+1] = conv2(t[k]) + net[k], t[k] = relu(conv1(net[k]) + b)
+  for (int k = nres - 1; k >= 0; --k) {
+    const int i1 = 1 + 2 * k, i2 = 2 + 2 * k;
+    if ((rc = wgrad(i2, B(ws.t[k]), B(ws.g_net[cur]), h, w))) return rc;
+    if ((rc = dgrad(i2, B(ws.g_net[cur]), nullptr, B(ws.t[k]), B(ws.g_t), h, w))) return rc;
+    if ((rc = wgrad(i1, B(ws.net[k]), B(ws.g_t), h, w))) return rc;
+    // d net[k] = dgrad(conv1) + d net[k+1]; net[0] = relu(conv.0) -> masked
+    if ((rc = dgrad(i1, B(ws.g_t), B(ws.g_net[cur]), k == 0 ? B(ws.net[0]) : nullptr, B(ws.g_net[cur ^ 1]), h, w))) return rc;
+    cur ^= 1;
+  }
+  if (nres == 0) {
+    // no trunk: the ConvT data gradient still has to pass conv.0's ReLU; reuse the mask path of a copy-free dgrad is not
+    // possible, so this configuration is rejected (the reference default is 16 blocks)
+    tg_set_error("gen_backward: num_resblock == 0 is not supported");
+    return TG_ERR_BAD_ARG;
+  }
+  // conv.0: 51 -> 64 + ReLU (its input is detached: no data gradient)
+  (void)px1;
+  return wgrad(0, B(ws.x_in), B(ws.g_net[cur]), h, w);
+}

@@ -389,3 +389,40 @@ extern "C" int tg_pack_nchw_to_nhwc64(const float* in, void* out, int n, int c, 
   TG_CUDA(cudaGetLastError());
   return TG_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Backward of the generator's final sigmoid (code/models.py:86), fused with the layout change the data-gradient
+// convolution needs: dz = dout * out * (1 - out), NCHW f32 [n,3,hw] -> NHWC bf16 [n,hw,64] (channels 3..63 zero).
+// ---------------------------------------------------------------------------------------------
+namespace tg {
+__global__ void __launch_bounds__(256)
+sigmoid_bwd_pack_kernel(const float* __restrict__ dout, const float* __restrict__ out, __nv_bfloat16* __restrict__ dz,
+                        int n, long long hw, long long dout_nstride, long long out_nstride) {
+  const long long total = static_cast<long long>(n) * hw;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / hw, px = i - b * hw;
+    float g[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float y = __ldg(out + b * out_nstride + c * hw + px);
+      g[c] = __ldg(dout + b * dout_nstride + c * hw + px) * y * (1.f - y);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(dz + i * 64);
+    dst[0] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], 0.f), 0u, 0u);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) dst[k] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+int sigmoid_bwd_pack_launch(const float* dout, const float* out, void* dz, int n, long long hw, long long dout_nstride,
+                            long long out_nstride, cudaStream_t st) {
+  const long long total = static_cast<long long>(n) * hw;
+  tg_prof_pre(TG_K_GLUE, (24.0 + 128.0) * total, st);
+  sigmoid_bwd_pack_kernel<<<grid_for(total, 256, 16), 256, 0, st>>>(dout, out, static_cast<__nv_bfloat16*>(dz), n, hw,
+                                                                    dout_nstride, out_nstride);
+  tg_prof_post(st);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+}  // namespace tg

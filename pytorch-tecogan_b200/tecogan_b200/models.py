@@ -21,8 +21,48 @@ def residual_block(inputs, output_channel=64, stride=1):
                          conv2(output_channel, 3, output_channel, stride, use_bias=False))
 
 
+class _GeneratorFn(torch.autograd.Function):
+    """generator.forward with gradients (code/train.py:336 back-propagates the content loss through it): the forward
+    keeps all activations in a per-call workspace, the backward runs the tcgen05 dgrad / wgrad kernels
+    (tg_gen_backward).  The input is detached in the reference (code/train.py:90,108): no input gradient."""
+
+    @staticmethod
+    def forward(ctx, x, module, *params):
+        lib = _nt.lib()
+        x = x.detach().float().contiguous()
+        n, _, h, w = x.shape
+        nres = int(module.num)
+        packed = module.packed_weights()
+        ws = torch.empty(lib.tg_gen_train_workspace_bytes(n, h, w, nres), dtype=torch.uint8, device=x.device)
+        out = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=x.device)
+        _nt.check(lib.tg_gen_forward_train(_nt.ptr(packed), nres, _nt.ptr(x), _nt.ptr(out), _nt.ptr(ws), ws.numel(), n, h, w,
+                                           _nt.stream_ptr()))
+        ctx.module, ctx.ws, ctx.shape = module, ws, (n, h, w)
+        ctx.packed_dgrad = module.packed_dgrad_weights()
+        ctx.save_for_backward(out)
+        ctx.mark_non_differentiable()
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _nt.lib()
+        (out,) = ctx.saved_tensors
+        n, h, w = ctx.shape
+        module = ctx.module
+        nres = int(module.num)
+        g = grad_out.float().contiguous()
+        flat = torch.zeros(lib.tg_gen_param_count(nres), dtype=torch.float32, device=out.device)
+        _nt.check(lib.tg_gen_backward(_nt.ptr(ctx.packed_dgrad), nres, _nt.ptr(g), _nt.ptr(out), _nt.ptr(flat), _nt.ptr(ctx.ws),
+                                      ctx.ws.numel(), n, h, w, _nt.stream_ptr()))
+        grads, o = [], 0
+        for p in module._param_list():
+            grads.append(flat[o:o + p.numel()].view_as(p).to(p.dtype))
+            o += p.numel()
+        return (None, None, *grads)
+
+
 class generator(nn.Module):
-    """code/models.py:61-86, B200-native forward."""
+    """code/models.py:61-86, B200-native forward and backward."""
 
     def __init__(self, gen_output_channels, args=None):
         super().__init__()
@@ -67,6 +107,19 @@ class generator(nn.Module):
             self._packed_key = key
         return self._packed
 
+    def packed_dgrad_weights(self):
+        """packed weights of the data-gradient convolutions (training only); same cache discipline."""
+        params = self._param_list()
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if getattr(self, "_packed_dgrad", None) is None or key != getattr(self, "_packed_dgrad_key", None):
+            lib = _nt.lib()
+            nres = int(self.num)
+            flat = torch.cat([p.detach().reshape(-1).float() for p in params])
+            buf = torch.empty(lib.tg_gen_packed_dgrad_bytes(nres), dtype=torch.uint8, device=flat.device)
+            _nt.check(lib.tg_gen_pack_dgrad(_nt.ptr(flat), nres, _nt.ptr(buf), _nt.stream_ptr()))
+            self._packed_dgrad, self._packed_dgrad_key = buf, key
+        return self._packed_dgrad
+
     def _workspace(self, n, h, w, dev):
         need = _nt.lib().tg_gen_workspace_bytes(n, h, w)
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
@@ -77,11 +130,15 @@ class generator(nn.Module):
     def forward(self, x, return_logits=False):
         if not x.is_cuda:
             raise RuntimeError("generator.forward: input must be a CUDA tensor (no CPU fallback)")
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError(
-                "tecogan_b200 generator: backward kernels are not built yet; call under torch.no_grad()")
         if x.dim() != 4 or x.shape[1] != 51:
             raise RuntimeError(f"generator.forward: expected [N,51,H,W], got {tuple(x.shape)}")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if x.requires_grad:
+                raise NotImplementedError("tecogan_b200 generator: no gradient w.r.t. the input (the reference detaches it, "
+                                          "code/train.py:90,108)")
+            if return_logits:
+                raise RuntimeError("return_logits is an inference-only probe")
+            return _GeneratorFn.apply(x, self, *self._param_list())
         lib = _nt.lib()
         x = x.float().contiguous()
         n, _, h, w = x.shape
