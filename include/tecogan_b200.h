@@ -152,6 +152,10 @@ int tg_conv3x3_dgrad(const void* dy, const void* packed_dgrad, const void* resid
                      void* dx, int n, int h, int w, int cin, int cout, void* stream);
 int tg_convT3x3s2_dgrad(const void* dy, const void* packed_dgrad, const void* mask, void* dx, int n, int h,
                         int w, int cin, int cout, void* stream);
+/* Adjoint of Conv2d(k4,s2,p1) (pack kind 5): dy [n,h,w,cout] -> dx [n,2h,2w,cin], four output-parity phases of 2x2
+ * taps.  mask_mode 1: ReLU backward (zero where mask == 0); 2: LeakyReLU(0.2) backward (x0.2 where mask <= 0). */
+int tg_conv4x4s2_dgrad(const void* dy, const void* packed_dgrad, const void* mask, int mask_mode, void* dx,
+                       int n, int h, int w, int cin, int cout, void* stream);
 
 /* ----------------------------------------------------------------- generator (41 convs) ---- */
 

@@ -93,16 +93,26 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
   const int ct_ky[9] = {1, 1, 1, 2, 0, 2, 2, 0, 0};
   const int ct_kx[9] = {1, 2, 0, 1, 1, 2, 0, 2, 0};
   const int kchunks = cin_pad / 64;
-  const int ntap = (kind == kConv4x4s2 || kind == kPackConvT3x3s2Dgrad) ? 16 : 9;
+  const int ntap = (kind == kConv4x4s2 || kind == kPackConvT3x3s2Dgrad || kind == kPackConv4x4s2Dgrad) ? 16 : 9;
   const long long total = static_cast<long long>(ntap) * cin_pad * cout_pad;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int ci_l = static_cast<int>(i % 64);
     long long r = i / 64;
     const int co_l = static_cast<int>(r % nt); r /= nt;
-    const int j = static_cast<int>(r % ntap); r /= ntap;
-    const int kc = static_cast<int>(r % kchunks); r /= kchunks;
-    const int chunk = static_cast<int>(r);
+    int j, kc, chunk;
+    if (kind == kPackConv4x4s2Dgrad) {
+      // four independent per-phase blobs: [phase][chunk][kc][tap][co][ci]
+      const int t = static_cast<int>(r % 4); r /= 4;
+      kc = static_cast<int>(r % kchunks); r /= kchunks;
+      const int nchunk = cout_pad / nt;
+      chunk = static_cast<int>(r % nchunk); r /= nchunk;
+      j = static_cast<int>(r) * 4 + t;
+    } else {
+      j = static_cast<int>(r % ntap); r /= ntap;
+      kc = static_cast<int>(r % kchunks); r /= kchunks;
+      chunk = static_cast<int>(r);
+    }
     const int ci = kc * 64 + ci_l, co = chunk * nt + co_l;
     float v = 0.f;
     if (ci < cin && co < cout) {
@@ -118,6 +128,13 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
         // dX = conv3x3(dY, W'), W'[ci_f][co_f][ky][kx] = W[co_f][ci_f][2-ky][2-kx]; here ci = co_f, co = ci_f, cout = cin_f
         const int ky = j / 3, kx = j % 3;
         v = w[((static_cast<long long>(ci) * cout + co) * 3 + (2 - ky)) * 3 + (2 - kx)];
+      } else if (kind == kPackConv4x4s2Dgrad) {
+        // adjoint of Conv2d(k4,s2,p1), output phase (py,px) = parity of the dX pixel: dX[2i+py] takes dY rows
+        // {i-1 (ky=3), i (ky=1)} for py = 0 and {i (ky=2), i+1 (ky=0)} for py = 1; here ci = co_f, co = ci_f, cout = cin_f
+        const int ph = j >> 2, t = j & 3;
+        const int ty = t >> 1, tx = t & 1, py = ph >> 1, px = ph & 1;
+        const int ky = py ? (ty ? 0 : 2) : (ty ? 1 : 3), kx = px ? (tx ? 0 : 2) : (tx ? 1 : 3);
+        v = w[((static_cast<long long>(ci) * cout + co) * 4 + ky) * 4 + kx];
       } else if (kind == kPackConvT3x3s2Dgrad) {
         // dX[ci_f] = conv k3 s2 p1 (dY[co_f], Wt[ci_f][co_f]) == conv k4 s2 p1 with a zero 4th row / column;
         // here ci = co_f, co = ci_f, cin = cout_f.  Tap order as kConv4x4s2.
@@ -139,10 +156,11 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
 // kinds 3 / 4 derive the data-gradient convolution of a forward layer: its input channels are the forward
 // layer's output channels and vice versa
 static void derived_channels(int kind, int cin, int cout, int* dcin, int* dcout, int* launch_kind) {
-  const bool dgrad = (kind == tg::kPackConv3x3Dgrad || kind == tg::kPackConvT3x3s2Dgrad);
+  const bool dgrad = (kind == tg::kPackConv3x3Dgrad || kind == tg::kPackConvT3x3s2Dgrad || kind == tg::kPackConv4x4s2Dgrad);
   *dcin = dgrad ? cout : cin;
   *dcout = dgrad ? cin : cout;
-  *launch_kind = kind == tg::kPackConv3x3Dgrad ? tg::kConv3x3 : (kind == tg::kPackConvT3x3s2Dgrad ? tg::kConv4x4s2 : kind);
+  *launch_kind = kind == tg::kPackConv3x3Dgrad ? tg::kConv3x3
+               : (kind == tg::kPackConvT3x3s2Dgrad || kind == tg::kPackConv4x4s2Dgrad) ? tg::kConv4x4s2 : kind;   // 16-tap size
 }
 
 extern "C" size_t tg_packed_conv_bytes(int kind, int cin, int cout) {
@@ -156,8 +174,8 @@ extern "C" size_t tg_packed_conv_bytes(int kind, int cin, int cout) {
 extern "C" int tg_pack_weights(int kind, const float* weight, const float* bias, int cin, int cout,
                                void* packed, void* stream) {
   TG_CHECK_ARG(weight && packed, "pack_weights: null pointer");
-  TG_CHECK_ARG(kind >= 0 && kind <= 4, "pack_weights: kind must be 0 (conv3x3), 1 (convT3x3s2), 2 (conv4x4s2), "
-               "3 (dgrad of conv3x3) or 4 (dgrad of convT3x3s2)");
+  TG_CHECK_ARG(kind >= 0 && kind <= 5, "pack_weights: kind must be 0 (conv3x3), 1 (convT3x3s2), 2 (conv4x4s2), "
+               "3 (dgrad of conv3x3), 4 (dgrad of convT3x3s2) or 5 (dgrad of conv4x4s2)");
   TG_CHECK_ARG(cin >= 1 && cin <= 128 && cout >= 1 && cout <= 128, "pack_weights: channels out of range");
   TG_CHECK_ARG(!(kind >= 3 && bias), "pack_weights: data-gradient convolutions have no bias");
   int lk;
@@ -226,4 +244,19 @@ extern "C" int tg_convT3x3s2_dgrad(const void* dy, const void* packed_dgrad, con
                                                      tg::packed_weight_bytes_k(tg::kConv4x4s2, dci, dco));
   return tg::launch_conv_tc(tg::kConv4x4s2, tg::kOutNHWCbf16, dy, packed_dgrad, bias, nullptr, dx, nullptr, n, 2 * h, 2 * w,
                             dci, dco, 0, TG_AMODE_HALO, 0, static_cast<cudaStream_t>(stream), mask);
+}
+
+extern "C" int tg_conv4x4s2_dgrad(const void* dy, const void* packed_dgrad, const void* mask, int mask_mode, void* dx,
+                                  int n, int h, int w, int cin, int cout, void* stream) {
+  // forward: x [n,2h,2w,cin] -> y [n,h,w,cout]; dX is produced one output-parity phase per launch (2x2 taps each)
+  const int dci = cout <= 64 ? 64 : 128, dco = cin <= 64 ? 64 : 128;
+  const size_t phase_bytes = static_cast<size_t>(4) * dci * dco * 2;
+  const float* zero_bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(packed_dgrad) + 4 * phase_bytes);
+  for (int ph = 0; ph < 4; ++ph) {
+    int rc = tg::launch_conv_tc(tg::kConvT4x4s2Phase, tg::kOutNHWCbf16, dy, static_cast<const uint8_t*>(packed_dgrad) + ph * phase_bytes,
+                                zero_bias, nullptr, dx, nullptr, n, h, w, dci, dco, 0, TG_AMODE_HALO, 0,
+                                static_cast<cudaStream_t>(stream), mask, mask_mode, ph);
+    if (rc) return rc;
+  }
+  return TG_OK;
 }

@@ -216,6 +216,174 @@ disc_head_kernel(const float* __restrict__ r, int n, int hw, const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// BatchNorm backward (training mode).  g_out = gradient w.r.t. the block output (bf16); if `act` is given the block
+// ended in LeakyReLU(0.2) and g = g_out * (act > 0 ? 1 : 0.2), else g = g_out.  With xh = (x - mean) * rstd:
+//   dbeta = sum g, dgamma = sum g*xh, dx = gamma*rstd * (g - dbeta/P - xh*dgamma/P).
+// Pass 1 reduces (deterministic partials + last-block finalize, like bn_stats), adds dgamma/dbeta into the
+// parameter gradient and leaves {dbeta/P, dgamma/P} in `red`; pass 2 writes dx as bf16 (the conv kernels' operand).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBnThreads)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g_out, const float* __restrict__ x, const float* __restrict__ act,
+                     long long pixels, int c, const float* __restrict__ stats, float* __restrict__ partial,
+                     unsigned int* __restrict__ ticket, float* __restrict__ red, float* dgamma, float* dbeta) {
+  __shared__ float s_sum[kBnThreads][9];
+  __shared__ float s_sq[kBnThreads][9];
+  __shared__ bool s_last;
+  const int groups = c / 8;
+  const int pix_per_iter = kBnThreads / groups;
+  const int gi = threadIdx.x % groups, pl = threadIdx.x / groups;
+  float mean[8], rstd[8], s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { mean[e] = stats[(gi * 8 + e) * 4 + 0]; rstd[e] = stats[(gi * 8 + e) * 4 + 1]; s1[e] = s2[e] = 0.f; }
+  for (long long p = static_cast<long long>(blockIdx.x) * pix_per_iter + pl; p < pixels;
+       p += static_cast<long long>(gridDim.x) * pix_per_iter) {
+    const uint4 gv = __ldg(reinterpret_cast<const uint4*>(g_out + p * c) + gi);
+    const uint32_t gu[4] = {gv.x, gv.y, gv.z, gv.w};
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + p * c) + 2 * gi);
+    const float4 x1 = __ldg(reinterpret_cast<const float4*>(x + p * c) + 2 * gi + 1);
+    const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    float av[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+    if (act) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(act + p * c) + 2 * gi);
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(act + p * c) + 2 * gi + 1);
+      av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float g = (e & 1) ? bf16_hi(gu[e >> 1]) : bf16_lo(gu[e >> 1]);
+      if (act && !(av[e] > 0.f)) g *= 0.2f;
+      s1[e] += g;
+      s2[e] += g * (xv[e] - mean[e]) * rstd[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s_sum[threadIdx.x][e] = s1[e]; s_sq[threadIdx.x][e] = s2[e]; }
+  __syncthreads();
+  if (threadIdx.x < c) {
+    const int g = threadIdx.x / 8, e = threadIdx.x % 8;
+    float a = 0.f, b = 0.f;
+    for (int r = 0; r < pix_per_iter; ++r) { a += s_sum[r * groups + g][e]; b += s_sq[r * groups + g][e]; }
+    partial[(static_cast<size_t>(blockIdx.x) * c + threadIdx.x) * 2 + 0] = a;
+    partial[(static_cast<size_t>(blockIdx.x) * c + threadIdx.x) * 2 + 1] = b;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < c) {
+    double a = 0.0, b = 0.0;
+    for (unsigned int k = 0; k < gridDim.x; ++k) {
+      a += static_cast<double>(__ldcg(partial + (static_cast<size_t>(k) * c + threadIdx.x) * 2 + 0));
+      b += static_cast<double>(__ldcg(partial + (static_cast<size_t>(k) * c + threadIdx.x) * 2 + 1));
+    }
+    dbeta[threadIdx.x] += static_cast<float>(a);
+    dgamma[threadIdx.x] += static_cast<float>(b);
+    red[threadIdx.x * 2 + 0] = static_cast<float>(a / static_cast<double>(pixels));
+    red[threadIdx.x * 2 + 1] = static_cast<float>(b / static_cast<double>(pixels));
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+__global__ void __launch_bounds__(kBnThreads)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g_out, const float* __restrict__ x, const float* __restrict__ act,
+                    __nv_bfloat16* __restrict__ dx, long long pixels, int c, const float* __restrict__ stats,
+                    const float* __restrict__ red) {
+  __shared__ float s_mean[128], s_rstd[128], s_a[128], s_m1[128], s_m2[128];
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    s_mean[i] = stats[i * 4 + 0]; s_rstd[i] = stats[i * 4 + 1]; s_a[i] = stats[i * 4 + 2];
+    s_m1[i] = red[i * 2 + 0]; s_m2[i] = red[i * 2 + 1];
+  }
+  __syncthreads();
+  const int groups = c / 4;
+  const long long total = pixels * groups;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g4 = static_cast<int>(i % groups) * 4;
+    const uint2 gv = __ldg(reinterpret_cast<const uint2*>(g_out) + i);
+    float g[4] = {bf16_lo(gv.x), bf16_hi(gv.x), bf16_lo(gv.y), bf16_hi(gv.y)};
+    const float4 xv4 = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+    if (act) {
+      const float4 a4 = __ldg(reinterpret_cast<const float4*>(act) + i);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (!(av[e] > 0.f)) g[e] *= 0.2f;
+    }
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float xh = (xv[e] - s_mean[g4 + e]) * s_rstd[g4 + e];
+      o[e] = s_a[g4 + e] * (g[e] - s_m1[g4 + e] - xh * s_m2[g4 + e]);
+    }
+    reinterpret_cast<uint2*>(dx)[i] = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+  }
+}
+
+// Backward of the discriminator head (disc_head_kernel), one block: dprob -> sigmoid -> fc -> LeakyReLU -> BatchNorm(3).
+// Writes d(raw block5 conv output) as NHWC bf16 [n][hw][64] (3 real channels) and ADDS the fc / BN parameter gradients.
+__global__ void __launch_bounds__(256)
+disc_head_bwd_kernel(const float* __restrict__ dprob, const float* __restrict__ prob, const float* __restrict__ y,
+                     const float* __restrict__ r, int n, int hw, const float* __restrict__ stats,
+                     const float* __restrict__ fc_w, float* d_fc_w, float* d_fc_b, float* dgamma, float* dbeta,
+                     float* __restrict__ dlogit, __nv_bfloat16* __restrict__ dr) {
+  __shared__ double s_red[2][256];
+  __shared__ float s_m[3][2];
+  const int feat = 3 * hw, per = n * hw;
+  for (int s = threadIdx.x; s < n; s += blockDim.x) dlogit[s] = dprob[s] * prob[s] * (1.f - prob[s]);
+  __syncthreads();
+  for (int k = threadIdx.x; k < feat; k += blockDim.x) {           // fc weight gradient
+    float a = 0.f;
+    for (int s = 0; s < n; ++s) a += dlogit[s] * y[s * feat + k];
+    d_fc_w[k] += a;
+  }
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int s = 0; s < n; ++s) a += dlogit[s];
+    d_fc_b[0] += a;
+  }
+  for (int ch = 0; ch < 3; ++ch) {                                  // BatchNorm reductions per channel
+    const float mean = stats[ch * 4 + 0], rstd = stats[ch * 4 + 1];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < per; i += blockDim.x) {
+      const int s = i / hw, k = ch * hw + i % hw;
+      float g = dlogit[s] * fc_w[k];
+      if (!(y[s * feat + k] > 0.f)) g *= 0.2f;
+      a += g; b += static_cast<double>(g) * (r[s * feat + k] - mean) * rstd;
+    }
+    s_red[0][threadIdx.x] = a; s_red[1][threadIdx.x] = b;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+      if (threadIdx.x < st) { s_red[0][threadIdx.x] += s_red[0][threadIdx.x + st]; s_red[1][threadIdx.x] += s_red[1][threadIdx.x + st]; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      dbeta[ch] += static_cast<float>(s_red[0][0]);
+      dgamma[ch] += static_cast<float>(s_red[1][0]);
+      s_m[ch][0] = static_cast<float>(s_red[0][0] / per); s_m[ch][1] = static_cast<float>(s_red[1][0] / per);
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < per; i += blockDim.x) {             // dx, NHWC64 bf16
+    const int s = i / hw, px = i % hw;
+    float o[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const int k = ch * hw + px;
+      float g = dlogit[s] * fc_w[k];
+      if (!(y[s * feat + k] > 0.f)) g *= 0.2f;
+      const float xh = (r[s * feat + k] - stats[ch * 4 + 0]) * stats[ch * 4 + 1];
+      o[ch] = stats[ch * 4 + 2] * (g - s_m[ch][0] - xh * s_m[ch][1]);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(dr + static_cast<size_t>(i) * 64);
+    dst[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], 0.f), 0u, 0u);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) dst[k] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // ------------------------------------------------------------------------------------ launchers
 int bn_stats_launch(const void* x, long long pixels, int c, const float* gamma, const float* beta, float* partial,
                     unsigned int* ticket, float* stats, float* running_mean, float* running_var,
@@ -277,6 +445,43 @@ int disc_head_launch(const float* r, int n, int hw, const float* gamma, const fl
   tg_prof_pre(TG_K_GLUE, 8.0 * n * 3 * hw, st);
   disc_head_kernel<<<1, 256, 0, st>>>(r, n, hw, gamma, beta, 1e-3f, 0.1f, training, running_mean, running_var, nbt, fc_w,
                                       fc_b, y, stats, logit, prob);
+  tg_prof_post(st);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+int bn_bwd_launch(const void* g_out, const void* x, const void* act, void* dx, long long pixels, int c, const float* stats,
+                  float* partial, unsigned int* ticket, float* red, float* dgamma, float* dbeta, cudaStream_t st) {
+  TG_CHECK_ARG(c == 64 || c == 128, "bn_bwd: channels must be 64 or 128 (got %d)", c);
+  const int pix_per_iter = kBnThreads / (c / 8);
+  long long blocks = (pixels + pix_per_iter * 4 - 1) / (pix_per_iter * 4);
+  if (blocks > kBnMaxBlocks) blocks = kBnMaxBlocks;
+  if (blocks < 1) blocks = 1;
+  tg_prof_pre(TG_K_GLUE, (act ? 10.0 : 6.0) * pixels * c, st);
+  bn_bwd_reduce_kernel<<<static_cast<int>(blocks), kBnThreads, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(g_out), static_cast<const float*>(x), static_cast<const float*>(act), pixels, c, stats,
+      partial, ticket, red, dgamma, dbeta);
+  tg_prof_post(st);
+  TG_CUDA(cudaGetLastError());
+  const long long total = pixels * (c / 4);
+  long long ab = (total + kBnThreads - 1) / kBnThreads;
+  const long long cap = static_cast<long long>(tg_num_sms()) * 8;
+  if (ab > cap) ab = cap;
+  tg_prof_pre(TG_K_GLUE, (act ? 12.0 : 8.0) * pixels * c, st);
+  bn_bwd_apply_kernel<<<static_cast<int>(ab), kBnThreads, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(g_out), static_cast<const float*>(x), static_cast<const float*>(act),
+      static_cast<__nv_bfloat16*>(dx), pixels, c, stats, red);
+  tg_prof_post(st);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+int disc_head_bwd_launch(const float* dprob, const float* prob, const float* y, const float* r, int n, int hw,
+                         const float* stats, const float* fc_w, float* d_fc_w, float* d_fc_b, float* dgamma, float* dbeta,
+                         float* dlogit, void* dr, cudaStream_t st) {
+  tg_prof_pre(TG_K_GLUE, 16.0 * n * 3 * hw, st);
+  disc_head_bwd_kernel<<<1, 256, 0, st>>>(dprob, prob, y, r, n, hw, stats, fc_w, d_fc_w, d_fc_b, dgamma, dbeta, dlogit,
+                                          static_cast<__nv_bfloat16*>(dr));
   tg_prof_post(st);
   TG_CUDA(cudaGetLastError());
   return TG_OK;

@@ -253,8 +253,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                   const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    if ((mw[e] & 0x7FFFu) == 0u) f[2 * e] = 0.f;
-                    if ((mw[e] & 0x7FFF0000u) == 0u) f[2 * e + 1] = 0.f;
+                    if (p.mask_mode == kMaskLrelu02) {       // saved <= 0 (zero or sign bit): slope 0.2
+                      if ((mw[e] & 0x7FFFu) == 0u || (mw[e] & 0x8000u)) f[2 * e] *= 0.2f;
+                      if ((mw[e] & 0x7FFF0000u) == 0u || (mw[e] & 0x80000000u)) f[2 * e + 1] *= 0.2f;
+                    } else {
+                      if ((mw[e] & 0x7FFFu) == 0u) f[2 * e] = 0.f;
+                      if ((mw[e] & 0x7FFF0000u) == 0u) f[2 * e + 1] = 0.f;
+                    }
                   }
                 }
                 uint4 o;
@@ -340,11 +345,14 @@ size_t packed_weight_bytes(int cin_pad, int cout_pad) {
 
 int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, const float* bias,
                    const void* resid, void* out, float* out2, int n, int h, int w, int cin_pad,
-                   int cout_pad, int relu, int amode, long long out_nstride, cudaStream_t stream, const void* mask) {
+                   int cout_pad, int relu, int amode, long long out_nstride, cudaStream_t stream, const void* mask,
+                   int mask_mode, int phase) {
   TG_CHECK_ARG(x && packed_w && out, "conv: null pointer");
   TG_CHECK_ARG(!(mask && out_mode != kOutNHWCbf16), "conv: mask only for the NHWC bf16 output");
   TG_CHECK_ARG(n > 0 && h > 0 && w > 0, "conv: bad shape n=%d h=%d w=%d", n, h, w);
-  TG_CHECK_ARG(kind == kConv3x3 || kind == kConvT3x3s2 || kind == kConv4x4s2, "conv: bad kind %d", kind);
+  TG_CHECK_ARG(kind == kConv3x3 || kind == kConvT3x3s2 || kind == kConv4x4s2 || kind == kConvT4x4s2Phase, "conv: bad kind %d", kind);
+  const bool tph = (kind == kConvT4x4s2Phase);
+  TG_CHECK_ARG(!tph || (phase >= 0 && phase < 4), "conv: bad phase %d", phase);
   TG_CHECK_ARG(cin_pad == 64 || cin_pad == 128, "conv: cin_pad must be 64 or 128 (got %d)", cin_pad);
   TG_CHECK_ARG(cout_pad == 16 || cout_pad == 64 || cout_pad == 128, "conv: cout_pad must be 16/64/128 (got %d)", cout_pad);
   const bool nchw_out = (out_mode == kOutNCHWf32Sigmoid || out_mode == kOutNCHWf32Raw);
@@ -373,7 +381,7 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   p.nphase = s2 ? 4 : 1;
   p.stages_per_item = p.kchunks * p.nphase;
   p.in_scale = s2 ? 2 : 1;
-  p.ntaps = s2 ? 4 : 9;
+  p.ntaps = (s2 || tph) ? 4 : 9;
   // staged box in pixels: tile + halo; the stride-2 conv stages one input-parity phase (every 2nd pixel)
   const int box_w = s2 ? kTileW + 1 : ((amode == TG_AMODE_HALO) ? kTileW + 2 : kTileW);
   const int box_h = s2 ? kTileH + 1 : kTileH + 2;
@@ -397,6 +405,7 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   for (int j = 0; j < p.ntaps; ++j) {
     int dy, dx;
     if (s2) { dy = j >> 1; dx = j & 1; }                    // kernel tap (2*dy + phase_y, 2*dx + phase_x)
+    else if (tph) { dy = (j >> 1) + (phase >> 1); dx = (j & 1) + (phase & 1); }   // dY rows {i-1,i} (even phase) / {i,i+1} (odd)
     else if (kind == kConv3x3) { dy = conv_dy[j]; dx = conv_dx[j]; }
     else { dy = ct_dy[j]; dx = ct_dx[j]; }
     p.taps[j].a_off = (amode == TG_AMODE_HALO) ? static_cast<uint32_t>((dy * box_w + dx) * 128)
@@ -428,13 +437,14 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
 
   p.out_mode = out_mode;
-  p.sy = p.sx = (kind == kConvT3x3s2) ? 2 : 1;
+  p.sy = p.sx = (kind == kConvT3x3s2 || tph) ? 2 : 1;
   p.oh = th * p.sy; p.ow = tw * p.sx;
   p.oc = nchw_out ? 3 : cout_pad;
   for (int a = 0; a < kMaxAcc; ++a) { p.acc_oy[a] = (kind == kConvT3x3s2) ? (a >> 1) : 0; p.acc_ox[a] = (kind == kConvT3x3s2) ? (a & 1) : 0; }
+  if (tph) { p.acc_oy[0] = phase >> 1; p.acc_ox[0] = phase & 1; }
   p.out_nstride = out_nstride > 0 ? out_nstride : static_cast<long long>(p.oc) * p.oh * p.ow;
   p.relu = relu;
-  p.out = out; p.out2 = out2; p.resid = resid; p.bias = bias; p.mask = mask;
+  p.out = out; p.out2 = out2; p.resid = resid; p.bias = bias; p.mask = mask; p.mask_mode = mask_mode;
 
   CUtensorMap tm_a, tm_w;
   {

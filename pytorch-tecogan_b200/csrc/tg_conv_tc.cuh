@@ -10,10 +10,12 @@ constexpr int kAccCols = 64;      // TMEM columns reserved per accumulator
 constexpr int kMaxTaps = 16;
 constexpr int kMaxAcc = 4;
 
-enum TcKind { kConv3x3 = 0, kConvT3x3s2 = 1, kConv4x4s2 = 2 };
+enum TcKind { kConv3x3 = 0, kConvT3x3s2 = 1, kConv4x4s2 = 2,
+              kConvT4x4s2Phase = 6 };   // one output-parity phase of the adjoint of Conv2d(k4,s2,p1): 2x2 taps, stride-2 stores
 enum TcOut { kOutNHWCbf16 = 0, kOutNCHWf32Sigmoid = 1, kOutNCHWf32Raw = 2, kOutNHWCf32 = 3 };   // 3: pre-BatchNorm conv outputs
 // tg_pack_weights kinds beyond TcKind: data-gradient convolutions derived from a forward layer's weights
-enum TcPackKind { kPackConv3x3Dgrad = 3, kPackConvT3x3s2Dgrad = 4 };
+enum TcPackKind { kPackConv3x3Dgrad = 3, kPackConvT3x3s2Dgrad = 4, kPackConv4x4s2Dgrad = 5 };
+enum TcMask { kMaskNone = 0, kMaskRelu = 1, kMaskLrelu02 = 2 };   // backward of the activation that produced `mask`
 enum TcAct { kActNone = 0, kActRelu = 1, kActLrelu02 = 2 };   // LeakyReLU(0.2): code/ops.py:71-72
 
 // One MMA group = one filter tap on one 64-channel K chunk: 4 x tcgen05.mma (K=16 each).
@@ -55,7 +57,8 @@ struct TcParams {
   void* out;
   float* out2;                // optional pre-sigmoid logits (NCHW f32)
   const void* resid;          // optional residual, same layout as out (NHWC bf16)
-  const void* mask;           // optional ReLU-backward mask, same layout as out: result zeroed where mask == 0
+  const void* mask;           // optional saved activation, same layout as out: ReLU backward zeroes the result where
+  int mask_mode;              // mask == 0; LeakyReLU(0.2) backward scales it by 0.2 where mask <= 0  (TcMask)
   const float* bias;          // padded bias for the whole layer (chunk offset added in-kernel)
 };
 
@@ -63,7 +66,7 @@ struct TcParams {
 int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, const float* bias,
                    const void* resid, void* out, float* out2, int n, int h, int w, int cin_pad,
                    int cout_pad, int relu, int amode, long long out_nstride, cudaStream_t stream,
-                   const void* mask = nullptr);
+                   const void* mask = nullptr, int mask_mode = kMaskRelu, int phase = 0);
 
 // SWIZZLE_128B bf16 tiled tensor map (cuTensorMapEncodeTiled through the runtime's driver entry point)
 int encode_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,

@@ -18,4 +18,12 @@ int disc_head_launch(const float* r, int n, int hw, const float* gamma, const fl
                      float* running_mean, float* running_var, long long* nbt, const float* fc_w, const float* fc_b,
                      float* y, float* stats, float* logit, float* prob, cudaStream_t st);
 
+// BatchNorm backward: g_out (bf16) = gradient of the block output; act != null: the block ended in LeakyReLU(0.2).
+// dx (bf16) = gradient of the raw conv output; dgamma/dbeta are ADDED to; red = 2*c floats of scratch.
+int bn_bwd_launch(const void* g_out, const void* x, const void* act, void* dx, long long pixels, int c, const float* stats,
+                  float* partial, unsigned int* ticket, float* red, float* dgamma, float* dbeta, cudaStream_t st);
+int disc_head_bwd_launch(const float* dprob, const float* prob, const float* y, const float* r, int n, int hw,
+                         const float* stats, const float* fc_w, float* d_fc_w, float* d_fc_b, float* dgamma, float* dbeta,
+                         float* dlogit, void* dr, cudaStream_t st);
+
 }  // namespace tg

@@ -55,6 +55,8 @@ SIGNATURES = {
                                   _c_void_p]),
     "tg_convT3x3s2_dgrad": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
                                      _c_void_p]),
+    "tg_conv4x4s2_dgrad": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                    _c_void_p]),
     "tg_gen_param_count": (_c_size_t, [_c_int]),
     "tg_gen_packed_bytes": (_c_size_t, [_c_int]),
     "tg_gen_pack": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p]),

@@ -165,3 +165,32 @@ def test_bias_grad(pixels, c):
     nt.check(lib.tg_bias_grad(nt.ptr(dyd), nt.ptr(db), pixels, c, nt.stream_ptr()))
     torch.cuda.synchronize()
     assert (db.cpu() - dy[:, :c].sum(0)).abs().max().item() <= 1e-3 * max(1.0, pixels ** 0.5)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,mask_mode", [(1, 16, 8, 64, 64, 0), (2, 19, 13, 64, 128, 2), (3, 16, 16, 128, 128, 1),
+                                                      (2, 8, 8, 128, 64, 0), (2, 4, 4, 64, 3, 2)])
+def test_conv4x4s2_dgrad(n, h, w, cin, cout, mask_mode):
+    """h, w = output size of the forward stride-2 conv; dX is [n,cin,2h,2w]."""
+    from tecogan_b200 import _native as nt
+    lib = nt.lib()
+    x = torch.zeros(n, cin, 2 * h, 2 * w, requires_grad=True)
+    wt = _bf(torch.from_numpy(synth.det_uniform((cout, cin, 4, 4), 2, -0.1, 0.1)))
+    dy = _bf(torch.from_numpy(synth.det_uniform((n, cout, h, w), 3, -1, 1)))
+    F.conv2d(x, wt, None, stride=2, padding=1).backward(dy)
+    want = x.grad
+    m = _bf(torch.from_numpy(synth.det_uniform((n, cin, 2 * h, 2 * w), 4, -1, 1)))
+    if mask_mode == 1:
+        m = m.relu()
+        want = want * (m > 0)
+    elif mask_mode == 2:
+        m = F.leaky_relu(m, 0.2)
+        want = want * torch.where(m > 0, 1.0, 0.2)
+    packed = _pack(5, wt, cin, cout)
+    dyd = _nhwc_bf16(dy, 64 if cout <= 64 else 128)
+    md = _nhwc_bf16(m, cin) if mask_mode else None
+    dx = torch.empty(n, 2 * h, 2 * w, cin, dtype=torch.bfloat16, device="cuda")
+    nt.check(lib.tg_conv4x4s2_dgrad(nt.ptr(dyd), nt.ptr(packed), nt.ptr(md), mask_mode, nt.ptr(dx), n, h, w, cin, cout,
+                                    nt.stream_ptr()))
+    torch.cuda.synchronize()
+    got = dx.float().cpu().permute(0, 3, 1, 2)
+    assert _rel(got, want) <= 6e-3, _rel(got, want)
