@@ -202,7 +202,7 @@ int tg_gen_forward_train(const void* packed, int num_resblock, const float* x_nc
 int tg_gen_backward(const void* packed_dgrad, int num_resblock, const float* dout, const float* out,
                     float* flat_grad, void* workspace, size_t workspace_bytes, int n, int h, int w, void* stream);
 
-/* -------------------------------------------------- spatio-temporal discriminator (forward) ---- */
+/* -------------------------------------------------- spatio-temporal discriminator ---- */
 
 /* discriminator(args) of code/models.py:97-146 with nb = args.discrim_resblocks, ch = args.discrim_channels
  * (64 or 128), fc_in = in-features of fc (48 in the reference = 128x128 inputs; 3*(h/32)*(w/32) in general).
@@ -223,6 +223,19 @@ size_t tg_disc_workspace_bytes(int n, int h, int w, int nb, int ch);
 int tg_disc_forward(const float* flat_params, const void* packed, int nb, int ch, int fc_in, const float* x,
                     float* prob, float* const* feats, void* const* bn_running, int training,
                     void* workspace, size_t workspace_bytes, int n, int h, int w, void* stream);
+
+/* discriminator backward (code/train.py:340, scaler.scale(discrim_loss).backward()).  The reference detaches the
+ * discriminator's inputs (code/train.py:181,199) and the layer features (code/train.py:214), so the gradient enters
+ * through prob only and no input gradient is produced.
+ *   tg_disc_pack_dgrad: packs the data-gradient convolutions of every conv but conv.0 from the flat f32 parameters.
+ *   tg_disc_backward  : dprob = dL/dprob [n] f32, prob = the forward result; ADDS the parameter gradients into flat_grad
+ *                       (f32, same flat layout as the parameters).  Uses the workspace of the matching tg_disc_forward
+ *                       call (training != 0), which holds every activation and the batch statistics. */
+size_t tg_disc_packed_dgrad_bytes(int nb, int ch);
+int tg_disc_pack_dgrad(const float* flat_params, int nb, int ch, void* packed_dgrad, void* stream);
+int tg_disc_backward(const float* flat_params, const void* packed_dgrad, int nb, int ch, int fc_in,
+                     const float* dprob, const float* prob, float* flat_grad, void* workspace,
+                     size_t workspace_bytes, int n, int h, int w, void* stream);
 
 #ifdef __cplusplus
 }

@@ -65,7 +65,11 @@ struct DWorkspace {
   // (conv operand); per resblock: relu(conv1) (bf16)
   std::vector<size_t> raw, act, act16, mid;
   size_t r5, y5;                      // block5 raw conv [n,3,hw] f32, head fc input [n,3*hw] f32
-  size_t stats, partial, tickets, logit, total;
+  size_t stats, partial, tickets, logit;
+  // backward scratch (tg_disc_backward): gradient ping-pong of the residual stream, d(raw conv output), d(relu(conv1)),
+  // d(conv.0 pre-activation), d(block5 raw output), d(logit), BatchNorm reduction results
+  size_t g[2], d_raw, d_mid, d_a0, d_r5, d_logit, red;
+  size_t total;
 };
 static DWorkspace disc_ws(int n, int h, int w, int nb, int ch) {
   DWorkspace ws;
@@ -92,6 +96,12 @@ static DWorkspace disc_ws(int n, int h, int w, int nb, int ch) {
   ws.partial = take(bn_partial_floats() * 4);
   ws.tickets = take(256);
   ws.logit = take(static_cast<size_t>(n) * 4);
+  const size_t gmax = (px >> 2) * 128 * 2;        // largest gradient tensor below a0: stage 1 (64 ch) / stage 2 (128 ch @ 1/16)
+  ws.g[0] = take(gmax); ws.g[1] = take(gmax); ws.d_raw = take(gmax); ws.d_mid = take(gmax);
+  ws.d_a0 = take(px * 64 * 2);
+  ws.d_r5 = take(p5 * 64 * 2);
+  ws.d_logit = take(static_cast<size_t>(n) * 4);
+  ws.red = take(2 * 128 * 4);
   ws.total = o;
   return ws;
 }
@@ -224,4 +234,150 @@ extern "C" int tg_disc_forward(const float* flat_params, const void* packed, int
                           reinterpret_cast<float*>(wsp + ws.logit), prob, st);
   }
   return rc;
+}
+
+// =====================================================================================================
+// Backward (reference code/train.py:340: scaler.scale(discrim_loss).backward() through discriminator.forward).
+// The reference detaches the discriminator's inputs (code/train.py:181,199) and its layer features
+// (code/train.py:214), so the gradient enters through `prob` only and stops at conv.0's weights.
+// =====================================================================================================
+namespace tg {
+// packed data-gradient convolutions: one blob per conv except conv.0
+static std::vector<size_t> disc_dgrad_offsets(const DLayout& L, size_t* total) {
+  std::vector<size_t> off(L.convs.size(), 0);
+  size_t o = 0;
+  for (size_t i = 1; i < L.convs.size(); ++i) {
+    off[i] = o;
+    o += tg_packed_conv_bytes(L.convs[i].kind == kConv3x3 ? kPackConv3x3Dgrad : kPackConv4x4s2Dgrad, L.convs[i].cin,
+                              L.convs[i].cout);
+  }
+  if (total) *total = o;
+  return off;
+}
+}  // namespace tg
+
+extern "C" size_t tg_disc_packed_dgrad_bytes(int nb, int ch) {
+  if (check_cfg(nb, ch)) return 0;
+  size_t t = 0;
+  disc_dgrad_offsets(disc_layout(nb, ch, 48), &t);
+  return t;
+}
+
+extern "C" int tg_disc_pack_dgrad(const float* flat_params, int nb, int ch, void* packed_dgrad, void* stream) {
+  TG_CHECK_ARG(flat_params && packed_dgrad, "disc_pack_dgrad: null pointer");
+  if (int rc = check_cfg(nb, ch)) return rc;
+  TG_CHECK_ARG((reinterpret_cast<uintptr_t>(packed_dgrad) & 255) == 0, "disc_pack_dgrad: buffer must be 256-byte aligned");
+  const DLayout L = disc_layout(nb, ch, 48);
+  const std::vector<size_t> off = disc_dgrad_offsets(L, nullptr);
+  for (size_t i = 1; i < L.convs.size(); ++i) {
+    const DConv& c = L.convs[i];
+    int rc = tg_pack_weights(c.kind == kConv3x3 ? kPackConv3x3Dgrad : kPackConv4x4s2Dgrad, flat_params + c.w_off, nullptr, c.cin,
+                             c.cout, static_cast<uint8_t*>(packed_dgrad) + off[i], stream);
+    if (rc) return rc;
+  }
+  return TG_OK;
+}
+
+extern "C" int tg_disc_backward(const float* flat_params, const void* packed_dgrad, int nb, int ch, int fc_in,
+                                const float* dprob, const float* prob, float* flat_grad, void* workspace,
+                                size_t workspace_bytes, int n, int h, int w, void* stream) {
+  TG_CHECK_ARG(flat_params && packed_dgrad && dprob && prob && flat_grad && workspace, "disc_backward: null pointer");
+  if (int rc = check_cfg(nb, ch)) return rc;
+  TG_CHECK_ARG(n >= 1 && h >= 32 && w >= 32 && (h % 32) == 0 && (w % 32) == 0, "disc_backward: bad shape");
+  TG_CHECK_ARG(fc_in == 3 * (h / 32) * (w / 32), "disc_backward: fc in-features do not match the input size");
+  const DWorkspace ws = disc_ws(n, h, w, nb, ch);
+  if (workspace_bytes < ws.total) {
+    tg_set_error("disc_backward: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+    return TG_ERR_WORKSPACE;
+  }
+  const DLayout L = disc_layout(nb, ch, fc_in);
+  const std::vector<size_t> doff = disc_dgrad_offsets(L, nullptr);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* wsp = static_cast<uint8_t*>(workspace);
+  const uint8_t* pd = static_cast<const uint8_t*>(packed_dgrad);
+  float* stats_all = reinterpret_cast<float*>(wsp + ws.stats);
+  float* partial = reinterpret_cast<float*>(wsp + ws.partial);
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(wsp + ws.tickets);
+  float* red = reinterpret_cast<float*>(wsp + ws.red);
+  auto B = [&](size_t off) { return static_cast<void*>(wsp + off); };
+  int rc;
+
+  // weight (+ bias) gradient of conv `ci`; (hh, ww) = the conv's OUTPUT size
+  auto wgrad = [&](int ci, const void* x, const void* dy, int hh, int ww) {
+    const DConv& c = L.convs[ci];
+    const int cp = cin_padded(c.cin), op = c.cout <= 64 ? 64 : 128;
+    int r = (c.kind == kConv3x3) ? launch_wgrad3x3(x, dy, flat_grad + c.w_off, n, hh, ww, c.cin, c.cout, cp, op, st)
+                                 : launch_wgrad_conv4x4s2(x, dy, flat_grad + c.w_off, n, hh, ww, c.cin, c.cout, cp, op, st);
+    if (r || !c.has_bias) return r;
+    return launch_bias_grad(dy, static_cast<long long>(n) * hh * ww, op, c.cout, flat_grad + c.b_off, st);
+  };
+  // data gradient of conv `ci`; (hh, ww) = the conv's OUTPUT size; dx has the conv's input size
+  auto dgrad = [&](int ci, const void* dy, const void* resid, const void* mask, int mask_mode, void* dx, int hh, int ww) {
+    const DConv& c = L.convs[ci];
+    if (c.kind == kConv3x3)
+      return tg_conv3x3_dgrad(dy, pd + doff[ci], resid, mask, dx, n, hh, ww, c.cin, c.cout, stream);
+    return tg_conv4x4s2_dgrad(dy, pd + doff[ci], mask, mask_mode, dx, n, hh, ww, c.cin, c.cout, stream);
+  };
+  auto bn_bwd = [&](int bi, const void* g_out, const void* raw, const void* act, void* dx, long long pixels) {
+    const DBn& b = L.bns[bi];
+    return bn_bwd_launch(g_out, raw, act, dx, pixels, b.c, stats_all + static_cast<size_t>(bi) * 128 * 4, partial, tickets, red,
+                         flat_grad + b.g_off, flat_grad + b.b_off, st);
+  };
+
+  const int n_conv = static_cast<int>(L.convs.size()), n_bn = static_cast<int>(L.bns.size());
+  // head: dprob -> sigmoid -> fc -> LeakyReLU -> BatchNorm(3) -> d(block5 conv output)
+  {
+    const DBn& b = L.bns[n_bn - 1];
+    const int hw5 = (h / 32) * (w / 32);
+    rc = disc_head_bwd_launch(dprob, prob, reinterpret_cast<const float*>(wsp + ws.y5), reinterpret_cast<const float*>(wsp + ws.r5), n,
+                              hw5, stats_all + static_cast<size_t>(n_bn - 1) * 128 * 4, flat_params + L.fc_w, flat_grad + L.fc_w,
+                              flat_grad + L.fc_b, flat_grad + b.g_off, flat_grad + b.b_off,
+                              reinterpret_cast<float*>(wsp + ws.d_logit), B(ws.d_r5), st);
+    if (rc) return rc;
+  }
+  // walk the forward structure backwards.  Indices at the END of the forward pass:
+  int ci = n_conv - 1;                 // block5 conv
+  int bi = n_bn - 2;                   // block4 BN
+  int li = static_cast<int>(ws.raw.size()) - 1, mi = static_cast<int>(ws.mid.size()) - 1;
+  int cur = 0;
+  // block5 conv (64 -> 3, k4 s2): input = block4 output act16[li]
+  {
+    const int hh = h / 32, ww = w / 32;
+    if ((rc = wgrad(ci, B(ws.act16[li]), B(ws.d_r5), hh, ww))) return rc;
+    if ((rc = dgrad(ci, B(ws.d_r5), nullptr, nullptr, 0, B(ws.g[cur]), hh, ww))) return rc;
+    --ci;
+  }
+  for (int s = 3; s >= 0; --s) {
+    const int hh = h >> (s + 1), ww = w >> (s + 1);
+    const long long pixels = static_cast<long long>(n) * hh * ww;
+    if (s < 3) {
+      for (int i = nb - 1; i >= 0; --i) {
+        // act[li] = BN(conv2(mid[mi])) + act[li-1];  mid[mi] = relu(conv1(act16[li-1]) + b)
+        if ((rc = bn_bwd(bi, B(ws.g[cur]), B(ws.raw[li]), nullptr, B(ws.d_raw), pixels))) return rc;
+        --bi;
+        if ((rc = wgrad(ci, B(ws.mid[mi]), B(ws.d_raw), hh, ww))) return rc;
+        if ((rc = dgrad(ci, B(ws.d_raw), nullptr, B(ws.mid[mi]), kMaskRelu, B(ws.d_mid), hh, ww))) return rc;
+        --ci;
+        if ((rc = wgrad(ci, B(ws.act16[li - 1]), B(ws.d_mid), hh, ww))) return rc;
+        if ((rc = dgrad(ci, B(ws.d_mid), B(ws.g[cur]), nullptr, 0, B(ws.g[cur ^ 1]), hh, ww))) return rc;
+        --ci;
+        cur ^= 1; --li; --mi;
+      }
+    }
+    // discriminator_block: act[li] = lrelu(BN(conv4x4s2(input)))
+    if ((rc = bn_bwd(bi, B(ws.g[cur]), B(ws.raw[li]), B(ws.act[li]), B(ws.d_raw), pixels))) return rc;
+    --bi;
+    const void* input = (s == 0) ? B(ws.a0) : B(ws.act16[li - 1]);
+    if ((rc = wgrad(ci, input, B(ws.d_raw), hh, ww))) return rc;
+    if (s == 0) {
+      // input = a0 = lrelu(conv.0(x) + b): the LeakyReLU backward rides on the data gradient's epilogue
+      if ((rc = dgrad(ci, B(ws.d_raw), nullptr, B(ws.a0), kMaskLrelu02, B(ws.d_a0), hh, ww))) return rc;
+    } else {
+      if ((rc = dgrad(ci, B(ws.d_raw), nullptr, nullptr, 0, B(ws.g[cur ^ 1]), hh, ww))) return rc;
+      cur ^= 1;
+    }
+    --ci; --li;
+  }
+  // conv.0 (27 -> 64, bias): its input is detached in the reference -> weight / bias gradient only
+  return wgrad(0, B(ws.x_in), B(ws.d_a0), h, w);
 }

@@ -228,22 +228,22 @@ class discriminator(nn.Module):
             self._flat, self._packed, self._key = flat, packed, key
         return self._flat, self._packed
 
-    def forward(self, x):
+    def _dgrad_weights(self):
+        """packed weights of the data-gradient convolutions (training only); rebuilt with the forward cache."""
+        flat, _ = self._weights()
+        if getattr(self, "_packed_dgrad_key", None) != self._key:
+            lib = _nt.lib()
+            buf = torch.empty(lib.tg_disc_packed_dgrad_bytes(self.nb, self.ch), dtype=torch.uint8, device=flat.device)
+            _nt.check(lib.tg_disc_pack_dgrad(_nt.ptr(flat), self.nb, self.ch, _nt.ptr(buf), _nt.stream_ptr()))
+            self._packed_dgrad, self._packed_dgrad_key = buf, self._key
+        return self._packed_dgrad
+
+    def _run(self, x, ws):
+        """one tg_disc_forward launch sequence into workspace `ws`; returns (prob, feats)."""
         import ctypes
-        if not x.is_cuda:
-            raise RuntimeError("discriminator.forward: input must be a CUDA tensor (no CPU fallback)")
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError(
-                "tecogan_b200 discriminator: backward kernels are not built yet; call under torch.no_grad()")
-        if x.dim() != 4 or x.shape[1] != 27:
-            raise RuntimeError(f"discriminator.forward: expected [N,27,H,W], got {tuple(x.shape)}")
         lib = _nt.lib()
-        x = x.float().contiguous()
         n, _, h, w = x.shape
         flat, packed = self._weights()
-        need = lib.tg_disc_workspace_bytes(n, h, w, self.nb, self.ch)
-        if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
         prob = torch.empty((n, 1), dtype=torch.float32, device=x.device)
         shapes = [(n, 64, h // 2, w // 2), (n, self.ch, h // 4, w // 4), (n, self.ch, h // 8, w // 8), (n, 64, h // 16, w // 16)]
         feats = [torch.empty(s, dtype=torch.float32, device=x.device) for s in shapes]
@@ -255,9 +255,72 @@ class discriminator(nn.Module):
             run[3 * i + 1] = m.running_var.data_ptr()
             run[3 * i + 2] = m.num_batches_tracked.data_ptr()
         _nt.check(lib.tg_disc_forward(_nt.ptr(flat), _nt.ptr(packed), self.nb, self.ch, self.fc.in_features, _nt.ptr(x),
-                                      _nt.ptr(prob), feat_ptrs, run, 1 if self.training else 0, _nt.ptr(self._ws),
-                                      self._ws.numel(), n, h, w, _nt.stream_ptr()))
+                                      _nt.ptr(prob), feat_ptrs, run, 1 if self.training else 0, _nt.ptr(ws),
+                                      ws.numel(), n, h, w, _nt.stream_ptr()))
         return prob, feats
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("discriminator.forward: input must be a CUDA tensor (no CPU fallback)")
+        if x.dim() != 4 or x.shape[1] != 27:
+            raise RuntimeError(f"discriminator.forward: expected [N,27,H,W], got {tuple(x.shape)}")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if x.requires_grad:
+                raise NotImplementedError("tecogan_b200 discriminator: no gradient w.r.t. the input (the reference detaches it, "
+                                          "code/train.py:181,199)")
+            if not self.training:
+                raise RuntimeError("discriminator: backward needs train-mode BatchNorm (the reference never leaves it)")
+            prob, *feats = _DiscriminatorFn.apply(x, self, *[p for _, p in self.named_parameters()])
+            return prob, feats
+        lib = _nt.lib()
+        x = x.float().contiguous()
+        n, _, h, w = x.shape
+        need = lib.tg_disc_workspace_bytes(n, h, w, self.nb, self.ch)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        return self._run(x, self._ws)
+
+
+class _DiscriminatorFn(torch.autograd.Function):
+    """discriminator.forward with parameter gradients (code/train.py:340).  Each call owns its workspace (the reference
+    keeps two forward graphs alive, real and fake, before one backward).  Gradients enter through `prob`; the layer
+    features are returned detached exactly as the reference consumes them (code/train.py:214)."""
+
+    @staticmethod
+    def forward(ctx, x, module, *params):
+        lib = _nt.lib()
+        x = x.detach().float().contiguous()
+        n, _, h, w = x.shape
+        ws = torch.empty(lib.tg_disc_workspace_bytes(n, h, w, module.nb, module.ch), dtype=torch.uint8, device=x.device)
+        prob, feats = module._run(x, ws)
+        ctx.module, ctx.ws, ctx.shape = module, ws, (n, h, w)
+        ctx.flat, _ = module._weights()
+        ctx.packed_dgrad = module._dgrad_weights()
+        ctx.save_for_backward(prob)
+        ctx.mark_non_differentiable(*feats)
+        return (prob, *feats)
+
+    @staticmethod
+    def backward(ctx, dprob, *dfeats):
+        lib = _nt.lib()
+        (prob,) = ctx.saved_tensors
+        n, h, w = ctx.shape
+        module = ctx.module
+        params = [p for _, p in module.named_parameters()]
+        bucket = getattr(module, "_grad_bucket", None)
+        flat_grad = bucket if bucket is not None else torch.zeros(ctx.flat.numel(), dtype=torch.float32, device=prob.device)
+        g = dprob.float().contiguous()
+        _nt.check(lib.tg_disc_backward(_nt.ptr(ctx.flat), _nt.ptr(ctx.packed_dgrad), module.nb, module.ch, module.fc.in_features,
+                                       _nt.ptr(g), _nt.ptr(prob), _nt.ptr(flat_grad), _nt.ptr(ctx.ws), ctx.ws.numel(), n, h, w,
+                                       _nt.stream_ptr()))
+        ctx.ws = None
+        if bucket is not None:          # gradients were accumulated in place into the bound flat bucket (p.grad are views)
+            return (None, None) + (None,) * len(params)
+        grads, o = [], 0
+        for p in params:
+            grads.append(flat_grad[o:o + p.numel()].view_as(p).to(p.dtype))
+            o += p.numel()
+        return (None, None, *grads)
 
 
 def f_net():
