@@ -201,8 +201,32 @@ int tg_gen_forward_train(const void* packed, int num_resblock, const float* x_nc
                          size_t workspace_bytes, int n, int h, int w, void* stream);
 int tg_gen_backward(const void* packed_dgrad, int num_resblock, const float* dout, const float* out,
                     float* flat_grad, void* workspace, size_t workspace_bytes, int n, int h, int w, void* stream);
+/* The recurrent generator loop of a training step (code/train.py:86-111) for b clips of t frames, every activation of
+ * every frame kept: lr [b,t,3,h,w] f32 (r_inputs as the reference holds it) -> out [t,b,3,4h,4w] f32, FRAME-major.
+ * Frame f's input is cat(lr[:,f], s2d(deprocess(warp(out[f-1], flow(lr[:,f-1]))))) (zeros for f = 0), produced by the
+ * fused frame-input kernel; the generator inputs are detached in the reference (code/train.py:90,108), so the frames
+ * are independent in the backward pass: workspace = tg_gen_train_workspace_bytes(t*b, h, w, ...) holds image f*b + clip,
+ * and ONE tg_gen_backward(..., dout [t,b,3,4h,4w], out, ..., n = t*b, ...) back-propagates all frames as one batch. */
+int tg_gen_clip_forward_train(const void* packed, int num_resblock, const float* lr, float* out, void* workspace,
+                              size_t workspace_bytes, int b, int t, int h, int w, void* stream);
 
 /* -------------------------------------------------- spatio-temporal discriminator ---- */
+
+/* The discriminator's 27-channel input for t_batch = tb frame triplets in one pass (code/train.py:139-198 with
+ * Dt_mergeDs=True, pingpang=False): out [tb,27,4h,4w] f32 NCHW =
+ *   cat( before9[s]                                          [tb,9,4h,4w]  the triplet's target frames (:175),
+ *        crop_pad(grid_sample(src frames 3s..3s+2, T_vel))   warped targets (real, :165) or generator outputs (fake, :187),
+ *                                                            centre window kept and a border of crop_off pixels zeroed (:160-174),
+ *        bilinear x4 of lr9[s]                               [tb,9,h,w] LR frames (functional.resize, :176-178) ).
+ * Frame m = 3s+j is read at src + (m / ts)*src_stride_b + (m % ts)*src_stride_t (elements; [3,4h,4w] planes), so both the
+ * clip-major targets and the frame-major generator output of tg_gen_clip_forward_train are addressed in place.
+ * T_vel (:147-158) is computed on the fly from gsrc [tb*3,2,h,w], the LR planes the reference up-scales into its
+ * velocity field: class m%3 == 0 -> up4(4*gsrc[m]); 1 -> zeros; 2 -> 2*up4(4*gsrc[m]) - 1; each [2,4h,4w] block re-viewed
+ * as [4h,4w,2] like the reference's reshape.  grid_fp16 != 0 rounds the grid to fp16 (the fake path's .half(), :187). */
+int tg_disc_input_assemble(const float* before9, const float* src, long long src_stride_b, long long src_stride_t,
+                           int ts, const float* gsrc, const float* lr9, float* out, int tb, int h, int w,
+                           int crop_off, int grid_fp16, void* stream);
+
 
 /* discriminator(args) of code/models.py:97-146 with nb = args.discrim_resblocks, ch = args.discrim_channels
  * (64 or 128), fc_in = in-features of fc (48 in the reference = 128x128 inputs; 3*(h/32)*(w/32) in general).

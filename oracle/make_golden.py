@@ -52,6 +52,61 @@ def run_reference_loop(ref_models, ref_ops, G, r_inputs, crop):
     return ns["gen_outputs"]
 
 
+def grad_fingerprint(module):
+    """per-parameter (norm, projection on a fixed PCG64 direction) of .grad — a small, order-sensitive fingerprint."""
+    from oracle import synth
+    rows = []
+    for i, (_, p) in enumerate(module.named_parameters()):
+        g = p.grad.detach().double().flatten()
+        d = torch.from_numpy(synth.det_uniform((g.numel(),), 9000 + i, -1.0, 1.0)).double()
+        rows.append((float(g.norm()), float(g @ d)))
+    return np.array(rows, np.float64)
+
+
+def write_train_golden(ref_models, out_dir):
+    """One step of the UNMODIFIED reference train.FRVSR_Train (code/train.py:374-377 -> TecoGAN, :49-370) on CPU.
+    Shims: torch.Tensor.cuda -> identity; F.grid_sample casts the grid to the image dtype (CPU grid_sample
+    rejects the fp16 grid of train.py:98,187; the fp16 rounding itself is kept).  GradScaler / autocast disable
+    themselves without CUDA, so the step is plain fp32."""
+    import warnings
+    from oracle import synth, train_oracle
+    F = torch.nn.functional
+    warnings.filterwarnings("ignore")
+    orig_cuda, orig_gs = torch.Tensor.cuda, F.grid_sample
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    F.grid_sample = lambda inp, grid, *a, **k: orig_gs(inp, grid.to(inp.dtype), *a, **k)
+    try:
+        import train as ref_train
+        args = train_oracle.default_train_args()
+        G = ref_models.generator(3, args=args)
+        D = ref_models.discriminator(args=args)
+        G.load_state_dict({k: torch.from_numpy(v) for k, v in synth.fill_state_dict(G.state_dict(), seed=1, gain=1.0).items()})
+        D.load_state_dict({k: torch.from_numpy(v) for k, v in synth.fill_state_dict(D.state_dict(), seed=2, gain=1.0).items()})
+        og = torch.optim.Adam(G.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps)   # main.py:239-243
+        od = torch.optim.Adam(D.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps)
+        b = 2
+        r_in = torch.from_numpy(synth.det_uniform((b, 10, 3, 32, 32), 51, 0.0, 1.0))
+        r_tg = torch.from_numpy(synth.det_uniform((b, 10, 3, 128, 128), 52, 0.0, 1.0))
+        w0 = G.conv[0].weight.detach().clone()
+        out = ref_train.FRVSR_Train(r_in, r_tg, args, D, G, 0, 0.0, 0.0, og, od)
+        n = len(out.update_list)
+        np.savez_compressed(
+            os.path.join(out_dir, "train.npz"),
+            names=np.array(out.update_list_name[:n]),
+            update_list=np.array([float(v) for v in out.update_list], np.float64),
+            update_list_avg=np.array([float(v) for v in out.update_list_avg[:n]], np.float64),
+            tb=np.float64(float(out.tb)), dt_ratio=np.float64(float(out.update_list_avg[n + 1])),
+            d_loss=np.float64(float(out.d_loss)), gen_loss=np.float64(float(out.gen_loss)),
+            gen_output_sub=out.gen_output.detach()[:, :, :, ::8, ::8].numpy().astype(np.float32),
+            target_sub=out.target.detach()[:, :, ::8, ::8].numpy().astype(np.float32),
+            g_grad=grad_fingerprint(G), d_grad=grad_fingerprint(D),
+            g_conv0_step=(G.conv[0].weight.detach() - w0)[:4, :4].numpy(),
+            d_running_mean_block1=D.block1[1].running_mean.numpy(),
+            batch=b)
+    finally:
+        torch.Tensor.cuda, F.grid_sample = orig_cuda, orig_gs
+
+
 def main():
     from oracle import synth
     ref_models, ref_ops = import_reference()
@@ -102,6 +157,7 @@ def main():
                         f_abs_mean=np.array([f.abs().mean().item() for f in feats], np.float64),
                         f_mean=np.array([f.mean().item() for f in feats], np.float64),
                         running_mean_block1=D.block1[1].running_mean.numpy())
+    write_train_golden(ref_models, out_dir)
     print("golden fixtures written to", out_dir)
     for f in sorted(os.listdir(out_dir)):
         print(" ", f, os.path.getsize(os.path.join(out_dir, f)), "bytes")

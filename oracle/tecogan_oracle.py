@@ -135,6 +135,33 @@ class OracleDiscriminator(nn.Module):
         return torch.sigmoid(net), layer_list
 
 
+class _RoundBf16(torch.autograd.Function):
+    """x -> bf16 -> f32 in the forward direction; the gradient is rounded the same way (or passed through)."""
+
+    @staticmethod
+    def forward(ctx, x, round_grad):
+        ctx.round_grad = round_grad
+        return x.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.to(torch.bfloat16).float() if ctx.round_grad else g), None
+
+
+def emulate_bf16_operands(module, round_grads=True):
+    """Turn an oracle network into the fp32 model of what the bf16 tensor-core path computes: every convolution sees
+    bf16-rounded weights and bf16-rounded input activations (and, in the backward direction, bf16-rounded gradient
+    tensors), everything else — accumulation, bias, BatchNorm, activations, residual adds — stays fp32.  Used by the
+    gradient parity tests to separate kernel errors from the rounding noise that any bf16 implementation of the same
+    network has (the reference itself trains under fp16 autocast, code/train.py:68,335-342).  In place; returns module."""
+    for m in module.modules():
+        if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+            with torch.no_grad():
+                m.weight.copy_(m.weight.to(torch.bfloat16).float())
+            m.register_forward_pre_hook(lambda mod, inp: (_RoundBf16.apply(inp[0], round_grads),))
+    return module
+
+
 def load_numpy_state(module, named):
     """copy {name: np.ndarray} into module (strict)."""
     sd = {k: torch.from_numpy(np.array(v, copy=True)) for k, v in named.items()}

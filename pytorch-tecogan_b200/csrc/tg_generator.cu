@@ -285,33 +285,38 @@ static GenTrainWs gen_train_ws(int n, int h, int w, int nres) {
   return ws;
 }
 
-// forward plan with one buffer per activation (nothing is overwritten)
-static std::vector<FrLayer> gen_plan_train(const std::vector<GenLayer>& L, int nres, float* out, uint8_t* wsp, int n, int h,
-                                           int w) {
-  const GenTrainWs ws = gen_train_ws(n, h, w, nres);
+// forward plan with one buffer per activation (nothing is overwritten).  The workspace is laid out for n_total images;
+// the plan covers the n images starting at image n0 (one frame of a clip batch, tg_gen_clip_forward_train).
+static std::vector<FrLayer> gen_plan_train(const std::vector<GenLayer>& L, int nres, float* out, uint8_t* wsp, int n_total,
+                                           int n0, int h, int w) {
+  const GenTrainWs ws = gen_train_ws(n_total, h, w, nres);
+  const size_t px = static_cast<size_t>(h) * w;
   std::vector<FrLayer> P;
   int li = 0;
-  auto add = [&](size_t in, void* o, const void* resid, int relu, int hh, int ww) {
+  // img_bytes: bytes of one image in the buffer at `off`
+  auto at = [&](size_t off, size_t img_bytes) { return wsp + off + static_cast<size_t>(n0) * img_bytes; };
+  auto add = [&](const void* in, void* o, const void* resid, int relu, int hh, int ww) {
     FrLayer f{};
     f.kind = L[li].kind; f.cin_pad = cin_padded(L[li].cin); f.cout_pad = cout_padded(L[li].cout);
     f.out_mode = kOutNHWCbf16; f.relu = relu; f.h = hh; f.w = ww;
-    f.in = wsp + in; f.out = o; f.resid = resid; f.out2 = nullptr; f.blob_off = L[li].p_off; f.out_nstride = 0;
+    f.in = in; f.out = o; f.resid = resid; f.out2 = nullptr; f.blob_off = L[li].p_off; f.out_nstride = 0;
     P.push_back(f);
     ++li;
   };
-  add(ws.x_in, wsp + ws.net[0], nullptr, 1, h, w);
+  const size_t s1 = px * 128, s2 = px * 4 * 128, s2w = px * 4 * 256, s4w = px * 16 * 256, s4 = px * 16 * 128;
+  add(at(ws.x_in, s1), at(ws.net[0], s1), nullptr, 1, h, w);
   for (int k = 0; k < nres; ++k) {
-    add(ws.net[k], wsp + ws.t[k], nullptr, 1, h, w);
-    add(ws.t[k], wsp + ws.net[k + 1], wsp + ws.net[k], 0, h, w);
+    add(at(ws.net[k], s1), at(ws.t[k], s1), nullptr, 1, h, w);
+    add(at(ws.t[k], s1), at(ws.net[k + 1], s1), at(ws.net[k], s1), 0, h, w);
   }
-  add(ws.net[nres], wsp + ws.b0, nullptr, 1, h, w);
-  add(ws.b0, wsp + ws.b1, nullptr, 1, 2 * h, 2 * w);
-  add(ws.b1, wsp + ws.b2, nullptr, 0, 2 * h, 2 * w);
-  add(ws.b2, wsp + ws.c0, nullptr, 1, 2 * h, 2 * w);
-  add(ws.c0, wsp + ws.c1, nullptr, 0, 2 * h, 2 * w);
-  add(ws.c1, wsp + ws.d, nullptr, 1, 2 * h, 2 * w);
-  add(ws.d, wsp + ws.e, nullptr, 1, 4 * h, 4 * w);
-  add(ws.e, out, nullptr, 0, 4 * h, 4 * w);
+  add(at(ws.net[nres], s1), at(ws.b0, s2), nullptr, 1, h, w);
+  add(at(ws.b0, s2), at(ws.b1, s2), nullptr, 1, 2 * h, 2 * w);
+  add(at(ws.b1, s2), at(ws.b2, s2), nullptr, 0, 2 * h, 2 * w);
+  add(at(ws.b2, s2), at(ws.c0, s2w), nullptr, 1, 2 * h, 2 * w);
+  add(at(ws.c0, s2w), at(ws.c1, s2w), nullptr, 0, 2 * h, 2 * w);
+  add(at(ws.c1, s2w), at(ws.d, s4w), nullptr, 1, 2 * h, 2 * w);
+  add(at(ws.d, s4w), at(ws.e, s4), nullptr, 1, 4 * h, 4 * w);
+  add(at(ws.e, s4), out, nullptr, 0, 4 * h, 4 * w);
   P.back().out_mode = kOutNCHWf32Sigmoid;
   return P;
 }
@@ -366,11 +371,48 @@ extern "C" int tg_gen_forward_train(const void* packed, int num_resblock, const 
   uint8_t* wsp = static_cast<uint8_t*>(workspace);
   int rc = tg_pack_nchw_to_nhwc64(x_nchw, wsp + ws.x_in, n, 51, h, w, stream);
   if (rc) return rc;
-  const std::vector<FrLayer> P = gen_plan_train(L, num_resblock, out, wsp, n, h, w);
+  const std::vector<FrLayer> P = gen_plan_train(L, num_resblock, out, wsp, n, 0, h, w);
   size_t pb = 0;
   for (auto& l : L) pb += tg_packed_conv_bytes(l.kind, l.cin, l.cout);
   return launch_frame(P.data(), static_cast<int>(P.size()), packed, pb, n, reinterpret_cast<uint32_t*>(wsp + ws.flags),
                       ws.flag_count, false, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tg_gen_clip_forward_train(const void* packed, int num_resblock, const float* lr, float* out, void* workspace,
+                                         size_t workspace_bytes, int b, int t, int h, int w, void* stream) {
+  TG_CHECK_ARG(packed && lr && out && workspace, "gen_clip_forward_train: null pointer");
+  TG_CHECK_ARG(b >= 1 && t >= 1 && h >= 1 && w >= 1, "gen_clip_forward_train: bad shape");
+  TG_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "gen_clip_forward_train: workspace must be 256-byte aligned");
+  const GenTrainWs ws = gen_train_ws(b * t, h, w, num_resblock);
+  if (workspace_bytes < ws.total) {
+    tg_set_error("gen_clip_forward_train: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+    return TG_ERR_WORKSPACE;
+  }
+  auto L = gen_layers(num_resblock, nullptr, nullptr);
+  uint8_t* wsp = static_cast<uint8_t*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  size_t pb = 0;
+  for (auto& l : L) pb += tg_packed_conv_bytes(l.kind, l.cin, l.cout);
+  const long long lr_frame = 3LL * h * w, hr_frame = 48LL * h * w;
+  for (int f = 0; f < t; ++f) {
+    float* out_f = out + static_cast<long long>(f) * b * hr_frame;
+    const std::vector<FrLayer> P = gen_plan_train(L, num_resblock, out_f, wsp, b * t, f * b, h, w);
+    const size_t nflags = frame_flag_count(P.data(), static_cast<int>(P.size()), b);
+    if (nflags > ws.flag_count) {
+      tg_set_error("gen_clip_forward_train: internal flag capacity (%zu > %zu)", nflags, ws.flag_count);
+      return TG_ERR_WORKSPACE;
+    }
+    void* x_f = wsp + ws.x_in + static_cast<size_t>(f) * b * h * w * 128;
+    // frame input (flow upscale + warp + s2d + concat, code/train.py:94-107); clears the frame kernel's counters
+    int rc = fused_input_launch(lr + f * lr_frame, f ? lr + (f - 1) * lr_frame : nullptr,
+                                f ? out + static_cast<long long>(f - 1) * b * hr_frame : nullptr, x_f, b, h, w, lr_frame * t,
+                                hr_frame, reinterpret_cast<uint32_t*>(wsp + ws.flags), nflags, st);
+    if (rc) return rc;
+    rc = launch_frame(P.data(), static_cast<int>(P.size()), packed, pb, b, reinterpret_cast<uint32_t*>(wsp + ws.flags),
+                      ws.flag_count, true, st);
+    if (rc) return rc;
+  }
+  return TG_OK;
 }
 
 extern "C" int tg_gen_backward(const void* packed_dgrad, int num_resblock, const float* dout, const float* out,

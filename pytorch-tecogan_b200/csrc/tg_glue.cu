@@ -160,6 +160,64 @@ __global__ void warp_kernel(const float* __restrict__ img, const float2* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused producer of the spatio-temporal discriminator's input (reference code/train.py:139-198, Dt_mergeDs=True):
+// out[s, 0:9]   = before9[s]                                  the three target frames of triplet s        (:175)
+// out[s, 9:18]  = crop_pad(grid_sample(src frames 3s..3s+2, T_vel))   centre window kept, border zeroed  (:165-174,187-196)
+// out[s, 18:27] = bilinear x4 of the three LR frames                                                     (:176-178)
+// T_vel of frame m (class m % 3): 0 -> up4(4*gsrc[m]) (the forward 'flow'), 1 -> zeros, 2 -> 2*up4(4*gsrc[m]) - 1
+// (preprocess of the backward 'flow'), each [2,Ho,Wo] block re-viewed as [Ho,Wo,2] exactly as the reference's reshape
+// does (:156-157).  The velocity field is computed on the fly from the LR planes; nothing but `out` is written.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+disc_input_kernel(const float* __restrict__ before9, const float* __restrict__ src, long long src_stride_b,
+                  long long src_stride_t, int ts, const float* __restrict__ gsrc, const float* __restrict__ lr9,
+                  float* __restrict__ out, int tb, int h, int w, int crop_off, int grid_fp16) {
+  const int ho = 4 * h, wo = 4 * w;
+  const long long hw = static_cast<long long>(ho) * wo;
+  const long long total = static_cast<long long>(tb) * hw;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int s = static_cast<int>(i / hw);
+    const long long pix = i - s * hw;
+    const int y = static_cast<int>(pix / wo), x = static_cast<int>(pix - static_cast<long long>(y) * wo);
+    float* o = out + static_cast<long long>(s) * 27 * hw + pix;
+    const float* bf = before9 + static_cast<long long>(s) * 9 * hw + pix;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[k * hw] = __ldg(bf + k * hw);
+    const bool inside = y >= crop_off && y < ho - crop_off && x >= crop_off && x < wo - crop_off;
+    for (int j = 0; j < 3; ++j) {
+      const int m = s * 3 + j;
+      float v[3] = {0.f, 0.f, 0.f};
+      if (inside) {
+        float g[2] = {0.f, 0.f};
+        const int cls = m % 3;
+        if (cls != 1) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const long long flat = pix * 2 + k;                       // index inside the [2,Ho,Wo] block
+            const int ch = static_cast<int>(flat / hw);
+            const long long rem = flat - ch * hw;
+            const int yy = static_cast<int>(rem / wo), xx = static_cast<int>(rem - static_cast<long long>(yy) * wo);
+            float u = up4_sample(gsrc + (static_cast<long long>(m) * 2 + ch) * h * w, h, w, yy, xx, 4.f);
+            if (cls == 2) u = __fsub_rn(__fmul_rn(u, 2.f), 1.f);    // preprocess(): image * 2 - 1, no fused rounding
+            g[k] = grid_fp16 ? round_fp16(u) : u;
+          }
+        }
+        const Taps t = make_taps(g[0], g[1], ho, wo);
+        const float* frame = src + (m / ts) * src_stride_b + (m % ts) * src_stride_t;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = gather(frame + c * hw, wo, t);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[(9 + j * 3 + c) * hw] = v[c];
+    }
+    const float* lp = lr9 + static_cast<long long>(s) * 9 * h * w;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[(18 + k) * hw] = up4_sample(lp + static_cast<long long>(k) * h * w, h, w, y, x, 1.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fused producer of the generator input (reference main.py:186-213 as one pass):
 // one CTA = 8x8 LR pixels = 32x32 HR pixels.  Each thread warps 4 HR pixels (flow computed on the
 // fly from LR_{t-1}, rounded to fp16 as the reference does), applies (v+1)/2, and drops the
@@ -426,3 +484,20 @@ int sigmoid_bwd_pack_launch(const float* dout, const float* out, void* dz, int n
   return TG_OK;
 }
 }  // namespace tg
+
+extern "C" int tg_disc_input_assemble(const float* before9, const float* src, long long src_stride_b,
+                                      long long src_stride_t, int ts, const float* gsrc, const float* lr9, float* out,
+                                      int tb, int h, int w, int crop_off, int grid_fp16, void* stream) {
+  TG_CHECK_ARG(before9 && src && gsrc && lr9 && out, "disc_input_assemble: null pointer");
+  TG_CHECK_ARG(tb >= 1 && h >= 1 && w >= 1 && ts >= 3 && ts % 3 == 0, "disc_input_assemble: bad shape");
+  TG_CHECK_ARG(crop_off >= 0 && 2 * crop_off < 4 * h && 2 * crop_off < 4 * w, "disc_input_assemble: bad crop offset %d", crop_off);
+  const long long work = static_cast<long long>(tb) * 16 * h * w;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // bytes per HR pixel of a triplet: 9 targets + 9 gathered + 27 written (f32)
+  tg_prof_pre(TG_K_GLUE, 4.0 * 45.0 * work, st);
+  tg::disc_input_kernel<<<grid_for(work, 256, 16), 256, 0, st>>>(before9, src, src_stride_b, src_stride_t, ts, gsrc, lr9, out, tb,
+                                                                h, w, crop_off, grid_fp16);
+  tg_prof_post(st);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}

@@ -72,8 +72,12 @@ SIGNATURES = {
     "tg_gen_pack_dgrad": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p]),
     "tg_gen_forward_train": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_int, _c_int, _c_int,
                                       _c_void_p]),
+    "tg_gen_clip_forward_train": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_int, _c_int, _c_int,
+                                           _c_int, _c_void_p]),
     "tg_gen_backward": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_int, _c_int,
                                  _c_int, _c_void_p]),
+    "tg_disc_input_assemble": (_c_int, [_c_void_p, _c_void_p, _c_ll, _c_ll, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
+                                        _c_int, _c_int, _c_int, _c_void_p]),
     "tg_disc_param_count": (_c_size_t, [_c_int, _c_int, _c_int]),
     "tg_disc_packed_bytes": (_c_size_t, [_c_int, _c_int]),
     "tg_disc_pack": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),

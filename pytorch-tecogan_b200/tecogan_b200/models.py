@@ -51,14 +51,58 @@ class _GeneratorFn(torch.autograd.Function):
         module = ctx.module
         nres = int(module.num)
         g = grad_out.float().contiguous()
-        flat = torch.zeros(lib.tg_gen_param_count(nres), dtype=torch.float32, device=out.device)
-        _nt.check(lib.tg_gen_backward(_nt.ptr(ctx.packed_dgrad), nres, _nt.ptr(g), _nt.ptr(out), _nt.ptr(flat), _nt.ptr(ctx.ws),
-                                      ctx.ws.numel(), n, h, w, _nt.stream_ptr()))
-        grads, o = [], 0
-        for p in module._param_list():
-            grads.append(flat[o:o + p.numel()].view_as(p).to(p.dtype))
-            o += p.numel()
-        return (None, None, *grads)
+        return (None, None) + _gen_backward(module, ctx.packed_dgrad, g, out, ctx.ws, n, h, w)
+
+
+def _gen_backward(module, packed_dgrad, dout, out, ws, n, h, w):
+    """tg_gen_backward over n images; returns the per-parameter gradients, or Nones when the module has a flat gradient
+    bucket bound (tecogan_b200.parallel.bind_flat_grads: p.grad are views of the bucket, the kernels add in place)."""
+    lib = _nt.lib()
+    nres = int(module.num)
+    params = module._param_list()
+    bucket = getattr(module, "_grad_bucket", None)
+    flat = bucket if bucket is not None else torch.zeros(lib.tg_gen_param_count(nres), dtype=torch.float32, device=out.device)
+    _nt.check(lib.tg_gen_backward(_nt.ptr(packed_dgrad), nres, _nt.ptr(dout), _nt.ptr(out), _nt.ptr(flat), _nt.ptr(ws),
+                                  ws.numel(), n, h, w, _nt.stream_ptr()))
+    if bucket is not None:
+        return (None,) * len(params)
+    grads, o = [], 0
+    for p in params:
+        grads.append(flat[o:o + p.numel()].view_as(p).to(p.dtype))
+        o += p.numel()
+    return tuple(grads)
+
+
+class _GeneratorClipFn(torch.autograd.Function):
+    """The recurrent generator loop of a training step (code/train.py:86-111) as ONE autograd node: the forward runs the
+    T frames sequentially on the device (fused frame-input kernel + persistent frame kernel per frame, activations kept),
+    the backward is a single batched pass over all B*T frames — the reference detaches every generator input
+    (code/train.py:90,108), so the frames are independent in the backward direction."""
+
+    @staticmethod
+    def forward(ctx, lr, module, *params):
+        lib = _nt.lib()
+        lr = _nt.require_cuda_f32(lr.detach(), "forward_clip_train(r_inputs)")
+        b, t, c, h, w = lr.shape
+        nres = int(module.num)
+        packed = module.packed_weights()
+        ws = torch.empty(lib.tg_gen_train_workspace_bytes(b * t, h, w, nres), dtype=torch.uint8, device=lr.device)
+        out = torch.empty((t, b, 3, 4 * h, 4 * w), dtype=torch.float32, device=lr.device)
+        _nt.check(lib.tg_gen_clip_forward_train(_nt.ptr(packed), nres, _nt.ptr(lr), _nt.ptr(out), _nt.ptr(ws), ws.numel(),
+                                                b, t, h, w, _nt.stream_ptr()))
+        ctx.module, ctx.ws, ctx.shape = module, ws, (b * t, h, w)
+        ctx.packed_dgrad = module.packed_dgrad_weights()
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (out,) = ctx.saved_tensors
+        n, h, w = ctx.shape
+        g = grad_out.float().contiguous()
+        grads = _gen_backward(ctx.module, ctx.packed_dgrad, g, out, ctx.ws, n, h, w)
+        ctx.ws = None
+        return (None, None) + grads
 
 
 class generator(nn.Module):
@@ -151,6 +195,13 @@ class generator(nn.Module):
         _nt.check(lib.tg_gen_forward(_nt.ptr(packed), int(self.num), _nt.ptr(x_nhwc), _nt.ptr(out), _nt.ptr(logits),
                                      _nt.ptr(ws), ws.numel(), n, h, w, int(self.amode), _nt.stream_ptr()))
         return (out, logits) if return_logits else out
+
+    def forward_clip_train(self, r_inputs):
+        """code/train.py:86-114 on the device: r_inputs [B,T,3,H,W] -> generator outputs [T,B,3,4H,4W] (FRAME-major, f32,
+        differentiable w.r.t. the parameters; ``.transpose(0, 1)`` gives the reference's [B,T,...] order)."""
+        if r_inputs.dim() != 5 or r_inputs.shape[2] != 3:
+            raise RuntimeError(f"forward_clip_train: expected [B,T,3,H,W], got {tuple(r_inputs.shape)}")
+        return _GeneratorClipFn.apply(r_inputs, self, *self._param_list())
 
     @torch.no_grad()
     def infer_clip(self, r_inputs):

@@ -1,0 +1,89 @@
+"""Data-parallel plumbing for the training step: one process per GPU, both networks replicated, the batch
+of clips split across ranks, and ONE exchange per network and step — an all-reduce (mean) of its flat f32 gradient
+bucket over NCCL / NVLink, issued right after that network's backward pass so that it overlaps the other network's
+backward.  No other collective exists on the path (BatchNorm statistics stay per rank, as torch DDP's default).
+
+The backward kernels ADD parameter gradients straight into a flat buffer laid out like the flat parameter vector
+(include/tecogan_b200.h: tg_gen_backward / tg_disc_backward ``flat_grad``).  ``bind_flat_grads`` makes every
+``p.grad`` a view of that buffer, so the optimizer (stock Adam, main.py:239-243) and GradScaler see ordinary gradients
+while the collective moves one contiguous 7 MB (generator) / 13 MB (discriminator) message.
+"""
+import torch
+import torch.distributed as dist
+
+
+def bind_flat_grads(module):
+    """Allocate (once) the module's flat gradient bucket and point every parameter's ``.grad`` into it."""
+    params = [p for _, p in module.named_parameters()]
+    bucket = getattr(module, "_grad_bucket", None)
+    total = sum(p.numel() for p in params)
+    if bucket is None or bucket.numel() != total or bucket.device != params[0].device:
+        bucket = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+        module._grad_bucket = bucket
+    o = 0
+    for p in params:
+        p.grad = bucket[o:o + p.numel()].view_as(p)
+        o += p.numel()
+    return bucket
+
+
+def zero_flat_grads(module):
+    """optimizer.zero_grad() for a bound module: clear the bucket and re-point the ``.grad`` views (the optimizer's own
+    zero_grad(set_to_none=True) would drop them)."""
+    bucket = bind_flat_grads(module)
+    bucket.zero_()
+    return bucket
+
+
+def unbind_flat_grads(module):
+    if getattr(module, "_grad_bucket", None) is not None:
+        module._grad_bucket = None
+        for p in module.parameters():
+            p.grad = None
+
+
+def world_size():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class GradSync:
+    """Asynchronous mean all-reduce of one flat bucket.  ``start`` enqueues the collective behind the kernels already on
+    the current stream (NCCL runs it on its own stream: later kernels of the current stream overlap it); ``finish``
+    makes the current stream wait for it and applies the 1/world scaling."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.work = None
+        self.bucket = None
+
+    def start(self, bucket):
+        if world_size() == 1:
+            return
+        self.bucket = bucket
+        self.work = dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self):
+        if self.work is None:
+            return
+        self.work.wait()
+        self.bucket.mul_(1.0 / dist.get_world_size(self.group))
+        self.work = None
+        self.bucket = None
+
+
+def shard_batch(t, rank=None, world=None):
+    """rank's contiguous share of the clip (batch) dimension; the global batch must divide evenly (cfg5: 32 clips)."""
+    world = world_size() if world is None else world
+    rank = (dist.get_rank() if world > 1 else 0) if rank is None else rank
+    if t.shape[0] % world:
+        raise RuntimeError(f"global batch {t.shape[0]} does not divide over {world} ranks")
+    per = t.shape[0] // world
+    return t[rank * per:(rank + 1) * per]
+
+
+def broadcast_parameters(module, src=0):
+    """make the replicas identical before the first step (parameters and BatchNorm buffers)."""
+    if world_size() == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src)

@@ -1,0 +1,236 @@
+"""Host-side mirror of the reference ``code/train.py``: ``TecoGAN`` / ``FRVSR_Train`` with the reference's signature,
+return type (the ``Network`` namedtuple, code/train.py:357-360) and logged quantities, running on the B200 kernels.
+
+What changes relative to the reference's step (same arithmetic):
+  * the recurrent generator loop (code/train.py:86-114) is one autograd node: T sequential device-side frames forward
+    (fused flow-upscale + warp + space-to-depth + concat kernel, then the persistent tcgen05 frame kernel), ONE batched
+    backward over all B*T frames (the reference detaches every generator input, :90,108);
+  * the discriminator's 27-channel inputs (:139-198: warp of 9-frame groups, centre crop + zero pad, LR resize, concat)
+    come from one fused kernel per branch (tg_disc_input_assemble), the velocity field computed on the fly;
+  * parameter gradients are accumulated by the wgrad kernels directly in one flat f32 bucket per network
+    (tecogan_b200.parallel); under torch.distributed each bucket is all-reduced asynchronously right after its
+    backward, overlapping the other network's backward;
+  * no ``.cpu()`` hops (:294-301) — every scalar stays on the device.
+Only the configuration the reference can actually run is supported: pingpang=False, Dt_mergeDs=True,
+vgg_scaling <= 0 (the VGG branch of the reference is broken); anything else raises.
+"""
+import collections
+
+import torch
+
+from . import _native as _nt
+from . import parallel as _par
+from .models import *  # noqa: F401,F403  (reference: `from models import *`, code/train.py:1)
+
+VGG_MEAN = [123.68, 116.78, 103.94]          # code/train.py:6
+identity = torch.nn.Identity()               # code/train.py:7
+
+scaler = None                                # code/train.py:9 (created on first use: needs a CUDA device)
+
+
+def _scaler():
+    global scaler
+    if scaler is None:
+        scaler = torch.amp.GradScaler("cuda")
+    return scaler
+
+
+class EMA(torch.nn.Module):
+    """code/train.py:13-26"""
+
+    def __init__(self, mu):
+        super().__init__()
+        self.mu = mu
+        self.shadow = {}
+
+    def register(self, name, val):
+        self.shadow[name] = val.clone()
+
+    def forward(self, name, x):
+        assert name in self.shadow
+        new_average = self.mu * x + (1.0 - self.mu) * self.shadow[name]
+        self.shadow[name] = new_average.clone()
+        return new_average
+
+
+def VGG19_slim(input, reuse, deep_list=None, norm_flag=True):
+    """code/train.py:30-45 cannot run in the reference (VGG19() lacks its required arguments, torch.min(...) + float;
+    SURVEY.md 8c) and vgg_scaling defaults to -0.002 (main.py:98), so the branch is never taken."""
+    raise NotImplementedError("the reference's VGG perceptual branch is unrunnable (SURVEY.md 8c); vgg_scaling must stay <= 0")
+
+
+Network = collections.namedtuple('Network', 'gen_output, learning_rate, update_list, update_list_name, update_list_avg, '
+                                            'global_step, d_loss, gen_loss, fnet_loss ,tb, target')
+
+
+def _check_args(args, r_inputs):
+    if getattr(args, "pingpang", False):
+        raise NotImplementedError("tecogan_b200.train: pingpang=True is not built (reference default False, main.py:101)")
+    if not getattr(args, "Dt_mergeDs", True):
+        raise NotImplementedError("tecogan_b200.train: Dt_mergeDs=False is not built (reference default True, main.py:117)")
+    if float(getattr(args, "vgg_scaling", -1.0)) > 0.0:
+        VGG19_slim(None, None)
+    if r_inputs.dim() != 5 or r_inputs.shape[2] != 3 or r_inputs.shape[3] != r_inputs.shape[4]:
+        raise RuntimeError(f"TecoGAN: r_inputs must be [B,T,3,crop,crop], got {tuple(r_inputs.shape)}")
+    if int(args.crop_size) != r_inputs.shape[3] or int(args.RNN_N) != r_inputs.shape[1]:
+        raise RuntimeError("TecoGAN: args.crop_size / args.RNN_N do not match r_inputs")
+
+
+def discriminator_inputs(r_inputs, r_targets, gen_tb, args):
+    """code/train.py:130-198 -> (real_input, fake_input), each [t_batch,27,4c,4c] f32.
+    r_inputs [B,T,3,c,c], r_targets [B,T,3,4c,4c], gen_tb = generator outputs FRAME-major [T,B,3,4c,4c]."""
+    lib = _nt.lib()
+    b, t, _, c, _ = r_inputs.shape
+    hc = 4 * c
+    ts = 3 * (t // 3)                                          # :130
+    tb = b * ts // 3                                           # :135
+    off = 0
+    if args.crop_dt < 1.0:                                     # :160-164
+        off = (hc - int(hc * args.crop_dt)) // 2
+    lr9 = r_inputs[:, :ts].contiguous()                        # :176-177, [B,ts,3,c,c] == [tb,9,c,c]
+    tgt9 = r_targets[:, :ts].contiguous()                      # :133-134,175
+    # LR planes the reference up-scales into T_vel (:139-158); class = frame % 3
+    gsrc = torch.zeros((b, ts // 3, 3, 2, c, c), dtype=torch.float32, device=r_inputs.device)
+    gsrc[:, :, 0] = r_inputs[:, 0:ts:3, 0:2]                   # VPre  = gen_flow[:, 0:ts:3]           (:147)
+    back = torch.cat((r_inputs[:, 2:ts:3], r_inputs[:, 1:ts:3]), dim=1).reshape(tb, 6, c, c)     # :139-141
+    gsrc[:, :, 2] = back[0:b].reshape(b, ts // 3, 2, c, c)     # VNxt = preprocess(up4(4 * back[0:B]))  (:143-145,149)
+    outs = []
+    for src, sb, st_, fp16 in ((tgt9, ts * 3 * hc * hc, 3 * hc * hc, 0),            # real: grid_sample(t_targets, T_vel)   (:165)
+                               (gen_tb.detach(), 3 * hc * hc, b * 3 * hc * hc, 1)):  # fake: grid_sample(t_gen, T_vel.half()) (:187)
+        out = torch.empty((tb, 27, hc, hc), dtype=torch.float32, device=r_inputs.device)
+        _nt.check(lib.tg_disc_input_assemble(_nt.ptr(tgt9), _nt.ptr(src), sb, st_, ts, _nt.ptr(gsrc), _nt.ptr(lr9), _nt.ptr(out),
+                                             tb, c, c, off, fp16, _nt.stream_ptr()))
+        outs.append(out)
+    return outs[0], outs[1]
+
+
+def _warp_loss(r_inputs):
+    """code/train.py:71-85,247-249 — logged only: LR frame t-1 sampled with LR_t[:, 0:2] re-viewed as a grid (f32)."""
+    b, t, _, c, _ = r_inputs.shape
+    pre = r_inputs[:, :-1].reshape(b * (t - 1), 3, c, c)
+    cur = r_inputs[:, 1:]
+    grid = cur[:, :, 0:2].reshape(b * (t - 1), c, c, 2)
+    s_warp = torch.nn.functional.grid_sample(pre, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+    return torch.mean(torch.sum(torch.square(cur.reshape(b * (t - 1), 3, c, c) - s_warp), dim=[3]))
+
+
+def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step, counter1, counter2, optimizer_g,
+            optimizer_d, GAN_FLAG=True):
+    """code/train.py:49-370."""
+    if not GAN_FLAG:
+        raise NotImplementedError("tecogan_b200.train: GAN_FLAG=False is not built (the reference always passes True)")
+    r_inputs = _nt.require_cuda_f32(r_inputs, "TecoGAN(r_inputs)")
+    r_targets = _nt.require_cuda_f32(r_targets, "TecoGAN(r_targets)")
+    _check_args(args, r_inputs)
+    Global_step += 1                                                                       # :52
+    b, t, _, c, _ = r_inputs.shape
+    hc = 4 * c
+    learning_rate = args.learning_rate
+
+    # ---- generator: all frames (:86-114)
+    gen_tb = generator_F.forward_clip_train(r_inputs)                                      # [T,B,3,hc,hc]
+    gen_outputs = gen_tb.transpose(0, 1)                                                   # [B,T,3,hc,hc] (view)
+    update_list, update_list_name = [], []
+
+    # ---- discriminator on real / fake triplets (:130-199)
+    real_in, fake_in = discriminator_inputs(r_inputs, r_targets, gen_tb, args)
+    tdiscrim_real_output, real_layers = discriminator_F(real_in)                           # :181
+    tdiscrim_fake_output, fake_layers = discriminator_F(fake_in)                           # :199 (input detached)
+
+    # ---- layer losses (:203-232), detached on both sides
+    sum_layer_loss = 0
+    if args.D_LAYERLOSS:
+        layer_norm = [12.0, 14.0, 24.0, 100.0]
+        for i, (rl, fl) in enumerate(zip(real_layers, fake_layers)):
+            layer_loss = torch.mean(torch.sum(torch.abs(rl.detach() - fl.detach()), dim=[3]))
+            update_list.append(layer_loss)
+            update_list_name.append("D_layer_%d_loss" % i)
+            sum_layer_loss = sum_layer_loss + 0.02 * layer_loss / layer_norm[i]
+        update_list.append(sum_layer_loss)
+        update_list_name.append("D_layer_loss_sum")
+
+    # ---- content / warp losses (:235-249)
+    content_loss = torch.mean(torch.sum(torch.square(gen_outputs - r_targets), dim=[4]))   # == mean over [B*T,3,hc] rows (:239)
+    update_list.append(content_loss)
+    update_list_name.append("l2_content_loss")
+    update_list.append(_warp_loss(r_inputs))
+    update_list_name.append("l2_warp_loss")
+
+    # ---- adversarial terms (:288-301).  gen_loss, fnet_loss and content_loss are ONE tensor in the reference (:243-244),
+    # updated in place: the adversarial term lands twice and the logged l2_content_loss equals All_loss_Gen.  Both extra
+    # terms are detached: the generator's gradient is the content loss's alone.
+    t_adversarial_loss = torch.mean(-torch.log(tdiscrim_fake_output.detach() + args.EPS))
+    d_adversarial_loss = torch.mean(-torch.log(tdiscrim_fake_output + args.EPS))
+    dt_ratio = torch.minimum(torch.tensor(float(args.Dt_ratio_max)),
+                             args.Dt_ratio_0 + args.Dt_ratio_add * torch.tensor(Global_step, dtype=torch.float32))
+    gen_loss = content_loss
+    fnet_loss = content_loss
+    gen_loss += args.ratio * t_adversarial_loss
+    fnet_loss += args.ratio * t_adversarial_loss
+    update_list.append(t_adversarial_loss)
+    update_list_name.append("t_adversarial_loss")
+    if args.D_LAYERLOSS:
+        gen_loss += sum_layer_loss * float(dt_ratio)
+
+    # ---- discriminator loss (:303-322)
+    t_discrim_fake_loss = torch.log(1 - tdiscrim_fake_output + args.EPS)
+    t_discrim_real_loss = torch.log(tdiscrim_real_output + args.EPS)
+    t_discrim_loss = torch.mean(-(t_discrim_fake_loss + t_discrim_real_loss))
+    t_balance = torch.mean(t_discrim_real_loss) + d_adversarial_loss
+    update_list += [t_discrim_loss, torch.mean(tdiscrim_real_output), torch.mean(tdiscrim_fake_output)]
+    update_list_name += ["t_discrim_loss", "t_discrim_real_output", "t_discrim_fake_output"]
+    discrim_loss = t_discrim_loss
+
+    # ---- EMA bookkeeping (:324-332): one shadow chained through the list, started from zero -> a lower-triangular
+    # weighting of the stacked scalars, done as one small mat-vec instead of 3 kernels per entry
+    tb = 0.99 * t_balance.detach()
+    update_list += [gen_loss]
+    update_list_name += ["All_loss_Gen"]
+    vals = torch.stack([v.detach().float().reshape(()) for v in update_list])
+    k = vals.numel()
+    idx = torch.arange(k, device=vals.device)
+    expo = (idx[:, None] - idx[None, :]).clamp(min=0).float()
+    tri = torch.where(idx[:, None] >= idx[None, :], 0.99 * torch.pow(torch.tensor(0.01, device=vals.device), expo),
+                      torch.zeros((), device=vals.device))
+    update_list_avg = list(tri @ vals)
+
+    # ---- backward + optimizer steps (:335-342).  Reference order: G backward, G step, update, D backward, D step, update.
+    # Here both backward passes run first (each followed by its asynchronous gradient all-reduce when data-parallel),
+    # then the steps in the reference's order; should the first update() change the loss scale, the discriminator's
+    # gradients are rescaled by the (power-of-two) ratio, which is what scaling its loss with the new scale produces.
+    sc = _scaler()
+    sync_g, sync_d = _par.GradSync(), _par.GradSync()
+    optimizer_g.zero_grad()
+    g_bucket = _par.zero_flat_grads(generator_F)
+    scale0 = sc.get_scale() if sc.is_enabled() else 1.0
+    sc.scale(gen_loss).backward()
+    sync_g.start(g_bucket)
+    optimizer_d.zero_grad()
+    d_bucket = _par.zero_flat_grads(discriminator_F)
+    sc.scale(discrim_loss).backward()
+    sync_d.start(d_bucket)
+    sync_g.finish()
+    sc.step(optimizer_g)
+    sc.update()
+    sync_d.finish()
+    scale1 = sc.get_scale() if sc.is_enabled() else 1.0
+    if scale1 != scale0:
+        d_bucket.mul_(scale1 / scale0)
+    sc.step(optimizer_d)
+    sc.update()
+
+    update_list_avg += [tb, dt_ratio]
+    update_list_name += ["t_balance", "Dst_ratio"]
+    update_list_avg += [counter1, counter2]
+    update_list_name += ["withD_counter", "w_o_D_counter"]
+    # callers .view() the generator output (main.py:287-289): hand it back contiguous in the reference's [B,T,...] order
+    return Network(gen_output=gen_outputs.contiguous(), learning_rate=learning_rate, update_list=update_list,
+                   update_list_name=update_list_name, update_list_avg=update_list_avg, global_step=Global_step,
+                   d_loss=discrim_loss, gen_loss=gen_loss, fnet_loss=fnet_loss, tb=tb, target=real_in)
+
+
+def FRVSR_Train(r_inputs, r_targets, args, discriminator_F, generator_F, step, counter1, counter2, optimizer_g,
+                optimizer_d):
+    """code/train.py:374-377"""
+    return TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, step, counter1, counter2, optimizer_g,
+                   optimizer_d)

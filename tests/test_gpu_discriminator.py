@@ -128,15 +128,28 @@ def _grad_report(D, ref):
     return rows
 
 
+def _global_cos(D, ref):
+    g_all = torch.cat([p.grad.detach().cpu().double().flatten() for p in D.parameters()])
+    w_all = torch.cat([p.grad.double().flatten() for p in ref.parameters()])
+    return float(torch.dot(g_all, w_all) / (g_all.norm() * w_all.norm()))
+
+
 @pytest.mark.parametrize("nb,ch,n", [(4, 128, 4), (1, 64, 12)])
 def test_backward_vs_oracle(nb, ch, n):
-    """code/train.py:303-307,340: discrim_loss = mean(-(log(1 - D(fake) + EPS) + log(D(real) + EPS))) back-propagated through
-    two forward passes that are alive at the same time.  Parameter gradients against torch CPU autograd on the oracle
-    (fp32).  Measured on B200: conv weights 0.97-0.9999, the per-channel BatchNorm / bias gradients (long reductions of
-    bf16 gradient tensors behind up to 27 bf16 layers and 13 re-normalising BatchNorms) 0.957-0.99; bars: cosine >= 0.95
-    per tensor, norm ratio within 10 %, global cosine >= 0.99."""
+    """code/train.py:303-307,340: discrim_loss = mean(-(log(1 - D(fake) + EPS) + log(D(real) + EPS))) back-propagated
+    through two forward passes that are alive at the same time; parameter gradients against torch CPU autograd.
+
+    A random-init discriminator on noise inputs is chaotic in its gradients: every (Leaky)ReLU whose input sits within
+    rounding noise of zero flips its mask, and 27 layers / 13 re-normalising BatchNorms amplify that.  Measured on CPU:
+    the fp32 oracle with bf16-rounded conv operands (O.emulate_bf16_operands — the arithmetic the tensor-core path
+    implements) has overall cosine 0.976 against the plain fp32 oracle (per tensor down to 0.954), i.e. any two correct
+    evaluations in different arithmetic sit ~0.98 apart.  Measured on B200: 0.985 / 0.997 against the bf16-operand
+    oracle, 0.978 / 0.991 against fp32 for the two configurations.  Bars: vs bf16-operand oracle cosine >= 0.97 per
+    tensor and >= 0.98 overall; vs fp32 overall >= 0.97 and gradient norm within 5 %."""
     torch.set_num_threads(8)
     ref, D = _make(nb, ch, 32)
+    emu, _ = _make(nb, ch, 32)
+    O.emulate_bf16_operands(emu)
     real = torch.from_numpy(synth.det_uniform((n, 27, 128, 128), 41, -1.0, 1.0))
     fake = torch.from_numpy(synth.det_uniform((n, 27, 128, 128), 42, -1.0, 1.0))
     eps = 1e-12
@@ -149,20 +162,23 @@ def test_backward_vs_oracle(nb, ch, n):
 
     lw = loss_of(ref, "cpu")
     lw.backward()
+    loss_of(emu, "cpu").backward()
     lg = loss_of(D, "cuda")
     (lg * 1024.0).backward()              # GradScaler-style loss scaling (code/train.py:340)
     for p in D.parameters():
         p.grad /= 1024.0
     assert abs(lg.item() - lw.item()) <= 1e-2 * max(1.0, abs(lw.item()))
-    rows = _grad_report(D, ref)
-    g_all = torch.cat([p.grad.detach().cpu().double().flatten() for p in D.parameters()])
-    w_all = torch.cat([p.grad.double().flatten() for p in ref.parameters()])
-    cos = float(torch.dot(g_all, w_all) / (g_all.norm() * w_all.norm()))
-    print(f"D backward nb={nb} ch={ch} n={n}: global cosine {cos:.5f}, worst tensors "
-          f"{sorted(rows, key=lambda r: r[1])[:4]}")
-    bad = [r for r in rows if r[1] < 0.95 or not (0.9 <= r[2] <= 1.1)]
-    assert not bad, (cos, bad)
-    assert cos >= 0.99, cos
+    rows = _grad_report(D, emu)
+    cos_emu, cos_f32 = _global_cos(D, emu), _global_cos(D, ref)
+    print(f"D backward nb={nb} ch={ch} n={n}: cosine vs bf16-operand oracle {cos_emu:.5f} (worst tensors "
+          f"{[(r[0], round(r[1], 4), round(r[2], 3)) for r in sorted(rows, key=lambda r: r[1])[:4]]}), vs fp32 oracle {cos_f32:.5f}")
+    bad = [r for r in rows if r[1] < 0.97 or not (0.9 <= r[2] <= 1.1)]
+    assert not bad, (cos_emu, bad)
+    assert cos_emu >= 0.98, cos_emu
+    assert cos_f32 >= 0.97, cos_f32
+    g_n = torch.cat([p.grad.detach().cpu().double().flatten() for p in D.parameters()]).norm()
+    w_n = torch.cat([p.grad.double().flatten() for p in ref.parameters()]).norm()
+    assert 0.95 <= float(g_n / w_n) <= 1.05
 
 
 def test_backward_needs_no_input_grad_and_accumulates():

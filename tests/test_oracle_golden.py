@@ -82,3 +82,42 @@ def test_discriminator_vs_reference(golden_dir):
     np.testing.assert_allclose(feats[3].numpy(), g["f4"], rtol=0, atol=1e-4)
     np.testing.assert_allclose([f.abs().mean().item() for f in feats], g["f_abs_mean"], rtol=1e-5)
     np.testing.assert_allclose(D.block1[1].running_mean.numpy(), g["running_mean_block1"], rtol=0, atol=1e-6)
+
+
+def test_train_step_oracle_vs_reference(golden_dir):
+    """oracle/train_oracle.py against one step of the unmodified reference train.FRVSR_Train (tests/golden/train.npz):
+    every logged scalar, the EMA list, the generator outputs, the discriminator's real input, both nets' gradients
+    (per-tensor norm + projection fingerprint) and the Adam update."""
+    from oracle import train_oracle as TO
+    g = _load(golden_dir, "train.npz")
+    torch.set_num_threads(8)
+    args = TO.default_train_args()
+    G = O.OracleGenerator(3, 16)
+    D = O.OracleDiscriminator(4, 128, 48)
+    O.load_numpy_state(G, synth.fill_state_dict(G.state_dict(), seed=1, gain=1.0))
+    O.load_numpy_state(D, synth.fill_state_dict(D.state_dict(), seed=2, gain=1.0))
+    og = torch.optim.Adam(G.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps)
+    od = torch.optim.Adam(D.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps)
+    b = int(g["batch"])
+    r_in = torch.from_numpy(synth.det_uniform((b, 10, 3, 32, 32), 51, 0.0, 1.0))
+    r_tg = torch.from_numpy(synth.det_uniform((b, 10, 3, 128, 128), 52, 0.0, 1.0))
+    w0 = G.conv[0].weight.detach().clone()
+    out = TO.train_step(G, D, og, od, r_in, r_tg, args, 0)
+    assert list(out["log"].keys()) == [str(n) for n in g["names"]]
+    np.testing.assert_allclose(list(out["log"].values()), g["update_list"], rtol=2e-5)
+    np.testing.assert_allclose(out["log_avg"], g["update_list_avg"], rtol=2e-5)
+    np.testing.assert_allclose([out["tb"], out["dt_ratio"], out["d_loss"], out["gen_loss"]],
+                               [g["tb"], g["dt_ratio"], g["d_loss"], g["gen_loss"]], rtol=2e-5)
+    np.testing.assert_allclose(out["gen_output"][:, :, :, ::8, ::8].numpy(), g["gen_output_sub"], atol=2e-6)
+    np.testing.assert_allclose(out["target"][:, :, ::8, ::8].numpy(), g["target_sub"], atol=2e-6)
+    for mod, key in ((G, "g_grad"), (D, "d_grad")):
+        for i, (name, p) in enumerate(mod.named_parameters()):
+            gr = p.grad.detach().double().flatten()
+            d = torch.from_numpy(synth.det_uniform((gr.numel(),), 9000 + i, -1.0, 1.0)).double()
+            want_norm, want_proj = g[key][i]
+            assert abs(float(gr.norm()) - want_norm) <= 3e-3 * want_norm + 1e-9, (name, float(gr.norm()), want_norm)
+            # fp32 summation order (thread count, oneDNN blocking) moves the discriminator's BatchNorm-coupled gradients by
+            # a few 1e-3 of their norm between runs of the reference itself
+            assert abs(float(gr @ d) - want_proj) <= 1e-2 * want_norm + 1e-9, (name, float(gr @ d), want_proj)
+    np.testing.assert_allclose((G.conv[0].weight.detach() - w0)[:4, :4].numpy(), g["g_conv0_step"], atol=2e-6)
+    np.testing.assert_allclose(D.block1[1].running_mean.numpy(), g["d_running_mean_block1"], atol=1e-6)
