@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py — TecoGAN x4 VSR inference throughput on B200 (BASELINE.json metric).
+"""bench.py — TecoGAN x4 VSR inference throughput and training-step throughput on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -12,6 +12,8 @@ One "step" = one batch of B independent 100-frame clips per GPU through the recu
   e2e        frames/s through ClipPipeline.run_host: pinned host LR in, every HR frame copied
              back to pinned host memory, copies inside the timed region
   roofline   dominant kernel (tg::frame_kernel: all 41 tcgen05 conv layers of a frame) timed per launch with CUDA events
+  train      second half of the metric ("train clips/s"): tecogan_b200.train.FRVSR_Train steps on cfg4 (N=1) and cfg5
+             (global batch 32 split over the N ranks, gradient all-reduce inside the step), device-timed + e2e
   cpu_baseline / --impl reference: the CPU oracle port (torch fp32 on the host cores) on a
              bounded sample of the same workload.  Only these legs import oracle/.
 """
@@ -47,6 +49,8 @@ def parse():
     ap.add_argument("--frames", type=int, default=T)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (train clips/s)")
+    ap.add_argument("--train-steps", type=int, default=10)
     return ap.parse_args()
 
 
@@ -133,7 +137,119 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_train:
+        tr = {}
+        for name, crop, cb in (("cfg4", 32, 4), ("cfg5", 64, 1)):
+            cps, step_s, c = cpu_oracle_train(crop, cb)
+            tr[name] = {"value": cps, "unit": "clips/s", "ms_per_step": step_s * 1e3, "cores": c, "kind": "port",
+                        "sample": f"one oracle train step on {cb} clip(s) of 10 frames, {crop}x{crop} LR"}
+        line["train"] = tr
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------- training leg
+# generator 8,445,312 FLOP per LR pixel forward, x3 forward+backward; discriminator 6.9018 GF per
+# 128x128 sample forward, 20.20 GF forward+backward (x4 at 256x256); two discriminator passes per step.
+def train_step_flops(b, t, crop):
+    g = b * t * crop * crop * FLOP_PER_LR_PIXEL * 3.0
+    tb = b * (3 * (t // 3)) // 3
+    d = 2 * tb * 20.20e9 * (crop / 32.0) ** 2
+    return g + d
+
+
+def train_args(crop):
+    import types
+    return types.SimpleNamespace(num_resblock=16, discrim_resblocks=4, discrim_channels=128, RNN_N=10, crop_size=crop,
+                                 pingpang=False, learning_rate=1e-4, vgg_scaling=-0.002, crop_dt=0.75, Dt_mergeDs=True,
+                                 D_LAYERLOSS=True, EPS=1e-12, ratio=0.01, Dt_ratio_max=1.0, Dt_ratio_0=1.0,
+                                 Dt_ratio_add=0.0, pp_scaling=1.0, beta=0.9, adameps=1e-8)
+
+
+def cpu_oracle_train(crop, b):
+    """clips/s of the CPU oracle port of the training step (oracle/train_oracle.py) — the reference's CPU path."""
+    import torch
+    from oracle import synth, tecogan_oracle as O, train_oracle as TO
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    torch.manual_seed(1)
+    args = TO.default_train_args(crop_size=crop)
+    G = O.OracleGenerator(3, 16)
+    D = O.OracleDiscriminator(4, 128, 48 * (crop // 32) ** 2)
+    og = torch.optim.Adam(G.parameters(), 1e-4, betas=(0.9, 0.999), eps=1e-8)
+    od = torch.optim.Adam(D.parameters(), 1e-4, betas=(0.9, 0.999), eps=1e-8)
+    r_in = torch.from_numpy(synth.det_uniform((b, 10, 3, crop, crop), 51, 0.0, 1.0))
+    r_tg = torch.from_numpy(synth.det_uniform((b, 10, 3, 4 * crop, 4 * crop), 52, 0.0, 1.0))
+    t0 = time.perf_counter()
+    TO.train_step(G, D, og, od, r_in, r_tg, args, 0)
+    dt = time.perf_counter() - t0
+    return b / dt, dt, torch.get_num_threads()
+
+
+def run_train_leg(name, crop, global_batch, world, rank, dev, steps, warmup, barrier, max_over_ranks, with_cpu):
+    """One training configuration: `steps` calls of tecogan_b200.train.FRVSR_Train (the reference's train entry point,
+    code/train.py:374-377) on this rank's share of the global batch; gradients all-reduced inside the step when
+    world > 1.  Returns the JSON sub-object (rank 0) or None."""
+    import torch
+    from tecogan_b200 import _native as nt, models, parallel, train as T
+    lib = nt.lib()
+    args = train_args(crop)
+    per = global_batch // world
+    torch.manual_seed(1)                                   # identical replicas on every rank
+    G = models.generator(3, args).to(dev)
+    D = models.discriminator(args).to(dev)
+    parallel.broadcast_parameters(G)
+    parallel.broadcast_parameters(D)
+    og = torch.optim.Adam(G.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps)    # main.py:239-243
+    od = torch.optim.Adam(D.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps)
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    r_in = torch.rand((per, 10, 3, crop, crop), device=dev, generator=gen)
+    r_tg = torch.rand((per, 10, 3, 4 * crop, 4 * crop), device=dev, generator=gen)
+    for i in range(warmup):
+        out = T.FRVSR_Train(r_in, r_tg, args, D, G, i, 0.0, 0.0, og, od)
+    barrier()
+    l0 = lib.tg_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        out = T.FRVSR_Train(r_in, r_tg, args, D, G, warmup + i, 0.0, 0.0, og, od)
+    e1.record()
+    barrier()
+    launches = lib.tg_launch_count() - l0
+    dev_s = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    losses = (float(out.gen_loss), float(out.d_loss))
+    # end to end: pinned host batches in (H2D inside the timed region), the two losses read back every step
+    h_in, h_tg = r_in.cpu().pin_memory(), r_tg.cpu().pin_memory()
+    d_in, d_tg = torch.empty_like(r_in), torch.empty_like(r_tg)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        d_in.copy_(h_in, non_blocking=True)
+        d_tg.copy_(h_tg, non_blocking=True)
+        out = T.FRVSR_Train(d_in, d_tg, args, D, G, warmup + steps + i, 0.0, 0.0, og, od)
+        host_losses = (float(out.gen_loss), float(out.d_loss))          # D2H read of the step's result
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    if rank != 0:
+        return None
+    flops = train_step_flops(global_batch, 10, crop)
+    res = {"workload": name, "value": global_batch * steps / dev_s, "unit": "clips/s", "ms_per_step": dev_s / steps * 1e3,
+           "global_batch": global_batch, "clips_per_gpu": per, "frames": 10, "lr_crop": crop, "steps": steps, "warmup": warmup,
+           "scaling": "strong" if world > 1 or name.startswith("cfg5") else "single GPU",
+           "parallelism": f"batch-data-parallel x{world}, flat-bucket gradient all-reduce (NCCL) overlapped with backward"
+                          if world > 1 else "single GPU",
+           "e2e": {"value": global_batch * steps / e2e_s, "unit": "clips/s",
+                   "h2d_bytes_per_step": int(h_in.numel() * 4 + h_tg.numel() * 4), "d2h_bytes_per_step": 8,
+                   "api": "tecogan_b200.train.FRVSR_Train (pinned host batch -> device, losses read back)"},
+           "gpu_launches": int(launches),
+           "step_tflops": flops / (dev_s / steps) / 1e12, "algorithmic_flops_per_step": flops,
+           "losses_finite": bool(all(v == v and abs(v) != float("inf") for v in losses + host_losses)),
+           "optimizer": "torch.optim.Adam + GradScaler (stock, as main.py:239-243 / code/train.py:335-342)"}
+    if with_cpu:
+        cb = 4 if crop == 32 else 1
+        cps, step_s, cores = cpu_oracle_train(crop, cb)
+        res["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port",
+                               "sample": f"one oracle train step (oracle/train_oracle.py, torch CPU fp32) on {cb} clip(s) of "
+                                         f"10 frames, {crop}x{crop} LR"}
+    return res
 
 
 # ------------------------------------------------------------------------------------- ours
@@ -274,6 +390,19 @@ def run_ours(args):
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": "one 3-frame 320x180 clip through oracle.infer_clip (torch CPU fp32)"}
 
+    # ---------------- training step (BASELINE.json metric, second half: train clips/s) ----------------
+    train = None
+    if not args.no_train:
+        del pipe, out, lr
+        torch.cuda.empty_cache()
+        train = {}
+        with_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
+        if world == 1:
+            train["cfg4"] = run_train_leg("cfg4: training step, batch 4 x 10 frames of 32x32 LR crops, single B200", 32, 4,
+                                          world, rank, dev, args.train_steps, 3, barrier, max_over_ranks, with_cpu)
+        train["cfg5"] = run_train_leg("cfg5: data-parallel training, global batch 32 x 10 frames of 64x64 LR crops", 64, 32,
+                                      world, rank, dev, max(3, args.train_steps // 2), 3, barrier, max_over_ranks, with_cpu)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -287,7 +416,7 @@ def run_ours(args):
                        "l2": "no explicit flush: every frame streams ~0.56 GB of activations per clip through the "
                              "126 MB L2, far larger than L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "outputs_finite": finite,
+            "outputs_finite": finite, "train": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

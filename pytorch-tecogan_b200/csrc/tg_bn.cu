@@ -7,7 +7,7 @@
 namespace tg {
 
 constexpr int kBnThreads = 256;
-constexpr int kBnMaxBlocks = 64;
+constexpr int kBnMaxBlocks = 296;   // two per SM: enough loads in flight to stream at HBM rate, short serial tail
 
 // ---------------------------------------------------------------------------------------------
 // Batch statistics of x [P pixels][C] f32 (raw conv outputs are kept in f32: normalisation amplifies rounding).  Every block reduces a strided slice of the pixels to

@@ -334,7 +334,8 @@ int launch_bias_grad(const void* dy, long long pixels, int cpad, int c, float* d
   TG_CHECK_ARG(dy && db && (cpad == 64 || cpad == 128) && c >= 1 && c <= cpad, "bias_grad: bad arguments");
   const int pix_per_iter = 256 / (cpad / 8);
   long long blocks = (pixels + pix_per_iter * 8 - 1) / (pix_per_iter * 8);
-  if (blocks > 64) blocks = 64;
+  const long long cap = static_cast<long long>(tg_num_sms()) * 4;     // enough loads in flight to stream at HBM rate
+  if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   tg_prof_pre(TG_K_GLUE, 2.0 * pixels * cpad, stream);
   bias_grad_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), pixels, cpad, c, db);
