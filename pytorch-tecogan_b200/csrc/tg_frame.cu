@@ -34,8 +34,7 @@ constexpr int kFrThreads = 352;                        // producer, MMA, 8 epilo
 constexpr int kEpiWarps = 8;                           // 2 per TMEM lane quarter: channels 0-31 / 32-63
 constexpr uint32_t kFrSmemLimit = 232448;
 constexpr uint32_t kWSlotBytes = 73728;               // 9 taps x 64 x 64 bf16
-constexpr uint32_t kABoxBytes = 18 * 10 * 128;        // {64ch, 10, 18} halo box
-constexpr uint32_t kAStride = 23552;                  // 1024-aligned
+constexpr uint32_t kAStride = 24576;                  // stage pitch: {64ch, 32, 6} wide box (24576 B) / {64ch, 10, 18} tall box (23040 B)
 constexpr int kFrStages = 3;
 constexpr int kWBoxRows = 48;                         // weight TMA box: 48 rows x 128 B
 constexpr int kGroupCols = 256;                       // TMEM columns per accumulator group (2 groups)
@@ -70,6 +69,37 @@ __device__ __forceinline__ void ld_global_cg_v8(const void* p, uint32_t (&v)[8])
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "l"(p)
                : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
+
+// 32 f32 accumulator columns of one pixel -> + bias, ReLU, + residual -> 32 bf16 channels (64 bytes, NHWC)
+__device__ __forceinline__ void epi_store_bf16(const uint32_t (&v)[32], const float* bias32, uint8_t* dst,
+                                               const uint8_t* res, bool relu) {
+#pragma unroll
+  for (int c16 = 0; c16 < 2; ++c16) {            // 16 channels = one 32-byte store
+    float f[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      f[e] = __uint_as_float(v[c16 * 16 + e]) + bias32[c16 * 16 + e];
+      if (relu) f[e] = fmaxf(f[e], 0.f);
+    }
+    if (res) {
+      uint32_t rv[8];
+      ld_global_cg_v8(res + c16 * 32, rv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { f[2 * e] += bf16_lo(rv[e]); f[2 * e + 1] += bf16_hi(rv[e]); }
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+    st_global_v8(dst + c16 * 32, o);
+  }
 }
 
 // Weight-slot LRU pair.  Producer and MMA warps run the same deterministic state machine over the
@@ -157,7 +187,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       const int ty = r % S.tiles_y;
       const int n = r / S.tiles_y;
       const int origin = (S.kind == kConv3x3) ? -1 : 0;
-      const int bx0 = tx * kTileW + origin, by0 = ty * kTileH + origin;
+      const int bx0 = tx * S.tile_w + origin, by0 = ty * S.tile_h + origin;
       for (int kc = 0; kc < S.kchunks; ++kc) {
         bool is_load;
         uint32_t nth;
@@ -178,15 +208,15 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         }
         if (kc == 0 && S.dep_nseg > 0 && !(P.dbg & 1)) {
           // producer tiles of the previous layer touched by the halo box (clipped to the image)
-          const int ya = max(by0, 0), yb = min(by0 + kTileH + 1, S.h - 1);
-          const int xa = max(bx0, 0), xb = min(bx0 + kTileW + 1, S.w - 1);
-          const int tya = (ya >> S.dep_shift_y), tyb = (yb >> S.dep_shift_y);
-          const int txa = (xa >> S.dep_shift_x), txb = (xb >> S.dep_shift_x);
+          const int ya = max(by0, 0), yb = min(by0 + S.box_h - 1, S.h - 1);
+          const int xa = max(bx0, 0), xb = min(bx0 + S.box_w - 1, S.w - 1);
+          const int tya = ya / S.dep_th, tyb = yb / S.dep_th;
+          const int txa = xa / S.dep_tw, txb = xb / S.dep_tw;
           const int nx = txb - txa + 1, ny = tyb - tya + 1;
           const int cnt = nx * ny * S.dep_nseg;
-          if (lane < cnt) {
-            const int ds = lane / (nx * ny);
-            const int q = lane - ds * (nx * ny);
+          for (int di = lane; di < cnt; di += 32) {
+            const int ds = di / (nx * ny);
+            const int q = di - ds * (nx * ny);
             const int dty = tya + q / nx, dtx = txa + q % nx;
             const uint32_t* f = P.flags + P.segs[S.dep_seg0 + ds].flag_off +
                                 (static_cast<uint32_t>(n) * S.dep_tiles_y + dty) * S.dep_tiles_x + dtx;
@@ -207,7 +237,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         mbar_wait(bar_aempty + 8 * st, ph ^ 1);
         if (elect_one()) {
           fence_proxy_async_global();   // generic-proxy writes of other CTAs (acquired above) -> async-proxy read
-          mbar_expect_tx(bar_afull + 8 * st, kABoxBytes);
+          mbar_expect_tx(bar_afull + 8 * st, static_cast<uint32_t>(S.box_w * S.box_h) * 128u);
           tma_load_4d(s_a + st * kAStride, &P.maps[S.map_a], bar_afull + 8 * st, kc * 64, bx0, by0, n);
         }
         __syncwarp();
@@ -229,7 +259,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         traced_si = si;
       }
       const bool last_in_seg = (it + G >= S.item_end);
-      const uint32_t idesc = umma_idesc_bf16(128, S.nt);
+      const uint32_t idesc = umma_idesc_bf16(128, S.wide ? 3 * S.nt : S.nt);
+      const bool wide = S.wide != 0;
       const uint32_t wtap_bytes = static_cast<uint32_t>(S.nt) * 128;
       const int kind = S.kind;
       mbar_wait(bar_cempty + 8 * g, gph ^ 1);
@@ -245,6 +276,17 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         if (elect_one()) {
           const uint32_t a_base = s_a + st * kAStride;
           const uint32_t w_base = s_w + slot * kWSlotBytes;
+          if (wide) {
+            // one MMA per (filter row, K=16 step): A = the box shifted by dy rows of 32 pixels (4096 B, so every
+            // descriptor keeps the canonical 1024-byte group pitch), B = the row's three taps stacked along N
+#pragma unroll 1
+            for (int dy = 0; dy < 3; ++dy) {
+              const uint64_t ad = umma_desc_sw128(a_base + dy * (kWideBoxW * 128), 1024);
+              const uint64_t bd = umma_desc_sw128(w_base + dy * 3 * wtap_bytes, 1024);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(d_base, ad + 2 * k, bd + 2 * k, idesc, (kc > 0 || dy > 0 || k > 0) ? 1u : 0u);
+            }
+          } else
 #pragma unroll 1
           for (int j = 0; j < 9; ++j) {
             const uint64_t ad = umma_desc_sw128(a_base + c_aoff[kind][j], 10 * 128);
@@ -294,10 +336,66 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       const int n = r / S.tiles_y;
       const int iy = ty * kTileH + pr, ix = tx * kTileW + pc;
       const bool valid = (iy < S.h) && (ix < S.w);
-      const int n_acc = (S.kind == kConv3x3) ? 1 : 4;
+      const int n_acc = S.wide ? 0 : ((S.kind == kConv3x3) ? 1 : 4);
       const int sc = (S.kind == kConv3x3) ? 1 : 2;
       mbar_wait(bar_cfull + 8 * g, gph);
       tc_fence_after();
+      if (S.wide) {
+        // GEMM row = (tile row q, box column lane); columns [dx*nt + c] hold the partial sum of filter column dx
+        // evaluated AT this box pixel: out[x] = P0[x-1] + P1[x] + P2[x+1]  ->  lanes l-1, l, l+1 of this warp
+        const int wy = ty * kWideH + q, wx = tx * kWideW - 1 + lane;
+        const bool wvalid = (lane >= 1) && (lane <= kWideW) && (wy < S.h) && (wx < S.w);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * kGroupCols);
+        if (S.out_mode == kOutNHWCbf16) {
+          uint32_t v0[32], v1[32], v2[32];
+          tmem_ld_32x32(taddr + half * 32, v0);
+          tmem_ld_32x32(taddr + 64 + half * 32, v1);
+          tmem_ld_32x32(taddr + 128 + half * 32, v2);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float l = __shfl_up_sync(0xFFFFFFFFu, __uint_as_float(v0[e]), 1);
+            const float r2 = __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(v2[e]), 1);
+            v1[e] = __float_as_uint((l + __uint_as_float(v1[e])) + r2);
+          }
+          if (wvalid) {
+            const size_t pix = (static_cast<size_t>(n) * S.oh + wy) * S.ow + wx;
+            const size_t off = (pix * S.oc + S.ch0) * 2 + half * 64;
+            epi_store_bf16(v1, s_bias + half * 32, static_cast<uint8_t*>(S.out) + off,
+                           S.resid ? static_cast<const uint8_t*>(S.resid) + off : nullptr, S.relu != 0);
+          }
+        } else {
+          uint32_t v0[4], v1[4], v2[4];                    // 3 output channels of each of the 3 partial sums
+          tmem_ld_32x4(taddr, v0);
+          tmem_ld_32x4(taddr + 16, v1);
+          tmem_ld_32x4(taddr + 32, v2);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
+          float z[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float l = __shfl_up_sync(0xFFFFFFFFu, __uint_as_float(v0[c]), 1);
+            const float r2 = __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(v2[c]), 1);
+            z[c] = (l + __uint_as_float(v1[c])) + r2 + s_bias[c];
+          }
+          if (wvalid) {
+            const size_t plane = static_cast<size_t>(S.oh) * S.ow;
+            const size_t o0 = static_cast<size_t>(n) * S.out_nstride + static_cast<size_t>(wy) * S.ow + wx;
+            // 3 output planes: warps of half 0 store planes 0 and 1, warps of half 1 store plane 2
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              if ((c >> 1) != half || c >= S.oc) continue;
+              if (S.out2) S.out2[o0 + c * plane] = z[c];
+              static_cast<float*>(S.out)[o0 + c * plane] = 1.f / (1.f + expf(-z[c]));
+            }
+          }
+        }
+      }
       for (int a = 0; a < n_acc; ++a) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>(g * kGroupCols + a * kAccCols);
@@ -314,28 +412,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           if (valid) {
             const size_t pix = (static_cast<size_t>(n) * S.oh + oy) * S.ow + ox;
             const size_t off = (pix * S.oc + S.ch0) * 2 + half * 64;
-            uint8_t* dst = static_cast<uint8_t*>(S.out) + off;
-            const uint8_t* res = S.resid ? static_cast<const uint8_t*>(S.resid) + off : nullptr;
-            const bool relu = S.relu != 0;
-#pragma unroll
-            for (int c16 = 0; c16 < 2; ++c16) {            // 16 channels = one 32-byte store
-              float f[16];
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                f[e] = __uint_as_float(v[c16 * 16 + e]) + s_bias[half * 32 + c16 * 16 + e];
-                if (relu) f[e] = fmaxf(f[e], 0.f);
-              }
-              if (res) {
-                uint32_t rv[8];
-                ld_global_cg_v8(res + c16 * 32, rv);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { f[2 * e] += bf16_lo(rv[e]); f[2 * e + 1] += bf16_hi(rv[e]); }
-              }
-              uint32_t o[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
-              st_global_v8(dst + c16 * 32, o);
-            }
+            epi_store_bf16(v, s_bias + half * 32, static_cast<uint8_t*>(S.out) + off,
+                           S.resid ? static_cast<const uint8_t*>(S.resid) + off : nullptr, S.relu != 0);
           }
         } else {
           uint32_t v[16];
@@ -399,12 +477,26 @@ void frame_set_trace(unsigned long long* buf, size_t words) { g_trace = buf; g_t
 
 static int layer_nt(const FrLayer& l) { return l.cout_pad == 16 ? 16 : 64; }
 
+// TG_FRAME_WIDE=0 keeps every layer on the tall 16x8 geometry (A/B measurements)
+static bool use_wide(int kind) {
+  static const bool on = []() { const char* e = getenv("TG_FRAME_WIDE"); return !(e && e[0] == '0'); }();
+  return on && kind == kConv3x3;
+}
+size_t frame_tiles(int kind, int h, int w) {
+  return use_wide(kind) ? static_cast<size_t>(tg_div_up(w, kWideW)) * tg_div_up(h, kWideH)
+                        : static_cast<size_t>(tg_div_up(w, kTileW)) * tg_div_up(h, kTileH);
+}
+size_t frame_tiles_max(int h, int w) {
+  const size_t a = static_cast<size_t>(tg_div_up(w, kWideW)) * tg_div_up(h, kWideH);
+  const size_t b = static_cast<size_t>(tg_div_up(w, kTileW)) * tg_div_up(h, kTileH);
+  return a > b ? a : b;
+}
+
 size_t frame_flag_count(const FrLayer* layers, int nlayers, int n) {
   size_t total = 0;
-  for (int i = 0; i < nlayers; ++i) {
-    const size_t tiles = static_cast<size_t>(n) * tg_div_up(layers[i].w, kTileW) * tg_div_up(layers[i].h, kTileH);
-    total += tiles * (layers[i].cout_pad / layer_nt(layers[i]));
-  }
+  for (int i = 0; i < nlayers; ++i)
+    total += static_cast<size_t>(n) * frame_tiles(layers[i].kind, layers[i].h, layers[i].w) *
+             (layers[i].cout_pad / layer_nt(layers[i]));
   return total;
 }
 
@@ -435,13 +527,16 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
       cuuint64_t strides[3] = {static_cast<cuuint64_t>(l.cin_pad) * 2, static_cast<cuuint64_t>(l.w) * l.cin_pad * 2,
                                static_cast<cuuint64_t>(l.h) * l.w * l.cin_pad * 2};
       cuuint32_t box[4] = {64, kTileW + 2, kTileH + 2, 1};
+      if (use_wide(l.kind)) { box[1] = kWideBoxW; box[2] = kWideBoxH; }
       int rc = encode_bf16(&P.maps[1 + li], l.in, 4, dims, strides, box);
       if (rc) return rc;
     }
     const int nt = layer_nt(l);
     const int chunks = l.cout_pad / nt;
     const int kchunks = l.cin_pad / 64;
-    const int tiles_x = tg_div_up(l.w, kTileW), tiles_y = tg_div_up(l.h, kTileH);
+    const bool wide = use_wide(l.kind);
+    const int tile_w = wide ? kWideW : kTileW, tile_h = wide ? kWideH : kTileH;
+    const int tiles_x = tg_div_up(l.w, tile_w), tiles_y = tg_div_up(l.h, tile_h);
     const int sc = (l.kind == kConv3x3) ? 1 : 2;
     first_seg[li] = nseg;
     nchunks[li] = chunks;
@@ -453,6 +548,8 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
       items += n * tiles_x * tiles_y;
       S.item_end = items;
       S.tiles_x = tiles_x; S.tiles_y = tiles_y; S.h = l.h; S.w = l.w;
+      S.wide = wide ? 1 : 0; S.tile_w = tile_w; S.tile_h = tile_h;
+      S.box_w = wide ? kWideBoxW : kTileW + 2; S.box_h = wide ? kWideBoxH : kTileH + 2;
       S.map_a = 1 + li;
       S.kchunks = kchunks; S.kind = l.kind; S.nt = nt;
       S.w_rows = 9u * nt;
@@ -473,9 +570,10 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
         const int psc = (pl.kind == kConv3x3) ? 1 : 2;
         TG_CHECK_ARG(pl.h * psc == l.h && pl.w * psc == l.w && pl.out == l.in, "frame: layer %d does not consume layer %d", li, li - 1);
         S.dep_seg0 = first_seg[li - 1]; S.dep_nseg = nchunks[li - 1];
-        S.dep_tiles_x = tg_div_up(pl.w, kTileW); S.dep_tiles_y = tg_div_up(pl.h, kTileH);
-        S.dep_shift_y = (psc == 1) ? 4 : 5;   // producer tile = 16 (32) output rows
-        S.dep_shift_x = (psc == 1) ? 3 : 4;   //                  8 (16) output columns
+        const bool pwide = use_wide(pl.kind);
+        const int ptw = pwide ? kWideW : kTileW, pth = pwide ? kWideH : kTileH;
+        S.dep_tiles_x = tg_div_up(pl.w, ptw); S.dep_tiles_y = tg_div_up(pl.h, pth);
+        S.dep_tw = ptw * psc; S.dep_th = pth * psc;   // producer tile footprint in this layer's input pixels
       }
       S.flag_off = static_cast<uint32_t>(S.item_begin);
       ++nseg;

@@ -8,11 +8,22 @@ namespace tg {
 constexpr int kFrMaxSegs = 56;     // 41 layers + one extra segment per 128-wide layer
 constexpr int kFrMaxMaps = 44;     // [0] packed weights, [1 + layer] input activation of the layer
 
-// One segment = one (layer, 64-wide output-channel chunk) pass over all 16x8 tiles of the layer.
+// Tile geometries.  "tall": 16 rows x 8 columns, halo box {64ch, 10, 18}, one tcgen05.mma group per filter tap
+// (N = nt); used by the transposed convs.  "wide" (3x3 convs): 4 rows x 32 columns of which the inner 30 are
+// outputs, box {64ch, 32, 6}; the three dx taps of a filter row share ONE A view and are ONE MMA of N = 3*nt
+// (weights of the row stacked along N), and the epilogue adds the three partial sums of neighbouring pixels
+// (out[x] = P0[x-1] + P1[x] + P2[x+1], a lane shuffle).  A tcgen05.mma costs ~43 + N/2 cycles with both operands
+// in shared memory (profiles/r01_mma_microbench.txt), so 12 MMAs of N=192 per 120 pixels replace 36 of N=64 per 128.
+constexpr int kWideW = 30, kWideH = 4, kWideBoxW = 32, kWideBoxH = 6;
+
+// One segment = one (layer, 64-wide output-channel chunk) pass over all tiles of the layer.
 struct FrSeg {
   int item_begin, item_end;   // global item range [begin, end)
   int tiles_x, tiles_y;       // tiles per image in the layer's input resolution
   int h, w;                   // input resolution
+  int wide;                   // tile geometry (see above)
+  int tile_w, tile_h;         // output pixels per tile (input resolution)
+  int box_w, box_h;           // staged halo box in pixels
   int map_a;                  // index of the input-activation tensor map
   int kchunks;                // input channels / 64
   int kind;                   // kConv3x3 / kConvT3x3s2
@@ -28,7 +39,7 @@ struct FrSeg {
   const float* bias;          // already offset to ch0
   // tile-level dependencies: the producer layer's segments
   int dep_seg0, dep_nseg;     // first producer segment, count (0 = input comes from a previous kernel)
-  int dep_tiles_x, dep_tiles_y, dep_shift_y, dep_shift_x;   // producer tile = (y >> shift_y, x >> shift_x)
+  int dep_tiles_x, dep_tiles_y, dep_tw, dep_th;   // producer tile = (y / dep_th, x / dep_tw) in this layer's input pixels
   uint32_t flag_off;          // offset of this segment's per-item completion counters
 };
 
@@ -52,6 +63,10 @@ struct FrLayer {              // host-side description of one conv layer of the 
 };
 
 size_t frame_flag_count(const FrLayer* layers, int nlayers, int n);
+// tiles of one image of an h x w layer input in the geometry launch_frame picks for `kind`
+size_t frame_tiles(int kind, int h, int w);
+// upper bound over both geometries (workspace sizing)
+size_t frame_tiles_max(int h, int w);
 // Builds the program and launches the frame kernel.  `flags` holds `flag_capacity` uint32 counters
 // (>= frame_flag_count()); flags_zeroed = an earlier kernel of the stream already cleared them.
 int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t packed_bytes, int n,

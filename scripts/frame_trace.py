@@ -41,10 +41,17 @@ t0 = t[t > 0].min()
 names = ["conv.0"] + [f"res{i // 2}.{'0' if i % 2 == 0 else '2'}" for i in range(32)] + ["convT64", "ct2.0 64@2x", "ct2.2 64@2x",
          "ct3.0 64->128 c0", "ct3.0 64->128 c1", "ct3.2 128->128 c0", "ct3.2 128->128 c1", "convT128 c0", "convT128 c1",
          "ct6 128->64@4x", "out 64->3", "END"]
-# MMA-bound time per segment: items/148 * 36*kchunks MMAs * 75 cycles (N=64) / 1.965 GHz
+# MMA-bound time per segment, in units of (36 MMAs x 75 cycles): tall geometry items/148 * 36*kchunks MMAs * 75 cycles
+# (N=64); wide geometry 12*kchunks MMAs * 139 cycles (N=192) per 30x4 tile; / 1.965 GHz
 px = N * H * W
-tiles1, tiles2, tiles4 = N * 40 * 12, N * 80 * 23, N * 160 * 45
-bound = [tiles1] * 34 + [tiles2] * 4 + [tiles2 * 2] * 4 + [tiles4 * 2, tiles4 * 52.7 / 75]
+WIDE = os.environ.get("TG_FRAME_WIDE", "1") != "0"
+if WIDE:
+    wt = lambda s: N * (-(-W * s // 30)) * (-(-H * s // 4)) * (12 * 139) / (36 * 75)
+    tall = lambda s: N * (-(-W * s // 8)) * (-(-H * s // 16))
+    bound = [wt(1)] * 33 + [tall(1)] + [wt(2)] * 4 + [wt(2) * 2] * 2 + [tall(2) * 2] * 2 + [wt(4) * 2, wt(4) * 67 / 139]
+else:
+    tiles1, tiles2, tiles4 = N * 40 * 12, N * 80 * 23, N * 160 * 45
+    bound = [tiles1] * 34 + [tiles2] * 4 + [tiles2 * 2] * 4 + [tiles4 * 2, tiles4 * 52.7 / 75]
 prev = None
 print(f"N={N}  total {(t[NSEG].max() - t0) / 1e3:.1f} us")
 for s in range(NSEG + 1):

@@ -110,35 +110,59 @@ def test_weight_cache_tracks_updates():
     assert (b - a).abs().min().item() > 0.1
 
 
-@pytest.mark.parametrize("shape", [(1, 51, 12, 20), (2, 51, 33, 17), (1, 51, 180, 320), (3, 51, 90, 100)])
-def test_frame_kernel_is_bit_identical_to_per_layer_path(shape):
+def _close_to_per_layer(got, want):
+    """Frame kernel vs per-layer path on the same bf16 operands: they differ only in the order of the fp32 partial
+    sums (the frame kernel adds three per-filter-column accumulators in its epilogue), i.e. by bf16 rounding flips:
+    worst element <= 2e-2 of the logit range, mean <= 1e-3 of it (measured ~3e-3 / 1e-4)."""
+    scale = want.abs().max().item()
+    d = (got - want).abs()
+    assert d.max().item() <= 2e-2 * scale, (d.max().item(), scale)
+    assert d.mean().item() <= 1e-3 * scale, (d.mean().item(), scale)
+
+
+@pytest.mark.parametrize("shape", [(1, 51, 12, 20), (2, 51, 33, 17), (1, 51, 180, 320), (3, 51, 90, 100), (1, 51, 7, 61)])
+def test_frame_kernel_matches_per_layer_path(shape):
     """Size-independent property used at the full BASELINE cfg2 size: the persistent frame kernel chains the
-    41 layers through per-tile counters instead of kernel boundaries but issues the same MMAs in the same order,
-    so its output must equal the per-layer path bit for bit (any missed dependency or stale read breaks this)."""
+    41 layers through per-tile counters instead of kernel boundaries (and tiles the 3x3 convs 30x4 with the three
+    filter columns fused into one N=192 MMA), so against the per-layer path any missed dependency, stale read or
+    tile-edge error shows up as a gross difference.  Two different inputs alternate through the same workspace so
+    that a stale tile of the previous launch cannot pass, and repeated launches must be bit-identical (the static
+    schedule has no data race)."""
     _, G = _make(1.7)
-    x = torch.from_numpy(synth.det_uniform(shape, 33, 0.0, 1.0)).cuda()
-    outs = {}
+    xs = [torch.from_numpy(synth.det_uniform(shape, 33 + i, 0.0, 1.0)).cuda() for i in range(2)]
+    want, got = {}, {}
     with torch.no_grad():
-        for amode in (PER_LAYER, FRAME):
-            G.amode = amode
-            for rep in range(3):                       # repeated launches reuse the workspace and its counters
-                y, lg = G(x, return_logits=True)
-                outs[(amode, rep)] = (y.clone(), lg.clone())
-    for rep in range(3):
-        assert torch.equal(outs[(PER_LAYER, 0)][1], outs[(FRAME, rep)][1])
-        assert torch.equal(outs[(PER_LAYER, 0)][0], outs[(FRAME, rep)][0])
+        G.amode = PER_LAYER
+        for i, x in enumerate(xs):
+            y, lg = G(x, return_logits=True)
+            want[i] = (y.clone(), lg.clone())
+        G.amode = FRAME
+        for rep in range(4):                       # repeated launches reuse the workspace and its counters
+            y, lg = G(xs[rep & 1], return_logits=True)
+            got[rep] = (y.clone(), lg.clone())
+    for rep in range(4):
+        _close_to_per_layer(got[rep][1], want[rep & 1][1])
+        assert (got[rep][0] - want[rep & 1][0]).abs().max().item() <= 1e-2
+    for rep in (2, 3):
+        assert torch.equal(got[rep][1], got[rep - 2][1]) and torch.equal(got[rep][0], got[rep - 2][0])
+    assert (want[0][1] - want[1][1]).abs().max().item() > 0.1     # the two inputs do differ
 
 
-def test_frame_clip_is_bit_identical_to_per_layer_clip():
-    """Recurrent loop at cfg2 frame size (2 clips x 4 frames of 320x180): frame kernel == per-layer path."""
+def test_frame_clip_matches_per_layer_clip():
+    """Recurrent loop at cfg2 frame size (2 clips x 4 frames of 320x180): frame kernel vs per-layer path, >= 50 dB
+    after 4 recurrent steps and bit-identical when repeated."""
     _, G = _make(1.0)
     r = torch.from_numpy(synth.clip_inputs(2, 4, 180, 320, seed=7, hi=0.25)).cuda()
     G.amode = PER_LAYER
     a = G.infer_clip(r)
     G.amode = FRAME
     b = G.infer_clip(r)
-    assert torch.equal(a, b)
+    b2 = G.infer_clip(r)
     assert torch.isfinite(b).all()
+    assert torch.equal(b, b2)
+    mse = ((a.double() - b.double()) ** 2).mean().item()
+    assert mse == 0 or 10 * math.log10(1.0 / mse) >= 50.0
+    assert (a - b).abs().max().item() <= 1e-2
 
 
 @pytest.mark.parametrize("nres,shape", [(2, (1, 51, 16, 16)), (16, (2, 51, 32, 32)), (3, (1, 51, 20, 12))])
