@@ -30,8 +30,9 @@
 
 namespace tg {
 
-constexpr int kFrThreads = 352;                        // producer, MMA, 8 epilogue warps, publisher
-constexpr int kEpiWarps = 8;                           // 2 per TMEM lane quarter: channels 0-31 / 32-63
+constexpr int kEpiWarps = 16;                          // 4 per TMEM lane quarter: 16 accumulator columns each
+constexpr int kFrThreads = 32 * (2 + kEpiWarps + 2);   // producer, MMA, epilogue warps, publisher, dependency warp
+constexpr int kDepRing = 4;                            // dependency warp runs at most this many items ahead of the producer
 constexpr uint32_t kFrSmemLimit = 232448;
 constexpr uint32_t kWSlotBytes = 73728;               // 9 taps x 64 x 64 bf16
 constexpr uint32_t kAStride = 24576;                  // stage pitch: {64ch, 32, 6} wide box (24576 B) / {64ch, 10, 18} tall box (23040 B)
@@ -53,6 +54,12 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -78,28 +85,25 @@ __device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t (&v)[4]) {
                : "memory");
 }
 
-// 32 f32 accumulator columns of one pixel -> + bias, ReLU, + residual -> 32 bf16 channels (64 bytes, NHWC)
-__device__ __forceinline__ void epi_store_bf16(const uint32_t (&v)[32], const float* bias32, uint8_t* dst,
+// 16 f32 accumulator columns of one pixel -> + bias, ReLU, + residual -> 16 bf16 channels (one 32-byte store, NHWC)
+__device__ __forceinline__ void epi_store_bf16(const uint32_t (&v)[16], const float* bias16, uint8_t* dst,
                                                const uint8_t* res, bool relu) {
+  float f[16];
 #pragma unroll
-  for (int c16 = 0; c16 < 2; ++c16) {            // 16 channels = one 32-byte store
-    float f[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      f[e] = __uint_as_float(v[c16 * 16 + e]) + bias32[c16 * 16 + e];
-      if (relu) f[e] = fmaxf(f[e], 0.f);
-    }
-    if (res) {
-      uint32_t rv[8];
-      ld_global_cg_v8(res + c16 * 32, rv);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { f[2 * e] += bf16_lo(rv[e]); f[2 * e + 1] += bf16_hi(rv[e]); }
-    }
-    uint32_t o[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
-    st_global_v8(dst + c16 * 32, o);
+  for (int e = 0; e < 16; ++e) {
+    f[e] = __uint_as_float(v[e]) + bias16[e];
+    if (relu) f[e] = fmaxf(f[e], 0.f);
   }
+  if (res) {
+    uint32_t rv[8];
+    ld_global_cg_v8(res, rv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { f[2 * e] += bf16_lo(rv[e]); f[2 * e + 1] += bf16_hi(rv[e]); }
+  }
+  uint32_t o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+  st_global_v8(dst, o);
 }
 
 // Weight-slot LRU pair.  Producer and MMA warps run the same deterministic state machine over the
@@ -125,6 +129,39 @@ struct WSlots {
   }
 };
 
+// Batch decode shared by the producer and the dependency warp: lane j owns item it0 + j*G of this CTA.
+//   l0 = segment | image << 8          l1 = box origin x (16 bit) | y << 16
+//   l2 = first producer tile x | y << 16     l3 = nx | ny << 4 | (65535/nx + 1) << 8   (0: nothing to wait for)
+__device__ __forceinline__ void decode_batch(const FrProgram& P, int it0, int lane, int G, int si_base, uint32_t& l0,
+                                             uint32_t& l1, uint32_t& l2, uint32_t& l3, int& l_si) {
+  const int my_it = it0 + lane * G;
+  l0 = l1 = l2 = l3 = 0;
+  l_si = si_base;
+  if (my_it < P.total_items) {
+    while (my_it >= P.segs[l_si].item_end) ++l_si;
+    const FrSeg& S = P.segs[l_si];
+    const uint32_t local = static_cast<uint32_t>(my_it - S.item_begin);
+    const uint32_t r = fdiv(local, S.fd_tiles_x);
+    const int tx = static_cast<int>(local - r * S.tiles_x);
+    const uint32_t n = fdiv(r, S.fd_tiles_y);
+    const int ty = static_cast<int>(r - n * S.tiles_y);
+    const int origin = (S.kind == kConv3x3) ? -1 : 0;
+    const int bx0 = tx * S.tile_w + origin, by0 = ty * S.tile_h + origin;
+    l0 = static_cast<uint32_t>(l_si) | (n << 8);
+    l1 = (static_cast<uint32_t>(bx0) & 0xFFFFu) | (static_cast<uint32_t>(by0) << 16);
+    if (S.dep_nseg > 0) {
+      // producer tiles of the previous layer touched by the halo box (clipped to the image)
+      const int ya = max(by0, 0), yb = min(by0 + S.box_h - 1, S.h - 1);
+      const int xa = max(bx0, 0), xb = min(bx0 + S.box_w - 1, S.w - 1);
+      const uint32_t tya = fdiv(ya, S.fd_dep_th), tyb = fdiv(yb, S.fd_dep_th);
+      const uint32_t txa = fdiv(xa, S.fd_dep_tw), txb = fdiv(xb, S.fd_dep_tw);
+      const uint32_t nx = txb - txa + 1, ny = tyb - tya + 1;
+      l2 = txa | (tya << 16);
+      l3 = nx | (ny << 4) | ((65535u / nx + 1u) << 8);          // q / nx == (q * inv) >> 16 for q < 256
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_constant__ FrProgram P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -138,9 +175,10 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
   const uint32_t bar_afull = bar0 + 32, bar_aempty = bar_afull + 8 * kFrStages;
   const uint32_t bar_cfull = bar_aempty + 8 * kFrStages, bar_cempty = bar_cfull + 16;
   const uint32_t bar_pfull = bar_cempty + 16, bar_pempty = bar_pfull + 16;
-  const uint32_t off_misc = (bar_pempty + 16) - base;
+  const uint32_t bar_dfull = bar_pempty + 16, bar_dempty = bar_dfull + 8 * kDepRing;
+  const uint32_t off_misc = (bar_dempty + 8 * kDepRing) - base;
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gbase + off_misc);
-  float* s_bias_all = reinterpret_cast<float*>(gbase + off_misc + 16);   // [8 warps][64]
+  float* s_bias_all = reinterpret_cast<float*>(gbase + off_misc + 16);   // [kEpiWarps][64]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -158,6 +196,10 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       mbar_init(bar_afull + 8 * i, 1);
       mbar_init(bar_aempty + 8 * i, 1);
     }
+    for (int i = 0; i < kDepRing; ++i) {
+      mbar_init(bar_dfull + 8 * i, 1);
+      mbar_init(bar_dempty + 8 * i, 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
@@ -171,78 +213,67 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
 
   if (warp == 0) {
     // ================================ TMA producer =========================================
+    // The producer is the one strictly serial role (item -> dependencies -> slot -> TMA), so its per-item latency
+    // bounds the item rate of the CTA.  Items are decoded 32 at a time, one per lane (segment search, tile
+    // coordinates), and broadcast by shuffles; the dependency wait itself (a gpu-scope acquire of up to 24 completion
+    // counters, an L2 round trip plus a fence) is done ahead of time by the dependency warp and handed over through
+    // a CTA-local mbarrier ring, which keeps the acquire -> TMA ordering (mbarrier arrive = release.cta, wait =
+    // acquire.cta; causality order is transitive).
     if (lane < P.nseg) tma_prefetch_desc(&P.maps[P.segs[lane].map_a]);
     if (lane == 0) tma_prefetch_desc(&P.maps[0]);
     WSlots ws;
     ws.init();
-    int si = 0, st = 0;
-    uint32_t ph = 0;
+    int st = 0;
+    uint32_t ph = 0, dk = 0;
     bool grid_waited = false;
-    for (int it = blockIdx.x; it < P.total_items; it += G) {
-      while (it >= P.segs[si].item_end) ++si;
-      const FrSeg& S = P.segs[si];
-      const int local = it - S.item_begin;
-      const int tx = local % S.tiles_x;
-      const int r = local / S.tiles_x;
-      const int ty = r % S.tiles_y;
-      const int n = r / S.tiles_y;
-      const int origin = (S.kind == kConv3x3) ? -1 : 0;
-      const int bx0 = tx * S.tile_w + origin, by0 = ty * S.tile_h + origin;
-      for (int kc = 0; kc < S.kchunks; ++kc) {
-        bool is_load;
-        uint32_t nth;
-        const int slot = ws.use(si * 2 + kc, &is_load, &nth);
-        if (is_load) {
-          mbar_wait(bar_wempty + 8 * slot, (nth & 1) ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(bar_wfull + 8 * slot, S.w_rows * 128);
-            for (uint32_t r0 = 0; r0 < S.w_rows; r0 += kWBoxRows)
-              tma_load_2d(s_w + slot * kWSlotBytes + r0 * 128, &P.maps[0], bar_wfull + 8 * slot, 0,
-                          static_cast<int>(S.w_row0[kc] + r0));
-          }
-          __syncwarp();
-        }
-        if (!grid_waited) {   // weights are constants; activations of a previous kernel are not
-          asm volatile("griddepcontrol.wait;" ::: "memory");
-          grid_waited = true;
-        }
-        if (kc == 0 && S.dep_nseg > 0 && !(P.dbg & 1)) {
-          // producer tiles of the previous layer touched by the halo box (clipped to the image)
-          const int ya = max(by0, 0), yb = min(by0 + S.box_h - 1, S.h - 1);
-          const int xa = max(bx0, 0), xb = min(bx0 + S.box_w - 1, S.w - 1);
-          const int tya = ya / S.dep_th, tyb = yb / S.dep_th;
-          const int txa = xa / S.dep_tw, txb = xb / S.dep_tw;
-          const int nx = txb - txa + 1, ny = tyb - tya + 1;
-          const int cnt = nx * ny * S.dep_nseg;
-          for (int di = lane; di < cnt; di += 32) {
-            const int ds = di / (nx * ny);
-            const int q = di - ds * (nx * ny);
-            const int dty = tya + q / nx, dtx = txa + q % nx;
-            const uint32_t* f = P.flags + P.segs[S.dep_seg0 + ds].flag_off +
-                                (static_cast<uint32_t>(n) * S.dep_tiles_y + dty) * S.dep_tiles_x + dtx;
-            if (ld_acquire_gpu(f) < kItemDone) {
-              const uint64_t t0 = global_ns();
-              uint32_t spins = 0;
-              while (ld_acquire_gpu(f) < kItemDone) {
-                __nanosleep(64);
-                if ((++spins & 0x3FFu) == 0 && global_ns() - t0 > 4000000000ull) {
-                  printf("tg: frame dependency timeout seg=%d item=%d block=%d\n", si, it, blockIdx.x);
-                  __trap();
-                }
-              }
+    int si_base = 0;
+    for (int it0 = blockIdx.x; it0 < P.total_items; it0 += 32 * G) {
+      uint32_t l0, l1, l2, l3;
+      int l_si;
+      decode_batch(P, it0, lane, G, si_base, l0, l1, l2, l3, l_si);
+      const int left = (P.total_items - it0 + G - 1) / G;
+      const int nb = left < 32 ? left : 32;
+      for (int j = 0; j < nb; ++j) {
+        const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, l0, j), b1 = __shfl_sync(0xFFFFFFFFu, l1, j);
+        const int si = static_cast<int>(b0 & 0xFFu), n = static_cast<int>(b0 >> 8);
+        const int bx0 = static_cast<int>(static_cast<int16_t>(b1 & 0xFFFFu)), by0 = static_cast<int>(b1) >> 16;
+        const FrSeg& S = P.segs[si];
+        for (int kc = 0; kc < S.kchunks; ++kc) {
+          bool is_load;
+          uint32_t nth;
+          const int slot = ws.use(si * 2 + kc, &is_load, &nth);
+          if (is_load) {
+            mbar_wait(bar_wempty + 8 * slot, (nth & 1) ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(bar_wfull + 8 * slot, S.w_rows * 128);
+              for (uint32_t r0 = 0; r0 < S.w_rows; r0 += kWBoxRows)
+                tma_load_2d(s_w + slot * kWSlotBytes + r0 * 128, &P.maps[0], bar_wfull + 8 * slot, 0,
+                            static_cast<int>(S.w_row0[kc] + r0));
             }
+            __syncwarp();
+          }
+          if (!grid_waited) {   // weights are constants; activations of a previous kernel are not
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            grid_waited = true;
+          }
+          if (kc == 0 && S.dep_nseg > 0 && !(P.dbg & 1)) {           // dependencies acquired by the dependency warp
+            const uint32_t ds = dk % kDepRing;
+            mbar_wait(bar_dfull + 8 * ds, (dk / kDepRing) & 1u);
+            __syncwarp();                                            // every lane has seen this phase before it can be reused
+            if (lane == 0) mbar_arrive(bar_dempty + 8 * ds);
+            ++dk;
+          }
+          mbar_wait(bar_aempty + 8 * st, ph ^ 1);
+          if (elect_one()) {
+            fence_proxy_async_global();   // generic-proxy writes of other CTAs (acquired above) -> async-proxy read
+            mbar_expect_tx(bar_afull + 8 * st, static_cast<uint32_t>(S.box_w * S.box_h) * 128u);
+            tma_load_4d(s_a + st * kAStride, &P.maps[S.map_a], bar_afull + 8 * st, kc * 64, bx0, by0, n);
           }
           __syncwarp();
+          if (++st == kFrStages) { st = 0; ph ^= 1; }
         }
-        mbar_wait(bar_aempty + 8 * st, ph ^ 1);
-        if (elect_one()) {
-          fence_proxy_async_global();   // generic-proxy writes of other CTAs (acquired above) -> async-proxy read
-          mbar_expect_tx(bar_afull + 8 * st, static_cast<uint32_t>(S.box_w * S.box_h) * 128u);
-          tma_load_4d(s_a + st * kAStride, &P.maps[S.map_a], bar_afull + 8 * st, kc * 64, bx0, by0, n);
-        }
-        __syncwarp();
-        if (++st == kFrStages) { st = 0; ph ^= 1; }
       }
+      si_base = __shfl_sync(0xFFFFFFFFu, l_si, nb - 1);
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ===========================================
@@ -286,15 +317,16 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
 #pragma unroll
               for (int k = 0; k < 4; ++k) umma_bf16(d_base, ad + 2 * k, bd + 2 * k, idesc, (kc > 0 || dy > 0 || k > 0) ? 1u : 0u);
             }
-          } else
+          } else {
 #pragma unroll 1
-          for (int j = 0; j < 9; ++j) {
-            const uint64_t ad = umma_desc_sw128(a_base + c_aoff[kind][j], 10 * 128);
-            const uint64_t bd = umma_desc_sw128(w_base + j * wtap_bytes, 1024);
-            const uint32_t d = d_base + c_acc[kind][j] * kAccCols;
-            const uint32_t keep = (kc > 0 || !c_first[kind][j]) ? 1u : 0u;
+            for (int j = 0; j < 9; ++j) {
+              const uint64_t ad = umma_desc_sw128(a_base + c_aoff[kind][j], 10 * 128);
+              const uint64_t bd = umma_desc_sw128(w_base + j * wtap_bytes, 1024);
+              const uint32_t d = d_base + c_acc[kind][j] * kAccCols;
+              const uint32_t keep = (kc > 0 || !c_first[kind][j]) ? 1u : 0u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
+              for (int k = 0; k < 4; ++k) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
+            }
           }
           umma_commit(bar_aempty + 8 * st);
           if (last_in_seg) umma_commit(bar_wempty + 8 * slot);
@@ -307,9 +339,12 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       if (g == 0) gph ^= 1;
     }
   } else if (warp < 2 + kEpiWarps) {
-    // ================================ epilogue (8 warps) ===================================
+    // ================================ epilogue (16 warps) ==================================
+    // warp = (TMEM lane quarter q, column part): 16 of the 64 accumulator columns of 32 pixels per item.  Sixteen
+    // narrow warps instead of eight wide ones: the per-item epilogue is a dependent chain (TMEM load -> shuffles ->
+    // bias/ReLU/residual -> pack -> store), its latency, not its instruction count, bounds the item rate.
     const int q = warp & 3;                                // TMEM lane quarter of this warp
-    const int half = (warp - 2) >> 2;                      // which 32 of the 64 accumulator columns
+    const int part = (warp - 2) >> 2;                      // which 16 of the 64 accumulator columns
     const int m = q * 32 + lane;
     const int pr = m >> 3, pc = m & 7;
     float* s_bias = s_bias_all + (warp - 2) * 64;
@@ -329,108 +364,89 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         __syncwarp();
         cur_si = si;
       }
-      const int local = it - S.item_begin;
-      const int tx = local % S.tiles_x;
-      const int r = local / S.tiles_x;
-      const int ty = r % S.tiles_y;
-      const int n = r / S.tiles_y;
-      const int iy = ty * kTileH + pr, ix = tx * kTileW + pc;
-      const bool valid = (iy < S.h) && (ix < S.w);
-      const int n_acc = S.wide ? 0 : ((S.kind == kConv3x3) ? 1 : 4);
-      const int sc = (S.kind == kConv3x3) ? 1 : 2;
+      const uint32_t local = static_cast<uint32_t>(it - S.item_begin);
+      const uint32_t r = fdiv(local, S.fd_tiles_x);
+      const int tx = static_cast<int>(local - r * S.tiles_x);
+      const int n = static_cast<int>(fdiv(r, S.fd_tiles_y));
+      const int ty = static_cast<int>(r) - n * S.tiles_y;
       mbar_wait(bar_cfull + 8 * g, gph);
       tc_fence_after();
+      const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * kGroupCols);
       if (S.wide) {
         // GEMM row = (tile row q, box column lane); columns [dx*nt + c] hold the partial sum of filter column dx
         // evaluated AT this box pixel: out[x] = P0[x-1] + P1[x] + P2[x+1]  ->  lanes l-1, l, l+1 of this warp
         const int wy = ty * kWideH + q, wx = tx * kWideW - 1 + lane;
         const bool wvalid = (lane >= 1) && (lane <= kWideW) && (wy < S.h) && (wx < S.w);
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * kGroupCols);
         if (S.out_mode == kOutNHWCbf16) {
-          uint32_t v0[32], v1[32], v2[32];
-          tmem_ld_32x32(taddr + half * 32, v0);
-          tmem_ld_32x32(taddr + 64 + half * 32, v1);
-          tmem_ld_32x32(taddr + 128 + half * 32, v2);
+          uint32_t v0[16], v1[16], v2[16];
+          tmem_ld_32x16(tq + part * 16, v0);
+          tmem_ld_32x16(tq + 64 + part * 16, v1);
+          tmem_ld_32x16(tq + 128 + part * 16, v2);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
+          for (int e = 0; e < 16; ++e) {
             const float l = __shfl_up_sync(0xFFFFFFFFu, __uint_as_float(v0[e]), 1);
             const float r2 = __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(v2[e]), 1);
             v1[e] = __float_as_uint((l + __uint_as_float(v1[e])) + r2);
           }
           if (wvalid) {
             const size_t pix = (static_cast<size_t>(n) * S.oh + wy) * S.ow + wx;
-            const size_t off = (pix * S.oc + S.ch0) * 2 + half * 64;
-            epi_store_bf16(v1, s_bias + half * 32, static_cast<uint8_t*>(S.out) + off,
+            const size_t off = (pix * S.oc + S.ch0) * 2 + part * 32;
+            epi_store_bf16(v1, s_bias + part * 16, static_cast<uint8_t*>(S.out) + off,
                            S.resid ? static_cast<const uint8_t*>(S.resid) + off : nullptr, S.relu != 0);
           }
         } else {
           uint32_t v0[4], v1[4], v2[4];                    // 3 output channels of each of the 3 partial sums
-          tmem_ld_32x4(taddr, v0);
-          tmem_ld_32x4(taddr + 16, v1);
-          tmem_ld_32x4(taddr + 32, v2);
+          tmem_ld_32x4(tq, v0);
+          tmem_ld_32x4(tq + 16, v1);
+          tmem_ld_32x4(tq + 32, v2);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
-          float z[3];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float l = __shfl_up_sync(0xFFFFFFFFu, __uint_as_float(v0[c]), 1);
-            const float r2 = __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(v2[c]), 1);
-            z[c] = (l + __uint_as_float(v1[c])) + r2 + s_bias[c];
-          }
-          if (wvalid) {
+          const int c = part < 3 ? part : 2;               // plane of this warp (part 3 idles)
+          const float l = __shfl_up_sync(0xFFFFFFFFu, __uint_as_float(c == 0 ? v0[0] : (c == 1 ? v0[1] : v0[2])), 1);
+          const float r2 = __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(c == 0 ? v2[0] : (c == 1 ? v2[1] : v2[2])), 1);
+          const float z = (l + __uint_as_float(c == 0 ? v1[0] : (c == 1 ? v1[1] : v1[2]))) + r2 + s_bias[c];
+          if (wvalid && part < 3 && part < S.oc) {
             const size_t plane = static_cast<size_t>(S.oh) * S.ow;
-            const size_t o0 = static_cast<size_t>(n) * S.out_nstride + static_cast<size_t>(wy) * S.ow + wx;
-            // 3 output planes: warps of half 0 store planes 0 and 1, warps of half 1 store plane 2
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              if ((c >> 1) != half || c >= S.oc) continue;
-              if (S.out2) S.out2[o0 + c * plane] = z[c];
-              static_cast<float*>(S.out)[o0 + c * plane] = 1.f / (1.f + expf(-z[c]));
-            }
+            const size_t o = static_cast<size_t>(n) * S.out_nstride + static_cast<size_t>(wy) * S.ow + wx + c * plane;
+            if (S.out2) S.out2[o] = z;
+            static_cast<float*>(S.out)[o] = 1.f / (1.f + expf(-z));
           }
         }
-      }
-      for (int a = 0; a < n_acc; ++a) {
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                               static_cast<uint32_t>(g * kGroupCols + a * kAccCols);
-        const int oy = iy * sc + (a >> 1), ox = ix * sc + (a & 1);
-        if (S.out_mode == kOutNHWCbf16) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + half * 32, v);
+      } else {
+        const int iy = ty * kTileH + pr, ix = tx * kTileW + pc;
+        const bool valid = (iy < S.h) && (ix < S.w);
+        const int n_acc = (S.kind == kConv3x3) ? 1 : 4;
+        const int sc = (S.kind == kConv3x3) ? 1 : 2;
+        for (int a = 0; a < n_acc; ++a) {
+          const uint32_t taddr = tq + static_cast<uint32_t>(a * kAccCols);
+          const int oy = iy * sc + (a >> 1), ox = ix * sc + (a & 1);
+          uint32_t v[16];
+          tmem_ld_32x16(taddr + (S.out_mode == kOutNHWCbf16 ? part * 16 : 0), v);
           tmem_ld_wait();
           if (a == n_acc - 1) {                            // TMEM drained -> hand the group back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
           }
-          if (valid) {
-            const size_t pix = (static_cast<size_t>(n) * S.oh + oy) * S.ow + ox;
-            const size_t off = (pix * S.oc + S.ch0) * 2 + half * 64;
-            epi_store_bf16(v, s_bias + half * 32, static_cast<uint8_t*>(S.out) + off,
-                           S.resid ? static_cast<const uint8_t*>(S.resid) + off : nullptr, S.relu != 0);
-          }
-        } else {
-          uint32_t v[16];
-          tmem_ld_32x16(taddr, v);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
-          if (valid) {
-            const size_t plane = static_cast<size_t>(S.oh) * S.ow;
-            const size_t o0 = static_cast<size_t>(n) * S.out_nstride + static_cast<size_t>(oy) * S.ow + ox;
-            // 3 output planes: warps of half 0 store planes 0 and 1, warps of half 1 store plane 2
-            for (int c = half * 2; c < min(S.oc, half * 2 + 2); ++c) {
-              const float z = __uint_as_float(v[c]) + s_bias[c];
-              if (S.out2) S.out2[o0 + c * plane] = z;
-              static_cast<float*>(S.out)[o0 + c * plane] = 1.f / (1.f + expf(-z));
+          if (S.out_mode == kOutNHWCbf16) {
+            if (valid) {
+              const size_t pix = (static_cast<size_t>(n) * S.oh + oy) * S.ow + ox;
+              const size_t off = (pix * S.oc + S.ch0) * 2 + part * 32;
+              epi_store_bf16(v, s_bias + part * 16, static_cast<uint8_t*>(S.out) + off,
+                             S.resid ? static_cast<const uint8_t*>(S.resid) + off : nullptr, S.relu != 0);
             }
+          } else if (valid && part < 3 && part < S.oc) {     // output conv, tall geometry: plane `part`
+            const size_t plane = static_cast<size_t>(S.oh) * S.ow;
+            const size_t o = static_cast<size_t>(n) * S.out_nstride + static_cast<size_t>(oy) * S.ow + ox + part * plane;
+            const float z = __uint_as_float(part == 0 ? v[0] : (part == 1 ? v[1] : v[2])) + s_bias[part];
+            if (S.out2) S.out2[o] = z;
+            static_cast<float*>(S.out)[o] = 1.f / (1.f + expf(-z));
           }
         }
       }
@@ -453,7 +469,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       const FrSeg& S = P.segs[si];
       if (S.out_mode == kOutNHWCbf16 && !(P.dbg & 2)) {
         const uint32_t pg = pk & 1u, pph = (pk >> 1) & 1u;
-        mbar_wait(bar_pfull + 8 * pg, pph);                  // all 256 epilogue threads stored (acquire.cta)
+        mbar_wait(bar_pfull + 8 * pg, pph);                  // all epilogue threads stored (acquire.cta)
         if (lane == 0) {
           red_release_gpu_add(P.flags + S.flag_off + (it - S.item_begin), kItemDone);   // cumulative gpu-scope release
           mbar_arrive(bar_pempty + 8 * pg);
@@ -461,6 +477,76 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         __syncwarp();
         ++pk;
       }
+    }
+  } else if (!(P.dbg & 1)) {
+    // ================================ dependency warp ======================================
+    // For every item whose input comes from a layer of this launch: wait until the producer tiles that the item's
+    // halo box touches are published (one counter per tile, one lane per counter), two items per round trip:
+    // relaxed gpu-scope loads of both items' counters in flight together, one fence.acq_rel.gpu for both in the
+    // common already-published case (relaxed load that observed the released value + fence = acquire), then one
+    // mbarrier arrive per item for the producer.
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // the counters are cleared by the previous kernel of the stream
+    uint32_t dk = 0;
+    int si_base = 0;
+    for (int it0 = blockIdx.x; it0 < P.total_items; it0 += 32 * G) {
+      uint32_t l0, l1, l2, l3;
+      int l_si;
+      decode_batch(P, it0, lane, G, si_base, l0, l1, l2, l3, l_si);
+      const int left = (P.total_items - it0 + G - 1) / G;
+      const int nb = left < 32 ? left : 32;
+      // counter address of this lane for batch item j (nullptr: no counter for this lane); *has = item has dependencies
+      auto dep_flag = [&](int j, bool* has) -> const uint32_t* {
+        const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, l0, j), b2 = __shfl_sync(0xFFFFFFFFu, l2, j),
+                       b3 = __shfl_sync(0xFFFFFFFFu, l3, j);
+        *has = b3 != 0;
+        if (b3 == 0) return nullptr;
+        const FrSeg& S = P.segs[b0 & 0xFFu];
+        const uint32_t nx = b3 & 15u, ny = (b3 >> 4) & 15u, inv = b3 >> 8;
+        const uint32_t nxy = nx * ny;
+        uint32_t q = static_cast<uint32_t>(lane);
+        if (q >= nxy * static_cast<uint32_t>(S.dep_nseg)) return nullptr;
+        const uint32_t ds = q >= nxy ? 1u : 0u;                     // dep_nseg <= 2 (host-checked)
+        q -= ds * nxy;
+        const uint32_t qy = (q * inv) >> 16, qx = q - qy * nx;
+        return P.flags + P.segs[S.dep_seg0 + ds].flag_off +
+               ((b0 >> 8) * S.dep_tiles_y + (b2 >> 16) + qy) * S.dep_tiles_x + (b2 & 0xFFFFu) + qx;
+      };
+      auto spin = [&](const uint32_t* f, int j) {
+        const uint64_t t0 = global_ns();
+        uint32_t spins = 0;
+        while (ld_relaxed_gpu(f) < kItemDone) {
+          __nanosleep(32);
+          if ((++spins & 0x3FFu) == 0 && global_ns() - t0 > 4000000000ull) {
+            printf("tg: frame dependency timeout item=%d block=%d\n", it0 + j * G, blockIdx.x);
+            __trap();
+          }
+        }
+      };
+      for (int j = 0; j < nb; j += 2) {
+        bool has0, has1 = false;
+        const uint32_t* p0 = dep_flag(j, &has0);
+        const uint32_t* p1 = (j + 1 < nb) ? dep_flag(j + 1, &has1) : nullptr;
+        if (!has0 && !has1) continue;
+        const uint32_t v0 = p0 ? ld_relaxed_gpu(p0) : kItemDone;
+        const uint32_t v1 = p1 ? ld_relaxed_gpu(p1) : kItemDone;
+        // Item j is handed over BEFORE item j+1 is waited for: j+1 may depend on j itself (a layer of exactly G tiles).
+        if (v0 < kItemDone) spin(p0, j);
+        if (!(P.dbg & 4)) fence_acq_rel_gpu();
+        for (int h = 0; h < 2; ++h) {
+          if (h == 1 && v1 < kItemDone) {                  // rare: not yet published at the paired load
+            spin(p1, j + 1);
+            if (!(P.dbg & 4)) fence_acq_rel_gpu();
+          }
+          __syncwarp();
+          if (!(h ? has1 : has0)) continue;
+          const uint32_t ds = dk % kDepRing;
+          mbar_wait(bar_dempty + 8 * ds, ((dk / kDepRing) & 1u) ^ 1u);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_dfull + 8 * ds);
+          ++dk;
+        }
+      }
+      si_base = __shfl_sync(0xFFFFFFFFu, l_si, nb - 1);
     }
   }
 
@@ -503,6 +589,7 @@ size_t frame_flag_count(const FrLayer* layers, int nlayers, int n) {
 int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t packed_bytes, int n,
                  uint32_t* flags, size_t flag_capacity, bool flags_zeroed, cudaStream_t stream) {
   TG_CHECK_ARG(nlayers >= 1 && nlayers + 1 <= kFrMaxMaps, "frame: too many layers (%d)", nlayers);
+  static_assert(kFrMaxSegs <= 256, "segment index is packed into 8 bits");
   TG_CHECK_ARG(packed && flags && (packed_bytes % 128) == 0, "frame: bad packed blob");
   static thread_local FrProgram P;   // 13 KB: keep it off the stack
   memset(&P, 0, sizeof(P));
@@ -521,6 +608,7 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
     TG_CHECK_ARG(l.cin_pad == 64 || l.cin_pad == 128, "frame: cin_pad must be 64 or 128");
     TG_CHECK_ARG(l.cout_pad == 16 || l.cout_pad == 64 || l.cout_pad == 128, "frame: cout_pad must be 16/64/128");
     TG_CHECK_ARG((l.blob_off % 128) == 0, "frame: packed blob offsets must be 128-byte aligned");
+    TG_CHECK_ARG(l.w < 32768 && l.h < 32768 && n < (1 << 23), "frame: layer size out of range");
     {
       cuuint64_t dims[4] = {static_cast<cuuint64_t>(l.cin_pad), static_cast<cuuint64_t>(l.w),
                             static_cast<cuuint64_t>(l.h), static_cast<cuuint64_t>(n)};
@@ -550,6 +638,7 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
       S.tiles_x = tiles_x; S.tiles_y = tiles_y; S.h = l.h; S.w = l.w;
       S.wide = wide ? 1 : 0; S.tile_w = tile_w; S.tile_h = tile_h;
       S.box_w = wide ? kWideBoxW : kTileW + 2; S.box_h = wide ? kWideBoxH : kTileH + 2;
+      S.fd_tiles_x = make_fastdiv(tiles_x); S.fd_tiles_y = make_fastdiv(tiles_y);
       S.map_a = 1 + li;
       S.kchunks = kchunks; S.kind = l.kind; S.nt = nt;
       S.w_rows = 9u * nt;
@@ -574,6 +663,11 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
         const int ptw = pwide ? kWideW : kTileW, pth = pwide ? kWideH : kTileH;
         S.dep_tiles_x = tg_div_up(pl.w, ptw); S.dep_tiles_y = tg_div_up(pl.h, pth);
         S.dep_tw = ptw * psc; S.dep_th = pth * psc;   // producer tile footprint in this layer's input pixels
+        S.fd_dep_tw = make_fastdiv(S.dep_tw); S.fd_dep_th = make_fastdiv(S.dep_th);
+        // one poll lane per producer tile touched by the halo box
+        const int mx = (S.box_w + S.dep_tw - 2) / S.dep_tw + 1, my = (S.box_h + S.dep_th - 2) / S.dep_th + 1;
+        TG_CHECK_ARG(S.dep_nseg <= 2 && mx <= 15 && my <= 15 && mx * my * S.dep_nseg <= 32,
+                     "frame: layer %d waits on too many producer tiles (%d x %d x %d)", li, mx, my, S.dep_nseg);
       }
       S.flag_off = static_cast<uint32_t>(S.item_begin);
       ++nseg;

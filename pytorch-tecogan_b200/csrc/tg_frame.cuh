@@ -16,6 +16,22 @@ constexpr int kFrMaxMaps = 44;     // [0] packed weights, [1 + layer] input acti
 // in shared memory (profiles/r01_mma_microbench.txt), so 12 MMAs of N=192 per 120 pixels replace 36 of N=64 per 128.
 constexpr int kWideW = 30, kWideH = 4, kWideBoxW = 32, kWideBoxH = 6;
 
+// Exact unsigned division by a launch-time constant (Granlund-Montgomery round-up): q = (umulhi(x, m) + x) >> s for
+// x < 2^31.  The item decode of every warp role sits on its per-item critical path; a hardware-free integer division
+// is ~100 cycles of dependent instructions, this is ~10.
+struct FastDiv { uint32_t m, s; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  FastDiv f;
+  f.m = static_cast<uint32_t>(((1ull << 32) * ((1ull << s) - d)) / d + 1);
+  f.s = s;
+  return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, FastDiv f) { return (__umulhi(x, f.m) + x) >> f.s; }
+#endif
+
 // One segment = one (layer, 64-wide output-channel chunk) pass over all tiles of the layer.
 struct FrSeg {
   int item_begin, item_end;   // global item range [begin, end)
@@ -40,6 +56,7 @@ struct FrSeg {
   // tile-level dependencies: the producer layer's segments
   int dep_seg0, dep_nseg;     // first producer segment, count (0 = input comes from a previous kernel)
   int dep_tiles_x, dep_tiles_y, dep_tw, dep_th;   // producer tile = (y / dep_th, x / dep_tw) in this layer's input pixels
+  FastDiv fd_tiles_x, fd_tiles_y, fd_dep_tw, fd_dep_th;
   uint32_t flag_off;          // offset of this segment's per-item completion counters
 };
 
@@ -49,7 +66,7 @@ struct FrProgram {
   int nseg, total_items;
   uint32_t* flags;            // zeroed before the launch; one counter per item (128 = complete)
   unsigned long long* trace;  // optional [nseg+1][grid] globaltimer stamps (tg_frame_set_trace), else null
-  int dbg;                    // measurement-only knobs (TG_FRAME_DBG): 1 no dependency wait, 2 no publish
+  int dbg;                    // measurement-only knobs (TG_FRAME_DBG): 1 no dependency wait, 2 no publish, 4 no acquire fence
 };
 
 struct FrLayer {              // host-side description of one conv layer of the frame
