@@ -99,12 +99,19 @@ static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) 
          blockIdx.y, threadIdx.x);
   __trap();
 }
+// The slow path is the idle loop of every waiting warp: it must stay a handful of instructions (try_wait suspends in
+// hardware for ~200 cycles per attempt; a timer read per attempt tripled the instructions a waiting warp issues).  The
+// clock is consulted once per 2^16 attempts.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_ns();
+  uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xFFu) == 0 && global_ns() - t0 > 4000000000ull) mbar_timeout(bar, parity);  // 4 s
+    if ((++spins & 0xFFFFu) == 0) {
+      const uint64_t now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) mbar_timeout(bar, parity);  // 4 s
+    }
   }
 }
 

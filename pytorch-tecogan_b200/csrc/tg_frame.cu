@@ -23,6 +23,14 @@
 //     set up once per frame.
 // The GEMM core is the one of tg_conv_tc.cu (A = activation halo box, nine row-shifted descriptor
 // views; B = weights; accumulators in TMEM; UMMA M=128, N=64, K=16).
+//
+// Pair mode (template kPair, the default): the CTAs of two SMs of a TPC form a cluster and run their items in
+// lock-step as ONE tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own item's activation box and HALF of
+// the weight rows (N/2), the leader CTA issues for both, every CTA keeps its own 128 accumulator lanes and its own
+// epilogue / publisher / dependency warps.  With both operands in shared memory a single-CTA MMA costs 43 + N/2
+// cycles (the A fetch is not hidden), the paired one N/2 (profiles/r01_mma_microbench_v2.txt: N=192 138 -> 96 cycles
+// for twice the work).  Segments are padded to an even item count; the padding ("phantom") item of the odd CTA loads
+// an out-of-range box (zero fill), computes, and is dropped by the epilogue.
 #include <stdlib.h>
 #include <string.h>
 
@@ -34,20 +42,28 @@ constexpr int kEpiWarps = 16;                          // 4 per TMEM lane quarte
 constexpr int kFrThreads = 32 * (2 + kEpiWarps + 2);   // producer, MMA, epilogue warps, publisher, dependency warp
 constexpr int kDepRing = 4;                            // dependency warp runs at most this many items ahead of the producer
 constexpr uint32_t kFrSmemLimit = 232448;
-constexpr uint32_t kWSlotBytes = 73728;               // 9 taps x 64 x 64 bf16
 constexpr uint32_t kAStride = 24576;                  // stage pitch: {64ch, 32, 6} wide box (24576 B) / {64ch, 10, 18} tall box (23040 B)
-constexpr int kFrStages = 3;
+constexpr uint32_t kBarBytes = 512;                   // mbarrier area
 constexpr int kWBoxRows = 48;                         // weight TMA box: 48 rows x 128 B
+template <bool kPair> struct FrCfg {
+  static constexpr uint32_t kWSlotBytes = kPair ? 36864u : 73728u;   // 9 taps x 64 x 64 bf16 (half of the rows per CTA of a pair)
+  static constexpr int kStages = kPair ? 6 : 3;                       // A ring depth
+  static constexpr uint32_t kSmemBytes = 2 * kWSlotBytes + kStages * kAStride + kBarBytes + 16 + kEpiWarps * 64 * 4 +
+                                         kFrMaxSegs * sizeof(FrSegS) + 1024;
+};
+static_assert(FrCfg<true>::kSmemBytes <= kFrSmemLimit && FrCfg<false>::kSmemBytes <= kFrSmemLimit, "smem budget");
 constexpr int kGroupCols = 256;                       // TMEM columns per accumulator group (2 groups)
 constexpr uint32_t kItemDone = 128;                   // counter value of a published tile
 
 // tap tables: [kind][j] ; A view offset inside the staged box, accumulator, "first tap of accumulator"
-__constant__ uint32_t c_aoff[2][9] = {
+// [2]: 3x3 conv on the WIDE box, one view per tap (row pitch 32 pixels = 4096 B)
+__constant__ uint32_t c_aoff[3][9] = {
     {0 * 128, 1 * 128, 2 * 128, 10 * 128, 11 * 128, 12 * 128, 20 * 128, 21 * 128, 22 * 128},
     //  phase:   00 | 01        | 10         | 11
-    {0 * 128, 0 * 128, 1 * 128, 0 * 128, 10 * 128, 0 * 128, 1 * 128, 10 * 128, 11 * 128}};
-__constant__ uint8_t c_acc[2][9] = {{0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 1, 1, 2, 2, 3, 3, 3, 3}};
-__constant__ uint8_t c_first[2][9] = {{1, 0, 0, 0, 0, 0, 0, 0, 0}, {1, 1, 0, 1, 0, 1, 0, 0, 0}};
+    {0 * 128, 0 * 128, 1 * 128, 0 * 128, 10 * 128, 0 * 128, 1 * 128, 10 * 128, 11 * 128},
+    {0 * 128, 1 * 128, 2 * 128, 32 * 128, 33 * 128, 34 * 128, 64 * 128, 65 * 128, 66 * 128}};
+__constant__ uint8_t c_acc[3][9] = {{0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 1, 1, 2, 2, 3, 3, 3, 3}, {0, 0, 0, 0, 0, 0, 0, 0, 0}};
+__constant__ uint8_t c_first[3][9] = {{1, 0, 0, 0, 0, 0, 0, 0, 0}, {1, 1, 0, 1, 0, 1, 0, 0, 0}, {1, 0, 0, 0, 0, 0, 0, 0, 0}};
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   uint32_t v;
@@ -85,26 +101,141 @@ __device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t (&v)[4]) {
                : "memory");
 }
 
-// 16 f32 accumulator columns of one pixel -> + bias, ReLU, + residual -> 16 bf16 channels (one 32-byte store, NHWC)
-__device__ __forceinline__ void epi_store_bf16(const uint32_t (&v)[16], const float* bias16, uint8_t* dst,
-                                               const uint8_t* res, bool relu) {
-  float f[16];
-#pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    f[e] = __uint_as_float(v[e]) + bias16[e];
-    if (relu) f[e] = fmaxf(f[e], 0.f);
+
+// ---- CTA-pair (cta_group::2) primitives ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  // relaxed: a release at cluster scope would first wait for the thread's earlier global stores (the previous item's
+  // epilogue); what this arrive orders - TMEM reads before the issuer's next MMA - is ordered by the tcgen05 fences
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0xFFFFu) == 0) {
+      const uint64_t now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) mbar_timeout(bar, parity);
+    }
   }
+}
+// TMA loads of a CTA pair: data lands in THIS CTA's shared memory, the transaction bytes are counted on `bar`, a
+// shared::cluster address that may belong to the peer (the leader's full barrier)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 from each CTA's smem] * B[N rows: N/2 from each CTA's smem]
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the same offset in BOTH CTAs once every MMA issued so far has completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+
+// Packed f32x2 arithmetic (FADD2): the epilogue's instruction count, not its math, is what it pays for.
+__device__ __forceinline__ uint64_t f2_pack(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t f2_to_bf16x2(uint64_t v) {
+  uint32_t lo, hi, r;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
+// 16 f32 accumulator columns of one pixel (8 f32x2 pairs) -> + bias, ReLU, + residual -> 16 bf16 channels (one 32-byte
+// store, NHWC).  ReLU commutes with the rounding to bf16, so it is one bf16x2 max per pair; a layer has a ReLU or a
+// residual, never both (launch_frame checks).
+__device__ __forceinline__ void epi_store_bf16(uint64_t (&a)[8], const float* bias16, uint8_t* dst, const uint8_t* res,
+                                               bool relu) {
+  const uint64_t* b2 = reinterpret_cast<const uint64_t*>(bias16);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = f2_add(a[e], b2[e]);
+  uint32_t o[8];
   if (res) {
     uint32_t rv[8];
     ld_global_cg_v8(res, rv);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { f[2 * e] += bf16_lo(rv[e]); f[2 * e + 1] += bf16_hi(rv[e]); }
-  }
-  uint32_t o[8];
+    for (int e = 0; e < 8; ++e) {
+      o[e] = f2_to_bf16x2(f2_add(a[e], f2_pack(rv[e] << 16, rv[e] & 0xFFFF0000u)));
+    }
+  } else {
 #pragma unroll
-  for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+    for (int e = 0; e < 8; ++e) {
+      o[e] = f2_to_bf16x2(a[e]);
+      if (relu) asm("max.bf16x2 %0, %1, %2;" : "=r"(o[e]) : "r"(o[e]), "r"(0u));
+    }
+  }
   st_global_v8(dst, o);
 }
+
+// Stall accounting (measurement only, FrProgram::stats != null): cycles a role spends in each of its waits.
+template <bool kOn>
+struct Tick {
+  long long t;
+  bool on;        // stats requested
+  bool gate;      // current item belongs to the selected segment (FrProgram::stat_seg, -1 = every segment)
+  __device__ __forceinline__ void start() { if (kOn && on) t = clock64(); }
+  __device__ __forceinline__ void stop(long long& acc) { if (kOn && on && gate) acc += clock64() - t; }
+};
 
 // Weight-slot LRU pair.  Producer and MMA warps run the same deterministic state machine over the
 // same item sequence, so they agree on slot and load parity without communicating.
@@ -149,7 +280,7 @@ __device__ __forceinline__ void decode_batch(const FrProgram& P, int it0, int la
     const int bx0 = tx * S.tile_w + origin, by0 = ty * S.tile_h + origin;
     l0 = static_cast<uint32_t>(l_si) | (n << 8);
     l1 = (static_cast<uint32_t>(bx0) & 0xFFFFu) | (static_cast<uint32_t>(by0) << 16);
-    if (S.dep_nseg > 0) {
+    if (S.dep_nseg > 0 && local < static_cast<uint32_t>(S.items_real)) {   // (a pair's padding item waits for nothing)
       // producer tiles of the previous layer touched by the halo box (clipped to the image)
       const int ya = max(by0, 0), yb = min(by0 + S.box_h - 1, S.h - 1);
       const int xa = max(bx0, 0), xb = min(bx0 + S.box_w - 1, S.w - 1);
@@ -162,10 +293,18 @@ __device__ __forceinline__ void decode_batch(const FrProgram& P, int it0, int la
   }
 }
 
+// kDbg: the measurement build (TG_FRAME_DBG knobs, segment trace, stall accounting); the production build has none of it.
+template <bool kPair, bool kDbg>
 __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_constant__ FrProgram P) {
+  const int dbg = kDbg ? P.dbg : 0;
+  unsigned long long* const trace = kDbg ? P.trace : nullptr;
+  unsigned long long* const stats = kDbg ? P.stats : nullptr;
+  const int stat_seg = kDbg ? P.stat_seg : -1;
+  constexpr uint32_t kWSlotBytes = FrCfg<kPair>::kWSlotBytes;
+  constexpr int kFrStages = FrCfg<kPair>::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t base = (raw + 1023u) & ~1023u;     // the same offset in both CTAs of a pair (same kernel, same layout)
   uint8_t* gbase = smem_raw + (base - raw);
 
   const uint32_t s_w = base;
@@ -176,24 +315,31 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
   const uint32_t bar_cfull = bar_aempty + 8 * kFrStages, bar_cempty = bar_cfull + 16;
   const uint32_t bar_pfull = bar_cempty + 16, bar_pempty = bar_pfull + 16;
   const uint32_t bar_dfull = bar_pempty + 16, bar_dempty = bar_dfull + 8 * kDepRing;
-  const uint32_t off_misc = (bar_dempty + 8 * kDepRing) - base;
+  static_assert(32 + 16 * FrCfg<kPair>::kStages + 64 + 16 * kDepRing <= kBarBytes, "barrier area");
+  const uint32_t off_misc = (bar0 + kBarBytes) - base;
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gbase + off_misc);
   float* s_bias_all = reinterpret_cast<float*>(gbase + off_misc + 16);   // [kEpiWarps][64]
+  FrSegS* segs = reinterpret_cast<FrSegS*>(gbase + off_misc + 16 + kEpiWarps * 64 * 4);   // [nseg]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // Pair mode: rank 0 of the cluster (the leader) issues the MMAs.  The "full" barriers (weights, activation stages)
+  // and the "accumulator drained" barriers the issuer waits on live in the leader and take one arrival per CTA;
+  // everything the MMA completion signals (stage / weight slot free, accumulator ready) is multicast to both CTAs.
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const uint32_t nctas = kPair ? 2u : 1u;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_wfull + 8 * i, 1);
+      mbar_init(bar_wfull + 8 * i, nctas);
       mbar_init(bar_wempty + 8 * i, 1);
       mbar_init(bar_cfull + 8 * i, 1);
-      mbar_init(bar_cempty + 8 * i, kEpiWarps);
+      mbar_init(bar_cempty + 8 * i, kEpiWarps * nctas);
       mbar_init(bar_pfull + 8 * i, kEpiWarps * 32);
       mbar_init(bar_pempty + 8 * i, 1);
     }
     for (int i = 0; i < kFrStages; ++i) {
-      mbar_init(bar_afull + 8 * i, 1);
+      mbar_init(bar_afull + 8 * i, nctas);
       mbar_init(bar_aempty + 8 * i, 1);
     }
     for (int i = 0; i < kDepRing; ++i) {
@@ -202,12 +348,35 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
+  if (warp == 1) {
+    if (kPair) tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
+    else tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
+  }
+  for (int i = threadIdx.x; i < P.nseg; i += kFrThreads) {
+    const FrSeg& S = P.segs[i];
+    FrSegS c;
+    c.item_begin = S.item_begin; c.item_end = S.item_end; c.items_real = S.items_real;
+    c.tiles_x = static_cast<uint16_t>(S.tiles_x); c.tiles_y = static_cast<uint16_t>(S.tiles_y);
+    c.h = static_cast<uint16_t>(S.h); c.w = static_cast<uint16_t>(S.w);
+    c.oh = static_cast<uint16_t>(S.oh); c.ow = static_cast<uint16_t>(S.ow);
+    c.oc = static_cast<uint16_t>(S.oc); c.ch0 = static_cast<uint16_t>(S.ch0);
+    c.wide = static_cast<uint8_t>(S.wide); c.out_mode = static_cast<uint8_t>(S.out_mode); c.relu = static_cast<uint8_t>(S.relu);
+    c.kind = static_cast<uint8_t>(S.kind); c.nt = static_cast<uint8_t>(S.nt); c.kchunks = static_cast<uint8_t>(S.kchunks);
+    c.pad0 = c.pad1 = 0;
+    c.fd_tiles_x = S.fd_tiles_x; c.fd_tiles_y = S.fd_tiles_y;
+    c.out_nstride = S.out_nstride; c.out = S.out; c.out2 = S.out2; c.resid = S.resid; c.bias = S.bias;
+    segs[i] = c;
+  }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();                    // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // leader-side barrier addresses (shared::cluster window; the CTA's own addresses when not paired)
+  const uint32_t lbar_wfull = kPair ? mapa_rank(bar_wfull, 0) : bar_wfull;
+  const uint32_t lbar_afull = kPair ? mapa_rank(bar_afull, 0) : bar_afull;
+  const uint32_t lbar_cempty = kPair ? mapa_rank(bar_cempty, 0) : bar_cempty;
 
   const int G = gridDim.x;
 
@@ -227,6 +396,9 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     uint32_t ph = 0, dk = 0;
     bool grid_waited = false;
     int si_base = 0;
+    Tick<kDbg> tk{0, stats != nullptr, true}, tall{0, stats != nullptr, true};
+    long long a_wempty = 0, a_dep = 0, a_aempty = 0, a_total = 0;
+    tall.start();
     for (int it0 = blockIdx.x; it0 < P.total_items; it0 += 32 * G) {
       uint32_t l0, l1, l2, l3;
       int l_si;
@@ -235,7 +407,9 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       const int nb = left < 32 ? left : 32;
       for (int j = 0; j < nb; ++j) {
         const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, l0, j), b1 = __shfl_sync(0xFFFFFFFFu, l1, j);
+        const bool has_dep = __shfl_sync(0xFFFFFFFFu, l3, j) != 0;
         const int si = static_cast<int>(b0 & 0xFFu), n = static_cast<int>(b0 >> 8);
+        tk.gate = stat_seg < 0 || si == stat_seg;
         const int bx0 = static_cast<int>(static_cast<int16_t>(b1 & 0xFFFFu)), by0 = static_cast<int>(b1) >> 16;
         const FrSeg& S = P.segs[si];
         for (int kc = 0; kc < S.kchunks; ++kc) {
@@ -243,12 +417,24 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           uint32_t nth;
           const int slot = ws.use(si * 2 + kc, &is_load, &nth);
           if (is_load) {
+            tk.start();
             mbar_wait(bar_wempty + 8 * slot, (nth & 1) ^ 1);
+            tk.stop(a_wempty);
             if (elect_one()) {
-              mbar_expect_tx(bar_wfull + 8 * slot, S.w_rows * 128);
-              for (uint32_t r0 = 0; r0 < S.w_rows; r0 += kWBoxRows)
-                tma_load_2d(s_w + slot * kWSlotBytes + r0 * 128, &P.maps[0], bar_wfull + 8 * slot, 0,
-                            static_cast<int>(S.w_row0[kc] + r0));
+              if (kPair) {
+                // this CTA's half of every N group: rows [rank * half, (rank + 1) * half) of the group's 2 * half rows
+                const uint32_t half = S.w_half_rows, box = S.w_box_rows;
+                mbar_expect_tx_cluster(lbar_wfull + 8 * slot, static_cast<uint32_t>(S.w_groups) * half * 128u);
+                for (uint32_t gi = 0; gi < static_cast<uint32_t>(S.w_groups); ++gi)
+                  for (uint32_t r0 = 0; r0 < half; r0 += box)
+                    tma_load_2d_pair(s_w + slot * kWSlotBytes + (gi * half + r0) * 128, &P.maps[S.w_map], lbar_wfull + 8 * slot, 0,
+                                     static_cast<int>(S.w_row0[kc] + gi * 2 * half + rank * half + r0));
+              } else {
+                mbar_expect_tx(bar_wfull + 8 * slot, S.w_rows * 128);
+                for (uint32_t r0 = 0; r0 < S.w_rows; r0 += kWBoxRows)
+                  tma_load_2d(s_w + slot * kWSlotBytes + r0 * 128, &P.maps[0], bar_wfull + 8 * slot, 0,
+                              static_cast<int>(S.w_row0[kc] + r0));
+              }
             }
             __syncwarp();
           }
@@ -256,18 +442,27 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
             asm volatile("griddepcontrol.wait;" ::: "memory");
             grid_waited = true;
           }
-          if (kc == 0 && S.dep_nseg > 0 && !(P.dbg & 1)) {           // dependencies acquired by the dependency warp
+          if (kc == 0 && has_dep && !(dbg & 1)) {                  // dependencies acquired by the dependency warp
             const uint32_t ds = dk % kDepRing;
+            tk.start();
             mbar_wait(bar_dfull + 8 * ds, (dk / kDepRing) & 1u);
+            tk.stop(a_dep);
             __syncwarp();                                            // every lane has seen this phase before it can be reused
             if (lane == 0) mbar_arrive(bar_dempty + 8 * ds);
             ++dk;
           }
+          tk.start();
           mbar_wait(bar_aempty + 8 * st, ph ^ 1);
+          tk.stop(a_aempty);
           if (elect_one()) {
-            fence_proxy_async_global();   // generic-proxy writes of other CTAs (acquired above) -> async-proxy read
-            mbar_expect_tx(bar_afull + 8 * st, static_cast<uint32_t>(S.box_w * S.box_h) * 128u);
-            tma_load_4d(s_a + st * kAStride, &P.maps[S.map_a], bar_afull + 8 * st, kc * 64, bx0, by0, n);
+            if (!(dbg & 64)) fence_proxy_async_global();   // generic-proxy writes of other CTAs (acquired above) -> async-proxy read
+            if (kPair) {
+              mbar_expect_tx_cluster(lbar_afull + 8 * st, static_cast<uint32_t>(S.box_w * S.box_h) * 128u);
+              tma_load_4d_pair(s_a + st * kAStride, &P.maps[S.map_a], lbar_afull + 8 * st, kc * 64, bx0, by0, n);
+            } else {
+              mbar_expect_tx(bar_afull + 8 * st, static_cast<uint32_t>(S.box_w * S.box_h) * 128u);
+              tma_load_4d(s_a + st * kAStride, &P.maps[S.map_a], bar_afull + 8 * st, kc * 64, bx0, by0, n);
+            }
           }
           __syncwarp();
           if (++st == kFrStages) { st = 0; ph ^= 1; }
@@ -275,34 +470,55 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       }
       si_base = __shfl_sync(0xFFFFFFFFu, l_si, nb - 1);
     }
+    tall.stop(a_total);
+    if (stats && lane == 0) {
+      unsigned long long* o = stats + blockIdx.x * 16;
+      o[9] = a_wempty; o[10] = a_dep; o[11] = a_aempty; o[12] = a_total;
+    }
   } else if (warp == 1) {
-    // ================================ MMA issuer ===========================================
+    // ================================ MMA issuer (leader CTA of a pair) ====================
+    if (rank == 0) {
     WSlots ws;
     ws.init();
     int si = 0, st = 0, g = 0;
     uint32_t ph = 0, gph = 0;
     int traced_si = -1;
+    Tick<kDbg> tk{0, stats != nullptr, true}, tall{0, stats != nullptr, true};
+    long long a_cempty = 0, a_wfull = 0, a_afull = 0, a_total = 0;
+    tall.start();
     for (int it = blockIdx.x; it < P.total_items; it += G) {
-      while (it >= P.segs[si].item_end) ++si;
-      const FrSeg& S = P.segs[si];
-      if (P.trace && si != traced_si) {
-        if (lane == 0) P.trace[static_cast<size_t>(si) * G + blockIdx.x] = global_ns();
+      while (it >= segs[si].item_end) ++si;
+      const FrSegS& S = segs[si];
+      if (trace && si != traced_si) {
+        if (lane == 0) trace[static_cast<size_t>(si) * G + blockIdx.x] = global_ns();
         traced_si = si;
       }
+      tk.gate = stat_seg < 0 || si == stat_seg;
       const bool last_in_seg = (it + G >= S.item_end);
-      const uint32_t idesc = umma_idesc_bf16(128, S.wide ? 3 * S.nt : S.nt);
-      const bool wide = S.wide != 0;
-      const uint32_t wtap_bytes = static_cast<uint32_t>(S.nt) * 128;
-      const int kind = S.kind;
-      mbar_wait(bar_cempty + 8 * g, gph ^ 1);
+      const uint32_t idesc = umma_idesc_bf16(kPair ? 256 : 128, S.wide == 1 ? 3 * S.nt : S.nt);
+      const bool wide = S.wide == 1;
+      const int tbl = S.wide == 2 ? 2 : S.kind;                // tap table (views inside the staged box)
+      const uint32_t sbo = S.wide == 2 ? 1024u : 10u * 128u;   // byte pitch of 8-pixel groups: wide rows are 32 pixels
+      const uint32_t wtap_bytes = static_cast<uint32_t>(S.nt) * (kPair ? 64 : 128);   // rows of one tap held by this CTA x 128 B
+      tk.start();
+      if (!(dbg & 8)) {
+        if (kPair && !(dbg & 32)) mbar_wait_cluster(bar_cempty + 8 * g, gph ^ 1);
+        else mbar_wait(bar_cempty + 8 * g, gph ^ 1);
+      }
+      tk.stop(a_cempty);
       tc_fence_after();
       const uint32_t d_base = tmem_base + static_cast<uint32_t>(g * kGroupCols);
       for (int kc = 0; kc < S.kchunks; ++kc) {
         bool is_load;
         uint32_t nth;
         const int slot = ws.use(si * 2 + kc, &is_load, &nth);
-        if (is_load) mbar_wait(bar_wfull + 8 * slot, nth & 1);
-        mbar_wait(bar_afull + 8 * st, ph);
+        tk.start();
+        if (is_load) { if (kPair && !(dbg & 32)) mbar_wait_cluster(bar_wfull + 8 * slot, nth & 1); else mbar_wait(bar_wfull + 8 * slot, nth & 1); }
+        tk.stop(a_wfull);
+        tk.start();
+        if (kPair && !(dbg & 32)) mbar_wait_cluster(bar_afull + 8 * st, ph);
+        else mbar_wait(bar_afull + 8 * st, ph);
+        tk.stop(a_afull);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_base = s_a + st * kAStride;
@@ -315,28 +531,60 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
               const uint64_t ad = umma_desc_sw128(a_base + dy * (kWideBoxW * 128), 1024);
               const uint64_t bd = umma_desc_sw128(w_base + dy * 3 * wtap_bytes, 1024);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(d_base, ad + 2 * k, bd + 2 * k, idesc, (kc > 0 || dy > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                if (kPair) umma_bf16_pair(d_base, ad + 2 * k, bd + 2 * k, idesc, (kc > 0 || dy > 0 || k > 0) ? 1u : 0u);
+                else umma_bf16(d_base, ad + 2 * k, bd + 2 * k, idesc, (kc > 0 || dy > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+          } else if (S.wide == 2) {
+            // one MMA group per tap on the wide box; everything but the two base descriptors is an immediate
+            const uint64_t ad0 = umma_desc_sw128(a_base, 1024), bd0 = umma_desc_sw128(w_base, 1024);
+            const uint64_t wstep = wtap_bytes >> 4;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+              const uint64_t ad = ad0 + static_cast<uint64_t>(((j / 3) * kWideBoxW * 128 + (j % 3) * 128) >> 4);
+              const uint64_t bd = bd0 + j * wstep;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (kPair) umma_bf16_pair(d_base, ad + 2 * k, bd + 2 * k, idesc, (kc > 0 || j > 0 || k > 0) ? 1u : 0u);
+                else umma_bf16(d_base, ad + 2 * k, bd + 2 * k, idesc, (kc > 0 || j > 0 || k > 0) ? 1u : 0u);
+              }
             }
           } else {
 #pragma unroll 1
             for (int j = 0; j < 9; ++j) {
-              const uint64_t ad = umma_desc_sw128(a_base + c_aoff[kind][j], 10 * 128);
+              const uint64_t ad = umma_desc_sw128(a_base + c_aoff[tbl][j], sbo);
               const uint64_t bd = umma_desc_sw128(w_base + j * wtap_bytes, 1024);
-              const uint32_t d = d_base + c_acc[kind][j] * kAccCols;
-              const uint32_t keep = (kc > 0 || !c_first[kind][j]) ? 1u : 0u;
+              const uint32_t d = d_base + c_acc[tbl][j] * kAccCols;
+              const uint32_t keep = (kc > 0 || !c_first[tbl][j]) ? 1u : 0u;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
+              for (int k = 0; k < 4; ++k) {
+                if (kPair) umma_bf16_pair(d, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
+                else umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
+              }
             }
           }
-          umma_commit(bar_aempty + 8 * st);
-          if (last_in_seg) umma_commit(bar_wempty + 8 * slot);
-          if (kc == S.kchunks - 1) umma_commit(bar_cfull + 8 * g);
+          if (kPair) {
+            umma_commit_pair(bar_aempty + 8 * st);
+            if (last_in_seg) umma_commit_pair(bar_wempty + 8 * slot);
+            if (kc == S.kchunks - 1) umma_commit_pair(bar_cfull + 8 * g);
+          } else {
+            umma_commit(bar_aempty + 8 * st);
+            if (last_in_seg) umma_commit(bar_wempty + 8 * slot);
+            if (kc == S.kchunks - 1) umma_commit(bar_cfull + 8 * g);
+          }
         }
         __syncwarp();
         if (++st == kFrStages) { st = 0; ph ^= 1; }
       }
       g ^= 1;
       if (g == 0) gph ^= 1;
+    }
+    tall.stop(a_total);
+    if (stats && lane == 0) {
+      unsigned long long* o = stats + blockIdx.x * 16;
+      o[0] = a_cempty; o[1] = a_wfull; o[2] = a_afull; o[3] = a_total;
+    }
     }
   } else if (warp < 2 + kEpiWarps) {
     // ================================ epilogue (16 warps) ==================================
@@ -355,28 +603,50 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     // the publisher warp then performs ONE gpu-scope release (MEMBAR.GPU + RED) for the whole tile, so the
     // fence latency never stalls the epilogue.
     uint32_t pk = 0;
+    Tick<kDbg> tk{0, stats != nullptr, true}, tall{0, stats != nullptr, true};
+    long long a_cfull = 0, a_body = 0, a_pub = 0, a_total = 0, a_tmem = 0;
+    tall.start();
+    float nb0 = 0.f, nb1 = 0.f;                            // bias of segment nb_si, fetched one segment ahead
+    int nb_si = -1;
     for (int it = blockIdx.x; it < P.total_items; it += G) {
-      while (it >= P.segs[si].item_end) ++si;
-      const FrSeg& S = P.segs[si];
+      while (it >= segs[si].item_end) ++si;
+      const FrSegS& S = segs[si];
       if (si != cur_si) {                                  // warp-private bias copy of this segment
         __syncwarp();
-        for (int c = lane; c < S.nt; c += 32) s_bias[c] = S.bias[c];
+        float b0 = nb0, b1 = nb1;
+        if (nb_si != si) {                                 // (first segment, or the CTA had no item in a segment)
+          b0 = lane < S.nt ? S.bias[lane] : 0.f;
+          b1 = lane + 32 < S.nt ? S.bias[lane + 32] : 0.f;
+        }
+        s_bias[lane] = b0;
+        s_bias[lane + 32] = b1;
         __syncwarp();
         cur_si = si;
+        if (si + 1 < P.nseg) {                             // in flight until the next segment starts
+          const FrSegS& N = segs[si + 1];
+          nb0 = lane < N.nt ? N.bias[lane] : 0.f;
+          nb1 = lane + 32 < N.nt ? N.bias[lane + 32] : 0.f;
+          nb_si = si + 1;
+        }
       }
       const uint32_t local = static_cast<uint32_t>(it - S.item_begin);
       const uint32_t r = fdiv(local, S.fd_tiles_x);
       const int tx = static_cast<int>(local - r * S.tiles_x);
       const int n = static_cast<int>(fdiv(r, S.fd_tiles_y));
       const int ty = static_cast<int>(r) - n * S.tiles_y;
+      const bool real = local < static_cast<uint32_t>(S.items_real);   // false: the padding item of a pair
+      tk.gate = stat_seg < 0 || si == stat_seg;
+      tk.start();
       mbar_wait(bar_cfull + 8 * g, gph);
+      tk.stop(a_cfull);
+      tk.start();
       tc_fence_after();
       const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * kGroupCols);
-      if (S.wide) {
+      if (S.wide == 1) {
         // GEMM row = (tile row q, box column lane); columns [dx*nt + c] hold the partial sum of filter column dx
         // evaluated AT this box pixel: out[x] = P0[x-1] + P1[x] + P2[x+1]  ->  lanes l-1, l, l+1 of this warp
         const int wy = ty * kWideH + q, wx = tx * kWideW - 1 + lane;
-        const bool wvalid = (lane >= 1) && (lane <= kWideW) && (wy < S.h) && (wx < S.w);
+        const bool wvalid = real && (lane >= 1) && (lane <= kWideW) && (wy < S.h) && (wx < S.w);
         if (S.out_mode == kOutNHWCbf16) {
           uint32_t v0[16], v1[16], v2[16];
           tmem_ld_32x16(tq + part * 16, v0);
@@ -385,17 +655,21 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
+          if (lane == 0) { if (kPair) mbar_arrive_cluster(lbar_cempty + 8 * g); else mbar_arrive(bar_cempty + 8 * g); }
+          tk.stop(a_tmem);
+          tk.start();
+          uint64_t a2[8];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float l = __shfl_up_sync(0xFFFFFFFFu, __uint_as_float(v0[e]), 1);
-            const float r2 = __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(v2[e]), 1);
-            v1[e] = __float_as_uint((l + __uint_as_float(v1[e])) + r2);
+          for (int e = 0; e < 8; ++e) {                        // (P0[x-1] + P1[x]) + P2[x+1], two channels per FADD2
+            const uint32_t l0 = __shfl_up_sync(0xFFFFFFFFu, v0[2 * e], 1), l1 = __shfl_up_sync(0xFFFFFFFFu, v0[2 * e + 1], 1);
+            const uint32_t r0 = __shfl_down_sync(0xFFFFFFFFu, v2[2 * e], 1), r1 = __shfl_down_sync(0xFFFFFFFFu, v2[2 * e + 1], 1);
+            a2[e] = f2_add(f2_add(f2_pack(l0, l1), f2_pack(v1[2 * e], v1[2 * e + 1])), f2_pack(r0, r1));
           }
-          if (wvalid) {
-            const size_t pix = (static_cast<size_t>(n) * S.oh + wy) * S.ow + wx;
-            const size_t off = (pix * S.oc + S.ch0) * 2 + part * 32;
-            epi_store_bf16(v1, s_bias + part * 16, static_cast<uint8_t*>(S.out) + off,
+          if (wvalid && !(dbg & 16)) {
+            // one 64-bit product per image, the rest in 32 bits (an image of a layer is < 4 GB: launch_frame checks)
+            const size_t off = static_cast<size_t>(n) * (static_cast<size_t>(S.oh) * S.ow * S.oc * 2) +
+                               ((static_cast<uint32_t>(wy) * S.ow + wx) * S.oc + S.ch0) * 2u + part * 32u;
+            epi_store_bf16(a2, s_bias + part * 16, static_cast<uint8_t*>(S.out) + off,
                            S.resid ? static_cast<const uint8_t*>(S.resid) + off : nullptr, S.relu != 0);
           }
         } else {
@@ -406,7 +680,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
+          if (lane == 0) { if (kPair) mbar_arrive_cluster(lbar_cempty + 8 * g); else mbar_arrive(bar_cempty + 8 * g); }
           const int c = part < 3 ? part : 2;               // plane of this warp (part 3 idles)
           const float l = __shfl_up_sync(0xFFFFFFFFu, __uint_as_float(c == 0 ? v0[0] : (c == 1 ? v0[1] : v0[2])), 1);
           const float r2 = __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(c == 0 ? v2[0] : (c == 1 ? v2[1] : v2[2])), 1);
@@ -419,8 +693,11 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           }
         }
       } else {
-        const int iy = ty * kTileH + pr, ix = tx * kTileW + pc;
-        const bool valid = (iy < S.h) && (ix < S.w);
+        // tall tile: GEMM row m = pixel (m / 8, m % 8); wide box with one view per tap: row = (tile row q, column lane),
+        // the view of tap dx starts dx pixels into the box row, so lane l IS output column l (30 valid)
+        const bool wtap = S.wide == 2;
+        const int iy = wtap ? ty * kWideH + q : ty * kTileH + pr, ix = wtap ? tx * kWideW + lane : tx * kTileW + pc;
+        const bool valid = real && (iy < S.h) && (ix < S.w) && (!wtap || lane < kWideW);
         const int n_acc = (S.kind == kConv3x3) ? 1 : 4;
         const int sc = (S.kind == kConv3x3) ? 1 : 2;
         for (int a = 0; a < n_acc; ++a) {
@@ -432,13 +709,16 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           if (a == n_acc - 1) {                            // TMEM drained -> hand the group back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
+            if (lane == 0) { if (kPair) mbar_arrive_cluster(lbar_cempty + 8 * g); else mbar_arrive(bar_cempty + 8 * g); }
           }
           if (S.out_mode == kOutNHWCbf16) {
             if (valid) {
-              const size_t pix = (static_cast<size_t>(n) * S.oh + oy) * S.ow + ox;
-              const size_t off = (pix * S.oc + S.ch0) * 2 + part * 32;
-              epi_store_bf16(v, s_bias + part * 16, static_cast<uint8_t*>(S.out) + off,
+              const size_t off = static_cast<size_t>(n) * (static_cast<size_t>(S.oh) * S.ow * S.oc * 2) +
+                                 ((static_cast<uint32_t>(oy) * S.ow + ox) * S.oc + S.ch0) * 2u + part * 32u;
+              uint64_t a2[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a2[e] = f2_pack(v[2 * e], v[2 * e + 1]);
+              epi_store_bf16(a2, s_bias + part * 16, static_cast<uint8_t*>(S.out) + off,
                              S.resid ? static_cast<const uint8_t*>(S.resid) + off : nullptr, S.relu != 0);
             }
           } else if (valid && part < 3 && part < S.oc) {     // output conv, tall geometry: plane `part`
@@ -450,35 +730,54 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           }
         }
       }
+      tk.stop(a_body);
       // the network output has no consumer inside the kernel: nothing to publish
-      if (S.out_mode == kOutNHWCbf16 && !(P.dbg & 2)) {
+      if (S.out_mode == kOutNHWCbf16 && real && !(dbg & 2)) {
         const uint32_t pg = pk & 1u, pph = (pk >> 1) & 1u;
+        tk.start();
         mbar_wait(bar_pempty + 8 * pg, pph ^ 1);             // publisher at most 2 tiles behind
         mbar_arrive(bar_pfull + 8 * pg);
+        tk.stop(a_pub);
         ++pk;
       }
       g ^= 1;
       if (g == 0) gph ^= 1;
     }
+    tall.stop(a_total);
+    if (stats && warp == 2 && lane == 0) {
+      unsigned long long* o = stats + blockIdx.x * 16;
+      o[4] = a_cfull; o[5] = a_body; o[6] = a_pub; o[7] = a_total; o[8] = a_tmem;
+    }
   } else if (warp == 2 + kEpiWarps) {
     // ================================ publisher ============================================
     int si = 0;
     uint32_t pk = 0;
+    Tick<kDbg> tk{0, stats != nullptr, true};
+    long long a_pfull = 0, a_red = 0;
     for (int it = blockIdx.x; it < P.total_items; it += G) {
-      while (it >= P.segs[si].item_end) ++si;
-      const FrSeg& S = P.segs[si];
-      if (S.out_mode == kOutNHWCbf16 && !(P.dbg & 2)) {
+      while (it >= segs[si].item_end) ++si;
+      const FrSegS& S = segs[si];
+      tk.gate = stat_seg < 0 || si == stat_seg;
+      if (S.out_mode == kOutNHWCbf16 && (it - S.item_begin) < S.items_real && !(dbg & 2)) {
         const uint32_t pg = pk & 1u, pph = (pk >> 1) & 1u;
+        tk.start();
         mbar_wait(bar_pfull + 8 * pg, pph);                  // all epilogue threads stored (acquire.cta)
+        tk.stop(a_pfull);
+        tk.start();
         if (lane == 0) {
-          red_release_gpu_add(P.flags + S.flag_off + (it - S.item_begin), kItemDone);   // cumulative gpu-scope release
+          red_release_gpu_add(P.flags + it, kItemDone);   // (flag_off == item_begin) cumulative gpu-scope release
           mbar_arrive(bar_pempty + 8 * pg);
         }
         __syncwarp();
+        tk.stop(a_red);
         ++pk;
       }
     }
-  } else if (!(P.dbg & 1)) {
+    if (stats && lane == 0) {
+      unsigned long long* o = stats + blockIdx.x * 16;
+      o[13] = a_pfull; o[14] = a_red;
+    }
+  } else if (!(dbg & 1)) {
     // ================================ dependency warp ======================================
     // For every item whose input comes from a layer of this launch: wait until the producer tiles that the item's
     // halo box touches are published (one counter per tile, one lane per counter), two items per round trip:
@@ -531,11 +830,11 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         const uint32_t v1 = p1 ? ld_relaxed_gpu(p1) : kItemDone;
         // Item j is handed over BEFORE item j+1 is waited for: j+1 may depend on j itself (a layer of exactly G tiles).
         if (v0 < kItemDone) spin(p0, j);
-        if (!(P.dbg & 4)) fence_acq_rel_gpu();
+        if (!(dbg & 4)) fence_acq_rel_gpu();
         for (int h = 0; h < 2; ++h) {
           if (h == 1 && v1 < kItemDone) {                  // rare: not yet published at the paired load
             spin(p1, j + 1);
-            if (!(P.dbg & 4)) fence_acq_rel_gpu();
+            if (!(dbg & 4)) fence_acq_rel_gpu();
           }
           __syncwarp();
           if (!(h ? has1 : has0)) continue;
@@ -552,8 +851,12 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (P.trace && threadIdx.x == 0) P.trace[static_cast<size_t>(P.nseg) * G + blockIdx.x] = global_ns();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (kPair) cluster_sync_all();                    // the leader's MMAs read the peer's shared memory and signal its barriers
+  if (trace && threadIdx.x == 0) trace[static_cast<size_t>(P.nseg) * G + blockIdx.x] = global_ns();
+  if (warp == 1) {
+    if (kPair) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ------------------------------------------------------------------------------------ host
@@ -568,6 +871,36 @@ static bool use_wide(int kind) {
   static const bool on = []() { const char* e = getenv("TG_FRAME_WIDE"); return !(e && e[0] == '0'); }();
   return on && kind == kConv3x3;
 }
+// Pair mode (cta_group::2) needs every 3x3 conv on the wide geometry and co-resident 2-CTA clusters; TG_FRAME_PAIR=0
+// selects the single-CTA kernel (A/B measurements).  Returns the number of clusters that can be resident (0: off).
+static int pair_clusters() {
+  static const int n = []() {
+    const char* e = getenv("TG_FRAME_PAIR");
+    if ((e && e[0] == '0') || !use_wide(kConv3x3)) return 0;
+    if (cudaFuncSetAttribute(frame_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<true>::kSmemBytes) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tg_num_sms() & ~1);
+    cfg.blockDim = dim3(kFrThreads);
+    cfg.dynamicSmemBytes = FrCfg<true>::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, frame_kernel<true, false>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    const int want = tg_num_sms() / 2;
+    return nc < want ? nc : want;
+  }();
+  return n;
+}
+
 size_t frame_tiles(int kind, int h, int w) {
   return use_wide(kind) ? static_cast<size_t>(tg_div_up(w, kWideW)) * tg_div_up(h, kWideH)
                         : static_cast<size_t>(tg_div_up(w, kTileW)) * tg_div_up(h, kTileH);
@@ -581,24 +914,31 @@ size_t frame_tiles_max(int h, int w) {
 size_t frame_flag_count(const FrLayer* layers, int nlayers, int n) {
   size_t total = 0;
   for (int i = 0; i < nlayers; ++i)
-    total += static_cast<size_t>(n) * frame_tiles(layers[i].kind, layers[i].h, layers[i].w) *
+    total += (static_cast<size_t>(n) * frame_tiles(layers[i].kind, layers[i].h, layers[i].w) + 1) *   // + 1: pair padding
              (layers[i].cout_pad / layer_nt(layers[i]));
   return total;
 }
 
 int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t packed_bytes, int n,
                  uint32_t* flags, size_t flag_capacity, bool flags_zeroed, cudaStream_t stream) {
-  TG_CHECK_ARG(nlayers >= 1 && nlayers + 1 <= kFrMaxMaps, "frame: too many layers (%d)", nlayers);
+  TG_CHECK_ARG(nlayers >= 1 && nlayers + 1 <= kFrMapW32, "frame: too many layers (%d)", nlayers);
   static_assert(kFrMaxSegs <= 256, "segment index is packed into 8 bits");
   TG_CHECK_ARG(packed && flags && (packed_bytes % 128) == 0, "frame: bad packed blob");
   static thread_local FrProgram P;   // 13 KB: keep it off the stack
   memset(&P, 0, sizeof(P));
+  const int clusters = pair_clusters();
+  const bool pair = clusters > 0;
+  P.pair = pair ? 1 : 0;
   {
     cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(packed_bytes / 128)};
     cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, kWBoxRows};
-    int rc = encode_bf16(&P.maps[0], packed, 2, dims, strides, box);
-    if (rc) return rc;
+    const int rows[3] = {kWBoxRows, 32, 24};
+    const int slot[3] = {0, kFrMapW32, kFrMapW24};
+    for (int i = 0; i < (pair ? 3 : 1); ++i) {
+      cuuint32_t box[2] = {64, static_cast<cuuint32_t>(rows[i])};
+      int rc = encode_bf16(&P.maps[slot[i]], packed, 2, dims, strides, box);
+      if (rc) return rc;
+    }
   }
   int nseg = 0, items = 0;
   int first_seg[kFrMaxMaps], nchunks[kFrMaxMaps];
@@ -608,7 +948,9 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
     TG_CHECK_ARG(l.cin_pad == 64 || l.cin_pad == 128, "frame: cin_pad must be 64 or 128");
     TG_CHECK_ARG(l.cout_pad == 16 || l.cout_pad == 64 || l.cout_pad == 128, "frame: cout_pad must be 16/64/128");
     TG_CHECK_ARG((l.blob_off % 128) == 0, "frame: packed blob offsets must be 128-byte aligned");
+    TG_CHECK_ARG(!(l.relu && l.resid), "frame: layer %d has both a ReLU and a residual", li);
     TG_CHECK_ARG(l.w < 32768 && l.h < 32768 && n < (1 << 23), "frame: layer size out of range");
+    TG_CHECK_ARG(4.0 * l.h * l.w * l.cout_pad * 2 < 4294967296.0, "frame: one image of layer %d exceeds 4 GB", li);
     {
       cuuint64_t dims[4] = {static_cast<cuuint64_t>(l.cin_pad), static_cast<cuuint64_t>(l.w),
                             static_cast<cuuint64_t>(l.h), static_cast<cuuint64_t>(n)};
@@ -633,15 +975,25 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
       TG_CHECK_ARG(nseg < kFrMaxSegs, "frame: too many segments");
       FrSeg& S = P.segs[nseg];
       S.item_begin = items;
-      items += n * tiles_x * tiles_y;
+      S.items_real = n * tiles_x * tiles_y;
+      items += pair ? ((S.items_real + 1) & ~1) : S.items_real;
       S.item_end = items;
       S.tiles_x = tiles_x; S.tiles_y = tiles_y; S.h = l.h; S.w = l.w;
-      S.wide = wide ? 1 : 0; S.tile_w = tile_w; S.tile_h = tile_h;
+      // wide tiles: N-stacked filter rows (1), or - in pair mode, where an N=64 MMA costs 43 cycles instead of 75 - one
+      // MMA group per tap on shifted views of the wide box (2): a third of the accumulator columns, no shuffles
+      static const bool tap_views = []() { const char* e = getenv("TG_FRAME_TAP"); return !(e && e[0] == '0'); }();
+      S.wide = wide ? ((pair && tap_views && nt == 64) ? 2 : 1) : 0; S.tile_w = tile_w; S.tile_h = tile_h;
       S.box_w = wide ? kWideBoxW : kTileW + 2; S.box_h = wide ? kWideBoxH : kTileH + 2;
       S.fd_tiles_x = make_fastdiv(tiles_x); S.fd_tiles_y = make_fastdiv(tiles_y);
       S.map_a = 1 + li;
       S.kchunks = kchunks; S.kind = l.kind; S.nt = nt;
       S.w_rows = 9u * nt;
+      if (S.wide == 1) { S.w_groups = 3; S.w_half_rows = 3 * nt / 2; }   // one MMA N group per filter row: 3 taps x nt rows
+      else      { S.w_groups = 9; S.w_half_rows = nt / 2; }          // one per tap
+      S.w_box_rows = S.w_half_rows == 96 ? kWBoxRows : S.w_half_rows;
+      S.w_map = S.w_box_rows == kWBoxRows ? 0 : (S.w_box_rows == 32 ? kFrMapW32 : kFrMapW24);
+      TG_CHECK_ARG(!pair || S.w_box_rows == kWBoxRows || S.w_box_rows == 32 || S.w_box_rows == 24,
+                   "frame: no pair-mode weight box for layer %d (%d rows per CTA)", li, S.w_half_rows);
       for (int kc = 0; kc < kchunks; ++kc)
         S.w_row0[kc] = static_cast<uint32_t>(l.blob_off / 128) + static_cast<uint32_t>(c * kchunks + kc) * S.w_rows;
       S.out_mode = l.out_mode; S.relu = l.relu;
@@ -679,32 +1031,47 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
   {
     static const int dbg = []() { const char* e = getenv("TG_FRAME_DBG"); return e ? atoi(e) : 0; }();
     P.dbg = dbg;
-    const int grid = items < tg_num_sms() ? items : tg_num_sms();
-    P.trace = (g_trace && g_trace_words >= static_cast<size_t>(nseg + 1) * grid) ? g_trace : nullptr;
+    static const int stat_seg = []() { const char* e = getenv("TG_FRAME_STAT_SEG"); return e ? atoi(e) : -1; }();
+    P.stat_seg = stat_seg;
   }
+  // one CTA per SM (pair mode: one 2-CTA cluster per TPC); items are dealt round-robin, so any grid size works
+  const int max_ctas = pair ? 2 * clusters : tg_num_sms();
+  const int grid = items < max_ctas ? items : max_ctas;           // pair mode: items and max_ctas are even
+  P.trace = (g_trace && g_trace_words >= static_cast<size_t>(nseg + 1) * grid) ? g_trace : nullptr;
+  // optional stall accounting behind the trace: 16 words per CTA (see Tick)
+  P.stats = (P.trace && g_trace_words >= static_cast<size_t>(nseg + 1 + 16) * grid) ? g_trace + static_cast<size_t>(nseg + 1) * grid : nullptr;
 
   static bool attr_done = false;
   if (!attr_done) {
-    TG_CUDA(cudaFuncSetAttribute(frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrSmemLimit));
+    TG_CUDA(cudaFuncSetAttribute(frame_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<false>::kSmemBytes));
+    TG_CUDA(cudaFuncSetAttribute(frame_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<true>::kSmemBytes));
+    TG_CUDA(cudaFuncSetAttribute(frame_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<false>::kSmemBytes));
+    TG_CUDA(cudaFuncSetAttribute(frame_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<true>::kSmemBytes));
     attr_done = true;
   }
   TG_CHECK_ARG(static_cast<size_t>(items) <= flag_capacity, "frame: %d items exceed the flag capacity %zu", items, flag_capacity);
   if (!flags_zeroed) TG_CUDA(cudaMemsetAsync(flags, 0, static_cast<size_t>(items) * sizeof(uint32_t), stream));
-  const uint32_t smem_bytes = 2 * kWSlotBytes + kFrStages * kAStride + 256 + kEpiWarps * 64 * 4 + 1024;
-  static_assert(2 * kWSlotBytes + kFrStages * kAStride + 256 + kEpiWarps * 64 * 4 + 1024 <= kFrSmemLimit, "smem budget");
   cudaLaunchConfig_t cfg{};
-  const int sms = tg_num_sms();
-  cfg.gridDim = dim3(items < sms ? items : sms);
+  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kFrThreads);
-  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.dynamicSmemBytes = pair ? FrCfg<true>::kSmemBytes : FrCfg<false>::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pair ? 2 : 1;
   tg_prof_pre(TG_K_FRAME, flops, stream);
-  TG_CUDA(cudaLaunchKernelEx(&cfg, frame_kernel, P));
+  const bool measure = P.dbg != 0 || P.trace != nullptr;
+  if (pair) {
+    if (measure) TG_CUDA(cudaLaunchKernelEx(&cfg, frame_kernel<true, true>, P));
+    else TG_CUDA(cudaLaunchKernelEx(&cfg, frame_kernel<true, false>, P));
+  } else {
+    if (measure) TG_CUDA(cudaLaunchKernelEx(&cfg, frame_kernel<false, true>, P));
+    else TG_CUDA(cudaLaunchKernelEx(&cfg, frame_kernel<false, false>, P));
+  }
   tg_prof_post(stream);
   TG_CUDA(cudaGetLastError());
   return TG_OK;

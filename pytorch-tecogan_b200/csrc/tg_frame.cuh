@@ -6,7 +6,9 @@
 namespace tg {
 
 constexpr int kFrMaxSegs = 56;     // 41 layers + one extra segment per 128-wide layer
-constexpr int kFrMaxMaps = 44;     // [0] packed weights, [1 + layer] input activation of the layer
+constexpr int kFrMaxMaps = 46;     // [0] packed weights (48-row box), [1 + layer] input activation of the layer,
+constexpr int kFrMapW32 = 44;      // [44] / [45] packed weights with 32- / 24-row boxes (pair mode: half of a tap group
+constexpr int kFrMapW24 = 45;      //   of the transposed convs / of the output conv per CTA)
 
 // Tile geometries.  "tall": 16 rows x 8 columns, halo box {64ch, 10, 18}, one tcgen05.mma group per filter tap
 // (N = nt); used by the transposed convs.  "wide" (3x3 convs): 4 rows x 32 columns of which the inner 30 are
@@ -34,7 +36,8 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t x, FastDiv f) { return (__umul
 
 // One segment = one (layer, 64-wide output-channel chunk) pass over all tiles of the layer.
 struct FrSeg {
-  int item_begin, item_end;   // global item range [begin, end)
+  int item_begin, item_end;   // global item range [begin, end); pair mode pads every segment to an even count
+  int items_real;             // items of the segment that exist (local index >= items_real: the pair's padding item)
   int tiles_x, tiles_y;       // tiles per image in the layer's input resolution
   int h, w;                   // input resolution
   int wide;                   // tile geometry (see above)
@@ -46,6 +49,8 @@ struct FrSeg {
   int nt;                     // UMMA N: 64, or 16 for the 3-channel output conv
   uint32_t w_row0[2];         // first 128-byte row of the weight block of K chunk 0/1 in the packed blob
   uint32_t w_rows;            // rows per weight block (9 taps * nt)
+  // pair mode: the block is w_groups MMA-N groups of 2 * w_half_rows rows; each CTA loads its half of every group
+  int w_groups, w_half_rows, w_box_rows, w_map;
   // epilogue
   int out_mode, relu, oh, ow, oc, ch0;   // ch0 = first output channel of this chunk
   long long out_nstride;
@@ -60,13 +65,33 @@ struct FrSeg {
   uint32_t flag_off;          // offset of this segment's per-item completion counters
 };
 
+// Shared-memory copy of the fields the per-item loops of the MMA, epilogue and publisher warps read.  FrProgram is
+// 17 KB of kernel parameters; indexing it dynamically per item costs a chain of constant-cache misses (measured:
+// 700-800 cycles of every ~2400-cycle item), so every CTA compacts it once at start.
+struct FrSegS {
+  int item_begin, item_end, items_real;
+  uint16_t tiles_x, tiles_y, h, w, oh, ow, oc, ch0;
+  uint8_t wide, out_mode, relu, kind, nt, kchunks, pad0, pad1;
+  FastDiv fd_tiles_x, fd_tiles_y;
+  long long out_nstride;
+  void* out;
+  float* out2;
+  const void* resid;
+  const float* bias;
+};
+static_assert(sizeof(FrSegS) == 96, "FrSegS layout");
+
 struct FrProgram {
   CUtensorMap maps[kFrMaxMaps];
   FrSeg segs[kFrMaxSegs];
   int nseg, total_items;
   uint32_t* flags;            // zeroed before the launch; one counter per item (128 = complete)
   unsigned long long* trace;  // optional [nseg+1][grid] globaltimer stamps (tg_frame_set_trace), else null
-  int dbg;                    // measurement-only knobs (TG_FRAME_DBG): 1 no dependency wait, 2 no publish, 4 no acquire fence
+  unsigned long long* stats;  // optional [grid][16] cycles per wait of every role (behind the trace buffer), else null
+  int dbg;                    // measurement-only knobs (TG_FRAME_DBG): 1 no dependency wait, 2 no publish, 4 no acquire fence,
+                              //   8 issuer ignores accumulator-drained, 16 no bf16 epilogue stores, 32 cta-scope waits in the pair issuer
+  int pair;                   // 1: launched as CTA pairs (cta_group::2)
+  int stat_seg;               // stall accounting restricted to this segment (TG_FRAME_STAT_SEG, -1 = all)
 };
 
 struct FrLayer {              // host-side description of one conv layer of the frame

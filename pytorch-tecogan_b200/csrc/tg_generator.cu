@@ -61,7 +61,7 @@ static GenWorkspace gen_ws(int n, int h, int w) {
   ws.e = take(px * 16 * 64 * 2);
   // per-item completion counters of the frame kernel: trunk/convT64 items at 1x, 2x items, 4x items
   auto tiles = [&](int s) { return static_cast<size_t>(n) * frame_tiles_max(h * s, w * s); };
-  ws.flag_count = 132 * tiles(1) + 16 * tiles(2) + 4 * tiles(4);   // covers num_resblock <= 64
+  ws.flag_count = 132 * tiles(1) + 16 * tiles(2) + 4 * tiles(4) + 256;   // covers num_resblock <= 64 (+ one pair-padding counter per segment)
   ws.flags = take(ws.flag_count * 4);
   ws.total = o;
   return ws;
@@ -279,7 +279,7 @@ static GenTrainWs gen_train_ws(int n, int h, int w, int nres) {
   ws.g_b[0] = take(px * 4 * 128); ws.g_b[1] = take(px * 4 * 128);
   ws.g_net[0] = take(px * 128); ws.g_net[1] = take(px * 128); ws.g_t = take(px * 128);
   auto tiles = [&](int s) { return static_cast<size_t>(n) * frame_tiles_max(h * s, w * s); };
-  ws.flag_count = static_cast<size_t>(2 * nres + 2) * tiles(1) + 8 * tiles(2) + 2 * tiles(4);
+  ws.flag_count = static_cast<size_t>(2 * nres + 2) * tiles(1) + 8 * tiles(2) + 2 * tiles(4) + 2 * nres + 16;   // + pair padding
   ws.flags = take(ws.flag_count * 4);
   ws.total = o;
   return ws;

@@ -22,7 +22,7 @@ x0 = torch.rand(N, H, W, 64, device="cuda").to(torch.bfloat16)
 out = torch.empty(N, 3, 4 * H, 4 * W, device="cuda")
 G = 148
 NSEG = 44
-trace = torch.zeros((NSEG + 1) * G, dtype=torch.int64, device="cuda")
+trace = torch.zeros((NSEG + 1 + 16) * G, dtype=torch.int64, device="cuda")
 
 
 def run():
@@ -36,7 +36,8 @@ nt.check(lib.tg_frame_set_trace(nt.ptr(trace), trace.numel() * 8))
 run()
 torch.cuda.synchronize()
 nt.check(lib.tg_frame_set_trace(None, 0))
-t = trace.view(NSEG + 1, G).cpu().double()
+stats = trace[(NSEG + 1) * G:].view(G, 16).cpu().double()
+t = trace[:(NSEG + 1) * G].view(NSEG + 1, G).cpu().double()
 t0 = t[t > 0].min()
 names = ["conv.0"] + [f"res{i // 2}.{'0' if i % 2 == 0 else '2'}" for i in range(32)] + ["convT64", "ct2.0 64@2x", "ct2.2 64@2x",
          "ct3.0 64->128 c0", "ct3.0 64->128 c1", "ct3.2 128->128 c0", "ct3.2 128->128 c1", "convT128 c0", "convT128 c1",
@@ -64,3 +65,14 @@ for s in range(NSEG + 1):
         b = bound[prev[0]] / 148 * 36 * 75 / 1.965
         print(f"{names[prev[0]]:22s} start med {prev[1] / 1e3:8.1f} us (min {prev[2] / 1e3:7.1f} max {prev[3] / 1e3:7.1f})  span {(med - prev[1]) / 1e3:7.1f} us   mma-bound {b / 1e3:6.1f} us")
     prev = (s, med, lo, hi)
+
+# stall accounting: mean cycles per CTA spent in each wait (leader CTAs only for the issuer in pair mode)
+lab = ["mma: wait acc drained", "mma: wait weights", "mma: wait A stage", "mma: loop total",
+       "epi(w2): wait acc ready", "epi(w2): math+store (+ld if not wide bf16)", "epi(w2): publish handoff", "epi(w2): loop total", "epi(w2): tmem ld (wide bf16)",
+       "prod: wait weight slot", "prod: wait dependencies", "prod: wait A stage free", "prod: loop total",
+       "pub: wait tile stored", "pub: release + arrive", "-"]
+for k, name in enumerate(lab):
+    col = stats[:, k]
+    col = col[col > 0]
+    if name != "-" and col.numel():
+        print(f"stat {name:28s} mean {col.mean().item() / 1e3:9.1f} kcycles  (max {col.max().item() / 1e3:9.1f}, {col.numel()} CTAs)")
