@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (train clips/s)")
+    ap.add_argument("--no-glue", action="store_true", help="skip the HBM roofline of the glue kernels (cfg3 sizes)")
     ap.add_argument("--train-steps", type=int, default=10)
     return ap.parse_args()
 
@@ -390,11 +391,19 @@ def run_ours(args):
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": "one 3-frame 320x180 clip through oracle.infer_clip (torch CPU fp32)"}
 
+    # ---------------- HBM roofline of the memory-bound glue kernels at cfg3 (4K) sizes ----------------
+    glue = None
+    del pipe, out, lr
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_glue:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import glue_bench
+        glue = glue_bench.measure(n=2, dev=dev)
+        torch.cuda.empty_cache()
+
     # ---------------- training step (BASELINE.json metric, second half: train clips/s) ----------------
     train = None
     if not args.no_train:
-        del pipe, out, lr
-        torch.cuda.empty_cache()
         train = {}
         with_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
         if world == 1:
@@ -416,7 +425,7 @@ def run_ours(args):
                        "l2": "no explicit flush: every frame streams ~0.56 GB of activations per clip through the "
                              "126 MB L2, far larger than L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "outputs_finite": finite, "train": train,
+            "outputs_finite": finite, "glue": glue, "train": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

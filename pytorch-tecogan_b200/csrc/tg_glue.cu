@@ -87,23 +87,42 @@ __device__ __forceinline__ float up4_sample(const float* __restrict__ plane, int
   return ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11);
 }
 
-__global__ void upscale4_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int h,
-                                int w, float pre) {
+// One thread = the four outputs 4x..4x+3 of one output row; they read source columns x-1, x, x+1 of two source rows,
+// so six loads (not sixteen) feed one 16-byte store.  One CTA walks whole output rows: no per-element 64-bit div/mod.
+// Arithmetic is up4_sample's, operand for operand (ATen upsample_bilinear2d, align_corners=False).  The kernel writes
+// 16 bytes for every byte it reads: its roofline is the HBM WRITE rate (scripts/glue_bench.py times a fill beside it).
+// (A 4x4-outputs-per-thread variant - nine loads, four stores - measured slower: 130 us vs 92 us at cfg3 sizes.)
+__global__ void __launch_bounds__(256)
+upscale4_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int h, int w, float pre) {
   const int wo = 4 * w, ho = 4 * h;
-  const long long total = static_cast<long long>(planes) * ho * w;   // one thread = 4 outputs in x
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int x = static_cast<int>(i % w);
-    long long r = i / w;
-    const int oy = static_cast<int>(r % ho);
+  const long long rows = static_cast<long long>(planes) * ho;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
     const long long pl = r / ho;
-    const float* plane = in + pl * static_cast<long long>(h) * w;
-    float4 v;
-    v.x = up4_sample(plane, h, w, oy, 4 * x + 0, pre);
-    v.y = up4_sample(plane, h, w, oy, 4 * x + 1, pre);
-    v.z = up4_sample(plane, h, w, oy, 4 * x + 2, pre);
-    v.w = up4_sample(plane, h, w, oy, 4 * x + 3, pre);
-    reinterpret_cast<float4*>(out + (pl * ho + oy) * static_cast<long long>(wo))[x] = v;
+    const int oy = static_cast<int>(r - pl * ho);
+    float sy = (oy + 0.5f) * 0.25f - 0.5f;
+    sy = sy < 0.f ? 0.f : sy;
+    const int y0 = min(static_cast<int>(sy), h - 1), y1 = min(y0 + 1, h - 1);
+    const float ly1 = sy - y0, ly0 = 1.f - ly1;
+    const float* r0 = in + (pl * h + y0) * static_cast<long long>(w);
+    const float* r1 = in + (pl * h + y1) * static_cast<long long>(w);
+    float4* orow = reinterpret_cast<float4*>(out + r * static_cast<long long>(wo));
+    for (int x = threadIdx.x; x < w; x += blockDim.x) {
+      const int xm = max(x - 1, 0), xp = min(x + 1, w - 1);
+      const float a0 = __ldg(r0 + xm) * pre, a1 = __ldg(r0 + x) * pre, a2 = __ldg(r0 + xp) * pre;
+      const float b0 = __ldg(r1 + xm) * pre, b1 = __ldg(r1 + x) * pre, b2 = __ldg(r1 + xp) * pre;
+      // sx = (4x + j + 0.5) / 4 - 0.5 is exact in f32, so the ATen weights lx1 = sx - floor(sx) are the constants
+      // .625 .875 .125 .375 (j = 0..3); only column 0 differs: sx clamps to 0 -> taps (x, x+1) with weights (1, 0).
+      const bool edge = x == 0;
+      const float l0 = edge ? a1 : a0, l1 = edge ? a2 : a1;      // taps of outputs j = 0, 1 on row y0
+      const float m0 = edge ? b1 : b0, m1 = edge ? b2 : b1;      // ... on row y1
+      const float w0 = edge ? 0.f : 0.625f, w1 = edge ? 0.f : 0.875f;
+      float o[4];
+      o[0] = ly0 * ((1.f - w0) * l0 + w0 * l1) + ly1 * ((1.f - w0) * m0 + w0 * m1);
+      o[1] = ly0 * ((1.f - w1) * l0 + w1 * l1) + ly1 * ((1.f - w1) * m0 + w1 * m1);
+      o[2] = ly0 * (0.875f * a1 + 0.125f * a2) + ly1 * (0.875f * b1 + 0.125f * b2);
+      o[3] = ly0 * (0.625f * a1 + 0.375f * a2) + ly1 * (0.625f * b1 + 0.375f * b2);
+      orow[x] = make_float4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 
@@ -155,6 +174,33 @@ __global__ void warp_kernel(const float* __restrict__ img, const float2* __restr
     for (int ch = 0; ch < c; ++ch) {
       const float* plane = img + (b * c + ch) * static_cast<long long>(h) * w;
       out[(b * c + ch) * static_cast<long long>(ho) * wo + pix] = gather(plane, w, t);
+    }
+  }
+}
+
+// Four consecutive output pixels per thread: the grid arrives as two 16-byte loads, every plane leaves as one 16-byte
+// store, and a thread keeps 16 gathers per plane in flight.  Needs wo % 4 == 0 and 16-byte aligned grid / out rows.
+__global__ void __launch_bounds__(256)
+warp4_kernel(const float* __restrict__ img, const float4* __restrict__ grid, float* __restrict__ out, int n, int c, int h,
+             int w, int ho, int wo) {
+  const long long plane_o = static_cast<long long>(ho) * wo;
+  const long long total = static_cast<long long>(n) * plane_o / 4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p0 = i * 4;                               // first of the four pixels (never straddles an image: wo % 4 == 0)
+    const long long b = p0 / plane_o;
+    const long long pix = p0 - b * plane_o;
+    const float4 g0 = __ldg(grid + 2 * i), g1 = __ldg(grid + 2 * i + 1);
+    Taps t[4];
+    t[0] = make_taps(round_fp16(g0.x), round_fp16(g0.y), h, w);
+    t[1] = make_taps(round_fp16(g0.z), round_fp16(g0.w), h, w);
+    t[2] = make_taps(round_fp16(g1.x), round_fp16(g1.y), h, w);
+    t[3] = make_taps(round_fp16(g1.z), round_fp16(g1.w), h, w);
+    for (int ch = 0; ch < c; ++ch) {
+      const float* plane = img + (b * c + ch) * static_cast<long long>(h) * w;
+      float4 v;
+      v.x = gather(plane, w, t[0]); v.y = gather(plane, w, t[1]); v.z = gather(plane, w, t[2]); v.w = gather(plane, w, t[3]);
+      *reinterpret_cast<float4*>(out + (b * c + ch) * plane_o + pix) = v;
     }
   }
 }
@@ -385,8 +431,12 @@ extern "C" int tg_warp_bilinear(const float* img, const float* grid, float* out,
   const long long work = static_cast<long long>(n) * ho * wo;
   if (work == 0) return TG_OK;
   tg_prof_pre(TG_K_GLUE, (8.0 * c + 4.0) * n * ho * wo, static_cast<cudaStream_t>(stream));   // f32 img in/out + fp16 grid
-  warp_kernel<<<grid_for(work, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      img, reinterpret_cast<const float2*>(grid), out, n, c, h, w, ho, wo);
+  if ((wo & 3) == 0 && ((reinterpret_cast<uintptr_t>(grid) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+    warp4_kernel<<<grid_for(work / 4, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        img, reinterpret_cast<const float4*>(grid), out, n, c, h, w, ho, wo);
+  else
+    warp_kernel<<<grid_for(work, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        img, reinterpret_cast<const float2*>(grid), out, n, c, h, w, ho, wo);
   tg_prof_post(static_cast<cudaStream_t>(stream));
   TG_CUDA(cudaGetLastError());
   return TG_OK;
@@ -399,7 +449,7 @@ extern "C" int tg_upscale4_bilinear(const float* in, float* out, int n, int c, i
   TG_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "upscale4: out must be 16-byte aligned");
   const long long planes = static_cast<long long>(n) * c;
   if (planes == 0) return TG_OK;
-  const long long work = planes * 4 * h * w;
+  const long long work = planes * 4 * h * w;                 // one thread per four outputs
   tg_prof_pre(TG_K_GLUE, 4.0 * planes * h * w * 17.0, static_cast<cudaStream_t>(stream));
   upscale4_kernel<<<grid_for(work, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, static_cast<int>(planes),
                                                                                        h, w, pre_scale);
