@@ -486,20 +486,26 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     Tick<kDbg> tk{0, stats != nullptr, true}, tall{0, stats != nullptr, true};
     long long a_cempty = 0, a_wfull = 0, a_afull = 0, a_total = 0;
     tall.start();
+    // per-segment values live in registers (no shared-memory round trip on the issue path of every item)
+    int seg_end = 0, m_wide = 0, m_kchunks = 1, tbl = 0;
+    uint32_t idesc = 0, sbo = 0, wtap_bytes = 0;
     for (int it = blockIdx.x; it < P.total_items; it += G) {
-      while (it >= segs[si].item_end) ++si;
-      const FrSegS& S = segs[si];
+      if (it >= seg_end) {
+        while (it >= segs[si].item_end) ++si;
+        const FrSegS& C = segs[si];
+        seg_end = C.item_end; m_wide = C.wide; m_kchunks = C.kchunks;
+        idesc = umma_idesc_bf16(kPair ? 256 : 128, C.wide == 1 ? 3 * C.nt : C.nt);
+        tbl = C.wide == 2 ? 2 : C.kind;                        // tap table (views inside the staged box)
+        sbo = C.wide == 2 ? 1024u : 10u * 128u;                // byte pitch of 8-pixel groups: wide rows are 32 pixels
+        wtap_bytes = static_cast<uint32_t>(C.nt) * (kPair ? 64 : 128);   // rows of one tap held by this CTA x 128 B
+      }
       if (trace && si != traced_si) {
         if (lane == 0) trace[static_cast<size_t>(si) * G + blockIdx.x] = global_ns();
         traced_si = si;
       }
       tk.gate = stat_seg < 0 || si == stat_seg;
-      const bool last_in_seg = (it + G >= S.item_end);
-      const uint32_t idesc = umma_idesc_bf16(kPair ? 256 : 128, S.wide == 1 ? 3 * S.nt : S.nt);
-      const bool wide = S.wide == 1;
-      const int tbl = S.wide == 2 ? 2 : S.kind;                // tap table (views inside the staged box)
-      const uint32_t sbo = S.wide == 2 ? 1024u : 10u * 128u;   // byte pitch of 8-pixel groups: wide rows are 32 pixels
-      const uint32_t wtap_bytes = static_cast<uint32_t>(S.nt) * (kPair ? 64 : 128);   // rows of one tap held by this CTA x 128 B
+      const bool last_in_seg = (it + G >= seg_end);
+      const bool wide = m_wide == 1;
       tk.start();
       if (!(dbg & 8)) {
         if (kPair && !(dbg & 32)) mbar_wait_cluster(bar_cempty + 8 * g, gph ^ 1);
@@ -508,7 +514,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       tk.stop(a_cempty);
       tc_fence_after();
       const uint32_t d_base = tmem_base + static_cast<uint32_t>(g * kGroupCols);
-      for (int kc = 0; kc < S.kchunks; ++kc) {
+      for (int kc = 0; kc < m_kchunks; ++kc) {
         bool is_load;
         uint32_t nth;
         const int slot = ws.use(si * 2 + kc, &is_load, &nth);
@@ -536,7 +542,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
                 else umma_bf16(d_base, ad + 2 * k, bd + 2 * k, idesc, (kc > 0 || dy > 0 || k > 0) ? 1u : 0u);
               }
             }
-          } else if (S.wide == 2) {
+          } else if (m_wide == 2) {
             // one MMA group per tap on the wide box; everything but the two base descriptors is an immediate
             const uint64_t ad0 = umma_desc_sw128(a_base, 1024), bd0 = umma_desc_sw128(w_base, 1024);
             const uint64_t wstep = wtap_bytes >> 4;
@@ -567,11 +573,11 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           if (kPair) {
             umma_commit_pair(bar_aempty + 8 * st);
             if (last_in_seg) umma_commit_pair(bar_wempty + 8 * slot);
-            if (kc == S.kchunks - 1) umma_commit_pair(bar_cfull + 8 * g);
+            if (kc == m_kchunks - 1) umma_commit_pair(bar_cfull + 8 * g);
           } else {
             umma_commit(bar_aempty + 8 * st);
             if (last_in_seg) umma_commit(bar_wempty + 8 * slot);
-            if (kc == S.kchunks - 1) umma_commit(bar_cfull + 8 * g);
+            if (kc == m_kchunks - 1) umma_commit(bar_cfull + 8 * g);
           }
         }
         __syncwarp();
@@ -608,8 +614,25 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     tall.start();
     float nb0 = 0.f, nb1 = 0.f;                            // bias of segment nb_si, fetched one segment ahead
     int nb_si = -1;
+    // per-segment scalars live in registers: a shared-memory load per item sits on the item's critical path
+    // (measured: the compare waiting for segs[si].item_end was the second hottest instruction of the kernel)
+    int seg_end = 0, seg_begin = 0, seg_real = 0, c_tiles_x = 1, c_tiles_y = 1, c_h = 0, c_w = 0;
+    FastDiv c_fdx{0, 0}, c_fdy{0, 0};
+    uint32_t c_row_bytes = 0, c_px_bytes = 0, c_img_bytes = 0;
+    uint8_t* c_out = nullptr;
+    const uint8_t* c_res = nullptr;
+    int c_wide = 0, c_mode = 0, c_relu = 0, c_kind = 0;
     for (int it = blockIdx.x; it < P.total_items; it += G) {
-      while (it >= segs[si].item_end) ++si;
+      if (it >= seg_end) {
+        while (it >= segs[si].item_end) ++si;
+        const FrSegS& C = segs[si];
+        seg_end = C.item_end; seg_begin = C.item_begin; seg_real = C.items_real;
+        c_tiles_x = C.tiles_x; c_tiles_y = C.tiles_y; c_fdx = C.fd_tiles_x; c_fdy = C.fd_tiles_y;
+        c_h = C.h; c_w = C.w; c_wide = C.wide; c_mode = C.out_mode; c_relu = C.relu; c_kind = C.kind;
+        c_px_bytes = C.oc * 2u; c_row_bytes = C.ow * c_px_bytes; c_img_bytes = C.oh * c_row_bytes;   // < 4 GB (launch_frame)
+        c_out = static_cast<uint8_t*>(C.out) + C.ch0 * 2u + part * 32u;
+        c_res = C.resid ? static_cast<const uint8_t*>(C.resid) + C.ch0 * 2u + part * 32u : nullptr;
+      }
       const FrSegS& S = segs[si];
       if (si != cur_si) {                                  // warp-private bias copy of this segment
         __syncwarp();
@@ -629,12 +652,12 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           nb_si = si + 1;
         }
       }
-      const uint32_t local = static_cast<uint32_t>(it - S.item_begin);
-      const uint32_t r = fdiv(local, S.fd_tiles_x);
-      const int tx = static_cast<int>(local - r * S.tiles_x);
-      const int n = static_cast<int>(fdiv(r, S.fd_tiles_y));
-      const int ty = static_cast<int>(r) - n * S.tiles_y;
-      const bool real = local < static_cast<uint32_t>(S.items_real);   // false: the padding item of a pair
+      const uint32_t local = static_cast<uint32_t>(it - seg_begin);
+      const uint32_t r = fdiv(local, c_fdx);
+      const int tx = static_cast<int>(local - r * c_tiles_x);
+      const int n = static_cast<int>(fdiv(r, c_fdy));
+      const int ty = static_cast<int>(r) - n * c_tiles_y;
+      const bool real = local < static_cast<uint32_t>(seg_real);      // false: the padding item of a pair
       tk.gate = stat_seg < 0 || si == stat_seg;
       tk.start();
       mbar_wait(bar_cfull + 8 * g, gph);
@@ -642,12 +665,12 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       tk.start();
       tc_fence_after();
       const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * kGroupCols);
-      if (S.wide == 1) {
+      if (c_wide == 1) {
         // GEMM row = (tile row q, box column lane); columns [dx*nt + c] hold the partial sum of filter column dx
         // evaluated AT this box pixel: out[x] = P0[x-1] + P1[x] + P2[x+1]  ->  lanes l-1, l, l+1 of this warp
         const int wy = ty * kWideH + q, wx = tx * kWideW - 1 + lane;
-        const bool wvalid = real && (lane >= 1) && (lane <= kWideW) && (wy < S.h) && (wx < S.w);
-        if (S.out_mode == kOutNHWCbf16) {
+        const bool wvalid = real && (lane >= 1) && (lane <= kWideW) && (wy < c_h) && (wx < c_w);
+        if (c_mode == kOutNHWCbf16) {
           uint32_t v0[16], v1[16], v2[16];
           tmem_ld_32x16(tq + part * 16, v0);
           tmem_ld_32x16(tq + 64 + part * 16, v1);
@@ -667,10 +690,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           }
           if (wvalid && !(dbg & 16)) {
             // one 64-bit product per image, the rest in 32 bits (an image of a layer is < 4 GB: launch_frame checks)
-            const size_t off = static_cast<size_t>(n) * (static_cast<size_t>(S.oh) * S.ow * S.oc * 2) +
-                               ((static_cast<uint32_t>(wy) * S.ow + wx) * S.oc + S.ch0) * 2u + part * 32u;
-            epi_store_bf16(a2, s_bias + part * 16, static_cast<uint8_t*>(S.out) + off,
-                           S.resid ? static_cast<const uint8_t*>(S.resid) + off : nullptr, S.relu != 0);
+            const size_t off = static_cast<size_t>(n) * c_img_bytes + (static_cast<uint32_t>(wy) * c_row_bytes + static_cast<uint32_t>(wx) * c_px_bytes);
+            epi_store_bf16(a2, s_bias + part * 16, c_out + off, c_res ? c_res + off : nullptr, c_relu != 0);
           }
         } else {
           uint32_t v0[4], v1[4], v2[4];                    // 3 output channels of each of the 3 partial sums
@@ -695,31 +716,29 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       } else {
         // tall tile: GEMM row m = pixel (m / 8, m % 8); wide box with one view per tap: row = (tile row q, column lane),
         // the view of tap dx starts dx pixels into the box row, so lane l IS output column l (30 valid)
-        const bool wtap = S.wide == 2;
+        const bool wtap = c_wide == 2;
         const int iy = wtap ? ty * kWideH + q : ty * kTileH + pr, ix = wtap ? tx * kWideW + lane : tx * kTileW + pc;
-        const bool valid = real && (iy < S.h) && (ix < S.w) && (!wtap || lane < kWideW);
-        const int n_acc = (S.kind == kConv3x3) ? 1 : 4;
-        const int sc = (S.kind == kConv3x3) ? 1 : 2;
+        const bool valid = real && (iy < c_h) && (ix < c_w) && (!wtap || lane < kWideW);
+        const int n_acc = (c_kind == kConv3x3) ? 1 : 4;
+        const int sc = (c_kind == kConv3x3) ? 1 : 2;
         for (int a = 0; a < n_acc; ++a) {
           const uint32_t taddr = tq + static_cast<uint32_t>(a * kAccCols);
           const int oy = iy * sc + (a >> 1), ox = ix * sc + (a & 1);
           uint32_t v[16];
-          tmem_ld_32x16(taddr + (S.out_mode == kOutNHWCbf16 ? part * 16 : 0), v);
+          tmem_ld_32x16(taddr + (c_mode == kOutNHWCbf16 ? part * 16 : 0), v);
           tmem_ld_wait();
           if (a == n_acc - 1) {                            // TMEM drained -> hand the group back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if (kPair) mbar_arrive_cluster(lbar_cempty + 8 * g); else mbar_arrive(bar_cempty + 8 * g); }
           }
-          if (S.out_mode == kOutNHWCbf16) {
+          if (c_mode == kOutNHWCbf16) {
             if (valid) {
-              const size_t off = static_cast<size_t>(n) * (static_cast<size_t>(S.oh) * S.ow * S.oc * 2) +
-                                 ((static_cast<uint32_t>(oy) * S.ow + ox) * S.oc + S.ch0) * 2u + part * 32u;
+              const size_t off = static_cast<size_t>(n) * c_img_bytes + (static_cast<uint32_t>(oy) * c_row_bytes + static_cast<uint32_t>(ox) * c_px_bytes);
               uint64_t a2[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) a2[e] = f2_pack(v[2 * e], v[2 * e + 1]);
-              epi_store_bf16(a2, s_bias + part * 16, static_cast<uint8_t*>(S.out) + off,
-                             S.resid ? static_cast<const uint8_t*>(S.resid) + off : nullptr, S.relu != 0);
+              epi_store_bf16(a2, s_bias + part * 16, c_out + off, c_res ? c_res + off : nullptr, c_relu != 0);
             }
           } else if (valid && part < 3 && part < S.oc) {     // output conv, tall geometry: plane `part`
             const size_t plane = static_cast<size_t>(S.oh) * S.ow;
@@ -732,7 +751,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       }
       tk.stop(a_body);
       // the network output has no consumer inside the kernel: nothing to publish
-      if (S.out_mode == kOutNHWCbf16 && real && !(dbg & 2)) {
+      if (c_mode == kOutNHWCbf16 && real && !(dbg & 2)) {
         const uint32_t pg = pk & 1u, pph = (pk >> 1) & 1u;
         tk.start();
         mbar_wait(bar_pempty + 8 * pg, pph ^ 1);             // publisher at most 2 tiles behind
@@ -754,11 +773,16 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     uint32_t pk = 0;
     Tick<kDbg> tk{0, stats != nullptr, true};
     long long a_pfull = 0, a_red = 0;
+    int seg_end = 0, seg_pub_end = 0;                        // publish items [.., seg_pub_end) of the current segment
     for (int it = blockIdx.x; it < P.total_items; it += G) {
-      while (it >= segs[si].item_end) ++si;
-      const FrSegS& S = segs[si];
+      if (it >= seg_end) {
+        while (it >= segs[si].item_end) ++si;
+        const FrSegS& C = segs[si];
+        seg_end = C.item_end;
+        seg_pub_end = C.out_mode == kOutNHWCbf16 ? C.item_begin + C.items_real : 0;
+      }
       tk.gate = stat_seg < 0 || si == stat_seg;
-      if (S.out_mode == kOutNHWCbf16 && (it - S.item_begin) < S.items_real && !(dbg & 2)) {
+      if (it < seg_pub_end && !(dbg & 2)) {
         const uint32_t pg = pk & 1u, pph = (pk >> 1) & 1u;
         tk.start();
         mbar_wait(bar_pfull + 8 * pg, pph);                  // all epilogue threads stored (acquire.cta)
