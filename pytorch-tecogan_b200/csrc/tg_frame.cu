@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       mbar_init(bar_wempty + 8 * i, 1);
       mbar_init(bar_cfull + 8 * i, 1);
       mbar_init(bar_cempty + 8 * i, kEpiWarps * nctas);
-      mbar_init(bar_pfull + 8 * i, kEpiWarps * 32);
+      mbar_init(bar_pfull + 8 * i, kEpiWarps);
       mbar_init(bar_pempty + 8 * i, 1);
     }
     for (int i = 0; i < kFrStages; ++i) {
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     asm volatile("griddepcontrol.wait;" ::: "memory");
     int si = 0, cur_si = -1, g = 0;
     uint32_t gph = 0;
-    // Publishing a tile: every epilogue thread arrives (release.cta) on a CTA-local mbarrier after its stores;
+    // Publishing a tile: every epilogue warp arrives (lane 0, release.cta, after a __syncwarp) on a CTA-local mbarrier after its stores;
     // the publisher warp then performs ONE gpu-scope release (MEMBAR.GPU + RED) for the whole tile, so the
     // fence latency never stalls the epilogue.
     uint32_t pk = 0;
@@ -754,8 +754,11 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       if (c_mode == kOutNHWCbf16 && real && !(dbg & 2)) {
         const uint32_t pg = pk & 1u, pph = (pk >> 1) & 1u;
         tk.start();
-        mbar_wait(bar_pempty + 8 * pg, pph ^ 1);             // publisher at most 2 tiles behind
-        mbar_arrive(bar_pfull + 8 * pg);
+        __syncwarp();                                        // orders the 32 lanes' stores before lane 0's release
+        if (lane == 0) {
+          mbar_wait(bar_pempty + 8 * pg, pph ^ 1);           // publisher at most 2 tiles behind
+          mbar_arrive(bar_pfull + 8 * pg);
+        }
         tk.stop(a_pub);
         ++pk;
       }
