@@ -120,7 +120,9 @@ def _close_to_per_layer(got, want):
     assert d.mean().item() <= 4e-3 * scale, (d.mean().item(), scale)
 
 
-@pytest.mark.parametrize("shape", [(1, 51, 12, 20), (2, 51, 33, 17), (1, 51, 180, 320), (3, 51, 90, 100), (1, 51, 7, 61)])
+@pytest.mark.parametrize("shape", [(1, 51, 12, 20), (2, 51, 33, 17), (1, 51, 180, 320), (3, 51, 90, 100), (1, 51, 7, 61),
+                                   (1, 51, 540, 960)],
+                         ids=["12x20", "2x33x17", "cfg2_180x320", "3x90x100", "7x61", "cfg3_540x960_4K"])
 def test_frame_kernel_matches_per_layer_path(shape):
     """Size-independent property used at the full BASELINE cfg2 size: the persistent frame kernel chains the
     41 layers through per-tile counters instead of kernel boundaries (and tiles the 3x3 convs 30x4 with the three
