@@ -13,6 +13,8 @@
 // N = 192 (three "channel blocks" with LBO = 128).
 // Work split: grid = (pixel slabs, 3 ky).  A CTA accumulates its slab in TMEM (<= 384 fp32 columns) and adds the
 // result into dW with fp32 atomics (split-K over slabs).
+#include <stdlib.h>
+
 #include "tg_conv_tc.cuh"
 
 namespace tg {
@@ -208,7 +210,8 @@ static int wgrad_launch_common(WgParams& p, const void* a, int a_pad, const void
   }
   // split-K over pixel slabs: enough CTAs to fill the machine on big layers, few on tiny ones (every CTA pays
   // rows x taps x cols atomics at the end)
-  int slabs = p.num_items / 8;
+  static const int tiles_per_slab = []() { const char* e = getenv("TG_WGRAD_TILES_PER_SLAB"); const int v = e ? atoi(e) : 8; return v > 0 ? v : 8; }();
+  int slabs = p.num_items / tiles_per_slab;
   const int max_slabs = tg_num_sms() / ngroups;
   if (slabs > max_slabs) slabs = max_slabs;
   if (slabs < 1) slabs = 1;
