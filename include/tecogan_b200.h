@@ -185,6 +185,15 @@ int tg_gen_clip_step(const void* packed, int num_resblock, const float* lr_t, co
                      const float* prev_hr, float* out_t, void* workspace, size_t workspace_bytes, int n,
                      int h, int w, long long lr_batch_stride, long long prev_batch_stride,
                      long long out_batch_stride, int amode, void* stream);
+/* Same step for a caller that chains frames the way main.py:199-216 does: prev_hr MUST be the out_t of the
+ * immediately preceding tg_gen_clip_step[_chained] call on this workspace (same n, h, w), unmodified.  In
+ * TG_AMODE_FRAME every step leaves a pixel-interleaved copy of its result in the workspace, and the chained step
+ * gathers the warp taps from that copy (one 16-byte load per tap instead of three 4-byte ones); results are
+ * bit-identical to tg_gen_clip_step.  tg_gen_clip_forward chains internally. */
+int tg_gen_clip_step_chained(const void* packed, int num_resblock, const float* lr_t, const float* lr_prev,
+                             const float* prev_hr, float* out_t, void* workspace, size_t workspace_bytes, int n,
+                             int h, int w, long long lr_batch_stride, long long prev_batch_stride,
+                             long long out_batch_stride, int amode, void* stream);
 
 /* Generator training (code/train.py:86-111,336): a forward that keeps every activation in the workspace and the
  * backward pass through all 41 layers.  The generator's inputs are detached in the reference (code/train.py:90,108),

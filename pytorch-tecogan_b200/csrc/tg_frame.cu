@@ -709,8 +709,13 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           if (wvalid && part < 3 && part < S.oc) {
             const size_t plane = static_cast<size_t>(S.oh) * S.ow;
             const size_t o = static_cast<size_t>(n) * S.out_nstride + static_cast<size_t>(wy) * S.ow + wx + c * plane;
+            const float y = 1.f / (1.f + expf(-z));
             if (S.out2) S.out2[o] = z;
-            static_cast<float*>(S.out)[o] = 1.f / (1.f + expf(-z));
+            static_cast<float*>(S.out)[o] = y;
+            // optional second copy, pixel-interleaved (float4 {R,G,B,-}, component `part` from this warp): the next
+            // frame's warp gathers three channels with one 16-byte load (tg_glue.cu: gather3)
+            if (S.resid != nullptr)
+              static_cast<float*>(const_cast<void*>(S.resid))[((static_cast<size_t>(n) * S.oh + wy) * S.ow + wx) * 4 + c] = y;
           }
         }
       } else {
@@ -1028,7 +1033,10 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
       S.oc = (l.out_mode == kOutNCHWf32Sigmoid) ? 3 : l.cout_pad;
       S.ch0 = c * 64;
       S.out_nstride = l.out_nstride > 0 ? l.out_nstride : static_cast<long long>(S.oc) * S.oh * S.ow;
-      S.out = l.out; S.out2 = l.out2; S.resid = l.resid;
+      S.out = l.out; S.out2 = l.out2;
+      S.resid = (l.out_mode == kOutNCHWf32Sigmoid) ? l.out_rgbx : l.resid;
+      TG_CHECK_ARG(l.out_rgbx == nullptr || (l.out_mode == kOutNCHWf32Sigmoid && wide && l.cout_pad == 16),
+                   "frame: the interleaved copy exists for the wide output conv only");
       S.bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(packed) + l.blob_off +
                                               packed_weight_bytes(l.cin_pad, l.cout_pad)) + c * 64;
       if (li == 0) {

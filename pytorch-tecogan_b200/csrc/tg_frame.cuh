@@ -76,7 +76,7 @@ struct FrSegS {
   long long out_nstride;
   void* out;
   float* out2;
-  const void* resid;
+  const void* resid;          // output conv: the optional interleaved float4 copy (FrLayer::out_rgbx) instead
   const float* bias;
 };
 static_assert(sizeof(FrSegS) == 96, "FrSegS layout");
@@ -102,6 +102,7 @@ struct FrLayer {              // host-side description of one conv layer of the 
   float* out2;
   size_t blob_off;            // byte offset of the layer's packed blob
   long long out_nstride;
+  void* out_rgbx;             // output conv only (optional): second copy of the result as float4 {R,G,B,0} per pixel
 };
 
 size_t frame_flag_count(const FrLayer* layers, int nlayers, int n);
@@ -118,9 +119,10 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
 void frame_set_trace(unsigned long long* buf, size_t words);
 
 // tg_glue.cu: the fused frame-input producer, optionally clearing `zero_count` uint32 at `zero`.
+// prev_rgbx: optional pixel-interleaved float4 copy of prev_hr [n][4h][4w] (gathered instead of the planar tensor).
 int fused_input_launch(const float* lr_t, const float* lr_prev, const float* prev_hr, void* x_nhwc, int n, int h,
                        int w, long long lr_bs, long long hr_bs, uint32_t* zero, size_t zero_count,
-                       cudaStream_t stream);
+                       cudaStream_t stream, const void* prev_rgbx = nullptr);
 
 // tg_glue.cu: dz = dout * out * (1 - out) as NHWC bf16 [n,hw,64] (backward of the final sigmoid)
 int sigmoid_bwd_pack_launch(const float* dout, const float* out, void* dz, int n, long long hw, long long dout_nstride,

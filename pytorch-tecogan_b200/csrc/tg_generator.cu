@@ -1,5 +1,6 @@
 // The generator (reference code/models.py:61-86) as a sequence of tensor-core conv launches, and
 // the recurrent clip loop (reference main.py:173-219) kept entirely on the device.
+#include <stdlib.h>
 #include <vector>
 
 #include "tg_frame.cuh"
@@ -46,7 +47,7 @@ static std::vector<GenLayer> gen_layers(int nres, size_t* n_params, size_t* pack
 static inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
 struct GenWorkspace {
-  size_t x0, a[3], b[2], c[2], d, e, flags, flag_count, total;
+  size_t x0, a[3], b[2], c[2], d, e, flags, flag_count, rgbx, total;
 };
 static GenWorkspace gen_ws(int n, int h, int w) {
   GenWorkspace ws;
@@ -63,13 +64,15 @@ static GenWorkspace gen_ws(int n, int h, int w) {
   auto tiles = [&](int s) { return static_cast<size_t>(n) * frame_tiles_max(h * s, w * s); };
   ws.flag_count = 132 * tiles(1) + 16 * tiles(2) + 4 * tiles(4) + 256;   // covers num_resblock <= 64 (+ one pair-padding counter per segment)
   ws.flags = take(ws.flag_count * 4);
+  ws.rgbx = take(px * 16 * 16);                    // float4 per HR pixel: interleaved copy of the last output (clip loops)
   ws.total = o;
   return ws;
 }
 
 // The 41 layers of one forward as a list (input/output/residual buffers inside the workspace).
 static std::vector<FrLayer> gen_plan(const std::vector<GenLayer>& L, int nres, const void* x, float* out,
-                                     float* logits, uint8_t* wsp, int n, int h, int w, long long out_nstride) {
+                                     float* logits, uint8_t* wsp, int n, int h, int w, long long out_nstride,
+                                     bool write_rgbx = false) {
   const GenWorkspace ws = gen_ws(n, h, w);
   std::vector<FrLayer> P;
   int li = 0;
@@ -109,14 +112,16 @@ static std::vector<FrLayer> gen_plan(const std::vector<GenLayer>& L, int nres, c
   P.back().out_mode = kOutNCHWf32Sigmoid;
   P.back().out2 = logits;
   P.back().out_nstride = out_nstride;
+  P.back().out_rgbx = write_rgbx ? wsp + ws.rgbx : nullptr;
   return P;
 }
 
 // flags_zeroed: the per-item completion counters were already cleared by an earlier kernel of the stream
 static int gen_forward_impl(const std::vector<GenLayer>& L, const uint8_t* packed, int nres, const void* x,
                             float* out, float* logits, uint8_t* wsp, int n, int h, int w, int amode,
-                            long long out_nstride, bool flags_zeroed, cudaStream_t st) {
-  const std::vector<FrLayer> P = gen_plan(L, nres, x, out, logits, wsp, n, h, w, out_nstride);
+                            long long out_nstride, bool flags_zeroed, cudaStream_t st, bool write_rgbx = false) {
+  const std::vector<FrLayer> P = gen_plan(L, nres, x, out, logits, wsp, n, h, w, out_nstride,
+                                          write_rgbx && amode == TG_AMODE_FRAME);
   if (amode == TG_AMODE_FRAME) {
     size_t pb = 0;
     for (auto& l : L) pb += tg_packed_conv_bytes(l.kind, l.cin, l.cout);
@@ -183,12 +188,17 @@ extern "C" int tg_gen_forward(const void* packed, int num_resblock, const void* 
 
 // One recurrent step: frame input (warp of the previous HR estimate + space-to-depth + concat) and
 // generator forward.  Batch strides are in elements.
+// chained: prev_hr is the unmodified output of the previous step on this workspace, so its interleaved copy in the
+// workspace may be gathered instead (frame mode only; every frame-mode step leaves that copy behind).
 static int gen_clip_step_impl(const std::vector<GenLayer>& L, const uint8_t* packed, int nres, const float* lr_t,
                               const float* lr_prev, const float* prev_hr, float* out_t, uint8_t* wsp, int n, int h,
-                              int w, long long lr_bs, long long prev_bs, long long out_bs, int amode, cudaStream_t st) {
+                              int w, long long lr_bs, long long prev_bs, long long out_bs, int amode, cudaStream_t st,
+                              bool chained = false) {
   const GenWorkspace ws = gen_ws(n, h, w);
   void* x0 = wsp + ws.x0;
   const bool frame_mode = (amode == TG_AMODE_FRAME);
+  static const bool rgbx_on = []() { const char* e = getenv("TG_RGBX"); return !(e && e[0] == '0'); }();   // A/B knob
+  if (!rgbx_on) chained = false;
   size_t nflags = 0;
   if (frame_mode) {
     const std::vector<FrLayer> P = gen_plan(L, nres, x0, out_t, nullptr, wsp, n, h, w, out_bs);
@@ -197,9 +207,10 @@ static int gen_clip_step_impl(const std::vector<GenLayer>& L, const uint8_t* pac
   // the frame-input kernel also clears the frame kernel's completion counters (it runs strictly
   // after the previous frame kernel and strictly before the next one)
   int rc = fused_input_launch(lr_t, lr_prev, prev_hr, x0, n, h, w, lr_bs, prev_bs,
-                              frame_mode ? reinterpret_cast<uint32_t*>(wsp + ws.flags) : nullptr, nflags, st);
+                              frame_mode ? reinterpret_cast<uint32_t*>(wsp + ws.flags) : nullptr, nflags, st,
+                              (chained && frame_mode && prev_hr) ? wsp + ws.rgbx : nullptr);
   if (rc) return rc;
-  return gen_forward_impl(L, packed, nres, x0, out_t, nullptr, wsp, n, h, w, amode, out_bs, frame_mode, st);
+  return gen_forward_impl(L, packed, nres, x0, out_t, nullptr, wsp, n, h, w, amode, out_bs, frame_mode, st, rgbx_on);
 }
 
 static int check_ws(const char* who, const void* workspace, size_t workspace_bytes, int n, int h, int w) {
@@ -211,10 +222,10 @@ static int check_ws(const char* who, const void* workspace, size_t workspace_byt
   return TG_OK;
 }
 
-extern "C" int tg_gen_clip_step(const void* packed, int num_resblock, const float* lr_t, const float* lr_prev,
-                                const float* prev_hr, float* out_t, void* workspace, size_t workspace_bytes, int n,
-                                int h, int w, long long lr_batch_stride, long long prev_batch_stride,
-                                long long out_batch_stride, int amode, void* stream) {
+static int clip_step_common(const void* packed, int num_resblock, const float* lr_t, const float* lr_prev,
+                            const float* prev_hr, float* out_t, void* workspace, size_t workspace_bytes, int n,
+                            int h, int w, long long lr_batch_stride, long long prev_batch_stride,
+                            long long out_batch_stride, int amode, void* stream, bool chained) {
   TG_CHECK_ARG(packed && lr_t && out_t && workspace, "gen_clip_step: null pointer");
   TG_CHECK_ARG(n >= 1 && h >= 1 && w >= 1, "gen_clip_step: bad shape");
   TG_CHECK_ARG(amode == TG_AMODE_HALO || amode == TG_AMODE_DX3 || amode == TG_AMODE_FRAME, "gen_clip_step: bad amode %d", amode);
@@ -223,7 +234,23 @@ extern "C" int tg_gen_clip_step(const void* packed, int num_resblock, const floa
   auto L = gen_layers(num_resblock, nullptr, nullptr);
   return gen_clip_step_impl(L, static_cast<const uint8_t*>(packed), num_resblock, lr_t, lr_prev, prev_hr, out_t,
                             static_cast<uint8_t*>(workspace), n, h, w, lr_batch_stride, prev_batch_stride,
-                            out_batch_stride, amode, static_cast<cudaStream_t>(stream));
+                            out_batch_stride, amode, static_cast<cudaStream_t>(stream), chained);
+}
+
+extern "C" int tg_gen_clip_step(const void* packed, int num_resblock, const float* lr_t, const float* lr_prev,
+                                const float* prev_hr, float* out_t, void* workspace, size_t workspace_bytes, int n,
+                                int h, int w, long long lr_batch_stride, long long prev_batch_stride,
+                                long long out_batch_stride, int amode, void* stream) {
+  return clip_step_common(packed, num_resblock, lr_t, lr_prev, prev_hr, out_t, workspace, workspace_bytes, n, h, w,
+                          lr_batch_stride, prev_batch_stride, out_batch_stride, amode, stream, false);
+}
+
+extern "C" int tg_gen_clip_step_chained(const void* packed, int num_resblock, const float* lr_t, const float* lr_prev,
+                                        const float* prev_hr, float* out_t, void* workspace, size_t workspace_bytes,
+                                        int n, int h, int w, long long lr_batch_stride, long long prev_batch_stride,
+                                        long long out_batch_stride, int amode, void* stream) {
+  return clip_step_common(packed, num_resblock, lr_t, lr_prev, prev_hr, out_t, workspace, workspace_bytes, n, h, w,
+                          lr_batch_stride, prev_batch_stride, out_batch_stride, amode, stream, true);
 }
 
 extern "C" int tg_gen_clip_forward(const void* packed, int num_resblock, const float* lr, float* out, void* workspace,
@@ -239,7 +266,7 @@ extern "C" int tg_gen_clip_forward(const void* packed, int num_resblock, const f
     int rc = gen_clip_step_impl(L, static_cast<const uint8_t*>(packed), num_resblock, lr + f * lr_frame,
                                 f ? lr + (f - 1) * lr_frame : nullptr, f ? out + (f - 1) * hr_frame : nullptr,
                                 out + f * hr_frame, static_cast<uint8_t*>(workspace), n, h, w, lr_bs, hr_bs, hr_bs, amode,
-                                static_cast<cudaStream_t>(stream));
+                                static_cast<cudaStream_t>(stream), /*chained=*/true);
     if (rc) return rc;
   }
   return TG_OK;

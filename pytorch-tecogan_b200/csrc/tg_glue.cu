@@ -272,9 +272,23 @@ disc_input_kernel(const float* __restrict__ before9, const float* __restrict__ s
 // ---------------------------------------------------------------------------------------------
 constexpr int kFT = 8;   // LR tile edge
 
+// prev_rgbx (optional): the same previous HR estimate as pixel-interleaved float4 {R,G,B,-} [n][4h][4w] (written by
+// the frame kernel's output conv next to the planar tensor).  The sample positions of the reference's "flow" are
+// scattered, so the gather is bound by L1 sectors touched per warp instruction: one 16-byte tap for three channels
+// instead of three 4-byte ones.  Same taps, same weights, same order of additions: bit-identical.
+__device__ __forceinline__ void gather3(const float4* __restrict__ img, int w, const Taps& t, float (&v)[3]) {
+  const float4* p = img + static_cast<long long>(t.y0) * w + t.x0;
+  v[0] = v[1] = v[2] = 0.f;
+  if (t.ok_nw) { const float4 a = __ldg(p); v[0] += a.x * t.wnw; v[1] += a.y * t.wnw; v[2] += a.z * t.wnw; }
+  if (t.ok_ne) { const float4 a = __ldg(p + 1); v[0] += a.x * t.wne; v[1] += a.y * t.wne; v[2] += a.z * t.wne; }
+  if (t.ok_sw) { const float4 a = __ldg(p + w); v[0] += a.x * t.wsw; v[1] += a.y * t.wsw; v[2] += a.z * t.wsw; }
+  if (t.ok_se) { const float4 a = __ldg(p + w + 1); v[0] += a.x * t.wse; v[1] += a.y * t.wse; v[2] += a.z * t.wse; }
+}
+
 __global__ void __launch_bounds__(256)
 fused_input_kernel(const float* __restrict__ lr_t, const float* __restrict__ lr_prev,
-                   const float* __restrict__ prev_hr, __nv_bfloat16* __restrict__ x, int n, int h, int w,
+                   const float* __restrict__ prev_hr, const float4* __restrict__ prev_rgbx,
+                   __nv_bfloat16* __restrict__ x, int n, int h, int w,
                    long long lr_bs, long long hr_bs, uint32_t* __restrict__ zero, size_t zero_count) {
   __shared__ __align__(16) __nv_bfloat16 tile[kFT * kFT][64];
   // clear the frame kernel's per-item completion counters (this kernel runs between two frame kernels)
@@ -318,9 +332,15 @@ fused_input_kernel(const float* __restrict__ lr_t, const float* __restrict__ lr_
         const float gx = round_fp16(up4_sample(fl, h, w, row, col, 4.f));
         const float gy = round_fp16(up4_sample(fl, h, w, row, col + 1, 4.f));
         const Taps t = make_taps(gx, gy, ho, wo);
-        const float* img = prev_hr + b * hr_bs;
+        if (prev_rgbx != nullptr) {
+          gather3(prev_rgbx + b * hw_o, wo, t, v);
+        } else {
+          const float* img = prev_hr + b * hr_bs;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) v[ch] = (gather(img + ch * hw_o, wo, t) + 1.f) / 2.f;
+          for (int ch = 0; ch < 3; ++ch) v[ch] = gather(img + ch * hw_o, wo, t);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) v[ch] = (v[ch] + 1.f) / 2.f;
       }
       const int px = (hy >> 2) * kFT + (hx >> 2);
       const int sub = (hy & 3) * 4 + (hx & 3);
@@ -460,7 +480,7 @@ extern "C" int tg_upscale4_bilinear(const float* in, float* out, int n, int c, i
 
 int tg::fused_input_launch(const float* lr_t, const float* lr_prev, const float* prev_hr, void* x_nhwc, int n, int h,
                            int w, long long lr_batch_stride, long long hr_batch_stride, uint32_t* zero,
-                           size_t zero_count, cudaStream_t stream) {
+                           size_t zero_count, cudaStream_t stream, const void* prev_rgbx) {
   TG_CHECK_ARG(lr_t && x_nhwc, "fused_warp_s2d_concat: null pointer");
   TG_CHECK_ARG(n >= 1 && h >= 1 && w >= 1, "fused_warp_s2d_concat: bad shape");
   TG_CHECK_ARG((reinterpret_cast<uintptr_t>(x_nhwc) & 15) == 0, "fused_warp_s2d_concat: x must be 16-byte aligned");
@@ -470,8 +490,10 @@ int tg::fused_input_launch(const float* lr_t, const float* lr_prev, const float*
   // algorithmic bytes, SURVEY.md 8(d): 12 B (prev HR f32) + 6.4 B (51 bf16 channels / 16) per HR pixel; the flow
   // is computed on the fly from the LR frame, so the 4 B/px grid read does not exist
   tg_prof_pre(TG_K_FUSED_INPUT, 18.4 * 16.0 * n * h * w, stream);
-  fused_input_kernel<<<blocks, 256, 0, stream>>>(lr_t, lr_prev, prev_hr, static_cast<__nv_bfloat16*>(x_nhwc), n, h, w,
-                                                 lr_batch_stride, hr_batch_stride, zero, zero_count);
+  if (!prev_hr) prev_rgbx = nullptr;
+  fused_input_kernel<<<blocks, 256, 0, stream>>>(lr_t, lr_prev, prev_hr, static_cast<const float4*>(prev_rgbx),
+                                                 static_cast<__nv_bfloat16*>(x_nhwc), n, h, w, lr_batch_stride, hr_batch_stride,
+                                                 zero, zero_count);
   tg_prof_post(stream);
   TG_CUDA(cudaGetLastError());
   return TG_OK;

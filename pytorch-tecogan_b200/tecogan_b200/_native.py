@@ -65,6 +65,8 @@ SIGNATURES = {
                                 _c_int, _c_int, _c_int, _c_void_p]),
     "tg_gen_clip_step": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_int,
                                   _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_int, _c_void_p]),
+    "tg_gen_clip_step_chained": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_int,
+                                  _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_int, _c_void_p]),
     "tg_gen_clip_forward": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_int, _c_int,
                                      _c_int, _c_int, _c_int, _c_void_p]),
     "tg_gen_train_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),

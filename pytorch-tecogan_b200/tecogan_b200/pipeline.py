@@ -67,9 +67,12 @@ class ClipPipeline:
             lr_prev = vp(lr_ptr + 4 * (f - 1) * lr_frame) if f else vp(0)
             prev_hr = vp(fr_ptr + 4 * (f - 1) * b * hr_frame) if f else vp(0)
             cur_hr = vp(fr_ptr + 4 * f * b * hr_frame)
-            _nt.check(lib.tg_gen_clip_step(_nt.ptr(packed), self.nres, lr_t, lr_prev, prev_hr, cur_hr, _nt.ptr(self.ws),
-                                           self.ws.numel(), b, h, w, t * lr_frame, hr_frame, hr_frame,
-                                           int(self.gen.amode), _nt.stream_ptr()))
+            # frame f-1's output is untouched between the two calls: the chained step may gather from the workspace's
+            # interleaved copy of it (bit-identical, 3x fewer L1 sectors per tap)
+            step = lib.tg_gen_clip_step_chained if f else lib.tg_gen_clip_step
+            _nt.check(step(_nt.ptr(packed), self.nres, lr_t, lr_prev, prev_hr, cur_hr, _nt.ptr(self.ws),
+                           self.ws.numel(), b, h, w, t * lr_frame, hr_frame, hr_frame,
+                           int(self.gen.amode), _nt.stream_ptr()))
             ev = torch.cuda.Event()
             ev.record(main)
             self._copy_stream.wait_event(ev)

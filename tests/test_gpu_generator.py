@@ -222,3 +222,38 @@ def test_backward_accumulates_over_frames_like_autograd():
     a = G.conv[0].weight.grad.cpu().double().flatten()
     b = ref.conv[0].weight.grad.double().flatten()
     assert (a @ b / (a.norm() * b.norm())).item() >= 0.99
+
+
+def test_chained_step_is_bit_identical_to_plain_step():
+    """tg_gen_clip_step_chained gathers the warp taps from the workspace's pixel-interleaved copy of the previous output
+    (written by the frame kernel's output conv) instead of the planar tensor: same taps, same weights, same order of
+    additions - every frame of a 2-clip x 4-frame loop must be bit-identical to the plain step, at a size with ragged
+    tiles, and the interleaved copy must not leak between two clips that alternate through one workspace."""
+    import ctypes
+    from tecogan_b200 import _native as nt
+    _, G = _make(1.7)
+    G.amode = FRAME
+    lib = nt.lib()
+    b, t, h, w = 2, 4, 37, 50
+    ws = torch.empty(lib.tg_gen_workspace_bytes(b, h, w), dtype=torch.uint8, device="cuda")
+    packed = G.packed_weights()
+    lr_frame, hr_frame = 3 * h * w, 48 * h * w
+    vp = ctypes.c_void_p
+    outs = {}
+    for chained in (False, True):
+        for clip_seed in (11, 12):
+            lr = torch.from_numpy(synth.clip_inputs(b, t, h, w, seed=clip_seed, hi=0.25)).cuda()
+            fr = torch.zeros((t, b, 3, 4 * h, 4 * w), device="cuda")
+            for f in range(t):
+                step = lib.tg_gen_clip_step_chained if (chained and f) else lib.tg_gen_clip_step
+                nt.check(step(nt.ptr(packed), int(G.num), vp(lr.data_ptr() + 4 * f * lr_frame),
+                              vp(lr.data_ptr() + 4 * (f - 1) * lr_frame) if f else vp(0),
+                              vp(fr.data_ptr() + 4 * (f - 1) * b * hr_frame) if f else vp(0),
+                              vp(fr.data_ptr() + 4 * f * b * hr_frame), nt.ptr(ws), ws.numel(), b, h, w, t * lr_frame,
+                              hr_frame, hr_frame, FRAME, nt.stream_ptr()))
+            torch.cuda.synchronize()
+            outs[(chained, clip_seed)] = fr
+    for clip_seed in (11, 12):
+        assert torch.isfinite(outs[(True, clip_seed)]).all()
+        assert torch.equal(outs[(True, clip_seed)], outs[(False, clip_seed)])
+    assert not torch.equal(outs[(True, 11)], outs[(True, 12)])
