@@ -60,6 +60,10 @@ int tg_profile_end(int max_entries, int* kernel_ids, float* ms, double* work);
  * kernel end in row nseg) into the device buffer; scripts/frame_trace.py turns them into a per-layer
  * timeline.  buf == NULL switches it off. */
 int tg_frame_set_trace(void* buf, size_t bytes);
+/* Test / measurement hook: the frame kernel runs as CTA pairs (tcgen05.mma.cta_group::2, one 2-CTA cluster per TPC)
+ * whenever such clusters can be co-resident, else as the single-CTA kernel.  on = 0 forces the single-CTA kernel,
+ * 1 the default choice, -1 returns control to the TG_FRAME_PAIR environment variable.  Both produce identical bits. */
+int tg_frame_set_pair(int on);
 
 /* ------------------------------------------------------------------ glue (HBM-bound) ------- */
 

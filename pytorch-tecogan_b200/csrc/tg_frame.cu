@@ -905,10 +905,11 @@ static bool use_wide(int kind) {
 }
 // Pair mode (cta_group::2) needs every 3x3 conv on the wide geometry and co-resident 2-CTA clusters; TG_FRAME_PAIR=0
 // selects the single-CTA kernel (A/B measurements).  Returns the number of clusters that can be resident (0: off).
-static int pair_clusters() {
+static int g_pair_override = -1;                     // tg_frame_set_pair: -1 = TG_FRAME_PAIR / default, 0 = off, 1 = on
+void frame_set_pair(int on) { g_pair_override = on < 0 ? -1 : (on ? 1 : 0); }
+static int pair_clusters_available() {
   static const int n = []() {
-    const char* e = getenv("TG_FRAME_PAIR");
-    if ((e && e[0] == '0') || !use_wide(kConv3x3)) return 0;
+    if (!use_wide(kConv3x3)) return 0;
     if (cudaFuncSetAttribute(frame_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<true>::kSmemBytes) != cudaSuccess) {
       cudaGetLastError();
       return 0;
@@ -931,6 +932,11 @@ static int pair_clusters() {
     return nc < want ? nc : want;
   }();
   return n;
+}
+static int pair_clusters() {
+  static const bool env_off = []() { const char* e = getenv("TG_FRAME_PAIR"); return e && e[0] == '0'; }();
+  if (g_pair_override == 0 || (g_pair_override < 0 && env_off)) return 0;
+  return pair_clusters_available();
 }
 
 size_t frame_tiles(int kind, int h, int w) {
@@ -1011,9 +1017,10 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
       items += pair ? ((S.items_real + 1) & ~1) : S.items_real;
       S.item_end = items;
       S.tiles_x = tiles_x; S.tiles_y = tiles_y; S.h = l.h; S.w = l.w;
-      // wide tiles: N-stacked filter rows (1), or - in pair mode, where an N=64 MMA costs 43 cycles instead of 75 - one
-      // MMA group per tap on shifted views of the wide box (2): a third of the accumulator columns, no shuffles
-      static const bool tap_views = []() { const char* e = getenv("TG_FRAME_TAP"); return !(e && e[0] == '0'); }();
+      // wide tiles: N-stacked filter rows (1, the default), or - TG_FRAME_TAP=1, pair mode only, where an N=64 MMA costs 43
+      // cycles instead of 75 - one MMA group per tap on shifted views of the wide box (2): a third of the accumulator
+      // columns and no shuffles, but the A tile is re-read nine times and shared-memory bandwidth makes it slower
+      static const bool tap_views = []() { const char* e = getenv("TG_FRAME_TAP"); return e && e[0] == '1'; }();   // off: measured slower
       S.wide = wide ? ((pair && tap_views && nt == 64) ? 2 : 1) : 0; S.tile_w = tile_w; S.tile_h = tile_h;
       S.box_w = wide ? kWideBoxW : kTileW + 2; S.box_h = wide ? kWideBoxH : kTileH + 2;
       S.fd_tiles_x = make_fastdiv(tiles_x); S.fd_tiles_y = make_fastdiv(tiles_y);

@@ -115,6 +115,9 @@ size_t frame_tiles_max(int h, int w);
 int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t packed_bytes, int n,
                  uint32_t* flags, size_t flag_capacity, bool flags_zeroed, cudaStream_t stream);
 
+// test / measurement hook: 1 = CTA pairs (default when 2-CTA clusters can be co-resident), 0 = single-CTA kernel,
+// -1 = back to the default (TG_FRAME_PAIR environment variable)
+void frame_set_pair(int on);
 // measurement hook: subsequent frame launches stamp [nseg+1][grid] globaltimer values into buf (null = off)
 void frame_set_trace(unsigned long long* buf, size_t words);
 

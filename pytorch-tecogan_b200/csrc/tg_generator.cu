@@ -272,6 +272,11 @@ extern "C" int tg_gen_clip_forward(const void* packed, int num_resblock, const f
   return TG_OK;
 }
 
+extern "C" int tg_frame_set_pair(int on) {
+  tg::frame_set_pair(on);
+  return TG_OK;
+}
+
 extern "C" int tg_frame_set_trace(void* buf, size_t bytes) {
   tg::frame_set_trace(static_cast<unsigned long long*>(buf), buf ? bytes / 8 : 0);
   return TG_OK;

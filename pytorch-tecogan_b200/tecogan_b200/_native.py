@@ -30,6 +30,7 @@ SIGNATURES = {
     "tg_profile_begin": (_c_int, []),
     "tg_profile_end": (_c_int, [_c_int, _c_void_p, _c_void_p, _c_void_p]),
     "tg_frame_set_trace": (_c_int, [_c_void_p, _c_size_t]),
+    "tg_frame_set_pair": (_c_int, [_c_int]),
     "tg_space_to_depth": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "tg_depth_to_space": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "tg_warp_bilinear": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
