@@ -21,13 +21,25 @@
 //    the same staged A tile (9 (phase,tap) pairs == 9 MMA groups, same FLOPs as a 3x3 conv).
 //  * Warp roles: warp0 = TMA producer, warp1 = TMEM owner + single-thread MMA issuer,
 //    warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU/residual -> global).
+//  * Pair mode (kPair, the default for 64-wide chunks): the CTAs of the two SMs of a TPC form a cluster and run their
+//    items in lock-step as ONE tcgen05.mma.cta_group::2 of M = 256; every CTA stages its own item's activations and
+//    HALF of the weight rows (32 of the 64 output channels of each tap block), the leader issues for both, the "full"
+//    barriers live in the leader and take one arrival + the TMA bytes of each CTA, MMA completion is multicast.  An
+//    N = 64 MMA with both operands in shared memory costs 75 cycles alone and 43 as a pair for twice the work
+//    (profiles/r01_mma_microbench_v2.txt).  An odd item count is padded with an out-of-range item (zero fill).
 #include <stdlib.h>
 
 #include "tg_conv_tc.cuh"
 
 namespace tg {
 
-constexpr int kThreads = 192;
+#ifndef TG_CONV_EPI_WARPS
+#define TG_CONV_EPI_WARPS 16
+#endif
+constexpr int kEpiWarps = TG_CONV_EPI_WARPS;            // (TMEM lane quarter) x (part of the 64 accumulator columns)
+constexpr int kEpiCols = 64 / (kEpiWarps / 4);          // columns per epilogue warp: 32 (8 warps) or 16 (16 warps)
+static_assert(kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps");
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kSmemLimit = 232448;   // 227 KB opt-in maximum per CTA
 
 struct SmemLayout {
@@ -47,7 +59,7 @@ __host__ __device__ inline SmemLayout make_layout(uint32_t w_bytes, uint32_t sta
   return l;
 }
 
-template <int NT>
+template <int NT, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                const __grid_constant__ TcParams p) {
@@ -70,70 +82,99 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int chunk = blockIdx.y;                             // 64-wide output channel chunk
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;    // pair mode: rank 0 issues the MMAs
+  const uint32_t nctas = kPair ? 2u : 1u;
+  const int num_items = kPair ? ((p.num_items + 1) & ~1) : p.num_items;   // (the padding item loads zeros, stores nothing)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_w);
-    mbar_init(bar_w, 1);
+    mbar_init(bar_w, nctas);
     for (int i = 0; i < p.nstages; ++i) {
-      mbar_init(bar_afull + 8 * i, 1);
+      mbar_init(bar_afull + 8 * i, nctas);
       mbar_init(bar_aempty + 8 * i, 1);
     }
     for (int i = 0; i < p.ngroups; ++i) {
       mbar_init(bar_cfull + 8 * i, 1);
-      mbar_init(bar_cempty + 8 * i, 4);                     // one arrive per epilogue warp
+      mbar_init(bar_cempty + 8 * i, kEpiWarps * nctas);     // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
+  if (warp == 1) {
+    if (kPair) tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
+    else tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
+  }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + NT) {
     const int c = threadIdx.x - 64;
     s_bias[c] = p.bias ? p.bias[chunk * NT + c] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();                            // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // leader-side barrier addresses (shared::cluster window; the CTA's own when not paired)
+  const uint32_t lbar_w = kPair ? mapa_rank(bar_w, 0) : bar_w;
+  const uint32_t lbar_afull = kPair ? mapa_rank(bar_afull, 0) : bar_afull;
+  const uint32_t lbar_cempty = kPair ? mapa_rank(bar_cempty, 0) : bar_cempty;
   // Programmatic dependent launch: the next layer's CTAs may start their prologue (barrier init,
   // TMEM alloc, weight TMA) as soon as SMs free up; they block in griddepcontrol.wait until this
   // grid has completed and flushed, before touching any activation.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int blocks_per_chunk = p.stages_per_item * p.ntaps;
-  constexpr uint32_t kWBlockBytes = NT * 128;
+  constexpr uint32_t kWBlockBytes = NT * 128 / (kPair ? 2 : 1);   // rows of one tap block held by this CTA x 128 B
+  constexpr int kWRows = NT / (kPair ? 2 : 1);
 
   if (warp == 0) {
     // ================================ TMA producer =========================================
     // Whole warp runs the (uniform) loop; one elected lane issues.  Keeps TMA operands in uniform
     // registers (no per-lane waterfall loops around UTMALDG).
     if (!p.w_stage_bytes && elect_one()) {
-      mbar_expect_tx(bar_w, p.w_bytes);
-      for (int b = 0; b < blocks_per_chunk; ++b)
-        tma_load_2d(s_w + b * kWBlockBytes, &tm_w, bar_w, 0, (chunk * blocks_per_chunk + b) * NT);
+      if (kPair) {
+        mbar_expect_tx_cluster(lbar_w, p.w_bytes);
+        for (int b = 0; b < blocks_per_chunk; ++b)
+          tma_load_2d_pair(s_w + b * kWBlockBytes, &tm_w, lbar_w, 0, (chunk * blocks_per_chunk + b) * NT + static_cast<int>(rank) * kWRows);
+      } else {
+        mbar_expect_tx(bar_w, p.w_bytes);
+        for (int b = 0; b < blocks_per_chunk; ++b)
+          tma_load_2d(s_w + b * kWBlockBytes, &tm_w, bar_w, 0, (chunk * blocks_per_chunk + b) * NT);
+      }
     }
     __syncwarp();
     asm volatile("griddepcontrol.wait;" ::: "memory");      // weights are constants; activations are not
     int s = 0;
     uint32_t ph = 0;
-    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+    for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       const int tx = it % p.tiles_x;
       const int r = it / p.tiles_x;
       const int ty = r % p.tiles_y;
-      const int n = r / p.tiles_y;
+      const int n = r / p.tiles_y;                           // == p.n for the padding item: every box out of range -> zeros
       const int x0 = tx * kTileW, y0 = ty * kTileH;
       for (int sidx = 0; sidx < p.stages_per_item; ++sidx) {
         const int kc = sidx / p.nphase, phs = sidx - kc * p.nphase;
         mbar_wait(bar_aempty + 8 * s, ph ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(bar_afull + 8 * s, p.stage_bytes + p.w_stage_bytes);
           const uint32_t dst = s_a + s * p.stage_stride;
-          for (int c = 0; c < p.ncopies; ++c)
-            tma_load_4d(dst + c * p.copy_bytes, &tm_a, bar_afull + 8 * s, kc * 64,
-                        x0 * p.in_scale + p.copy_dx[c] + (phs & 1), y0 * p.in_scale + p.box_y0 + (phs >> 1), n);
-          if (p.w_stage_bytes)                               // weights of this (K chunk, phase) ride in the stage
-            for (int j = 0; j < p.ntaps; ++j)
-              tma_load_2d(dst + p.a_region + j * kWBlockBytes, &tm_w, bar_afull + 8 * s, 0,
-                          ((chunk * p.stages_per_item + sidx) * p.ntaps + j) * NT);
+          if (kPair) {
+            mbar_expect_tx_cluster(lbar_afull + 8 * s, p.stage_bytes + p.w_stage_bytes);
+            for (int c = 0; c < p.ncopies; ++c)
+              tma_load_4d_pair(dst + c * p.copy_bytes, &tm_a, lbar_afull + 8 * s, kc * 64,
+                               x0 * p.in_scale + p.copy_dx[c] + (phs & 1), y0 * p.in_scale + p.box_y0 + (phs >> 1), n);
+            if (p.w_stage_bytes)                             // this CTA's half of the weights of this (K chunk, phase)
+              for (int j = 0; j < p.ntaps; ++j)
+                tma_load_2d_pair(dst + p.a_region + j * kWBlockBytes, &tm_w, lbar_afull + 8 * s, 0,
+                                 ((chunk * p.stages_per_item + sidx) * p.ntaps + j) * NT + static_cast<int>(rank) * kWRows);
+          } else {
+            mbar_expect_tx(bar_afull + 8 * s, p.stage_bytes + p.w_stage_bytes);
+            for (int c = 0; c < p.ncopies; ++c)
+              tma_load_4d(dst + c * p.copy_bytes, &tm_a, bar_afull + 8 * s, kc * 64,
+                          x0 * p.in_scale + p.copy_dx[c] + (phs & 1), y0 * p.in_scale + p.box_y0 + (phs >> 1), n);
+            if (p.w_stage_bytes)                             // weights of this (K chunk, phase) ride in the stage
+              for (int j = 0; j < p.ntaps; ++j)
+                tma_load_2d(dst + p.a_region + j * kWBlockBytes, &tm_w, bar_afull + 8 * s, 0,
+                            ((chunk * p.stages_per_item + sidx) * p.ntaps + j) * NT);
+          }
         }
         __syncwarp();
         if (++s == p.nstages) { s = 0; ph ^= 1; }
@@ -141,12 +182,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ===========================================
-    constexpr uint32_t idesc = umma_idesc_bf16(128, NT);
+    constexpr uint32_t idesc = umma_idesc_bf16(kPair ? 256 : 128, NT);
+    if (rank == 0) {                                        // (pair mode: the peer's issuer warp only owns its TMEM)
     if (!p.w_stage_bytes) mbar_wait(bar_w, 0);
     tc_fence_after();
     int s = 0, g = 0;
     uint32_t ph = 0, gph = 0;
-    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+    for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       mbar_wait(bar_cempty + 8 * g, gph ^ 1);
       tc_fence_after();
       const uint32_t d_base = tmem_base + static_cast<uint32_t>(g * p.n_acc * kAccCols);
@@ -163,32 +205,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const uint32_t d = d_base + tap.acc * kAccCols;
             const uint32_t keep = (sidx > 0 || !tap.first) ? 1u : 0u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)   // 4 x (K=16 bf16 = 32 bytes) inside the 128B swizzle row
-              umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
+            for (int k = 0; k < 4; ++k) {  // 4 x (K=16 bf16 = 32 bytes) inside the 128B swizzle row
+              if (kPair) umma_bf16_pair(d, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
+              else umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
+            }
           }
-          umma_commit(bar_aempty + 8 * s);                 // stage reusable once these MMAs retire
-          if (sidx == p.stages_per_item - 1) umma_commit(bar_cfull + 8 * g);   // accumulators of this item complete
+          if (kPair) {
+            umma_commit_pair(bar_aempty + 8 * s);            // both CTAs' stages reusable once these MMAs retire
+            if (sidx == p.stages_per_item - 1) umma_commit_pair(bar_cfull + 8 * g);
+          } else {
+            umma_commit(bar_aempty + 8 * s);                 // stage reusable once these MMAs retire
+            if (sidx == p.stages_per_item - 1) umma_commit(bar_cfull + 8 * g);   // accumulators of this item complete
+          }
         }
         __syncwarp();
         if (++s == p.nstages) { s = 0; ph ^= 1; }
       }
       if (++g == p.ngroups) { g = 0; gph ^= 1; }
     }
+    }
   } else {
-    // ================================ epilogue (4 warps) ===================================
+    // ================================ epilogue (8 warps) ===================================
+    // Eight warps, each 32 of the 64 accumulator columns of its lane quarter: with CTA pairs an item's MMAs take ~1550
+    // cycles and four warps doing 64 channels per lane no longer keep up.
     const int q = warp & 3;                                // TMEM lane quarter of this warp
+    const int h2 = (warp - 2) >> 2;                        // which kEpiCols of the 64 columns
     const int m = q * 32 + lane;                           // GEMM row == pixel within sub-tile
     const int pr = m >> 3, pc = m & 7;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     int g = 0;
     uint32_t gph = 0;
-    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+    for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       const int tx = it % p.tiles_x;
       const int r = it / p.tiles_x;
       const int ty = r % p.tiles_y;
       const int n = r / p.tiles_y;
       const int iy = ty * kTileH + pr, ix = tx * kTileW + pc;
-      const bool valid = (iy < p.h) && (ix < p.w);
+      const bool valid = (it < p.num_items) && (iy < p.h) && (ix < p.w);
       mbar_wait(bar_cfull + 8 * g, gph);
       tc_fence_after();
       for (int a = 0; a < p.n_acc; ++a) {
@@ -196,28 +249,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                                static_cast<uint32_t>((g * p.n_acc + a) * kAccCols);
         const int oy = iy * p.sy + p.acc_oy[a], ox = ix * p.sx + p.acc_ox[a];
         if constexpr (NT == 64) {
-          uint32_t v0[32], v1[32];
-          tmem_ld_32x32(taddr, v0);
-          tmem_ld_32x32(taddr + 32, v1);
+          uint32_t v[kEpiCols];
+          if constexpr (kEpiCols == 32) tmem_ld_32x32(taddr + h2 * 32, reinterpret_cast<uint32_t(&)[32]>(v));
+          else tmem_ld_32x16(taddr + h2 * 16, reinterpret_cast<uint32_t(&)[16]>(v));
           tmem_ld_wait();
           if (a == p.n_acc - 1) {                          // TMEM drained -> hand the slot back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
+            if (lane == 0) { if (kPair) mbar_arrive_cluster(lbar_cempty + 8 * g); else mbar_arrive(bar_cempty + 8 * g); }
           }
           if (valid && p.out_mode == kOutNHWCf32) {          // raw f32 (bias, no activation): BatchNorm input
             const size_t pix = (static_cast<size_t>(n) * p.oh + oy) * p.ow + ox;
             float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + pix * p.oc + chunk * 64);
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              uint32_t* v = h2 ? v1 : v0;
-#pragma unroll
-              for (int c4 = 0; c4 < 8; ++c4)
-                dst[h2 * 8 + c4] = make_float4(__uint_as_float(v[c4 * 4 + 0]) + s_bias[h2 * 32 + c4 * 4 + 0],
-                                               __uint_as_float(v[c4 * 4 + 1]) + s_bias[h2 * 32 + c4 * 4 + 1],
-                                               __uint_as_float(v[c4 * 4 + 2]) + s_bias[h2 * 32 + c4 * 4 + 2],
-                                               __uint_as_float(v[c4 * 4 + 3]) + s_bias[h2 * 32 + c4 * 4 + 3]);
-            }
+            for (int c4 = 0; c4 < kEpiCols / 4; ++c4)
+              dst[h2 * (kEpiCols / 4) + c4] = make_float4(__uint_as_float(v[c4 * 4 + 0]) + s_bias[h2 * kEpiCols + c4 * 4 + 0],
+                                                          __uint_as_float(v[c4 * 4 + 1]) + s_bias[h2 * kEpiCols + c4 * 4 + 1],
+                                                          __uint_as_float(v[c4 * 4 + 2]) + s_bias[h2 * kEpiCols + c4 * 4 + 2],
+                                                          __uint_as_float(v[c4 * 4 + 3]) + s_bias[h2 * kEpiCols + c4 * 4 + 3]);
           } else if (valid) {
             const size_t pix = (static_cast<size_t>(n) * p.oh + oy) * p.ow + ox;
             uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix * p.oc +
@@ -229,27 +278,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const uint4* msk = p.mask ? reinterpret_cast<const uint4*>(
                                             static_cast<const __nv_bfloat16*>(p.mask) + pix * p.oc + chunk * 64)
                                       : nullptr;
+            {
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              uint32_t* v = h2 ? v1 : v0;
-#pragma unroll
-              for (int c8 = 0; c8 < 4; ++c8) {             // 8 channels = one 16-byte store
+              for (int c8 = 0; c8 < kEpiCols / 8; ++c8) {  // 8 channels = one 16-byte store
                 float f[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  f[e] = __uint_as_float(v[c8 * 8 + e]) + s_bias[h2 * 32 + c8 * 8 + e];
+                  f[e] = __uint_as_float(v[c8 * 8 + e]) + s_bias[h2 * kEpiCols + c8 * 8 + e];
                   if (p.relu == kActRelu) f[e] = fmaxf(f[e], 0.f);
                   else if (p.relu == kActLrelu02) f[e] = f[e] > 0.f ? f[e] : 0.2f * f[e];
                 }
                 if (res) {
-                  const uint4 rv = __ldg(res + h2 * 4 + c8);
+                  const uint4 rv = __ldg(res + h2 * (kEpiCols / 8) + c8);
                   f[0] += bf16_lo(rv.x); f[1] += bf16_hi(rv.x);
                   f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
                   f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z);
                   f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
                 }
                 if (msk) {                                   // ReLU backward: gradient flows where the saved output > 0
-                  const uint4 mv = __ldg(msk + h2 * 4 + c8);
+                  const uint4 mv = __ldg(msk + h2 * (kEpiCols / 8) + c8);
                   const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
@@ -267,7 +314,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 o.y = pack_bf16x2(f[2], f[3]);
                 o.z = pack_bf16x2(f[4], f[5]);
                 o.w = pack_bf16x2(f[6], f[7]);
-                dst[h2 * 4 + c8] = o;
+                dst[h2 * (kEpiCols / 8) + c8] = o;
               }
             }
           }
@@ -278,9 +325,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           if (a == p.n_acc - 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_cempty + 8 * g);
+            if (lane == 0) { if (kPair) mbar_arrive_cluster(lbar_cempty + 8 * g); else mbar_arrive(bar_cempty + 8 * g); }
           }
-          if (valid) {
+          if (valid && h2 == 0) {                          // (the 3-channel output conv needs one warp per lane quarter)
             const size_t plane = static_cast<size_t>(p.oh) * p.ow;
             const size_t o0 = static_cast<size_t>(n) * p.out_nstride + static_cast<size_t>(oy) * p.ow + ox;
             for (int c = 0; c < p.oc; ++c) {
@@ -297,7 +344,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (kPair) cluster_sync_all();                            // the leader's MMAs read the peer's shared memory
+  if (warp == 1) {
+    if (kPair) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ------------------------------------------------------------------------------------ host
@@ -369,6 +420,10 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
 
   const int nt = cout_pad == 16 ? 16 : 64;
   const int chunks = cout_pad / nt;
+  // CTA pairs (cta_group::2) for the 64-wide chunks; TG_CONV_PAIR=0 selects the single-CTA kernel (A/B measurements)
+  static const bool pair_on = []() { const char* e = getenv("TG_CONV_PAIR"); return !(e && e[0] == '0'); }();
+  const bool pair = pair_on && nt == 64;
+  const int wdiv = pair ? 2 : 1;                            // each CTA of a pair holds half of the weight rows
   // tile space: the output resolution for the stride-2 conv, the input resolution otherwise
   const int th = s2 ? h / 2 : h, tw = s2 ? w / 2 : w;
 
@@ -420,10 +475,10 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   p.stage_bytes = p.ncopies * p.copy_bytes;
   p.a_region = (p.stage_bytes + 1023u) & ~1023u;
   // 4x4 weights (16 taps x Cin x 64) do not fit next to the A ring: stream the block of each (K chunk, phase)
-  p.w_stage_bytes = s2 ? static_cast<uint32_t>(p.ntaps * nt * 128) : 0u;
+  p.w_stage_bytes = s2 ? static_cast<uint32_t>(p.ntaps * nt * 128 / wdiv) : 0u;
   p.stage_stride = p.a_region + p.w_stage_bytes;
   p.ngroups = 8 / p.n_acc;
-  p.w_bytes = s2 ? 0u : static_cast<uint32_t>(p.stages_per_item * p.ntaps * nt * 128);
+  p.w_bytes = s2 ? 0u : static_cast<uint32_t>(p.stages_per_item * p.ntaps * nt * 128 / wdiv);
   // A ring depth from what is left of the 227 KB
   int nstages = 8;
   while (nstages > 0 && make_layout(p.w_bytes, p.stage_stride, nstages, p.ngroups, nt).total + 1024 > kSmemLimit)
@@ -461,15 +516,19 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
     const int rows = chunks * p.stages_per_item * p.ntaps * nt;
     cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(rows)};
     cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(nt)};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(nt / wdiv)};
     int rc = encode_bf16(&tm_w, packed_w, 2, dims, strides, box);
     if (rc) return rc;
   }
 
   int per_chunk = tg_num_sms() / chunks;
   if (per_chunk < 1) per_chunk = 1;
-  dim3 grid(p.num_items < per_chunk ? p.num_items : per_chunk, chunks);
-  static bool attr_done[2] = {false, false};
+  int gx = p.num_items < per_chunk ? p.num_items : per_chunk;
+  if (pair) gx = (gx + 1) & ~1;                             // whole 2-CTA clusters (an odd item count is padded in-kernel)
+  if (pair && gx > per_chunk) gx -= 2;
+  if (pair && gx < 2) gx = 2;
+  dim3 grid(gx, chunks);
+  static bool attr_done[3] = {false, false, false};
   // algorithmic FLOPs (MAC = 2) on the padded channel counts; bench.py uses SURVEY.md's unpadded figure
   tg_prof_pre(nt == 64 ? TG_K_CONV64 : TG_K_CONV16,
               2.0 * (s2 ? 16.0 : 9.0) * cin_pad * (nt == 64 ? cout_pad : 3) * n * th * tw, stream);
@@ -479,17 +538,29 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
-  if (nt == 64) {
-    if (!attr_done[0]) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); attr_done[0] = true; }
-    TG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64>, tm_a, tm_w, p));
+  cfg.numAttrs = na;
+  if (pair) {
+    if (!attr_done[2]) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); attr_done[2] = true; }
+    TG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, true>, tm_a, tm_w, p));
+  } else if (nt == 64) {
+    if (!attr_done[0]) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); attr_done[0] = true; }
+    TG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false>, tm_a, tm_w, p));
   } else {
-    if (!attr_done[1]) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); attr_done[1] = true; }
-    TG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<16>, tm_a, tm_w, p));
+    if (!attr_done[1]) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); attr_done[1] = true; }
+    TG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false>, tm_a, tm_w, p));
   }
   tg_prof_post(stream);
   TG_CUDA(cudaGetLastError());
