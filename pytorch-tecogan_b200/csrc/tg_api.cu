@@ -86,9 +86,9 @@ extern "C" int tg_check_device(void) {
 // the global image is plain row-major.
 namespace tg {
 
-__global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const float* __restrict__ bias,
-                                    int cin, int cout, int cin_pad, int cout_pad, int nt,
-                                    __nv_bfloat16* __restrict__ dst, float* __restrict__ bias_dst) {
+__device__ __forceinline__ void pack_weights_body(int kind, const float* __restrict__ w, const float* __restrict__ bias,
+                                                  int cin, int cout, int cin_pad, int cout_pad, int nt,
+                                                  __nv_bfloat16* __restrict__ dst, float* __restrict__ bias_dst) {
   // conv taps in (ky,kx) raster order; transposed conv in (phase,tap) order, see launch_conv_tc
   const int ct_ky[9] = {1, 1, 1, 2, 0, 2, 2, 0, 0};
   const int ct_kx[9] = {1, 2, 0, 1, 1, 2, 0, 2, 0};
@@ -151,6 +151,19 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
     for (int c = threadIdx.x; c < cout_pad; c += blockDim.x) bias_dst[c] = (bias && c < cout) ? bias[c] : 0.f;
 }
 
+__global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const float* __restrict__ bias,
+                                    int cin, int cout, int cin_pad, int cout_pad, int nt,
+                                    __nv_bfloat16* __restrict__ dst, float* __restrict__ bias_dst) {
+  pack_weights_body(kind, w, bias, cin, cout, cin_pad, cout_pad, nt, dst, bias_dst);
+}
+
+// All layers of a network in one launch (blockIdx.y = layer): after every optimizer step the training loop re-packs
+// ~70 + ~70 small tensors, one launch each was 5 % of a cfg4 step.
+__global__ void pack_weights_batched_kernel(const __grid_constant__ PackJobs jobs) {
+  const PackJob& j = jobs.j[blockIdx.y];
+  pack_weights_body(j.kind, j.w, j.bias, j.cin, j.cout, j.cin_pad, j.cout_pad, j.nt, static_cast<__nv_bfloat16*>(j.dst), j.bias_dst);
+}
+
 }  // namespace tg
 
 // kinds 3 / 4 derive the data-gradient convolution of a forward layer: its input channels are the forward
@@ -169,6 +182,39 @@ extern "C" size_t tg_packed_conv_bytes(int kind, int cin, int cout) {
   const int cp = tg::cin_padded(dci), op = tg::cout_padded(dco);
   size_t b = tg::packed_weight_bytes_k(lk, cp, op) + static_cast<size_t>(op) * 4;
   return (b + 255) & ~static_cast<size_t>(255);
+}
+
+// Fills one PackJob (validation + derived channel counts); shared by the single and the batched entry points.
+static int make_pack_job(int kind, const float* weight, const float* bias, int cin, int cout, void* packed, tg::PackJob* job) {
+  TG_CHECK_ARG(weight && packed, "pack_weights: null pointer");
+  TG_CHECK_ARG(kind >= 0 && kind <= 5, "pack_weights: kind must be 0 (conv3x3), 1 (convT3x3s2), 2 (conv4x4s2), "
+               "3 (dgrad of conv3x3), 4 (dgrad of convT3x3s2) or 5 (dgrad of conv4x4s2)");
+  TG_CHECK_ARG(cin >= 1 && cin <= 128 && cout >= 1 && cout <= 128, "pack_weights: channels out of range");
+  TG_CHECK_ARG(!(kind >= 3 && bias), "pack_weights: data-gradient convolutions have no bias");
+  int lk;
+  { int a, b; derived_channels(kind, cin, cout, &a, &b, &lk); cin = a; cout = b; }   // from here: the derived conv's channels
+  const int cp = tg::cin_padded(cin), op = tg::cout_padded(cout);
+  job->kind = kind; job->w = weight; job->bias = bias; job->cin = cin; job->cout = cout; job->cin_pad = cp; job->cout_pad = op;
+  job->nt = op == 16 ? 16 : 64;
+  job->dst = packed;
+  job->bias_dst = reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + tg::packed_weight_bytes_k(lk, cp, op));
+  return TG_OK;
+}
+
+int tg::pack_weights_batched(const PackJobSpec* specs, int n, cudaStream_t stream) {
+  static thread_local PackJobs jobs;
+  for (int i0 = 0; i0 < n; i0 += kPackBatch) {
+    const int m = n - i0 < kPackBatch ? n - i0 : kPackBatch;
+    for (int i = 0; i < m; ++i) {
+      const PackJobSpec& sp = specs[i0 + i];
+      if (int rc = make_pack_job(sp.kind, sp.weight, sp.bias, sp.cin, sp.cout, sp.packed, &jobs.j[i])) return rc;
+    }
+    tg_prof_pre(TG_K_PACK, 0.0, stream);
+    pack_weights_batched_kernel<<<dim3(64, m), 256, 0, stream>>>(jobs);
+    tg_prof_post(stream);
+    TG_CUDA(cudaGetLastError());
+  }
+  return TG_OK;
 }
 
 extern "C" int tg_pack_weights(int kind, const float* weight, const float* bias, int cin, int cout,

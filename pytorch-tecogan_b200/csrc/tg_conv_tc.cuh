@@ -83,6 +83,16 @@ int launch_wgrad_conv4x4s2(const void* x, const void* dy, float* dw, int n, int 
                            int cin_pad, int cout_pad, cudaStream_t stream);
 int launch_bias_grad(const void* dy, long long pixels, int cpad, int c, float* db, cudaStream_t stream);
 
+// Batched weight packing (tg_api.cu): all layers of a network in one launch.
+constexpr int kPackBatch = 64;
+struct PackJob {
+  const float* w; const float* bias; void* dst; float* bias_dst;
+  int kind, cin, cout, cin_pad, cout_pad, nt;
+};
+struct PackJobs { PackJob j[kPackBatch]; };
+struct PackJobSpec { int kind; const float* weight; const float* bias; int cin, cout; void* packed; };   // tg_pack_weights arguments
+int pack_weights_batched(const PackJobSpec* specs, int n, cudaStream_t stream);
+
 // packed layout helpers
 size_t packed_weight_bytes(int cin_pad, int cout_pad);   // bf16 blocks only, 3x3 kernels
 size_t packed_weight_bytes_k(int kind, int cin_pad, int cout_pad);   // ... 16 taps for kConv4x4s2

@@ -129,12 +129,11 @@ extern "C" int tg_disc_pack(const float* flat_params, int nb, int ch, void* pack
   if (int rc = check_cfg(nb, ch)) return rc;
   TG_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 255) == 0, "disc_pack: packed must be 256-byte aligned");
   const DLayout L = disc_layout(nb, ch, 48);
-  for (auto& c : L.convs) {
-    int rc = tg_pack_weights(c.kind, flat_params + c.w_off, c.has_bias ? flat_params + c.b_off : nullptr, c.cin, c.cout,
-                             static_cast<uint8_t*>(packed) + c.p_off, stream);
-    if (rc) return rc;
-  }
-  return TG_OK;
+  std::vector<PackJobSpec> jobs;
+  for (auto& c : L.convs)
+    jobs.push_back(PackJobSpec{c.kind, flat_params + c.w_off, c.has_bias ? flat_params + c.b_off : nullptr, c.cin, c.cout,
+                               static_cast<uint8_t*>(packed) + c.p_off});
+  return pack_weights_batched(jobs.data(), static_cast<int>(jobs.size()), static_cast<cudaStream_t>(stream));
 }
 extern "C" size_t tg_disc_workspace_bytes(int n, int h, int w, int nb, int ch) {
   if (n <= 0 || h <= 0 || w <= 0 || check_cfg(nb, ch)) return 0;
@@ -269,13 +268,13 @@ extern "C" int tg_disc_pack_dgrad(const float* flat_params, int nb, int ch, void
   TG_CHECK_ARG((reinterpret_cast<uintptr_t>(packed_dgrad) & 255) == 0, "disc_pack_dgrad: buffer must be 256-byte aligned");
   const DLayout L = disc_layout(nb, ch, 48);
   const std::vector<size_t> off = disc_dgrad_offsets(L, nullptr);
+  std::vector<PackJobSpec> jobs;
   for (size_t i = 1; i < L.convs.size(); ++i) {
     const DConv& c = L.convs[i];
-    int rc = tg_pack_weights(c.kind == kConv3x3 ? kPackConv3x3Dgrad : kPackConv4x4s2Dgrad, flat_params + c.w_off, nullptr, c.cin,
-                             c.cout, static_cast<uint8_t*>(packed_dgrad) + off[i], stream);
-    if (rc) return rc;
+    jobs.push_back(PackJobSpec{c.kind == kConv3x3 ? kPackConv3x3Dgrad : kPackConv4x4s2Dgrad, flat_params + c.w_off, nullptr, c.cin,
+                               c.cout, static_cast<uint8_t*>(packed_dgrad) + off[i]});
   }
-  return TG_OK;
+  return pack_weights_batched(jobs.data(), static_cast<int>(jobs.size()), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tg_disc_backward(const float* flat_params, const void* packed_dgrad, int nb, int ch, int fc_in,

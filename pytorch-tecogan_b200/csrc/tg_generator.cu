@@ -158,12 +158,11 @@ extern "C" int tg_gen_pack(const float* flat_params, int num_resblock, void* pac
   TG_CHECK_ARG(num_resblock >= 0 && num_resblock <= 64, "gen_pack: bad num_resblock %d", num_resblock);
   TG_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 255) == 0, "gen_pack: packed must be 256-byte aligned");
   auto L = gen_layers(num_resblock, nullptr, nullptr);
-  for (auto& l : L) {
-    int rc = tg_pack_weights(l.kind, flat_params + l.w_off, l.has_bias ? flat_params + l.b_off : nullptr, l.cin,
-                             l.cout, static_cast<uint8_t*>(packed) + l.p_off, stream);
-    if (rc) return rc;
-  }
-  return TG_OK;
+  std::vector<PackJobSpec> jobs;
+  for (auto& l : L)
+    jobs.push_back(PackJobSpec{l.kind, flat_params + l.w_off, l.has_bias ? flat_params + l.b_off : nullptr, l.cin, l.cout,
+                               static_cast<uint8_t*>(packed) + l.p_off});
+  return pack_weights_batched(jobs.data(), static_cast<int>(jobs.size()), static_cast<cudaStream_t>(stream));
 }
 extern "C" size_t tg_gen_workspace_bytes(int n, int h, int w) {
   if (n <= 0 || h <= 0 || w <= 0) return 0;
@@ -381,12 +380,11 @@ extern "C" int tg_gen_pack_dgrad(const float* flat_params, int num_resblock, voi
   TG_CHECK_ARG(num_resblock >= 0 && num_resblock <= 64, "gen_pack_dgrad: bad num_resblock %d", num_resblock);
   auto L = gen_layers(num_resblock, nullptr, nullptr);
   const std::vector<size_t> off = gen_dgrad_offsets(L, nullptr);
-  for (size_t i = 1; i < L.size(); ++i) {
-    int rc = tg_pack_weights(L[i].kind == kConv3x3 ? kPackConv3x3Dgrad : kPackConvT3x3s2Dgrad, flat_params + L[i].w_off, nullptr,
-                             L[i].cin, L[i].cout, static_cast<uint8_t*>(packed_dgrad) + off[i], stream);
-    if (rc) return rc;
-  }
-  return TG_OK;
+  std::vector<PackJobSpec> jobs;
+  for (size_t i = 1; i < L.size(); ++i)
+    jobs.push_back(PackJobSpec{L[i].kind == kConv3x3 ? kPackConv3x3Dgrad : kPackConvT3x3s2Dgrad, flat_params + L[i].w_off, nullptr,
+                               L[i].cin, L[i].cout, static_cast<uint8_t*>(packed_dgrad) + off[i]});
+  return pack_weights_batched(jobs.data(), static_cast<int>(jobs.size()), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tg_gen_forward_train(const void* packed, int num_resblock, const float* x_nchw, float* out, void* workspace,
