@@ -449,11 +449,15 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           const uint32_t w_base = s_w + slot * kWSlotBytes;
           if (wide) {
             // one MMA per (filter row, K=16 step): A = the box shifted by dy rows of 32 pixels (4096 B, so every
-            // descriptor keeps the canonical 1024-byte group pitch), B = the row's three taps stacked along N
-#pragma unroll 1
+            // descriptor keeps the canonical 1024-byte group pitch), B = the row's three taps stacked along N.
+            // Fully unrolled, descriptors advanced by immediates: for the N = 48 output conv the issue path, not
+            // the MMAs, bounds the item rate.
+            const uint64_t ad0 = umma_desc_sw128(a_base, 1024), bd0 = umma_desc_sw128(w_base, 1024);
+            const uint64_t wrow = (3 * wtap_bytes) >> 4;
+#pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
-              const uint64_t ad = umma_desc_sw128(a_base + dy * (kWideBoxW * 128), 1024);
-              const uint64_t bd = umma_desc_sw128(w_base + dy * 3 * wtap_bytes, 1024);
+              const uint64_t ad = ad0 + static_cast<uint64_t>((dy * kWideBoxW * 128) >> 4);
+              const uint64_t bd = bd0 + dy * wrow;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 if (kPair) umma_bf16_pair(d_base, ad + 2 * k, bd + 2 * k, idesc, (kc > 0 || dy > 0 || k > 0) ? 1u : 0u);

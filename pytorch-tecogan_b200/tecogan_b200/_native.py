@@ -10,6 +10,11 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libtecogan_b200.so")
+# Measurement only: TG_LIB_PATH points the binding at another build of the library (same-box A/B of two commits,
+# scripts/gpu_ab2.sh); symbols that build does not export are then left unbound instead of failing the load.
+_ALT_LIB = os.environ.get("TG_LIB_PATH")
+if _ALT_LIB:
+    LIB_PATH = os.path.abspath(_ALT_LIB)
 
 AMODE_HALO = 0
 AMODE_DX3 = 1
@@ -107,7 +112,12 @@ def load():
                 "`python pytorch-tecogan_b200/build.py` — there is no CPU or PyTorch fallback")
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
-            fn = getattr(lib, name)          # AttributeError if the symbol is missing
+            try:
+                fn = getattr(lib, name)      # AttributeError if the symbol is missing
+            except AttributeError:
+                if _ALT_LIB:
+                    continue
+                raise
             fn.restype = res
             fn.argtypes = args
         _lib = lib
