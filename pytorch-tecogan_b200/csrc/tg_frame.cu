@@ -54,6 +54,14 @@ template <bool kPair> struct FrCfg {
 static_assert(FrCfg<true>::kSmemBytes <= kFrSmemLimit && FrCfg<false>::kSmemBytes <= kFrSmemLimit, "smem budget");
 constexpr int kGroupCols = 256;                       // TMEM columns per accumulator group (2 groups)
 constexpr uint32_t kItemDone = 128;                   // counter value of a published tile
+// Epilogue organisation.  true: two SETS of 8 warps, set s drains accumulator group s, i.e. every other item, so two
+// items' epilogues are in flight at once (a warp = lane quarter x 32 columns, worked off as two 16-column passes with the
+// three partial sums loaded one after the other into the same registers).  false: all 16 warps on every item.
+#ifndef TG_FRAME_TWO_SETS
+#define TG_FRAME_TWO_SETS 1
+#endif
+constexpr bool kTwoSets = TG_FRAME_TWO_SETS != 0;
+constexpr int kSetWarps = kTwoSets ? kEpiWarps / 2 : kEpiWarps;   // arrivals per accumulator hand-back / publish
 
 // tap tables: [kind][j] ; A view offset inside the staged box, accumulator, "first tap of accumulator"
 // [2]: 3x3 conv on the WIDE box, one view per tap (row pitch 32 pixels = 4096 B)
@@ -252,8 +260,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       mbar_init(bar_wfull + 8 * i, nctas);
       mbar_init(bar_wempty + 8 * i, 1);
       mbar_init(bar_cfull + 8 * i, 1);
-      mbar_init(bar_cempty + 8 * i, kEpiWarps * nctas);
-      mbar_init(bar_pfull + 8 * i, kEpiWarps);
+      mbar_init(bar_cempty + 8 * i, kSetWarps * nctas);
+      mbar_init(bar_pfull + 8 * i, kSetWarps);
       mbar_init(bar_pempty + 8 * i, 1);
     }
     for (int i = 0; i < kFrStages; ++i) {
@@ -514,6 +522,199 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       o[0] = a_cempty; o[1] = a_wfull; o[2] = a_afull; o[3] = a_total;
     }
     }
+  } else if (kTwoSets && warp < 2 + kEpiWarps) {
+    // ================================ epilogue, two sets of 8 warps =========================
+    // Set s (warps 2+8s .. 9+8s) drains accumulator group s = the items k with (k & 1) == s of this CTA's sequence, so
+    // the epilogue of item k+1 runs while item k's is still waiting on TMEM, shuffles or stores.  A warp owns one TMEM
+    // lane quarter and 32 of the 64 output channels, in two passes of 16; per pass the partial sums P0, P1, P2 are
+    // loaded one after the other (16 registers in flight instead of 48) and combined in the order (P0[x-1] + P1[x]) + P2[x+1].
+    const int ew = warp - 2;
+    const int set = ew >> 3;
+    const int q = warp & 3;                                // TMEM lane quarter of this warp
+    const int half = (ew >> 2) & 1;                        // which 32 of the 64 accumulator columns
+    const int m = q * 32 + lane;
+    const int pr = m >> 3, pc = m & 7;
+    float* s_bias = s_bias_all + ew * 64;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    int si = 0, cur_si = -1;
+    uint32_t gph = 0, pk = 0;
+    Tick<kDbg> tk{0, stats != nullptr, true}, tall{0, stats != nullptr, true};
+    long long a_cfull = 0, a_body = 0, a_pub = 0, a_total = 0, a_tmem = 0;
+    tall.start();
+    float nb0 = 0.f, nb1 = 0.f;                            // bias of segment nb_si, fetched one segment ahead
+    int nb_si = -1;
+    int seg_end = 0, seg_begin = 0, seg_real = 0, c_tiles_x = 1, c_tiles_y = 1, c_h = 0, c_w = 0;
+    FastDiv c_fdx{0, 0}, c_fdy{0, 0};
+    uint32_t c_row_bytes = 0, c_px_bytes = 0, c_img_bytes = 0;
+    uint8_t* c_out = nullptr;
+    const uint8_t* c_res = nullptr;
+    int c_wide = 0, c_mode = 0, c_relu = 0, c_kind = 0;
+    const uint32_t bar_cf = bar_cfull + 8 * set, bar_pf = bar_pfull + 8 * set, bar_pe = bar_pempty + 8 * set;
+    const uint32_t bar_ce = lbar_cempty + 8 * set, bar_ce_local = bar_cempty + 8 * set;
+    auto hand_back = [&]() {                               // TMEM group drained by this warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { if (kPair) mbar_arrive_cluster(bar_ce); else mbar_arrive(bar_ce_local); }
+    };
+    for (int it = blockIdx.x + set * G; it < P.total_items; it += 2 * G) {
+      if (it >= seg_end) {
+        while (it >= segs[si].item_end) ++si;
+        const FrSegS& C = segs[si];
+        seg_end = C.item_end; seg_begin = C.item_begin; seg_real = C.items_real;
+        c_tiles_x = C.tiles_x; c_tiles_y = C.tiles_y; c_fdx = C.fd_tiles_x; c_fdy = C.fd_tiles_y;
+        c_h = C.h; c_w = C.w; c_wide = C.wide; c_mode = C.out_mode; c_relu = C.relu; c_kind = C.kind;
+        c_px_bytes = C.oc * 2u; c_row_bytes = C.ow * c_px_bytes; c_img_bytes = C.oh * c_row_bytes;   // < 4 GB (launch_frame)
+        c_out = static_cast<uint8_t*>(C.out) + C.ch0 * 2u + half * 64u;
+        c_res = C.resid ? static_cast<const uint8_t*>(C.resid) + C.ch0 * 2u + half * 64u : nullptr;
+      }
+      const FrSegS& S = segs[si];
+      if (si != cur_si) {                                  // warp-private bias copy of this segment
+        __syncwarp();
+        float b0 = nb0, b1 = nb1;
+        if (nb_si != si) {                                 // (first segment, or the set had no item in a segment)
+          b0 = lane < S.nt ? S.bias[lane] : 0.f;
+          b1 = lane + 32 < S.nt ? S.bias[lane + 32] : 0.f;
+        }
+        s_bias[lane] = b0;
+        s_bias[lane + 32] = b1;
+        __syncwarp();
+        cur_si = si;
+        if (si + 1 < P.nseg) {                             // in flight until the next segment starts
+          const FrSegS& N = segs[si + 1];
+          nb0 = lane < N.nt ? N.bias[lane] : 0.f;
+          nb1 = lane + 32 < N.nt ? N.bias[lane + 32] : 0.f;
+          nb_si = si + 1;
+        }
+      }
+      const uint32_t local = static_cast<uint32_t>(it - seg_begin);
+      const uint32_t r = fdiv(local, c_fdx);
+      const int tx = static_cast<int>(local - r * c_tiles_x);
+      const int n = static_cast<int>(fdiv(r, c_fdy));
+      const int ty = static_cast<int>(r) - n * c_tiles_y;
+      const bool real = local < static_cast<uint32_t>(seg_real);      // false: the padding item of a pair
+      tk.gate = stat_seg < 0 || si == stat_seg;
+      tk.start();
+      mbar_wait(bar_cf, gph);
+      tk.stop(a_cfull);
+      tk.start();
+      tc_fence_after();
+      const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(set * kGroupCols);
+      if (c_wide == 1) {
+        const int wy = ty * kWideH + q, wx = tx * kWideW - 1 + lane;
+        const bool wvalid = real && (lane >= 1) && (lane <= kWideW) && (wy < c_h) && (wx < c_w);
+        if (c_mode == kOutNHWCbf16) {
+          const size_t off = static_cast<size_t>(n) * c_img_bytes + (static_cast<uint32_t>(wy) * c_row_bytes + static_cast<uint32_t>(wx) * c_px_bytes);
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            const uint32_t col = static_cast<uint32_t>(half * 32 + pass * 16);
+            uint32_t v[16];
+            uint64_t a2[8];
+            tmem_ld_32x16(tq + col, v);                    // P0: the left neighbour's value is needed
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              a2[e] = f2_pack(__shfl_up_sync(0xFFFFFFFFu, v[2 * e], 1), __shfl_up_sync(0xFFFFFFFFu, v[2 * e + 1], 1));
+            tmem_ld_32x16(tq + 64 + col, v);               // P1
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a2[e] = f2_add(a2[e], f2_pack(v[2 * e], v[2 * e + 1]));
+            tmem_ld_32x16(tq + 128 + col, v);              // P2: the right neighbour's value
+            tmem_ld_wait();
+            if (pass == 1) hand_back();
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              a2[e] = f2_add(a2[e], f2_pack(__shfl_down_sync(0xFFFFFFFFu, v[2 * e], 1), __shfl_down_sync(0xFFFFFFFFu, v[2 * e + 1], 1)));
+            if (wvalid && !(dbg & 16))
+              epi_store_bf16(a2, s_bias + col, c_out + off + pass * 32u, c_res ? c_res + off + pass * 32u : nullptr, c_relu != 0);
+          }
+        } else {
+          uint32_t v0[4], v1[4], v2[4];                    // 3 output channels of each of the 3 partial sums
+          tmem_ld_32x4(tq, v0);
+          tmem_ld_32x4(tq + 16, v1);
+          tmem_ld_32x4(tq + 32, v2);
+          tmem_ld_wait();
+          hand_back();
+          // half 0: planes 0 and 1, half 1: plane 2
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int c = half == 0 ? k : 2;
+            if (half == 1 && k == 1) break;
+            const float l = __shfl_up_sync(0xFFFFFFFFu, __uint_as_float(c == 0 ? v0[0] : (c == 1 ? v0[1] : v0[2])), 1);
+            const float r2 = __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(c == 0 ? v2[0] : (c == 1 ? v2[1] : v2[2])), 1);
+            const float z = (l + __uint_as_float(c == 0 ? v1[0] : (c == 1 ? v1[1] : v1[2]))) + r2 + s_bias[c];
+            if (wvalid && c < S.oc) {
+              const size_t plane = static_cast<size_t>(S.oh) * S.ow;
+              const size_t o = static_cast<size_t>(n) * S.out_nstride + static_cast<size_t>(wy) * S.ow + wx + c * plane;
+              const float y = 1.f / (1.f + expf(-z));
+              if (S.out2) S.out2[o] = z;
+              static_cast<float*>(S.out)[o] = y;
+              if (S.resid != nullptr)                      // pixel-interleaved second copy (tg_glue.cu: gather3)
+                static_cast<float*>(const_cast<void*>(S.resid))[((static_cast<size_t>(n) * S.oh + wy) * S.ow + wx) * 4 + c] = y;
+            }
+          }
+        }
+      } else {
+        // tall tile: GEMM row m = pixel (m / 8, m % 8); wide box with one view per tap: row = (tile row q, column lane)
+        const bool wtap = c_wide == 2;
+        const int iy = wtap ? ty * kWideH + q : ty * kTileH + pr, ix = wtap ? tx * kWideW + lane : tx * kTileW + pc;
+        const bool valid = real && (iy < c_h) && (ix < c_w) && (!wtap || lane < kWideW);
+        const int n_acc = (c_kind == kConv3x3) ? 1 : 4;
+        const int sc = (c_kind == kConv3x3) ? 1 : 2;
+        for (int a = 0; a < n_acc; ++a) {
+          const uint32_t taddr = tq + static_cast<uint32_t>(a * kAccCols);
+          const int oy = iy * sc + (a >> 1), ox = ix * sc + (a & 1);
+          if (c_mode == kOutNHWCbf16) {
+            const size_t off = static_cast<size_t>(n) * c_img_bytes + (static_cast<uint32_t>(oy) * c_row_bytes + static_cast<uint32_t>(ox) * c_px_bytes);
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+              const uint32_t col = static_cast<uint32_t>(half * 32 + pass * 16);
+              uint32_t v[16];
+              tmem_ld_32x16(taddr + col, v);
+              tmem_ld_wait();
+              if (a == n_acc - 1 && pass == 1) hand_back();
+              if (valid) {
+                uint64_t a2[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a2[e] = f2_pack(v[2 * e], v[2 * e + 1]);
+                epi_store_bf16(a2, s_bias + col, c_out + off + pass * 32u, c_res ? c_res + off + pass * 32u : nullptr, c_relu != 0);
+              }
+            }
+          } else {                                           // output conv on the tall geometry (TG_FRAME_WIDE=0)
+            uint32_t v[16];
+            tmem_ld_32x16(taddr, v);
+            tmem_ld_wait();
+            if (a == n_acc - 1) hand_back();
+            if (valid && half == 0) {
+              const size_t plane = static_cast<size_t>(S.oh) * S.ow;
+              for (int c = 0; c < 3 && c < S.oc; ++c) {
+                const size_t o = static_cast<size_t>(n) * S.out_nstride + static_cast<size_t>(oy) * S.ow + ox + c * plane;
+                const float z = __uint_as_float(c == 0 ? v[0] : (c == 1 ? v[1] : v[2])) + s_bias[c];
+                if (S.out2) S.out2[o] = z;
+                static_cast<float*>(S.out)[o] = 1.f / (1.f + expf(-z));
+              }
+            }
+          }
+        }
+      }
+      tk.stop(a_body);
+      // the network output has no consumer inside the kernel: nothing to publish
+      if (c_mode == kOutNHWCbf16 && real && !(dbg & 2)) {
+        tk.start();
+        __syncwarp();                                        // orders the 32 lanes' stores before lane 0's release
+        if (lane == 0) {
+          mbar_wait(bar_pe, (pk & 1u) ^ 1u);                 // the publisher has released this set's previous tile
+          mbar_arrive(bar_pf);
+        }
+        tk.stop(a_pub);
+        ++pk;
+      }
+      gph ^= 1;
+    }
+    tall.stop(a_total);
+    if (stats && warp == 2 && lane == 0) {
+      unsigned long long* o = stats + blockIdx.x * 16;
+      o[4] = a_cfull; o[5] = a_body; o[6] = a_pub; o[7] = a_total; o[8] = a_tmem;
+    }
   } else if (warp < 2 + kEpiWarps) {
     // ================================ epilogue (16 warps) ==================================
     // warp = (TMEM lane quarter q, column part): 16 of the 64 accumulator columns of 32 pixels per item.  Sixteen
@@ -700,7 +901,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
   } else if (warp == 2 + kEpiWarps) {
     // ================================ publisher ============================================
     int si = 0;
-    uint32_t pk = 0;
+    uint32_t pk = 0, pkset[2] = {0, 0};
     Tick<kDbg> tk{0, stats != nullptr, true};
     long long a_pfull = 0, a_red = 0;
     int seg_end = 0, seg_pub_end = 0;                        // publish items [.., seg_pub_end) of the current segment
@@ -712,8 +913,11 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         seg_pub_end = C.out_mode == kOutNHWCbf16 ? C.item_begin + C.items_real : 0;
       }
       tk.gate = stat_seg < 0 || si == stat_seg;
+      const uint32_t kseq = static_cast<uint32_t>(it - static_cast<int>(blockIdx.x)) / static_cast<uint32_t>(G);   // k-th item of this CTA
       if (it < seg_pub_end && !(dbg & 2)) {
-        const uint32_t pg = pk & 1u, pph = (pk >> 1) & 1u;
+        // single epilogue set: two barriers used alternately; two sets: set (k & 1) has its own barrier pair
+        const uint32_t pg = kTwoSets ? (kseq & 1u) : (pk & 1u);
+        const uint32_t pph = kTwoSets ? (pkset[pg] & 1u) : ((pk >> 1) & 1u);
         tk.start();
         mbar_wait(bar_pfull + 8 * pg, pph);                  // all epilogue threads stored (acquire.cta)
         tk.stop(a_pfull);
@@ -725,6 +929,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         __syncwarp();
         tk.stop(a_red);
         ++pk;
+        ++pkset[pg];
       }
     }
     if (stats && lane == 0) {
