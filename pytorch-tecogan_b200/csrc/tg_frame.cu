@@ -39,7 +39,16 @@
 namespace tg {
 
 constexpr int kEpiWarps = 16;                          // 4 per TMEM lane quarter: 16 accumulator columns each
-constexpr int kFrThreads = 32 * (2 + kEpiWarps + 2);   // producer, MMA, epilogue warps, publisher, dependency warp
+// Epilogue organisation.  true: two SETS of 8 warps, set s drains accumulator group s, i.e. every other item, so two
+// items' epilogues are in flight at once (a warp = lane quarter x 32 columns, worked off as two 16-column passes with the
+// three partial sums loaded one after the other into the same registers).  false: all 16 warps on every item.
+#ifndef TG_FRAME_TWO_SETS
+#define TG_FRAME_TWO_SETS 1
+#endif
+constexpr bool kTwoSets = TG_FRAME_TWO_SETS != 0;
+constexpr int kSetWarps = kTwoSets ? kEpiWarps / 2 : kEpiWarps;   // arrivals per accumulator hand-back / publish
+constexpr int kPubWarps = 1;                          // (a second publisher WARP would be the 21st: 80 registers, spills - measured slower)
+constexpr int kFrThreads = 32 * (2 + kEpiWarps + kPubWarps + 1);   // producer, MMA, epilogue warps, publisher(s), dependency warp
 constexpr int kDepRing = 4;                            // dependency warp runs at most this many items ahead of the producer
 constexpr uint32_t kFrSmemLimit = 232448;
 constexpr uint32_t kAStride = 24576;                  // stage pitch: {64ch, 32, 6} wide box (24576 B) / {64ch, 10, 18} tall box (23040 B)
@@ -54,14 +63,6 @@ template <bool kPair> struct FrCfg {
 static_assert(FrCfg<true>::kSmemBytes <= kFrSmemLimit && FrCfg<false>::kSmemBytes <= kFrSmemLimit, "smem budget");
 constexpr int kGroupCols = 256;                       // TMEM columns per accumulator group (2 groups)
 constexpr uint32_t kItemDone = 128;                   // counter value of a published tile
-// Epilogue organisation.  true: two SETS of 8 warps, set s drains accumulator group s, i.e. every other item, so two
-// items' epilogues are in flight at once (a warp = lane quarter x 32 columns, worked off as two 16-column passes with the
-// three partial sums loaded one after the other into the same registers).  false: all 16 warps on every item.
-#ifndef TG_FRAME_TWO_SETS
-#define TG_FRAME_TWO_SETS 1
-#endif
-constexpr bool kTwoSets = TG_FRAME_TWO_SETS != 0;
-constexpr int kSetWarps = kTwoSets ? kEpiWarps / 2 : kEpiWarps;   // arrivals per accumulator hand-back / publish
 
 // tap tables: [kind][j] ; A view offset inside the staged box, accumulator, "first tap of accumulator"
 // [2]: 3x3 conv on the WIDE box, one view per tap (row pitch 32 pixels = 4096 B)
@@ -898,43 +899,44 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       unsigned long long* o = stats + blockIdx.x * 16;
       o[4] = a_cfull; o[5] = a_body; o[6] = a_pub; o[7] = a_total; o[8] = a_tmem;
     }
-  } else if (warp == 2 + kEpiWarps) {
+  } else if (warp < 2 + kEpiWarps + kPubWarps) {
     // ================================ publisher ============================================
-    int si = 0;
-    uint32_t pk = 0, pkset[2] = {0, 0};
-    Tick<kDbg> tk{0, stats != nullptr, true};
-    long long a_pfull = 0, a_red = 0;
-    int seg_end = 0, seg_pub_end = 0;                        // publish items [.., seg_pub_end) of the current segment
-    for (int it = blockIdx.x; it < P.total_items; it += G) {
-      if (it >= seg_end) {
-        while (it >= segs[si].item_end) ++si;
-        const FrSegS& C = segs[si];
-        seg_end = C.item_end;
-        seg_pub_end = C.out_mode == kOutNHWCbf16 ? C.item_begin + C.items_real : 0;
-      }
-      tk.gate = stat_seg < 0 || si == stat_seg;
-      const uint32_t kseq = static_cast<uint32_t>(it - static_cast<int>(blockIdx.x)) / static_cast<uint32_t>(G);   // k-th item of this CTA
-      if (it < seg_pub_end && !(dbg & 2)) {
-        // single epilogue set: two barriers used alternately; two sets: set (k & 1) has its own barrier pair
-        const uint32_t pg = kTwoSets ? (kseq & 1u) : (pk & 1u);
-        const uint32_t pph = kTwoSets ? (pkset[pg] & 1u) : ((pk >> 1) & 1u);
-        tk.start();
-        mbar_wait(bar_pfull + 8 * pg, pph);                  // all epilogue threads stored (acquire.cta)
-        tk.stop(a_pfull);
-        tk.start();
-        if (lane == 0) {
-          red_release_gpu_add(P.flags + it, kItemDone);   // (flag_off == item_begin) cumulative gpu-scope release
-          mbar_arrive(bar_pempty + 8 * pg);
+    // A gpu-scope release (MEMBAR.GPU + RED) takes ~1300 cycles, more than an item's MMAs, so with two epilogue sets
+    // two releases must be in flight: lanes 0 and 1 of this warp are two independent publishers (independent thread
+    // scheduling lets one lane issue while the other sits in its fence), lane pw releasing the tiles of set pw.
+    const int pw = lane;
+    if (pw < (kTwoSets ? 2 : 1)) {
+      int si = 0;
+      uint32_t pk = 0;
+      Tick<kDbg> tk{0, stats != nullptr, true};
+      long long a_pfull = 0, a_red = 0;
+      int seg_end = 0, seg_pub_end = 0;                      // publish items [.., seg_pub_end) of the current segment
+      for (int it = blockIdx.x + (kTwoSets ? pw * G : 0); it < P.total_items; it += (kTwoSets ? 2 * G : G)) {
+        if (it >= seg_end) {
+          while (it >= segs[si].item_end) ++si;
+          const FrSegS& C = segs[si];
+          seg_end = C.item_end;
+          seg_pub_end = C.out_mode == kOutNHWCbf16 ? C.item_begin + C.items_real : 0;
         }
-        __syncwarp();
-        tk.stop(a_red);
-        ++pk;
-        ++pkset[pg];
+        tk.gate = stat_seg < 0 || si == stat_seg;
+        if (it < seg_pub_end && !(dbg & 2)) {
+          // single epilogue set: two barriers used alternately; two sets: set pw has its own barrier pair
+          const uint32_t pg = kTwoSets ? static_cast<uint32_t>(pw) : (pk & 1u);
+          const uint32_t pph = kTwoSets ? (pk & 1u) : ((pk >> 1) & 1u);
+          tk.start();
+          mbar_wait(bar_pfull + 8 * pg, pph);                // all epilogue warps stored (acquire.cta)
+          tk.stop(a_pfull);
+          tk.start();
+          red_release_gpu_add(P.flags + it, kItemDone);      // (flag_off == item_begin) cumulative gpu-scope release
+          mbar_arrive(bar_pempty + 8 * pg);
+          tk.stop(a_red);
+          ++pk;
+        }
       }
-    }
-    if (stats && lane == 0) {
-      unsigned long long* o = stats + blockIdx.x * 16;
-      o[13] = a_pfull; o[14] = a_red;
+      if (stats && pw == 0) {
+        unsigned long long* o = stats + blockIdx.x * 16;
+        o[13] = a_pfull; o[14] = a_red;
+      }
     }
   } else if (!(dbg & 1)) {
     // ================================ dependency warp ======================================
