@@ -608,17 +608,15 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
 #pragma unroll
           for (int pass = 0; pass < 2; ++pass) {
             const uint32_t col = static_cast<uint32_t>(half * 32 + pass * 16);
-            uint32_t v[16];
+            uint32_t v[16], vb[16];
             uint64_t a2[8];
             tmem_ld_32x16(tq + col, v);                    // P0: the left neighbour's value is needed
+            tmem_ld_32x16(tq + 64 + col, vb);              // P1 (same round trip)
             tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-              a2[e] = f2_pack(__shfl_up_sync(0xFFFFFFFFu, v[2 * e], 1), __shfl_up_sync(0xFFFFFFFFu, v[2 * e + 1], 1));
-            tmem_ld_32x16(tq + 64 + col, v);               // P1
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 8; ++e) a2[e] = f2_add(a2[e], f2_pack(v[2 * e], v[2 * e + 1]));
+              a2[e] = f2_add(f2_pack(__shfl_up_sync(0xFFFFFFFFu, v[2 * e], 1), __shfl_up_sync(0xFFFFFFFFu, v[2 * e + 1], 1)),
+                             f2_pack(vb[2 * e], vb[2 * e + 1]));
             tmem_ld_32x16(tq + 128 + col, v);              // P2: the right neighbour's value
             tmem_ld_wait();
             if (pass == 1) hand_back();
