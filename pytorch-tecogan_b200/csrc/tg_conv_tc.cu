@@ -37,7 +37,14 @@ namespace tg {
 #define TG_CONV_EPI_WARPS 16
 #endif
 constexpr int kEpiWarps = TG_CONV_EPI_WARPS;            // (TMEM lane quarter) x (part of the 64 accumulator columns)
-constexpr int kEpiCols = 64 / (kEpiWarps / 4);          // columns per epilogue warp: 32 (8 warps) or 16 (16 warps)
+// Two SETS of eight warps, set s draining every other item (s, s+2, ...): two items' epilogues in flight.  A warp then
+// owns 32 columns of its lane quarter.  (TG_CONV_TWO_SETS=0: all warps on every item, 64 / (warps / 4) columns each.)
+#ifndef TG_CONV_TWO_SETS
+#define TG_CONV_TWO_SETS 1
+#endif
+constexpr bool kTwoSets = TG_CONV_TWO_SETS != 0 && kEpiWarps == 16;
+constexpr int kSetWarps = kTwoSets ? kEpiWarps / 2 : kEpiWarps;
+constexpr int kEpiCols = 64 / (kSetWarps / 4);          // columns per epilogue warp: 32 (8 warps per item) or 16 (16)
 static_assert(kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps");
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kSmemLimit = 232448;   // 227 KB opt-in maximum per CTA
@@ -96,7 +103,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
     for (int i = 0; i < p.ngroups; ++i) {
       mbar_init(bar_cfull + 8 * i, 1);
-      mbar_init(bar_cempty + 8 * i, kEpiWarps * nctas);     // one arrive per epilogue warp (of both CTAs)
+      mbar_init(bar_cempty + 8 * i, kSetWarps * nctas);     // one arrive per epilogue warp of the item's set (of both CTAs)
     }
     fence_barrier_init();
   }
@@ -225,17 +232,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
     }
   } else {
-    // ================================ epilogue (8 warps) ===================================
-    // Eight warps, each 32 of the 64 accumulator columns of its lane quarter: with CTA pairs an item's MMAs take ~1550
-    // cycles and four warps doing 64 channels per lane no longer keep up.
+    // ================================ epilogue (16 warps, two sets) ========================
+    // With four warps doing 64 channels per lane the kernel was epilogue-bound.  Sixteen warps in two sets of eight:
+    // set s drains the items s, s+2, ... of this CTA (accumulator groups of the same parity; the ring has 8 or 2
+    // groups), a warp = one TMEM lane quarter x 32 of the 64 columns.
     const int q = warp & 3;                                // TMEM lane quarter of this warp
-    const int h2 = (warp - 2) >> 2;                        // which kEpiCols of the 64 columns
+    const int set = kTwoSets ? (warp - 2) >> 3 : 0;        // which items this warp works on (two sets)
+    const int h2 = ((warp - 2) >> 2) & (kSetWarps / 4 - 1);   // which kEpiCols of the 64 columns
     const int m = q * 32 + lane;                           // GEMM row == pixel within sub-tile
     const int pr = m >> 3, pc = m & 7;
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    int g = 0;
+    const int gstep = kTwoSets ? 2 : 1;
+    int g = set % p.ngroups;
     uint32_t gph = 0;
-    for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+    for (int it = blockIdx.x + set * gridDim.x; it < num_items; it += gstep * gridDim.x) {
       const int tx = it % p.tiles_x;
       const int r = it / p.tiles_x;
       const int ty = r % p.tiles_y;
@@ -338,7 +348,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           }
         }
       }
-      if (++g == p.ngroups) { g = 0; gph ^= 1; }
+      g += gstep;
+      if (g >= p.ngroups) { g -= p.ngroups; gph ^= 1; }
     }
   }
 
