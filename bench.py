@@ -199,8 +199,11 @@ def run_train_leg(name, crop, global_batch, world, rank, dev, steps, warmup, bar
     D = models.discriminator(args).to(dev)
     parallel.broadcast_parameters(G)
     parallel.broadcast_parameters(D)
-    og = torch.optim.Adam(G.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps)    # main.py:239-243
-    od = torch.optim.Adam(D.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps)
+    # main.py:239-243's optimizer; fused=True is torch's own single-kernel implementation of the same update, and the only
+    # one GradScaler.step() can drive without reading found_inf back to the host (TG_BENCH_FUSED_ADAM=0: the plain one)
+    fused = os.environ.get("TG_BENCH_FUSED_ADAM", "1") != "0"
+    og = torch.optim.Adam(G.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps, fused=fused)
+    od = torch.optim.Adam(D.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps, fused=fused)
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
     r_in = torch.rand((per, 10, 3, crop, crop), device=dev, generator=gen)
     r_tg = torch.rand((per, 10, 3, 4 * crop, 4 * crop), device=dev, generator=gen)
@@ -243,7 +246,8 @@ def run_train_leg(name, crop, global_batch, world, rank, dev, steps, warmup, bar
            "gpu_launches": int(launches),
            "step_tflops": flops / (dev_s / steps) / 1e12, "algorithmic_flops_per_step": flops,
            "losses_finite": bool(all(v == v and abs(v) != float("inf") for v in losses + host_losses)),
-           "optimizer": "torch.optim.Adam + GradScaler (stock, as main.py:239-243 / code/train.py:335-342)"}
+           "optimizer": ("torch.optim.Adam(fused=True)" if fused else "torch.optim.Adam") +
+                        " + GradScaler (stock torch, as main.py:239-243 / code/train.py:335-342)"}
     if with_cpu:
         cb = 4 if crop == 32 else 1
         cps, step_s, cores = cpu_oracle_train(crop, cb)

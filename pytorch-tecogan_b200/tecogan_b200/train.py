@@ -198,11 +198,14 @@ def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step
     # Here both backward passes run first (each followed by its asynchronous gradient all-reduce when data-parallel),
     # then the steps in the reference's order; should the first update() change the loss scale, the discriminator's
     # gradients are rescaled by the (power-of-two) ratio, which is what scaling its loss with the new scale produces.
+    # The ratio stays on the device (GradScaler.get_scale() is a host synchronisation; scale(1) is not): with a fused
+    # optimizer the whole step enqueues without the host ever waiting for the GPU.
     sc = _scaler()
     sync_g, sync_d = _par.GradSync(), _par.GradSync()
     optimizer_g.zero_grad()
     g_bucket = _par.zero_flat_grads(generator_F)
-    scale0 = sc.get_scale() if sc.is_enabled() else 1.0
+    one = torch.ones((), dtype=torch.float32, device=g_bucket.device)
+    scale0 = sc.scale(one) if sc.is_enabled() else None
     sc.scale(gen_loss).backward()
     sync_g.start(g_bucket)
     optimizer_d.zero_grad()
@@ -213,9 +216,8 @@ def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step
     sc.step(optimizer_g)
     sc.update()
     sync_d.finish()
-    scale1 = sc.get_scale() if sc.is_enabled() else 1.0
-    if scale1 != scale0:
-        d_bucket.mul_(scale1 / scale0)
+    if scale0 is not None:
+        d_bucket.mul_(sc.scale(one) / scale0)              # exactly 1.0 unless update() just changed the scale
     sc.step(optimizer_d)
     sc.update()
 
