@@ -4,25 +4,28 @@
 // Why: at 320x180 the 33 trunk layers are 3.6 us of tensor work each; as separate launches they
 // cost 13-18 us (launch, prologue, weight fetch, pipeline fill/drain, 3.04-wave quantisation; see
 // profiles/r01_summary_v1_perlayer.md).  Here the whole frame is one ordered queue of work items
-//     item = (segment = layer x 64-wide Cout chunk, image, 16x8 pixel tile)
+//     item = (segment = layer x 64-wide Cout chunk, image, pixel tile)
 // statically dealt round-robin to the CTAs, and layers are chained by per-tile completion counters
 // in global memory instead of kernel boundaries:
-//   * warp roles: TMA producer, single-thread MMA issuer, 8 epilogue warps (two per TMEM lane quarter, 32
-//     accumulator columns each), one publisher warp;
-//   * an item's TMA producer waits (ld.acquire.gpu) until the <= 3x3 producer tiles of the previous
-//     layer that its halo box touches have been published (one red.release.gpu per tile by a publisher warp,
-//     after the 256 epilogue threads arrived on a CTA-local mbarrier),
-//     then issues the box load; MMAs and epilogues of earlier items never wait on later ones, all
-//     CTAs are co-resident (1 per SM) and every dependency points to an earlier item of the queue,
-//     so the schedule cannot deadlock;
-//   * weights live in two 72 KB shared-memory slots managed as an LRU pair: a layer with one K chunk
+//   * warp roles (20 warps): TMA producer, single-thread MMA issuer, 16 epilogue warps in two sets of 8 (set s drains
+//     accumulator group s = every other item: two items' epilogues in flight; a warp = one TMEM lane quarter x 32
+//     output channels), one publisher warp (lane s publishes set s's tiles), one dependency warp;
+//   * an item's TMA producer waits until the <= 3x3 producer tiles of the previous layer that its halo box touches
+//     have been published (one red.release.gpu per tile by a publisher lane, after the set's 8 warps arrived on a
+//     CTA-local mbarrier; the acquire side - relaxed polls + one fence - runs ahead in the dependency warp and is
+//     handed over through an mbarrier ring), then issues the box load; MMAs and epilogues of earlier items never
+//     wait on later ones, all CTAs are co-resident (1 per SM) and every dependency points to an earlier item of the
+//     queue, so the schedule cannot deadlock;
+//   * weights live in two shared-memory slots (72 KB each, 36 KB per CTA of a pair) managed as an LRU pair: a layer with one K chunk
 //     prefetches the next layer's block into the idle slot while it computes; a layer with two K
 //     chunks keeps both blocks resident.  A block is released (tcgen05.commit -> mbarrier) after the
 //     CTA's last item of the segment;
 //   * the tensor pipe therefore never drains between layers; TMEM, barriers and tensor maps are
 //     set up once per frame.
-// The GEMM core is the one of tg_conv_tc.cu (A = activation halo box, nine row-shifted descriptor
-// views; B = weights; accumulators in TMEM; UMMA M=128, N=64, K=16).
+// The GEMM core: A = activation halo box (TMA, SWIZZLE_128B), B = weights, accumulators in TMEM, K = 16 per MMA.
+// 3x3 convs: 4 x 32-pixel "wide" tiles, the three taps of a filter row stacked along N (one MMA of N = 192 per
+// filter row and K step, partial sums combined by lane shuffles in the epilogue); transposed convs: 16 x 8 tiles,
+// nine row-shifted descriptor views of the box into four output-phase accumulators (N = 64), as in tg_conv_tc.cu.
 //
 // Pair mode (template kPair, the default): the CTAs of two SMs of a TPC form a cluster and run their items in
 // lock-step as ONE tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own item's activation box and HALF of
