@@ -650,8 +650,13 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
               const float y = 1.f / (1.f + expf(-z));
               if (S.out2) S.out2[o] = z;
               static_cast<float*>(S.out)[o] = y;
-              if (S.resid != nullptr)                      // pixel-interleaved second copy (tg_glue.cu: gather3)
-                static_cast<float*>(const_cast<void*>(S.resid))[((static_cast<size_t>(n) * S.oh + wy) * S.ow + wx) * 4 + c] = y;
+              if (S.resid != nullptr) {                    // pixel-interleaved second copy (tg_glue.cu: gather3)
+                float* px = static_cast<float*>(const_cast<void*>(S.resid)) + ((static_cast<size_t>(n) * S.oh + wy) * S.ow + wx) * 4;
+                // the blue warp also writes the unused fourth component: every byte of the copy is written, so no
+                // sector is ever partially dirty (a partial sector costs a read-modify-write in ECC DRAM)
+                if (c == 2) *reinterpret_cast<float2*>(px + 2) = make_float2(y, 0.f);
+                else px[c] = y;
+              }
             }
           }
         }
@@ -839,8 +844,11 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
             static_cast<float*>(S.out)[o] = y;
             // optional second copy, pixel-interleaved (float4 {R,G,B,-}, component `part` from this warp): the next
             // frame's warp gathers three channels with one 16-byte load (tg_glue.cu: gather3)
-            if (S.resid != nullptr)
-              static_cast<float*>(const_cast<void*>(S.resid))[((static_cast<size_t>(n) * S.oh + wy) * S.ow + wx) * 4 + c] = y;
+            if (S.resid != nullptr) {
+              float* px = static_cast<float*>(const_cast<void*>(S.resid)) + ((static_cast<size_t>(n) * S.oh + wy) * S.ow + wx) * 4;
+              if (c == 2) *reinterpret_cast<float2*>(px + 2) = make_float2(y, 0.f);
+              else px[c] = y;
+            }
           }
         }
       } else {
