@@ -31,19 +31,28 @@ __global__ void s2d4_kernel(const uint4* __restrict__ in, uint32_t* __restrict__
 
 __global__ void d2s4_kernel(const uint32_t* __restrict__ in, uint4* __restrict__ out, int planes, int hi,
                             int wi) {
+  // two output groups per thread iteration: eight 4-byte plane loads in flight feed two 16-byte stores
   const long long total = static_cast<long long>(planes) * 4 * hi * wi;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int x = static_cast<int>(i % wi);
-    long long r = i / wi;
-    const int oy = static_cast<int>(r % (4 * hi));
-    const long long pl = r / (4 * hi);
-    const int y = oy >> 2, dy = oy & 3;
-    const uint32_t* s = in + ((pl * 16 + dy * 4) * hi + y) * static_cast<long long>(wi) + x;
-    const long long ps = static_cast<long long>(hi) * wi;
-    uint4 v;
-    v.x = __ldg(s); v.y = __ldg(s + ps); v.z = __ldg(s + 2 * ps); v.w = __ldg(s + 3 * ps);
-    out[i] = v;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long ps = static_cast<long long>(hi) * wi;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += 2 * stride) {
+    uint4 v[2];
+    long long idx[2] = {i, i + stride};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (idx[u] < total) {
+        const int x = static_cast<int>(idx[u] % wi);
+        long long r = idx[u] / wi;
+        const int oy = static_cast<int>(r % (4 * hi));
+        const long long pl = r / (4 * hi);
+        const int y = oy >> 2, dy = oy & 3;
+        const uint32_t* s = in + ((pl * 16 + dy * 4) * hi + y) * static_cast<long long>(wi) + x;
+        v[u].x = __ldg(s); v[u].y = __ldg(s + ps); v[u].z = __ldg(s + 2 * ps); v[u].w = __ldg(s + 3 * ps);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (idx[u] < total) out[idx[u]] = v[u];
   }
 }
 
