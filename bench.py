@@ -33,7 +33,7 @@ for p in (ROOT, os.path.join(ROOT, "pytorch-tecogan_b200")):
 H, W, T = 180, 320, 100
 FLOP_PER_LR_PIXEL = 8445312           # whole generator, MAC=2, padding not counted
 FLOP_PER_LR_PIXEL_OUTCONV = 2 * 9 * 64 * 3 * 16
-TRAFFIC_BYTES_PER_LAUNCH = 2.538e9     # ncu --set full, frame_kernel v7 (pairs, two epilogue sets), 2 clips/launch: dram read 1.331 GB + write 1.207 GB (profiles/r01_summary_v5_to_v8_frame.md)
+TRAFFIC_BYTES_PER_LAUNCH = 2.522e9     # ncu --set full, final frame_kernel, 2 clips/launch: dram read 1.314 GB + write 1.208 GB (profiles/r01_frame_v10.ncu-rep)
 METRIC = "720p output frames/s (x4 VSR inference)"
 WORKLOAD = "cfg2: generator inference 320x180 -> 1280x720, 100-frame synthetic clips, sharded by clip"
 
