@@ -50,7 +50,9 @@ int tg_check_device(void);
  * per-launch CUDA-event timing.  Between tg_profile_begin() and tg_profile_end() every launch is
  * bracketed by events on its stream; tg_profile_end synchronises and returns up to max_entries
  * records (kernel id: 0 conv_tc<64>, 1 output conv, 2 fused frame input, 3 other glue, 4 pack, 5 frame kernel;
- * duration in ms; algorithmic work = FLOPs for convs, bytes for glue).  Not graph-capturable. */
+ * duration in ms; algorithmic work = FLOPs for convs, bytes for glue).  Not graph-capturable.  The launch counter is
+ * thread-safe; the timing mode is a single-threaded measurement mode (while it is on, all launches must come from one
+ * host thread) and is the only process-wide mutable state of the library besides the two frame-kernel test hooks below. */
 long long tg_launch_count(void);
 int tg_profile_begin(void);
 int tg_profile_end(int max_entries, int* kernel_ids, float* ms, double* work);
@@ -199,6 +201,23 @@ int tg_gen_clip_step_chained(const void* packed, int num_resblock, const float* 
                              int h, int w, long long lr_batch_stride, long long prev_batch_stride,
                              long long out_batch_stride, int amode, void* stream);
 
+/* The chained step with a COMPACT result for the host side of the clip pipeline.  The recurrence
+ * keeps running on the workspace's f32 interleaved copy of every estimate, so out_t is only what leaves the GPU:
+ *   TG_OUT_F32  planar [n,3,4h,4w] float   (the parity default; same bits as tg_gen_clip_step_chained)
+ *   TG_OUT_F16  planar [n,3,4h,4w] __half  = the f32 result rounded to nearest fp16: what the reference's GPU path
+ *               emits under autocast (main.py:171-172,214)
+ *   TG_OUT_U8   interleaved [n,4h,4w,3] uint8 = (uint8)(x * 255): exactly what save_as_gif turns the frames into
+ *               before writing them (code/ops.py:234-237: transpose (0,2,3,1), * 255, astype(uint8))
+ * first_frame != 0 selects the zero-state input (main.py:191-195) and MUST be used for frame 0 of a clip; every other
+ * call must directly follow the previous frame's call on this workspace (same n, h, w).  out_batch_stride is in
+ * elements of the output type (a multiple of 3).  TG_AMODE_FRAME only. */
+#define TG_OUT_F32 0
+#define TG_OUT_F16 1
+#define TG_OUT_U8 2
+int tg_gen_clip_step_fmt(const void* packed, int num_resblock, const float* lr_t, const float* lr_prev, int first_frame,
+                         void* out_t, int out_format, void* workspace, size_t workspace_bytes, int n, int h, int w,
+                         long long lr_batch_stride, long long out_batch_stride, void* stream);
+
 /* Generator training (code/train.py:86-111,336): a forward that keeps every activation in the workspace and the
  * backward pass through all 41 layers.  The generator's inputs are detached in the reference (code/train.py:90,108),
  * so no input gradient is produced.
@@ -235,7 +254,9 @@ int tg_gen_clip_forward_train(const void* packed, int num_resblock, const float*
  * clip-major targets and the frame-major generator output of tg_gen_clip_forward_train are addressed in place.
  * T_vel (:147-158) is computed on the fly from gsrc [tb*3,2,h,w], the LR planes the reference up-scales into its
  * velocity field: class m%3 == 0 -> up4(4*gsrc[m]); 1 -> zeros; 2 -> 2*up4(4*gsrc[m]) - 1; each [2,4h,4w] block re-viewed
- * as [4h,4w,2] like the reference's reshape.  grid_fp16 != 0 rounds the grid to fp16 (the fake path's .half(), :187). */
+ * as [4h,4w,2] like the reference's reshape.  grid_fp16 is a bit set: bit 0 rounds the grid to fp16 (the fake path's
+ * .half(), :187); bit 1 leaves class 2 un-preprocessed, up4(4*gsrc[m]) (pingpang=True takes the flipped forward flow
+ * as it is, :155). */
 int tg_disc_input_assemble(const float* before9, const float* src, long long src_stride_b, long long src_stride_t,
                            int ts, const float* gsrc, const float* lr9, float* out, int tb, int h, int w,
                            int crop_off, int grid_fp16, void* stream);
@@ -273,6 +294,32 @@ int tg_disc_pack_dgrad(const float* flat_params, int nb, int ch, void* packed_dg
 int tg_disc_backward(const float* flat_params, const void* packed_dgrad, int nb, int ch, int fc_in,
                      const float* dprob, const float* prob, float* flat_grad, void* workspace,
                      size_t workspace_bytes, int n, int h, int w, void* stream);
+
+/* ------------------------------------------------------------ BatchNorm building blocks ---- */
+
+/* nn.BatchNorm2d(eps=1e-3, momentum=0.1) in training mode (code/ops.py:75-77; code/models.py:90-94,106,130) on NHWC
+ * tensors, the three passes tg_disc_forward / tg_disc_backward are made of.  c in {64,128}; `stats` is [c][4] f32 =
+ * {mean, rstd, a = gamma*rstd, b = beta - mean*a}; workspace = tg_workspace_bytes_bn() bytes, 256-byte aligned.
+ *   tg_bn_stats: batch statistics of x [pixels][c] f32 (deterministic two-level reduction) -> stats; when
+ *                running_mean != NULL also the in-place running-statistics update (unbiased variance,
+ *                num_batches_tracked += 1) exactly as nn.BatchNorm2d does.
+ *   tg_bn_apply: y = act(a*x + b) (+ skip); act 0 none / 2 LeakyReLU(0.2); written as f32 (y_f32) and / or bf16 (y_bf16).
+ *   tg_bn_bwd  : g_out [pixels][c] bf16 = dL/dy, x = the forward input, act_out = the forward f32 OUTPUT when the block
+ *                ended in LeakyReLU(0.2) (else NULL); dx [pixels][c] bf16 = dL/dx; dgamma / dbeta are ADDED to. */
+size_t tg_workspace_bytes_bn(void);
+int tg_bn_stats(const float* x, long long pixels, int c, const float* gamma, const float* beta, float* stats,
+                float* running_mean, float* running_var, long long* num_batches_tracked, void* workspace,
+                size_t workspace_bytes, void* stream);
+int tg_bn_apply(const float* x, const float* skip, float* y_f32, void* y_bf16, long long pixels, int c,
+                const float* stats, int act, void* stream);
+int tg_bn_bwd(const void* g_out, const float* x, const float* act_out, void* dx, long long pixels, int c,
+              const float* stats, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Workspace queries under the names SURVEY.md 8b lists (tg_workspace_bytes_<op>); the single-layer conv / glue entry
+ * points need no workspace.  Same values as tg_gen_workspace_bytes / tg_gen_train_workspace_bytes / tg_disc_workspace_bytes. */
+size_t tg_workspace_bytes_gen_forward(int n, int h, int w);
+size_t tg_workspace_bytes_gen_train(int n, int h, int w, int num_resblock);
+size_t tg_workspace_bytes_disc(int n, int h, int w, int nb, int ch);
 
 #ifdef __cplusplus
 }

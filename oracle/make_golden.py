@@ -63,11 +63,16 @@ def grad_fingerprint(module):
     return np.array(rows, np.float64)
 
 
-def write_train_golden(ref_models, out_dir):
+def write_train_golden(ref_models, out_dir, name="train.npz", crop=32, sub=8, **flags):
     """One step of the UNMODIFIED reference train.FRVSR_Train (code/train.py:374-377 -> TecoGAN, :49-370) on CPU.
     Shims: torch.Tensor.cuda -> identity; F.grid_sample casts the grid to the image dtype (CPU grid_sample
     rejects the fp16 grid of train.py:98,187; the fp16 rounding itself is kept).  GradScaler / autocast disable
-    themselves without CUDA, so the step is plain fp32."""
+    themselves without CUDA, so the step is plain fp32.
+
+    crop=64 is BASELINE cfg5's shape (256x256 HR): the reference discriminator hard-codes fc = denselayer(48, 1)
+    (code/models.py:123) and colab/README.md:15-22 tells users to edit that line to denselayer(192, 1); the same edit is
+    applied here to the constructed module (nothing else of the reference changes).  **flags override argparse defaults
+    (e.g. pingpang=True, code/train.py:56-62,153-156,275-285)."""
     import warnings
     from oracle import synth, train_oracle
     F = torch.nn.functional
@@ -77,32 +82,35 @@ def write_train_golden(ref_models, out_dir):
     F.grid_sample = lambda inp, grid, *a, **k: orig_gs(inp, grid.to(inp.dtype), *a, **k)
     try:
         import train as ref_train
-        args = train_oracle.default_train_args()
+        import ops as ref_ops
+        args = train_oracle.default_train_args(crop_size=crop, **flags)
         G = ref_models.generator(3, args=args)
         D = ref_models.discriminator(args=args)
+        if crop != 32:
+            D.fc = ref_ops.denselayer(48 * (crop // 32) ** 2, 1)          # colab/README.md:15-22
         G.load_state_dict({k: torch.from_numpy(v) for k, v in synth.fill_state_dict(G.state_dict(), seed=1, gain=1.0).items()})
         D.load_state_dict({k: torch.from_numpy(v) for k, v in synth.fill_state_dict(D.state_dict(), seed=2, gain=1.0).items()})
         og = torch.optim.Adam(G.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps)   # main.py:239-243
         od = torch.optim.Adam(D.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps)
         b = 2
-        r_in = torch.from_numpy(synth.det_uniform((b, 10, 3, 32, 32), 51, 0.0, 1.0))
-        r_tg = torch.from_numpy(synth.det_uniform((b, 10, 3, 128, 128), 52, 0.0, 1.0))
+        r_in = torch.from_numpy(synth.det_uniform((b, 10, 3, crop, crop), 51, 0.0, 1.0))
+        r_tg = torch.from_numpy(synth.det_uniform((b, 10, 3, 4 * crop, 4 * crop), 52, 0.0, 1.0))
         w0 = G.conv[0].weight.detach().clone()
         out = ref_train.FRVSR_Train(r_in, r_tg, args, D, G, 0, 0.0, 0.0, og, od)
         n = len(out.update_list)
         np.savez_compressed(
-            os.path.join(out_dir, "train.npz"),
+            os.path.join(out_dir, name),
             names=np.array(out.update_list_name[:n]),
             update_list=np.array([float(v) for v in out.update_list], np.float64),
             update_list_avg=np.array([float(v) for v in out.update_list_avg[:n]], np.float64),
             tb=np.float64(float(out.tb)), dt_ratio=np.float64(float(out.update_list_avg[n + 1])),
             d_loss=np.float64(float(out.d_loss)), gen_loss=np.float64(float(out.gen_loss)),
-            gen_output_sub=out.gen_output.detach()[:, :, :, ::8, ::8].numpy().astype(np.float32),
-            target_sub=out.target.detach()[:, :, ::8, ::8].numpy().astype(np.float32),
+            gen_output_sub=out.gen_output.detach()[:, :, :, ::sub, ::sub].numpy().astype(np.float32),
+            target_sub=out.target.detach()[:, :, ::sub, ::sub].numpy().astype(np.float32),
             g_grad=grad_fingerprint(G), d_grad=grad_fingerprint(D),
             g_conv0_step=(G.conv[0].weight.detach() - w0)[:4, :4].numpy(),
             d_running_mean_block1=D.block1[1].running_mean.numpy(),
-            batch=b)
+            batch=b, crop=crop)
     finally:
         torch.Tensor.cuda, F.grid_sample = orig_cuda, orig_gs
 
@@ -158,6 +166,8 @@ def main():
                         f_mean=np.array([f.mean().item() for f in feats], np.float64),
                         running_mean_block1=D.block1[1].running_mean.numpy())
     write_train_golden(ref_models, out_dir)
+    write_train_golden(ref_models, out_dir, name="train_cfg5.npz", crop=64, sub=16)        # BASELINE cfg5 shape
+    write_train_golden(ref_models, out_dir, name="train_pingpang.npz", pingpang=True)       # code/train.py:56-62,153-156,275-285
     print("golden fixtures written to", out_dir)
     for f in sorted(os.listdir(out_dir)):
         print(" ", f, os.path.getsize(os.path.join(out_dir, f)), "bytes")

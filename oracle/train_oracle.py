@@ -1,10 +1,11 @@
 """torch-CPU fp32 restatement of the reference training step (TEST INFRASTRUCTURE, see oracle/__init__.py).
 
-Follows /root/reference/code/train.py:49-370 (``TecoGAN``) for the reference's default flags
-(main.py:98-125: pingpang=False, crop_dt=0.75, Dt_mergeDs=True, D_LAYERLOSS=True, vgg_scaling<0) — the only
-configuration the reference can run (the VGG branch is broken).  kind = "port": pure Python over
-PyTorch, restated over torch CPU ops.  PINNED by tests/golden/train.npz, which oracle/make_golden.py writes by running
-the unmodified reference ``train.FRVSR_Train`` on CPU (``.cuda()`` patched to identity, grid cast to the image dtype).
+Follows /root/reference/code/train.py:49-370 (``TecoGAN``) for the configurations the reference can run: its default
+flags (main.py:98-125: pingpang=False, crop_dt=0.75, Dt_mergeDs=True, D_LAYERLOSS=True, vgg_scaling<0) and
+pingpang=True (train.py:56-62,153-156,275-285).  The VGG branch, Dt_mergeDs=False and GAN_FLAG=False crash in the
+reference itself and are not restated.  kind = "port": pure Python over
+PyTorch, restated over torch CPU ops.  PINNED by tests/golden/train.npz, train_cfg5.npz (64x64 crops, fc = 192 features) and train_pingpang.npz,
+which oracle/make_golden.py writes by running the unmodified reference ``train.FRVSR_Train`` on CPU (``.cuda()`` patched to identity, grid cast to the image dtype).
 
 The step is split into the same three stages the B200 implementation has, so tests can compare stage by stage:
 ``generator_loop`` (train.py:67-114), ``discriminator_inputs`` (train.py:130-198) and ``train_step`` (losses
@@ -57,17 +58,20 @@ def _crop_pad(x, off):
 
 
 def discriminator_inputs(r_inputs, r_targets, gen_outputs, flow, args):
-    """train.py:130-198 for pingpang=False, Dt_mergeDs=True.  Returns (real_input, fake_input) [t_batch,27,4c,4c]."""
+    """train.py:130-198 for Dt_mergeDs=True (both pingpang settings).  Returns (real_input, fake_input) [t_batch,27,4c,4c]."""
     b, t, _, c, _ = r_inputs.shape
     hc = 4 * c
     ts = 3 * (t // 3)                                                                                        # :130
     tb = b * ts // 3                                                                                         # :135
     t_gen = gen_outputs[:, :ts].reshape(b * ts, 3, hc, hc)                                                   # :131-132
     t_tgt = r_targets[:, :ts].reshape(b * ts, 3, hc, hc)                                                     # :133-134
-    back = torch.cat((r_inputs[:, 2:ts:3], r_inputs[:, 1:ts:3]), dim=1).reshape(tb, 6, c, c)                 # :139-141
-    flow_back = O.upscale_four(back[0:b] * 4.0).reshape(b, ts // 3, 2, hc, hc)                               # :143-145
-    v_pre = flow[:, 0:ts:3]                                                                                  # :147
-    v_nxt = O.preprocess(flow_back)                                                                          # :149
+    v_pre = flow[:, 0:ts:3]                                                                                  # :147,153
+    if not getattr(args, "pingpang", False):
+        back = torch.cat((r_inputs[:, 2:ts:3], r_inputs[:, 1:ts:3]), dim=1).reshape(tb, 6, c, c)             # :139-141
+        flow_back = O.upscale_four(back[0:b] * 4.0).reshape(b, ts // 3, 2, hc, hc)                           # :143-145
+        v_nxt = O.preprocess(flow_back)                                                                      # :149
+    else:
+        v_nxt = torch.flip(flow, dims=[1])[:, 1:ts:3]                                                        # :155 (no preprocess)
     t_vel = torch.stack([v_pre, torch.zeros_like(v_pre), v_nxt], dim=2).reshape(b * ts, hc, hc, 2).detach()  # :156-158
     off = 0
     if args.crop_dt < 1.0:                                                                                   # :160-164
@@ -89,6 +93,10 @@ def train_step(G, D, opt_g, opt_d, r_inputs, r_targets, args, global_step=0):
     the discriminator's real input and the two losses.  Parameter gradients are left in ``.grad`` (unscaled: GradScaler
     is disabled on CPU), parameters are updated by the two Adam steps."""
     global_step += 1
+    rnn_n = r_inputs.shape[1]
+    if getattr(args, "pingpang", False):                                                                     # :56-62
+        r_inputs = torch.cat([r_inputs, torch.flip(r_inputs, dims=[1])[:, 1:]], dim=1)
+        r_targets = torch.cat([r_targets, torch.flip(r_targets, dims=[1])[:, 1:]], dim=1)
     b, t, _, c, _ = r_inputs.shape
     gen_outputs, flow = generator_loop(G, r_inputs)
     s_gen = gen_outputs.reshape(b * t, 3, 4 * c, 4 * c)                                                      # :116-118
@@ -111,6 +119,12 @@ def train_step(G, D, opt_g, opt_d, r_inputs, r_targets, args, global_step=0):
     cur = r_inputs[:, 1:]
     s_warp = F.grid_sample(pre, cur[:, :, 0:2].reshape(b * (t - 1), c, c, 2), align_corners=False)
     log["l2_warp_loss"] = torch.mean(torch.sum(torch.square(cur.reshape(b * (t - 1), 3, c, c) - s_warp), dim=[3]))
+    pploss = None
+    if getattr(args, "pingpang", False):                                                                     # :275-285
+        first = gen_outputs[:, 0:rnn_n - 1]
+        last_rev = torch.flip(gen_outputs, dims=[1])[:, :rnn_n - 1]
+        pploss = torch.mean(torch.abs(first - last_rev))
+        log["PingPang"] = pploss
     t_adv = torch.mean(-torch.log(p_fake.detach() + args.EPS))                                               # :289
     d_adv = torch.mean(-torch.log(p_fake + args.EPS))                                                        # :290
     dt_ratio = min(args.Dt_ratio_max, args.Dt_ratio_0 + args.Dt_ratio_add * float(global_step))              # :291-292
@@ -118,6 +132,9 @@ def train_step(G, D, opt_g, opt_d, r_inputs, r_targets, args, global_step=0):
     # term is added twice and the logged l2_content_loss ends up equal to All_loss_Gen.  Values only: both extra terms are
     # detached, the generator's gradient is that of the content loss alone.
     gen_loss = content
+    if pploss is not None and args.pp_scaling > 0:                                                           # :281-283 (NOT detached; added
+        gen_loss += pploss * args.pp_scaling                                                                 #  twice: gen_loss is fnet_loss)
+        gen_loss += pploss * args.pp_scaling
     gen_loss += args.ratio * t_adv
     gen_loss += args.ratio * t_adv
     log["t_adversarial_loss"] = t_adv

@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "tg_conv_tc.cuh"
@@ -16,44 +17,61 @@ void tg_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// Per-device read-only configuration ("no global mutable state except a per-device read-only config"):
+// the SM count of the CURRENT device, cached per ordinal so that one process can drive several GPUs.
+int tg_current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= TG_MAX_DEVICES) dev = 0;
+  return dev;
+}
 int tg_num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  static std::atomic<int> sms[TG_MAX_DEVICES];
+  const int dev = tg_current_device();
+  int v = sms[dev].load(std::memory_order_relaxed);
+  if (!v) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev].store(v, std::memory_order_relaxed);
   }
-  return sms;
+  return v;
 }
 
 // ------------------------------------------------------------------- launch accounting / profiling
+// The launch counter is a relaxed atomic (any thread, any stream).  Per-launch event timing is a MEASUREMENT mode: the
+// list is guarded by a mutex, but tg_prof_pre / tg_prof_post of one launch are paired by position, so while it is on
+// all launches must come from one host thread (include/tecogan_b200.h says so); off, the hooks cost one atomic load.
 struct ProfEntry { cudaEvent_t a, b; int kid; double work; };
 static std::atomic<long long> g_launches{0};
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
 static std::vector<ProfEntry> g_prof;
 
 void tg_prof_pre(int kernel_id, double work, cudaStream_t stream) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  if (!g_prof_on) return;
+  if (!g_prof_on.load(std::memory_order_acquire)) return;
   ProfEntry e{nullptr, nullptr, kernel_id, work};
   cudaEventCreate(&e.a);
   cudaEventCreate(&e.b);
   cudaEventRecord(e.a, stream);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof.push_back(e);
 }
 void tg_prof_post(cudaStream_t stream) {
-  if (g_prof_on && !g_prof.empty()) cudaEventRecord(g_prof.back().b, stream);
+  if (!g_prof_on.load(std::memory_order_acquire)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.empty()) cudaEventRecord(g_prof.back().b, stream);
 }
 
 extern "C" long long tg_launch_count(void) { return g_launches.load(); }
 extern "C" int tg_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (auto& e : g_prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   g_prof.clear();
-  g_prof_on = true;
+  g_prof_on.store(true, std::memory_order_release);
   return TG_OK;
 }
 extern "C" int tg_profile_end(int max_entries, int* kernel_ids, float* ms, double* work) {
-  g_prof_on = false;
+  g_prof_on.store(false, std::memory_order_release);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   int n = 0;
   for (auto& e : g_prof) {
     float t = 0.f;

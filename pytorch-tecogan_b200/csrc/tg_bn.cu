@@ -120,8 +120,8 @@ bn_apply_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ skip
       const float4 s4 = __ldg(reinterpret_cast<const float4*>(skip) + i);
       f[0] += s4.x; f[1] += s4.y; f[2] += s4.z; f[3] += s4.w;
     }
-    reinterpret_cast<float4*>(y32)[i] = make_float4(f[0], f[1], f[2], f[3]);
-    reinterpret_cast<uint2*>(y16)[i] = make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
+    if (y32) reinterpret_cast<float4*>(y32)[i] = make_float4(f[0], f[1], f[2], f[3]);
+    if (y16) reinterpret_cast<uint2*>(y16)[i] = make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
   }
 }
 
@@ -488,3 +488,65 @@ int disc_head_bwd_launch(const float* dprob, const float* prob, const float* y, 
 }
 
 }  // namespace tg
+
+// ------------------------------------------------------------------------------------ C ABI (tg_bn_{stats,apply,bwd})
+using namespace tg;
+
+namespace {
+struct BnWs { size_t partial, ticket, red, total; };
+BnWs bn_ws() {
+  BnWs w;
+  w.partial = 0;
+  w.ticket = (bn_partial_floats() * 4 + 255) & ~static_cast<size_t>(255);
+  w.red = w.ticket + 256;
+  w.total = w.red + 2 * 128 * 4;
+  return w;
+}
+int bn_check_ws(const char* who, const void* ws, size_t bytes) {
+  TG_CHECK_ARG(ws && (reinterpret_cast<uintptr_t>(ws) & 255) == 0, "%s: workspace must be non-null and 256-byte aligned", who);
+  if (bytes < bn_ws().total) {
+    tg_set_error("%s: workspace too small (%zu < %zu)", who, bytes, bn_ws().total);
+    return TG_ERR_WORKSPACE;
+  }
+  return TG_OK;
+}
+}  // namespace
+
+extern "C" size_t tg_workspace_bytes_bn(void) { return bn_ws().total; }
+
+extern "C" int tg_bn_stats(const float* x, long long pixels, int c, const float* gamma, const float* beta, float* stats,
+                           float* running_mean, float* running_var, long long* num_batches_tracked, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  TG_CHECK_ARG(x && gamma && beta && stats, "bn_stats: null pointer");
+  if (int rc = bn_check_ws("bn_stats", workspace, workspace_bytes)) return rc;
+  const BnWs w = bn_ws();
+  uint8_t* wsp = static_cast<uint8_t*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TG_CUDA(cudaMemsetAsync(wsp + w.ticket, 0, 256, st));
+  return bn_stats_launch(x, pixels, c, gamma, beta, reinterpret_cast<float*>(wsp + w.partial),
+                         reinterpret_cast<unsigned int*>(wsp + w.ticket), stats, running_mean, running_var,
+                         num_batches_tracked, st);
+}
+
+extern "C" int tg_bn_apply(const float* x, const float* skip, float* y_f32, void* y_bf16, long long pixels, int c,
+                           const float* stats, int act, void* stream) {
+  TG_CHECK_ARG(x && stats && (y_f32 || y_bf16), "bn_apply: null pointer");
+  TG_CHECK_ARG(act == kActNone || act == kActLrelu02, "bn_apply: act must be 0 (none) or 2 (LeakyReLU 0.2)");
+  TG_CHECK_ARG(pixels >= 1, "bn_apply: empty batch");
+  return bn_apply_launch(x, skip, y_f32, y_bf16, pixels, c, stats, act, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tg_bn_bwd(const void* g_out, const float* x, const float* act_out, void* dx, long long pixels, int c,
+                         const float* stats, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  TG_CHECK_ARG(g_out && x && dx && stats && dgamma && dbeta, "bn_bwd: null pointer");
+  TG_CHECK_ARG(pixels >= 1, "bn_bwd: empty batch");
+  if (int rc = bn_check_ws("bn_bwd", workspace, workspace_bytes)) return rc;
+  const BnWs w = bn_ws();
+  uint8_t* wsp = static_cast<uint8_t*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TG_CUDA(cudaMemsetAsync(wsp + w.ticket, 0, 256, st));
+  return bn_bwd_launch(g_out, x, act_out, dx, pixels, c, stats, reinterpret_cast<float*>(wsp + w.partial),
+                       reinterpret_cast<unsigned int*>(wsp + w.ticket), reinterpret_cast<float*>(wsp + w.red), dgamma,
+                       dbeta, st);
+}

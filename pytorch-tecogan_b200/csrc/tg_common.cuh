@@ -30,7 +30,15 @@ void tg_set_error(const char* fmt, ...);
   } while (0)
 
 static inline int tg_div_up(int a, int b) { return (a + b - 1) / b; }
-int tg_num_sms();
+#define TG_MAX_DEVICES 64
+int tg_current_device();   // ordinal of the calling thread's current device (0 if out of range)
+int tg_num_sms();          // SM count of the current device (cached per device)
+
+// cudaFuncSetAttribute is per device: remember per (kernel call site, device) that it was done.
+struct TgPerDeviceOnce {
+  bool done[TG_MAX_DEVICES] = {};
+  bool need() { const int d = tg_current_device(); if (done[d]) return false; done[d] = true; return true; }
+};
 
 // Launch accounting + optional per-launch CUDA-event timing (tg_profile_begin / tg_profile_end).
 // kernel ids: 0 conv_tc<64>, 1 conv_tc<16> (output conv), 2 fused frame input, 3 other glue, 4 pack,

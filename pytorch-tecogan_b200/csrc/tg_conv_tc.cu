@@ -539,7 +539,7 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   if (pair && gx > per_chunk) gx -= 2;
   if (pair && gx < 2) gx = 2;
   dim3 grid(gx, chunks);
-  static bool attr_done[3] = {false, false, false};
+  static TgPerDeviceOnce attr_once[3];
   // algorithmic FLOPs (MAC = 2) on the padded channel counts; bench.py uses SURVEY.md's unpadded figure
   tg_prof_pre(nt == 64 ? TG_K_CONV64 : TG_K_CONV16,
               2.0 * (s2 ? 16.0 : 9.0) * cin_pad * (nt == 64 ? cout_pad : 3) * n * th * tw, stream);
@@ -564,13 +564,13 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   cfg.attrs = attr;
   cfg.numAttrs = na;
   if (pair) {
-    if (!attr_done[2]) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); attr_done[2] = true; }
+    if (attr_once[2].need()) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); }
     TG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, true>, tm_a, tm_w, p));
   } else if (nt == 64) {
-    if (!attr_done[0]) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); attr_done[0] = true; }
+    if (attr_once[0].need()) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); }
     TG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false>, tm_a, tm_w, p));
   } else {
-    if (!attr_done[1]) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); attr_done[1] = true; }
+    if (attr_once[1].need()) { TG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); }
     TG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false>, tm_a, tm_w, p));
   }
   tg_prof_post(stream);

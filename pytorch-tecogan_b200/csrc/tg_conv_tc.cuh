@@ -12,7 +12,11 @@ constexpr int kMaxAcc = 4;
 
 enum TcKind { kConv3x3 = 0, kConvT3x3s2 = 1, kConv4x4s2 = 2,
               kConvT4x4s2Phase = 6 };   // one output-parity phase of the adjoint of Conv2d(k4,s2,p1): 2x2 taps, stride-2 stores
-enum TcOut { kOutNHWCbf16 = 0, kOutNCHWf32Sigmoid = 1, kOutNCHWf32Raw = 2, kOutNHWCf32 = 3 };   // 3: pre-BatchNorm conv outputs
+enum TcOut { kOutNHWCbf16 = 0, kOutNCHWf32Sigmoid = 1, kOutNCHWf32Raw = 2, kOutNHWCf32 = 3,   // 3: pre-BatchNorm conv outputs
+             // frame kernel only, compact network outputs for the D2H side of the clip pipeline (TG_OUT_F16 / TG_OUT_U8):
+             kOutNCHWf16Sigmoid = 4,      // sigmoid, rounded to fp16, planar [n,3,h,w] (what the reference's autocast path emits)
+             kOutNHWCu8Sigmoid = 5 };     // sigmoid, (y * 255) truncated to uint8, interleaved [n,h,w,3] (code/ops.py:234-237)
+inline bool tc_out_is_network_output(int m) { return m == kOutNCHWf32Sigmoid || m == kOutNCHWf16Sigmoid || m == kOutNHWCu8Sigmoid; }
 // tg_pack_weights kinds beyond TcKind: data-gradient convolutions derived from a forward layer's weights
 enum TcPackKind { kPackConv3x3Dgrad = 3, kPackConvT3x3s2Dgrad = 4, kPackConv4x4s2Dgrad = 5 };
 enum TcMask { kMaskNone = 0, kMaskRelu = 1, kMaskLrelu02 = 2 };   // backward of the activation that produced `mask`

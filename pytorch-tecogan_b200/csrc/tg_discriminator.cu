@@ -140,6 +140,8 @@ extern "C" size_t tg_disc_workspace_bytes(int n, int h, int w, int nb, int ch) {
   return disc_ws(n, h, w, nb, ch).total;
 }
 
+extern "C" size_t tg_workspace_bytes_disc(int n, int h, int w, int nb, int ch) { return tg_disc_workspace_bytes(n, h, w, nb, ch); }
+
 extern "C" int tg_disc_forward(const float* flat_params, const void* packed, int nb, int ch, int fc_in, const float* x,
                                float* prob, float* const* feats, void* const* bn_running, int training,
                                void* workspace, size_t workspace_bytes, int n, int h, int w, void* stream) {

@@ -37,6 +37,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "tg_frame.cuh"
 
 namespace tg {
@@ -155,6 +158,14 @@ __device__ __forceinline__ void epi_store_bf16(uint64_t (&a)[8], const float* bi
     }
   }
   st_global_v8(dst, o);
+}
+
+// Store one channel of one pixel of the network output in the segment's format.  o = n * out_nstride + y * ow + x
+// (+ c * plane for the planar formats); the uint8 format is pixel-interleaved: element (o_px * 3 + c).
+__device__ __forceinline__ void store_network_output(void* out, int mode, size_t o_planar, size_t o_px, int c, float y) {
+  if (mode == kOutNCHWf32Sigmoid) static_cast<float*>(out)[o_planar] = y;
+  else if (mode == kOutNCHWf16Sigmoid) static_cast<__half*>(out)[o_planar] = __float2half_rn(y);
+  else static_cast<uint8_t*>(out)[o_px * 3 + c] = static_cast<uint8_t>(__float2uint_rz(__fmul_rn(y, 255.f)));
 }
 
 // Stall accounting (measurement only, FrProgram::stats != null): cycles a role spends in each of its waits.
@@ -646,10 +657,11 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
             const float z = (l + __uint_as_float(c == 0 ? v1[0] : (c == 1 ? v1[1] : v1[2]))) + r2 + s_bias[c];
             if (wvalid && c < S.oc) {
               const size_t plane = static_cast<size_t>(S.oh) * S.ow;
-              const size_t o = static_cast<size_t>(n) * S.out_nstride + static_cast<size_t>(wy) * S.ow + wx + c * plane;
+              const size_t opx = static_cast<size_t>(wy) * S.ow + wx;
+              const size_t o = static_cast<size_t>(n) * S.out_nstride + opx + c * plane;
               const float y = 1.f / (1.f + expf(-z));
-              if (S.out2) S.out2[o] = z;
-              static_cast<float*>(S.out)[o] = y;
+              if (S.out2) S.out2[static_cast<size_t>(n) * 3 * plane + opx + c * plane] = z;
+              if (S.out) store_network_output(S.out, c_mode, o, static_cast<size_t>(n) * (S.out_nstride / 3) + opx, c, y);
               if (S.resid != nullptr) {                    // pixel-interleaved second copy (tg_glue.cu: gather3)
                 float* px = static_cast<float*>(const_cast<void*>(S.resid)) + ((static_cast<size_t>(n) * S.oh + wy) * S.ow + wx) * 4;
                 // the blue warp also writes the unused fourth component: every byte of the copy is written, so no
@@ -838,10 +850,11 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           const float z = (l + __uint_as_float(c == 0 ? v1[0] : (c == 1 ? v1[1] : v1[2]))) + r2 + s_bias[c];
           if (wvalid && part < 3 && part < S.oc) {
             const size_t plane = static_cast<size_t>(S.oh) * S.ow;
-            const size_t o = static_cast<size_t>(n) * S.out_nstride + static_cast<size_t>(wy) * S.ow + wx + c * plane;
+            const size_t opx = static_cast<size_t>(wy) * S.ow + wx;
+            const size_t o = static_cast<size_t>(n) * S.out_nstride + opx + c * plane;
             const float y = 1.f / (1.f + expf(-z));
-            if (S.out2) S.out2[o] = z;
-            static_cast<float*>(S.out)[o] = y;
+            if (S.out2) S.out2[static_cast<size_t>(n) * 3 * plane + opx + c * plane] = z;
+            if (S.out) store_network_output(S.out, c_mode, o, static_cast<size_t>(n) * (S.out_nstride / 3) + opx, c, y);
             // optional second copy, pixel-interleaved (float4 {R,G,B,-}, component `part` from this warp): the next
             // frame's warp gathers three channels with one 16-byte load (tg_glue.cu: gather3)
             if (S.resid != nullptr) {
@@ -1043,15 +1056,32 @@ static bool use_wide(int kind) {
 }
 // Pair mode (cta_group::2) needs every 3x3 conv on the wide geometry and co-resident 2-CTA clusters; TG_FRAME_PAIR=0
 // selects the single-CTA kernel (A/B measurements).  Returns the number of clusters that can be resident (0: off).
-static int g_pair_override = -1;                     // tg_frame_set_pair: -1 = TG_FRAME_PAIR / default, 0 = off, 1 = on
-void frame_set_pair(int on) { g_pair_override = on < 0 ? -1 : (on ? 1 : 0); }
-static int pair_clusters_available() {
-  static const int n = []() {
-    if (!use_wide(kConv3x3)) return 0;
-    if (cudaFuncSetAttribute(frame_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<true>::kSmemBytes) != cudaSuccess) {
-      cudaGetLastError();
-      return 0;
-    }
+static std::atomic<int> g_pair_override{-1};                     // tg_frame_set_pair: -1 = TG_FRAME_PAIR / default, 0 = off, 1 = on
+void frame_set_pair(int on) { g_pair_override.store(on < 0 ? -1 : (on ? 1 : 0)); }
+// Co-residency is what makes the static schedule deadlock-free (every CTA spins on tiles other CTAs produce), so the
+// grid is sized from the occupancy the CURRENT device / context reports - an MPS active-thread limit or a green context
+// shrinks it - cached per device ordinal.  What the occupancy API cannot see (an unrelated long-running kernel holding
+// SMs) cannot hang the GPU either: every wait in the kernel is bounded and traps after 4 s.
+struct FrDev { bool probed = false; int pair_clusters = 0; int single_ctas = 0; };
+static FrDev g_frdev[TG_MAX_DEVICES];
+static std::mutex g_frdev_mu;
+static const FrDev& frame_device() {
+  const int dev = tg_current_device();
+  std::lock_guard<std::mutex> lk(g_frdev_mu);
+  FrDev& d = g_frdev[dev];
+  if (d.probed) return d;
+  d.probed = true;
+  bool ok = true;
+  ok &= cudaFuncSetAttribute(frame_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<false>::kSmemBytes) == cudaSuccess;
+  ok &= cudaFuncSetAttribute(frame_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<true>::kSmemBytes) == cudaSuccess;
+  ok &= cudaFuncSetAttribute(frame_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<false>::kSmemBytes) == cudaSuccess;
+  ok &= cudaFuncSetAttribute(frame_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<true>::kSmemBytes) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); return d; }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_kernel<false, false>, kFrThreads, FrCfg<false>::kSmemBytes) == cudaSuccess)
+    d.single_ctas = (per_sm > 0 ? 1 : 0) * tg_num_sms();             // one CTA per SM (each allocates all of TMEM)
+  else cudaGetLastError();
+  if (use_wide(kConv3x3)) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(tg_num_sms() & ~1);
     cfg.blockDim = dim3(kFrThreads);
@@ -1062,18 +1092,18 @@ static int pair_clusters_available() {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, frame_kernel<true, false>, &cfg) != cudaSuccess) {
-      cudaGetLastError();
-      return 0;
-    }
-    const int want = tg_num_sms() / 2;
-    return nc < want ? nc : want;
-  }();
-  return n;
+    if (cudaOccupancyMaxActiveClusters(&nc, frame_kernel<true, false>, &cfg) == cudaSuccess) {
+      const int want = tg_num_sms() / 2;
+      d.pair_clusters = nc < want ? nc : want;
+    } else cudaGetLastError();
+  }
+  return d;
 }
+static int pair_clusters_available() { return frame_device().pair_clusters; }
 static int pair_clusters() {
   static const bool env_off = []() { const char* e = getenv("TG_FRAME_PAIR"); return e && e[0] == '0'; }();
-  if (g_pair_override == 0 || (g_pair_override < 0 && env_off)) return 0;
+  const int ov = g_pair_override.load();
+  if (ov == 0 || (ov < 0 && env_off)) return 0;
   return pair_clusters_available();
 }
 
@@ -1175,13 +1205,17 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
         S.w_row0[kc] = static_cast<uint32_t>(l.blob_off / 128) + static_cast<uint32_t>(c * kchunks + kc) * S.w_rows;
       S.out_mode = l.out_mode; S.relu = l.relu;
       S.oh = l.h * sc; S.ow = l.w * sc;
-      S.oc = (l.out_mode == kOutNCHWf32Sigmoid) ? 3 : l.cout_pad;
+      const bool net_out = tc_out_is_network_output(l.out_mode);
+      S.oc = net_out ? 3 : l.cout_pad;
       S.ch0 = c * 64;
       S.out_nstride = l.out_nstride > 0 ? l.out_nstride : static_cast<long long>(S.oc) * S.oh * S.ow;
       S.out = l.out; S.out2 = l.out2;
-      S.resid = (l.out_mode == kOutNCHWf32Sigmoid) ? l.out_rgbx : l.resid;
-      TG_CHECK_ARG(l.out_rgbx == nullptr || (l.out_mode == kOutNCHWf32Sigmoid && wide && l.cout_pad == 16),
+      S.resid = net_out ? l.out_rgbx : l.resid;
+      TG_CHECK_ARG(l.out_rgbx == nullptr || (net_out && wide && l.cout_pad == 16),
                    "frame: the interleaved copy exists for the wide output conv only");
+      TG_CHECK_ARG(l.out_mode == kOutNHWCbf16 || net_out, "frame: bad output mode %d", l.out_mode);
+      TG_CHECK_ARG(!(net_out && l.out_mode != kOutNCHWf32Sigmoid) || (wide && l.out2 == nullptr && S.out_nstride % 3 == 0),
+                   "frame: the fp16 / uint8 network outputs need the wide geometry and take no logits");
       S.bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(packed) + l.blob_off +
                                               packed_weight_bytes(l.cin_pad, l.cout_pad)) + c * 64;
       if (li == 0) {
@@ -1215,20 +1249,13 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
     P.stat_seg = stat_seg;
   }
   // one CTA per SM (pair mode: one 2-CTA cluster per TPC); items are dealt round-robin, so any grid size works
-  const int max_ctas = pair ? 2 * clusters : tg_num_sms();
+  const int max_ctas = pair ? 2 * clusters : frame_device().single_ctas;
+  TG_CHECK_ARG(max_ctas >= 1, "frame: the kernel cannot be resident on this device / context (occupancy 0)");
   const int grid = items < max_ctas ? items : max_ctas;           // pair mode: items and max_ctas are even
   P.trace = (g_trace && g_trace_words >= static_cast<size_t>(nseg + 1) * grid) ? g_trace : nullptr;
   // optional stall accounting behind the trace: 16 words per CTA (see Tick)
   P.stats = (P.trace && g_trace_words >= static_cast<size_t>(nseg + 1 + 16) * grid) ? g_trace + static_cast<size_t>(nseg + 1) * grid : nullptr;
 
-  static bool attr_done = false;
-  if (!attr_done) {
-    TG_CUDA(cudaFuncSetAttribute(frame_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<false>::kSmemBytes));
-    TG_CUDA(cudaFuncSetAttribute(frame_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<true>::kSmemBytes));
-    TG_CUDA(cudaFuncSetAttribute(frame_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<false>::kSmemBytes));
-    TG_CUDA(cudaFuncSetAttribute(frame_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<true>::kSmemBytes));
-    attr_done = true;
-  }
   TG_CHECK_ARG(static_cast<size_t>(items) <= flag_capacity, "frame: %d items exceed the flag capacity %zu", items, flag_capacity);
   if (!flags_zeroed) TG_CUDA(cudaMemsetAsync(flags, 0, static_cast<size_t>(items) * sizeof(uint32_t), stream));
   cudaLaunchConfig_t cfg{};

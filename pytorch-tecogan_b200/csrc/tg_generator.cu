@@ -70,9 +70,9 @@ static GenWorkspace gen_ws(int n, int h, int w) {
 }
 
 // The 41 layers of one forward as a list (input/output/residual buffers inside the workspace).
-static std::vector<FrLayer> gen_plan(const std::vector<GenLayer>& L, int nres, const void* x, float* out,
+static std::vector<FrLayer> gen_plan(const std::vector<GenLayer>& L, int nres, const void* x, void* out,
                                      float* logits, uint8_t* wsp, int n, int h, int w, long long out_nstride,
-                                     bool write_rgbx = false) {
+                                     bool write_rgbx = false, int out_mode = kOutNCHWf32Sigmoid) {
   const GenWorkspace ws = gen_ws(n, h, w);
   std::vector<FrLayer> P;
   int li = 0;
@@ -109,7 +109,7 @@ static std::vector<FrLayer> gen_plan(const std::vector<GenLayer>& L, int nres, c
   add(c1, d, nullptr, 1, 2 * h, 2 * w);                                      // conv_trans.4 (x2) + ReLU
   add(d, e, nullptr, 1, 4 * h, 4 * w);                                       // conv_trans.6 + ReLU
   add(e, out, nullptr, 0, 4 * h, 4 * w);                                     // output + sigmoid
-  P.back().out_mode = kOutNCHWf32Sigmoid;
+  P.back().out_mode = out_mode;
   P.back().out2 = logits;
   P.back().out_nstride = out_nstride;
   P.back().out_rgbx = write_rgbx ? wsp + ws.rgbx : nullptr;
@@ -118,10 +118,12 @@ static std::vector<FrLayer> gen_plan(const std::vector<GenLayer>& L, int nres, c
 
 // flags_zeroed: the per-item completion counters were already cleared by an earlier kernel of the stream
 static int gen_forward_impl(const std::vector<GenLayer>& L, const uint8_t* packed, int nres, const void* x,
-                            float* out, float* logits, uint8_t* wsp, int n, int h, int w, int amode,
-                            long long out_nstride, bool flags_zeroed, cudaStream_t st, bool write_rgbx = false) {
+                            void* out, float* logits, uint8_t* wsp, int n, int h, int w, int amode,
+                            long long out_nstride, bool flags_zeroed, cudaStream_t st, bool write_rgbx = false,
+                            int out_mode = kOutNCHWf32Sigmoid) {
+  TG_CHECK_ARG(out_mode == kOutNCHWf32Sigmoid || amode == TG_AMODE_FRAME, "generator: fp16 / uint8 outputs need TG_AMODE_FRAME");
   const std::vector<FrLayer> P = gen_plan(L, nres, x, out, logits, wsp, n, h, w, out_nstride,
-                                          write_rgbx && amode == TG_AMODE_FRAME);
+                                          write_rgbx && amode == TG_AMODE_FRAME, out_mode);
   if (amode == TG_AMODE_FRAME) {
     size_t pb = 0;
     for (auto& l : L) pb += tg_packed_conv_bytes(l.kind, l.cin, l.cout);
@@ -169,6 +171,8 @@ extern "C" size_t tg_gen_workspace_bytes(int n, int h, int w) {
   return gen_ws(n, h, w).total;
 }
 
+extern "C" size_t tg_workspace_bytes_gen_forward(int n, int h, int w) { return tg_gen_workspace_bytes(n, h, w); }
+
 extern "C" int tg_gen_forward(const void* packed, int num_resblock, const void* x_nhwc, float* out,
                               float* logits_or_null, void* workspace, size_t workspace_bytes, int n, int h, int w,
                               int amode, void* stream) {
@@ -190,9 +194,9 @@ extern "C" int tg_gen_forward(const void* packed, int num_resblock, const void* 
 // chained: prev_hr is the unmodified output of the previous step on this workspace, so its interleaved copy in the
 // workspace may be gathered instead (frame mode only; every frame-mode step leaves that copy behind).
 static int gen_clip_step_impl(const std::vector<GenLayer>& L, const uint8_t* packed, int nres, const float* lr_t,
-                              const float* lr_prev, const float* prev_hr, float* out_t, uint8_t* wsp, int n, int h,
+                              const float* lr_prev, const float* prev_hr, void* out_t, uint8_t* wsp, int n, int h,
                               int w, long long lr_bs, long long prev_bs, long long out_bs, int amode, cudaStream_t st,
-                              bool chained = false) {
+                              bool chained = false, int out_mode = kOutNCHWf32Sigmoid) {
   const GenWorkspace ws = gen_ws(n, h, w);
   void* x0 = wsp + ws.x0;
   const bool frame_mode = (amode == TG_AMODE_FRAME);
@@ -209,7 +213,7 @@ static int gen_clip_step_impl(const std::vector<GenLayer>& L, const uint8_t* pac
                               frame_mode ? reinterpret_cast<uint32_t*>(wsp + ws.flags) : nullptr, nflags, st,
                               (chained && frame_mode && prev_hr) ? wsp + ws.rgbx : nullptr);
   if (rc) return rc;
-  return gen_forward_impl(L, packed, nres, x0, out_t, nullptr, wsp, n, h, w, amode, out_bs, frame_mode, st, rgbx_on);
+  return gen_forward_impl(L, packed, nres, x0, out_t, nullptr, wsp, n, h, w, amode, out_bs, frame_mode, st, rgbx_on, out_mode);
 }
 
 static int check_ws(const char* who, const void* workspace, size_t workspace_bytes, int n, int h, int w) {
@@ -250,6 +254,27 @@ extern "C" int tg_gen_clip_step_chained(const void* packed, int num_resblock, co
                                         long long out_batch_stride, int amode, void* stream) {
   return clip_step_common(packed, num_resblock, lr_t, lr_prev, prev_hr, out_t, workspace, workspace_bytes, n, h, w,
                           lr_batch_stride, prev_batch_stride, out_batch_stride, amode, stream, true);
+}
+
+extern "C" int tg_gen_clip_step_fmt(const void* packed, int num_resblock, const float* lr_t, const float* lr_prev,
+                                    int first_frame, void* out_t, int out_format, void* workspace, size_t workspace_bytes,
+                                    int n, int h, int w, long long lr_batch_stride, long long out_batch_stride, void* stream) {
+  TG_CHECK_ARG(packed && lr_t && out_t && workspace, "gen_clip_step_fmt: null pointer");
+  TG_CHECK_ARG(n >= 1 && h >= 1 && w >= 1, "gen_clip_step_fmt: bad shape");
+  TG_CHECK_ARG(out_format == TG_OUT_F32 || out_format == TG_OUT_F16 || out_format == TG_OUT_U8, "gen_clip_step_fmt: bad out_format %d", out_format);
+  TG_CHECK_ARG(first_frame || lr_prev, "gen_clip_step_fmt: lr_prev is needed for every frame but the first");
+  TG_CHECK_ARG(out_batch_stride % 3 == 0, "gen_clip_step_fmt: out_batch_stride must be a multiple of 3");
+  static const bool rgbx_on = []() { const char* e = getenv("TG_RGBX"); return !(e && e[0] == '0'); }();
+  TG_CHECK_ARG(rgbx_on, "gen_clip_step_fmt: needs the workspace's interleaved copy (TG_RGBX=0 disables it)");
+  if (int rc = check_ws("gen_clip_step_fmt", workspace, workspace_bytes, n, h, w)) return rc;
+  auto L = gen_layers(num_resblock, nullptr, nullptr);
+  const int mode = out_format == TG_OUT_F32 ? kOutNCHWf32Sigmoid : (out_format == TG_OUT_F16 ? kOutNCHWf16Sigmoid : kOutNHWCu8Sigmoid);
+  uint8_t* wsp = static_cast<uint8_t*>(workspace);
+  // the previous estimate is gathered from the workspace's interleaved f32 copy (chained step): prev_hr only says "not the first frame"
+  const float* prev_marker = first_frame ? nullptr : reinterpret_cast<const float*>(wsp + gen_ws(n, h, w).rgbx);
+  return gen_clip_step_impl(L, static_cast<const uint8_t*>(packed), num_resblock, lr_t, first_frame ? nullptr : lr_prev, prev_marker,
+                            out_t, wsp, n, h, w, lr_batch_stride, 0, out_batch_stride, TG_AMODE_FRAME,
+                            static_cast<cudaStream_t>(stream), /*chained=*/true, mode);
 }
 
 extern "C" int tg_gen_clip_forward(const void* packed, int num_resblock, const float* lr, float* out, void* workspace,
@@ -369,6 +394,9 @@ static std::vector<size_t> gen_dgrad_offsets(const std::vector<GenLayer>& L, siz
 extern "C" size_t tg_gen_train_workspace_bytes(int n, int h, int w, int num_resblock) {
   if (n <= 0 || h <= 0 || w <= 0 || num_resblock < 0 || num_resblock > 64) return 0;
   return gen_train_ws(n, h, w, num_resblock).total;
+}
+extern "C" size_t tg_workspace_bytes_gen_train(int n, int h, int w, int num_resblock) {
+  return tg_gen_train_workspace_bytes(n, h, w, num_resblock);
 }
 extern "C" size_t tg_gen_packed_dgrad_bytes(int num_resblock) {
   size_t t = 0;

@@ -225,13 +225,15 @@ warp4_kernel(const float* __restrict__ img, const float4* __restrict__ grid, flo
 // out[s, 9:18]  = crop_pad(grid_sample(src frames 3s..3s+2, T_vel))   centre window kept, border zeroed  (:165-174,187-196)
 // out[s, 18:27] = bilinear x4 of the three LR frames                                                     (:176-178)
 // T_vel of frame m (class m % 3): 0 -> up4(4*gsrc[m]) (the forward 'flow'), 1 -> zeros, 2 -> 2*up4(4*gsrc[m]) - 1
-// (preprocess of the backward 'flow'), each [2,Ho,Wo] block re-viewed as [Ho,Wo,2] exactly as the reference's reshape
+// (preprocess of the backward 'flow', :149; with pingpang the reference takes the flipped forward flow WITHOUT
+// preprocess, :155 -> flags bit 1), each [2,Ho,Wo] block re-viewed as [Ho,Wo,2] exactly as the reference's reshape
 // does (:156-157).  The velocity field is computed on the fly from the LR planes; nothing but `out` is written.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 disc_input_kernel(const float* __restrict__ before9, const float* __restrict__ src, long long src_stride_b,
                   long long src_stride_t, int ts, const float* __restrict__ gsrc, const float* __restrict__ lr9,
-                  float* __restrict__ out, int tb, int h, int w, int crop_off, int grid_fp16) {
+                  float* __restrict__ out, int tb, int h, int w, int crop_off, int flags) {
+  const bool grid_fp16 = (flags & 1) != 0, raw_next = (flags & 2) != 0;
   const int ho = 4 * h, wo = 4 * w;
   const long long hw = static_cast<long long>(ho) * wo;
   const long long total = static_cast<long long>(tb) * hw;
@@ -259,7 +261,7 @@ disc_input_kernel(const float* __restrict__ before9, const float* __restrict__ s
             const long long rem = flat - ch * hw;
             const int yy = static_cast<int>(rem / wo), xx = static_cast<int>(rem - static_cast<long long>(yy) * wo);
             float u = up4_sample(gsrc + (static_cast<long long>(m) * 2 + ch) * h * w, h, w, yy, xx, 4.f);
-            if (cls == 2) u = __fsub_rn(__fmul_rn(u, 2.f), 1.f);    // preprocess(): image * 2 - 1, no fused rounding
+            if (cls == 2 && !raw_next) u = __fsub_rn(__fmul_rn(u, 2.f), 1.f);    // preprocess(): image * 2 - 1, no fused rounding
             g[k] = grid_fp16 ? round_fp16(u) : u;
           }
         }

@@ -215,11 +215,8 @@ static int wgrad_launch_common(WgParams& p, const void* a, int a_pad, const void
   const int max_slabs = tg_num_sms() / ngroups;
   if (slabs > max_slabs) slabs = max_slabs;
   if (slabs < 1) slabs = 1;
-  static bool attr_done = false;
-  if (!attr_done) {
-    TG_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemLimit));
-    attr_done = true;
-  }
+  static TgPerDeviceOnce attr_once;
+  if (attr_once.need()) TG_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemLimit));
   tg_prof_pre(TG_K_WGRAD, flops, stream);
   wgrad3x3_kernel<<<dim3(slabs, ngroups), kWgThreads, smem_bytes, stream>>>(tm_a, tm_b, p);
   tg_prof_post(stream);

@@ -9,15 +9,11 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libtecogan_b200.so")
-# Measurement only: TG_LIB_PATH points the binding at another build of the library (same-box A/B of two commits,
-# scripts/gpu_ab2.sh); symbols that build does not export are then left unbound instead of failing the load.
-_ALT_LIB = os.environ.get("TG_LIB_PATH")
-if _ALT_LIB:
-    LIB_PATH = os.path.abspath(_ALT_LIB)
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libtecogan_b200.so")   # the in-tree build; nothing in the environment redirects it
 
 AMODE_HALO = 0
 AMODE_DX3 = 1
+OUT_F32, OUT_F16, OUT_U8 = 0, 1, 2   # tg_gen_clip_step_fmt output formats (include/tecogan_b200.h)
 AMODE_FRAME = 2     # whole generator forward as one persistent kernel (tg_gen_forward / tg_gen_clip_forward)
 
 _c_void_p = ctypes.c_void_p
@@ -73,6 +69,8 @@ SIGNATURES = {
                                   _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_int, _c_void_p]),
     "tg_gen_clip_step_chained": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_int,
                                   _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_int, _c_void_p]),
+    "tg_gen_clip_step_fmt": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_size_t,
+                                      _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_void_p]),
     "tg_gen_clip_forward": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_int, _c_int,
                                      _c_int, _c_int, _c_int, _c_void_p]),
     "tg_gen_train_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),
@@ -96,6 +94,15 @@ SIGNATURES = {
     "tg_disc_pack_dgrad": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
     "tg_disc_backward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                   _c_size_t, _c_int, _c_int, _c_int, _c_void_p]),
+    "tg_workspace_bytes_bn": (_c_size_t, []),
+    "tg_bn_stats": (_c_int, [_c_void_p, _c_ll, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                             _c_size_t, _c_void_p]),
+    "tg_bn_apply": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int, _c_void_p, _c_int, _c_void_p]),
+    "tg_bn_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                           _c_size_t, _c_void_p]),
+    "tg_workspace_bytes_gen_forward": (_c_size_t, [_c_int, _c_int, _c_int]),
+    "tg_workspace_bytes_gen_train": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),
+    "tg_workspace_bytes_disc": (_c_size_t, [_c_int, _c_int, _c_int, _c_int, _c_int]),
 }
 
 _lib = None
@@ -112,12 +119,7 @@ def load():
                 "`python pytorch-tecogan_b200/build.py` — there is no CPU or PyTorch fallback")
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
-            try:
-                fn = getattr(lib, name)      # AttributeError if the symbol is missing
-            except AttributeError:
-                if _ALT_LIB:
-                    continue
-                raise
+            fn = getattr(lib, name)          # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
         _lib = lib
@@ -142,8 +144,9 @@ def check(rc):
         raise RuntimeError(f"libtecogan_b200 error {rc}: {msg}")
 
 
-def stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    """current torch stream of `device` (default: the current device) as the void* the C ABI takes."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def ptr(t):

@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as _nt
+from . import parallel as _par
 from .ops import *  # noqa: F401,F403  (reference star-import chain: code/models.py:1 -> dataloader -> ops)
 from .ops import conv2, conv2_tran, lrelu, batchnorm, denselayer
 
@@ -60,7 +61,7 @@ def _gen_backward(module, packed_dgrad, dout, out, ws, n, h, w):
     lib = _nt.lib()
     nres = int(module.num)
     params = module._param_list()
-    bucket = getattr(module, "_grad_bucket", None)
+    bucket = module._grad_bucket if _par.bucket_bound(module, params) else None
     flat = bucket if bucket is not None else torch.zeros(lib.tg_gen_param_count(nres), dtype=torch.float32, device=out.device)
     _nt.check(lib.tg_gen_backward(_nt.ptr(packed_dgrad), nres, _nt.ptr(dout), _nt.ptr(out), _nt.ptr(flat), _nt.ptr(ws),
                                   ws.numel(), n, h, w, _nt.stream_ptr()))
@@ -131,6 +132,18 @@ class generator(nn.Module):
     def _param_list(self):
         # state_dict iteration order == the flat layout tg_gen_pack expects
         return [p for _, p in self.named_parameters()]
+
+    def invalidate_packed(self):
+        """Drop the packed bf16 weight caches.  They are keyed on (data_ptr, tensor version); a write through ``p.data``
+        bumps neither, so code that writes that way (EMA weight swaps, ``p.data.clamp_()``) calls this afterwards.
+        ``load_state_dict`` and ``tecogan_b200.parallel.broadcast_parameters`` do it themselves."""
+        self._packed_key = None
+        self._packed_dgrad_key = None
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.invalidate_packed()
+        return r
 
     def packed_weights(self):
         """bf16 MMA-ordered weight blocks + f32 biases; a derived cache, rebuilt whenever a
@@ -257,6 +270,16 @@ class discriminator(nn.Module):
         self._key = None
         self._ws = None
 
+    def invalidate_packed(self):
+        """Drop the packed bf16 weight caches (see generator.invalidate_packed)."""
+        self._key = None
+        self._packed_dgrad_key = None
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.invalidate_packed()
+        return r
+
     def _bn_modules(self):
         mods = [self.block1[1]] + [r[1] for r in self.resids1] + [self.block2[1]] + [r[1] for r in self.resids2]
         mods += [self.block3[1]] + [r[1] for r in self.resids3] + [self.block4[1], self.block5[1]]
@@ -282,7 +305,7 @@ class discriminator(nn.Module):
     def _dgrad_weights(self):
         """packed weights of the data-gradient convolutions (training only); rebuilt with the forward cache."""
         flat, _ = self._weights()
-        if getattr(self, "_packed_dgrad_key", None) != self._key:
+        if getattr(self, "_packed_dgrad_key", None) is None or self._packed_dgrad_key != self._key:
             lib = _nt.lib()
             buf = torch.empty(lib.tg_disc_packed_dgrad_bytes(self.nb, self.ch), dtype=torch.uint8, device=flat.device)
             _nt.check(lib.tg_disc_pack_dgrad(_nt.ptr(flat), self.nb, self.ch, _nt.ptr(buf), _nt.stream_ptr()))
@@ -358,7 +381,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         n, h, w = ctx.shape
         module = ctx.module
         params = [p for _, p in module.named_parameters()]
-        bucket = getattr(module, "_grad_bucket", None)
+        bucket = module._grad_bucket if _par.bucket_bound(module, params) else None
         flat_grad = bucket if bucket is not None else torch.zeros(ctx.flat.numel(), dtype=torch.float32, device=prob.device)
         g = dprob.float().contiguous()
         _nt.check(lib.tg_disc_backward(_nt.ptr(ctx.flat), _nt.ptr(ctx.packed_dgrad), module.nb, module.ch, module.fc.in_features,

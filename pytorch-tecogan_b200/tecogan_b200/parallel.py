@@ -82,8 +82,29 @@ def shard_batch(t, rank=None, world=None):
 
 
 def broadcast_parameters(module, src=0):
-    """make the replicas identical before the first step (parameters and BatchNorm buffers)."""
-    if world_size() == 1:
-        return
-    for t in list(module.parameters()) + list(module.buffers()):
-        dist.broadcast(t.data, src=src)
+    """make the replicas identical before the first step (parameters and BatchNorm buffers).  The in-place write goes
+    through ``detach()`` (shares the parameter's version counter, unlike ``.data``) and the module's packed bf16 weight
+    caches are dropped explicitly, so a broadcast after the first forward cannot leave stale packed weights behind."""
+    if world_size() > 1:
+        with torch.no_grad():
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t.detach(), src=src)
+    if hasattr(module, "invalidate_packed"):
+        module.invalidate_packed()
+
+
+def bucket_bound(module, params=None):
+    """True when the module's flat gradient bucket is live: every parameter's ``.grad`` IS the bucket view laid out by
+    bind_flat_grads.  An ordinary backward after ``zero_grad(set_to_none=True)`` (p.grad None) is not: the backward
+    kernels must then return gradients to autograd instead of adding into a bucket nobody reads."""
+    bucket = getattr(module, "_grad_bucket", None)
+    if bucket is None:
+        return False
+    params = [p for _, p in module.named_parameters()] if params is None else params
+    o = bucket.data_ptr()
+    for p in params:
+        g = p.grad
+        if g is None or g.data_ptr() != o or g.dtype != torch.float32:
+            return False
+        o += 4 * p.numel()
+    return True

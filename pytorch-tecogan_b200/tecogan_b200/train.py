@@ -11,8 +11,11 @@ What changes relative to the reference's step (same arithmetic)
     (tecogan_b200.parallel); under torch.distributed each bucket is all-reduced asynchronously right after its
     backward, overlapping the other network's backward (SURVEY.md 8e);
   * no ``.cpu()`` hops (:294-301) — every scalar stays on the device.
-Only the configuration the reference can actually run is supported: pingpang=False, Dt_mergeDs=True,
-vgg_scaling <= 0 (the VGG branch of the reference is broken); anything else raises.
+Supported: everything the reference itself can run — its default flags and pingpang=True (code/train.py:56-62,153-156,
+275-285).  Dt_mergeDs=False feeds a 9-channel tensor to the 27-channel discriminator and GAN_FLAG=False reads an unbound
+t_adversarial_loss: both raise inside the reference (probed) and raise here.  vgg_scaling > 0 selects
+the reference's VGG branch, which cannot run either; here it selects the labelled, non-parity stand-in of
+tecogan_b200.perceptual when that module is enabled, else raises.
 """
 import collections
 
@@ -64,10 +67,11 @@ Network = collections.namedtuple('Network', 'gen_output, learning_rate, update_l
 
 
 def _check_args(args, r_inputs):
-    if getattr(args, "pingpang", False):
-        raise NotImplementedError("tecogan_b200.train: pingpang=True is not built (reference default False, main.py:101)")
     if not getattr(args, "Dt_mergeDs", True):
-        raise NotImplementedError("tecogan_b200.train: Dt_mergeDs=False is not built (reference default True, main.py:117)")
+        # code/train.py:183-184: discriminator_F(real_warp) with the 9-channel cropped tensor -> "expected input ... to
+        # have 27 channels" in the reference's own conv (code/models.py:102); same exception type here
+        raise RuntimeError("TecoGAN: Dt_mergeDs=False feeds a 9-channel input to the 27-channel discriminator "
+                           "(code/train.py:183-184 raises in the reference as well)")
     if float(getattr(args, "vgg_scaling", -1.0)) > 0.0:
         VGG19_slim(None, None)
     if r_inputs.dim() != 5 or r_inputs.shape[2] != 3 or r_inputs.shape[3] != r_inputs.shape[4]:
@@ -91,15 +95,22 @@ def discriminator_inputs(r_inputs, r_targets, gen_tb, args):
     tgt9 = r_targets[:, :ts].contiguous()                      # :133-134,175
     # LR planes the reference up-scales into T_vel (:139-158); class = frame % 3
     gsrc = torch.zeros((b, ts // 3, 3, 2, c, c), dtype=torch.float32, device=r_inputs.device)
-    gsrc[:, :, 0] = r_inputs[:, 0:ts:3, 0:2]                   # VPre  = gen_flow[:, 0:ts:3]           (:147)
-    back = torch.cat((r_inputs[:, 2:ts:3], r_inputs[:, 1:ts:3]), dim=1).reshape(tb, 6, c, c)     # :139-141
-    gsrc[:, :, 2] = back[0:b].reshape(b, ts // 3, 2, c, c)     # VNxt = preprocess(up4(4 * back[0:B]))  (:143-145,149)
+    gsrc[:, :, 0] = r_inputs[:, 0:ts:3, 0:2]                   # VPre  = gen_flow[:, 0:ts:3]           (:147,153)
+    raw_next = 0
+    if not getattr(args, "pingpang", False):
+        back = torch.cat((r_inputs[:, 2:ts:3], r_inputs[:, 1:ts:3]), dim=1).reshape(tb, 6, c, c)     # :139-141
+        gsrc[:, :, 2] = back[0:b].reshape(b, ts // 3, 2, c, c)     # VNxt = preprocess(up4(4 * back[0:B]))  (:143-145,149)
+    else:
+        # VNxt = flip(gen_flow, t)[:, 1:ts:3] (:155), gen_flow[:, i] = up4(4 * r_inputs[:, i])[:, 0:2] -> frames t-2-1, t-2-4, ...
+        idx = torch.arange(t - 3, -1, -3, device=r_inputs.device)[: ts // 3]
+        gsrc[:, :, 2] = r_inputs[:, idx, 0:2]
+        raw_next = 2                                           # no preprocess() on this branch
     outs = []
     for src, sb, st_, fp16 in ((tgt9, ts * 3 * hc * hc, 3 * hc * hc, 0),            # real: grid_sample(t_targets, T_vel)   (:165)
                                (gen_tb.detach(), 3 * hc * hc, b * 3 * hc * hc, 1)):  # fake: grid_sample(t_gen, T_vel.half()) (:187)
         out = torch.empty((tb, 27, hc, hc), dtype=torch.float32, device=r_inputs.device)
         _nt.check(lib.tg_disc_input_assemble(_nt.ptr(tgt9), _nt.ptr(src), sb, st_, ts, _nt.ptr(gsrc), _nt.ptr(lr9), _nt.ptr(out),
-                                             tb, c, c, off, fp16, _nt.stream_ptr()))
+                                             tb, c, c, off, fp16 | raw_next, _nt.stream_ptr()))
         outs.append(out)
     return outs[0], outs[1]
 
@@ -118,11 +129,18 @@ def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step
             optimizer_d, GAN_FLAG=True):
     """code/train.py:49-370."""
     if not GAN_FLAG:
-        raise NotImplementedError("tecogan_b200.train: GAN_FLAG=False is not built (the reference always passes True)")
+        # code/train.py:293 reads t_adversarial_loss, which only the GAN_FLAG branch (:287-291) defines
+        raise UnboundLocalError("TecoGAN: GAN_FLAG=False leaves t_adversarial_loss unbound (code/train.py:293 raises in "
+                                "the reference as well; FRVSR_Train always passes True)")
     r_inputs = _nt.require_cuda_f32(r_inputs, "TecoGAN(r_inputs)")
     r_targets = _nt.require_cuda_f32(r_targets, "TecoGAN(r_targets)")
     _check_args(args, r_inputs)
     Global_step += 1                                                                       # :52
+    rnn_n = r_inputs.shape[1]
+    pingpang = bool(getattr(args, "pingpang", False))
+    if pingpang:                                                                           # :56-62: forward + reversed clip
+        r_inputs = torch.cat([r_inputs, torch.flip(r_inputs, dims=[1])[:, 1:]], dim=1)
+        r_targets = torch.cat([r_targets, torch.flip(r_targets, dims=[1])[:, 1:]], dim=1)
     b, t, _, c, _ = r_inputs.shape
     hc = 4 * c
     learning_rate = args.learning_rate
@@ -155,6 +173,11 @@ def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step
     update_list_name.append("l2_content_loss")
     update_list.append(_warp_loss(r_inputs))
     update_list_name.append("l2_warp_loss")
+    pploss = None
+    if pingpang:                                                                           # :275-285
+        pploss = torch.mean(torch.abs(gen_outputs[:, 0:rnn_n - 1] - torch.flip(gen_outputs, dims=[1])[:, :rnn_n - 1]))
+        update_list.append(pploss)
+        update_list_name.append("PingPang")
 
     # ---- adversarial terms (:288-301).  gen_loss, fnet_loss and content_loss are ONE tensor in the reference (:243-244),
     # updated in place: the adversarial term lands twice and the logged l2_content_loss equals All_loss_Gen.  Both extra
@@ -165,6 +188,9 @@ def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step
                              args.Dt_ratio_0 + args.Dt_ratio_add * torch.tensor(Global_step, dtype=torch.float32))
     gen_loss = content_loss
     fnet_loss = content_loss
+    if pploss is not None and args.pp_scaling > 0:         # :281-283, NOT detached: the generator also descends the ping-pong term
+        gen_loss += pploss * args.pp_scaling
+        fnet_loss += pploss * args.pp_scaling
     gen_loss += args.ratio * t_adversarial_loss
     fnet_loss += args.ratio * t_adversarial_loss
     update_list.append(t_adversarial_loss)

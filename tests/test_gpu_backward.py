@@ -194,3 +194,60 @@ def test_conv4x4s2_dgrad(n, h, w, cin, cout, mask_mode):
     torch.cuda.synchronize()
     got = dx.float().cpu().permute(0, 3, 1, 2)
     assert _rel(got, want) <= 6e-3, _rel(got, want)
+
+
+@pytest.mark.parametrize("pixels,c,act,skip", [(4096, 64, 2, False), (1000, 128, 0, True), (12 * 64 * 64, 64, 2, False),
+                                               (37, 128, 0, False)])
+def test_bn_abi_stats_apply_bwd_vs_torch(pixels, c, act, skip):
+    """tg_bn_stats / tg_bn_apply / tg_bn_bwd (nn.BatchNorm2d(eps=1e-3) in training mode + LeakyReLU(0.2) /
+    skip, code/ops.py:75-77, code/models.py:90-94,106,130) against torch fp32 autograd on the same NHWC tensors."""
+    from tecogan_b200 import _native as nt
+    lib = nt.lib()
+    x = torch.from_numpy(synth.det_uniform((pixels, c), 5, -2.0, 3.0))
+    sk = torch.from_numpy(synth.det_uniform((pixels, c), 6, -1.0, 1.0)) if skip else None
+    gamma = torch.from_numpy(synth.det_uniform((c,), 7, 0.5, 1.5))
+    beta = torch.from_numpy(synth.det_uniform((c,), 8, -0.3, 0.3))
+    g_out = _bf(torch.from_numpy(synth.det_uniform((pixels, c), 9, -1.0, 1.0)))
+    bn = torch.nn.BatchNorm2d(c, eps=1e-3)
+    with torch.no_grad():
+        bn.weight.copy_(gamma)
+        bn.bias.copy_(beta)
+    bn.train()
+    xr = x.clone().requires_grad_(True)
+    y = bn(xr.t().reshape(1, c, pixels, 1))
+    if act == 2:
+        y = F.leaky_relu(y, 0.2)
+    y = y.reshape(c, pixels).t()
+    if skip:
+        y = y + sk
+    y.backward(g_out)
+    ws = torch.zeros(lib.tg_workspace_bytes_bn(), dtype=torch.uint8, device="cuda")
+    stats = torch.empty((c, 4), device="cuda")
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    xd, gd, bd = x.cuda(), gamma.cuda(), beta.cuda()
+    nt.check(lib.tg_bn_stats(nt.ptr(xd), pixels, c, nt.ptr(gd), nt.ptr(bd), nt.ptr(stats), nt.ptr(rm), nt.ptr(rv), nt.ptr(nbt),
+                             nt.ptr(ws), ws.numel(), nt.stream_ptr()))
+    y32 = torch.empty((pixels, c), device="cuda")
+    y16 = torch.empty((pixels, c), dtype=torch.bfloat16, device="cuda")
+    skd = sk.cuda() if skip else None
+    nt.check(lib.tg_bn_apply(nt.ptr(xd), nt.ptr(skd), nt.ptr(y32), nt.ptr(y16), pixels, c, nt.ptr(stats), act, nt.stream_ptr()))
+    assert _rel(y32.cpu(), y.detach()) <= 2e-5
+    assert torch.equal(y16.cpu(), y32.cpu().to(torch.bfloat16))
+    assert int(nbt) == 1
+    assert (rm.cpu() - bn.running_mean).abs().max().item() <= 1e-5 and _rel(rv.cpu(), bn.running_var) <= 1e-4
+    # only one of the two outputs requested
+    y_only = torch.empty((pixels, c), device="cuda")
+    nt.check(lib.tg_bn_apply(nt.ptr(xd), nt.ptr(skd), nt.ptr(y_only), None, pixels, c, nt.ptr(stats), act, nt.stream_ptr()))
+    assert torch.equal(y_only, y32)
+    dx = torch.empty((pixels, c), dtype=torch.bfloat16, device="cuda")
+    dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    act_out = y32 if act == 2 else None                          # the block's f32 output (LeakyReLU sign test)
+    nt.check(lib.tg_bn_bwd(nt.ptr(g_out.to(torch.bfloat16).cuda()), nt.ptr(xd), nt.ptr(act_out), nt.ptr(dx), pixels, c,
+                           nt.ptr(stats), nt.ptr(dg), nt.ptr(db), nt.ptr(ws), ws.numel(), nt.stream_ptr()))
+    torch.cuda.synchronize()
+    assert _rel(dg.cpu(), bn.weight.grad) <= 2e-3 and _rel(db.cpu(), bn.bias.grad) <= 2e-3
+    assert _rel(dx.float().cpu(), xr.grad) <= 1.5e-2            # bf16 output
+    # workspace too small -> TG_ERR_WORKSPACE, not a crash
+    rc = lib.tg_bn_stats(nt.ptr(xd), pixels, c, nt.ptr(gd), nt.ptr(bd), nt.ptr(stats), None, None, None, nt.ptr(ws), 16, nt.stream_ptr())
+    assert rc == -4

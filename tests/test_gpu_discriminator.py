@@ -1,6 +1,7 @@
 """GPU parity of the spatio-temporal discriminator forward (tcgen05 convs + BatchNorm/LeakyReLU kernels through
 the C ABI) against the CPU oracle (oracle/tecogan_oracle.py, pinned to the reference by tests/golden/disc.npz).
 Bar (BASELINE.json north_star): bf16 conv path, <= 1e-2 relative max-abs vs the fp32 reference output."""
+import copy
 import os
 import types
 
@@ -37,14 +38,21 @@ def _psnr(a, b):
 
 
 # Tolerances (BASELINE.json north_star, bf16 conv path): >= 50 dB PSNR vs the fp32 reference and <= 1e-2 relative
-# max-abs.  Every returned tensor meets the PSNR bar and the probability meets 1e-2; the max-abs of the deep feature
-# maps grows with depth (measured 0.9 % after 9 bf16 convs, 2.2 % after 27 — operand rounding accumulating through
-# 13 re-normalising BatchNorm layers; keeping the residual stream and pre-BN outputs in f32 does not change it), so
-# only f1 is held to 1e-2 and f2..f4 to 3e-2.
+# max-abs.  Two oracles:
+#  * the fp32 oracle with bf16-rounded conv operands (O.emulate_bf16_operands) is the arithmetic this path implements;
+#    every feature map f1..f4 and the probability are held to 1e-2 relative max-abs against it (FEAT_MAX_REL_BF16);
+#  * against the plain fp32 oracle every returned tensor meets the PSNR bar and the probability 1e-2; the max-abs of
+#    the deep feature maps is the operand-rounding noise of ANY bf16 evaluation of a random-init discriminator (the
+#    bf16-operand oracle itself sits 0.9 % from fp32 after 9 convs and 2.2 % after 27, measured on CPU), so on the
+#    default-init network f2..f4 are held to 3e-2 there — and to 1e-2 on the well-conditioned network of
+#    test_forward_and_backward_well_conditioned, where the activation masks are stable and that noise is not amplified.
 FEAT_MAX_REL = (1e-2, 3e-2, 3e-2, 3e-2)
+FEAT_MAX_REL_BF16 = (1e-2, 1e-2, 1e-2, 1e-2)
 
 
-@pytest.mark.parametrize("nb,ch,n,size,crop", [(4, 128, 3, 128, 32), (1, 64, 2, 64, 16), (2, 128, 12, 128, 32)])
+@pytest.mark.parametrize("nb,ch,n,size,crop", [(4, 128, 3, 128, 32), (1, 64, 2, 64, 16), (2, 128, 12, 128, 32),
+                                               (4, 128, 6, 256, 64)],
+                         ids=["cfg4_128", "small_64", "n12_128", "cfg5_256_fc192"])
 def test_forward_vs_oracle(nb, ch, n, size, crop):
     torch.set_num_threads(8)
     if size == 64:
@@ -57,15 +65,23 @@ def test_forward_vs_oracle(nb, ch, n, size, crop):
     else:
         ref, D = _make(nb, ch, crop)
     x = torch.from_numpy(synth.det_uniform((n, 27, size, size), 31, -1.0, 1.0))
+    emu = copy.deepcopy(ref)
+    O.emulate_bf16_operands(emu)
     with torch.no_grad():
         want_p, want_f = ref(x)
+        emu_p, emu_f = emu(x)
         got_p, got_f = D(x.cuda())
     assert got_p.shape == want_p.shape == (n, 1)
-    for g, wnt, tol in zip(got_f, want_f, FEAT_MAX_REL):
+    rels = []
+    for g, wnt, we, tol, tol_e in zip(got_f, want_f, emu_f, FEAT_MAX_REL, FEAT_MAX_REL_BF16):
         assert g.shape == wnt.shape and g.is_contiguous()
         assert _psnr(g.cpu(), wnt) >= 50.0, _psnr(g.cpu(), wnt)
-        assert _rel(g.cpu(), wnt) <= tol, _rel(g.cpu(), wnt)
+        rels.append((round(_rel(g.cpu(), we), 5), round(_rel(g.cpu(), wnt), 5)))
+        assert _rel(g.cpu(), wnt) <= tol, rels
+        assert _rel(g.cpu(), we) <= tol_e, rels
+    print(f"D forward nb={nb} ch={ch} n={n} {size}x{size}: feature rel max-abs (vs bf16-operand oracle, vs fp32 oracle) {rels}")
     assert (got_p.cpu() - want_p).abs().max().item() <= 1e-2
+    assert (got_p.cpu() - emu_p).abs().max().item() <= 1e-2
     # running statistics of every BatchNorm layer were updated in place exactly like nn.BatchNorm2d does
     for mg, mw in zip(D._bn_modules(), [ref.block1[1]] + [r[1] for r in ref.resids1] + [ref.block2[1]] +
                       [r[1] for r in ref.resids2] + [ref.block3[1]] + [r[1] for r in ref.resids3] +
@@ -134,8 +150,9 @@ def _global_cos(D, ref):
     return float(torch.dot(g_all, w_all) / (g_all.norm() * w_all.norm()))
 
 
-@pytest.mark.parametrize("nb,ch,n", [(4, 128, 4), (1, 64, 12)])
-def test_backward_vs_oracle(nb, ch, n):
+@pytest.mark.parametrize("nb,ch,n,crop", [(4, 128, 4, 32), (1, 64, 12, 32), (4, 128, 3, 64)],
+                         ids=["cfg4_128", "nb1_ch64", "cfg5_256_fc192"])
+def test_backward_vs_oracle(nb, ch, n, crop):
     """code/train.py:303-307,340: discrim_loss = mean(-(log(1 - D(fake) + EPS) + log(D(real) + EPS))) back-propagated
     through two forward passes that are alive at the same time; parameter gradients against torch CPU autograd.
 
@@ -151,11 +168,11 @@ def test_backward_vs_oracle(nb, ch, n):
     15 % for tensors of >= 64 elements, >= 0.975 overall vs the bf16-operand oracle, >= 0.965 vs fp32, total gradient
     norm within 5 %.  The strict per-kernel gradient checks (single layers, no chaos) are in test_gpu_backward.py."""
     torch.set_num_threads(8)
-    ref, D = _make(nb, ch, 32)
-    emu, _ = _make(nb, ch, 32)
+    ref, D = _make(nb, ch, crop)
+    emu, _ = _make(nb, ch, crop)
     O.emulate_bf16_operands(emu)
-    real = torch.from_numpy(synth.det_uniform((n, 27, 128, 128), 41, -1.0, 1.0))
-    fake = torch.from_numpy(synth.det_uniform((n, 27, 128, 128), 42, -1.0, 1.0))
+    real = torch.from_numpy(synth.det_uniform((n, 27, 4 * crop, 4 * crop), 41, -1.0, 1.0))
+    fake = torch.from_numpy(synth.det_uniform((n, 27, 4 * crop, 4 * crop), 42, -1.0, 1.0))
     eps = 1e-12
 
     def loss_of(model, dev):
@@ -174,7 +191,7 @@ def test_backward_vs_oracle(nb, ch, n):
     assert abs(lg.item() - lw.item()) <= 1e-2 * max(1.0, abs(lw.item()))
     rows = _grad_report(D, emu)
     cos_emu, cos_f32 = _global_cos(D, emu), _global_cos(D, ref)
-    print(f"D backward nb={nb} ch={ch} n={n}: cosine vs bf16-operand oracle {cos_emu:.5f} (worst tensors "
+    print(f"D backward nb={nb} ch={ch} n={n} crop={crop}: cosine vs bf16-operand oracle {cos_emu:.5f} (worst tensors "
           f"{[(r[0], round(r[1], 4), round(r[2], 3)) for r in sorted(rows, key=lambda r: r[1])[:4]]}), vs fp32 oracle {cos_f32:.5f}")
     numel = {name: p.numel() for name, p in D.named_parameters()}
     bad = [r for r in rows if r[1] < 0.95 or (numel[r[0]] >= 64 and not (0.85 <= r[2] <= 1.15))]
@@ -184,6 +201,80 @@ def test_backward_vs_oracle(nb, ch, n):
     g_n = torch.cat([p.grad.detach().cpu().double().flatten() for p in D.parameters()]).norm()
     w_n = torch.cat([p.grad.double().flatten() for p in ref.parameters()]).norm()
     assert 0.95 <= float(g_n / w_n) <= 1.05
+
+
+def _condition(module, bias_conv=8.0, beta=3.0):
+    """Make a discriminator WELL-CONDITIONED for a gradient comparison: every conv bias +8 and every BatchNorm beta +3
+    with gamma in [0.1, 0.2), so that all ReLU / LeakyReLU inputs sit many sigma above zero.  The activation masks are
+    then identical in every arithmetic and the network is smooth: the chaos of the default-init case (mask flips amplified
+    by 13 BatchNorms) is gone and what remains is the kernels' own arithmetic.  Measured on CPU (128x128 and 256x256
+    inputs): the bf16-operand oracle then agrees with the fp32 oracle to cosine 0.9999996 overall and >= 0.9998 for every
+    tensor that carries >= 1 % of the gradient norm."""
+    mods = dict(module.named_modules())
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            owner = mods[name.rsplit(".", 1)[0]]
+            if isinstance(owner, torch.nn.BatchNorm2d):
+                if name.endswith("bias"):
+                    p.fill_(beta)
+                else:
+                    p.copy_(torch.from_numpy(synth.det_uniform(tuple(p.shape), 777, 0.1, 0.2)).to(p.device))
+            elif isinstance(owner, torch.nn.Conv2d) and name.endswith("bias"):
+                p.fill_(bias_conv)
+    if hasattr(module, "invalidate_packed"):
+        module.invalidate_packed()
+    return module
+
+
+@pytest.mark.parametrize("nb,ch,n,crop", [(4, 128, 4, 32), (4, 128, 2, 64)], ids=["cfg4_128", "cfg5_256_fc192"])
+def test_forward_and_backward_well_conditioned(nb, ch, n, crop):
+    """The discriminating version of test_backward_vs_oracle (code/train.py:303-307,340): same loss, same two live forward
+    graphs, but on a network whose activation masks are stable (see _condition), so the bars can be tight:
+    features f1..f4 <= 1e-2 relative max-abs against BOTH oracles, overall gradient cosine >= 0.999 against both, total
+    norm within 2 %, and cosine >= 0.999 / norm within 3 % for every tensor that carries >= 1 % of the gradient norm
+    (the rest are BatchNorm-cancelled conv biases whose true gradient is ~0)."""
+    torch.set_num_threads(8)
+    ref, D = _make(nb, ch, crop)
+    emu, _ = _make(nb, ch, crop)
+    for m in (ref, D, emu):
+        _condition(m)
+    O.emulate_bf16_operands(emu)
+    real = torch.from_numpy(synth.det_uniform((n, 27, 4 * crop, 4 * crop), 41, -1.0, 1.0))
+    fake = torch.from_numpy(synth.det_uniform((n, 27, 4 * crop, 4 * crop), 42, -1.0, 1.0))
+    eps = 1e-12
+    feats = {}
+
+    def loss_of(model, dev, tag):
+        pr, fr = model(real.to(dev))
+        pf, _ = model(fake.to(dev))
+        feats[tag] = [f.detach().cpu() for f in fr]
+        return torch.mean(-(torch.log(1 - pf + eps) + torch.log(pr + eps)))
+
+    lw = loss_of(ref, "cpu", "ref")
+    lw.backward()
+    loss_of(emu, "cpu", "emu").backward()
+    lg = loss_of(D, "cuda", "got")
+    (lg * 1024.0).backward()
+    for p in D.parameters():
+        p.grad /= 1024.0
+    assert abs(lg.item() - lw.item()) <= 1e-2 * max(1.0, abs(lw.item()))
+    rels = [(round(_rel(g, e), 5), round(_rel(g, r), 5)) for g, e, r in zip(feats["got"], feats["emu"], feats["ref"])]
+    assert all(a <= 1e-2 and b <= 1e-2 for a, b in rels), rels
+    cos_emu, cos_f32 = _global_cos(D, emu), _global_cos(D, ref)
+    g_all = torch.cat([p.grad.detach().cpu().double().flatten() for p in D.parameters()])
+    w_all = torch.cat([p.grad.double().flatten() for p in ref.parameters()])
+    ratio = float(g_all.norm() / w_all.norm())
+    rows = _grad_report(D, ref)
+    norms = {name: float(p.grad.double().norm()) for name, p in ref.named_parameters()}
+    big = [r for r in rows if norms[r[0]] >= 1e-2 * float(w_all.norm())]
+    print(f"D well-conditioned nb={nb} ch={ch} n={n} crop={crop}: feature rel (vs bf16-operand, vs fp32) {rels}; gradient cosine "
+          f"{cos_emu:.6f} (bf16-operand oracle) {cos_f32:.6f} (fp32 oracle), norm ratio {ratio:.4f}, {len(big)} significant tensors, "
+          f"worst {[(r[0], round(r[1], 5), round(r[2], 4)) for r in sorted(big, key=lambda r: r[1])[:3]]}")
+    assert cos_emu >= 0.999 and cos_f32 >= 0.999, (cos_emu, cos_f32)
+    assert 0.98 <= ratio <= 1.02, ratio
+    assert len(big) >= 5
+    bad = [r for r in big if r[1] < 0.999 or not (0.97 <= r[2] <= 1.03)]
+    assert not bad, bad
 
 
 def test_backward_needs_no_input_grad_and_accumulates():

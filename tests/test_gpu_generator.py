@@ -88,6 +88,51 @@ def test_cfg1_loop_vs_oracle(amode):
         assert min(per) >= 50.0, per
 
 
+@pytest.mark.parametrize("shape", [(1, 51, 180, 320), (1, 51, 540, 960)], ids=["cfg2_720p", "cfg3_4K"])
+@pytest.mark.parametrize("gain", [1.0, 1.7], ids=["default_init", "gain1.7"])
+def test_frame_kernel_vs_oracle_at_baseline_sizes(shape, gain):
+    """The persistent frame kernel against the CPU fp32 oracle DIRECTLY at BASELINE cfg2 (320x180 -> 1280x720) and cfg3
+    (960x540 -> 4K) frame sizes — not through the per-layer path.  Bars of BASELINE.json north_star on the output
+    (>= 50 dB PSNR, <= 1e-2 relative max-abs) and 3e-2 of the logit range on the pre-sigmoid values (41 bf16 layers deep).
+    With the reference's default initialisation scale the outputs sit near 0.5 and the bars hold with a wide margin; the
+    gain-1.7 weights are the stress case SURVEY.md H4.6 asks for (logits up to +-6): PSNR and the logit bar are asserted,
+    the worst single output element of the millions is reported and held to 2e-2."""
+    if gain != 1.0 and shape[2] > 200:
+        pytest.skip("the 4K stress variant adds 20 s of CPU oracle time and no coverage over the 720p one")
+    torch.set_num_threads(max(8, torch.get_num_threads()))
+    ref, G = _make(gain, amode=FRAME)
+    x = torch.from_numpy(synth.det_uniform(shape, 21, 0.0, 1.0))
+    with torch.no_grad():
+        want_logits = ref.features(x)
+        want = torch.sigmoid(want_logits)
+        got, got_logits = G(x.cuda(), return_logits=True)
+    got, got_logits = got.cpu(), got_logits.cpu()
+    rel_logit = (got_logits - want_logits).abs().max().item() / want_logits.abs().max().item()
+    rel_out = (got - want).abs().max().item() / want.abs().max().item()
+    print(f"frame kernel vs fp32 oracle {shape} gain {gain}: PSNR {_psnr(got, want):.1f} dB, output rel max-abs {rel_out:.2e}, "
+          f"logit rel max-abs {rel_logit:.2e} (logit range {want_logits.abs().max().item():.2f})")
+    assert _psnr(got, want) >= 50.0
+    assert rel_logit <= 3e-2, rel_logit
+    assert rel_out <= (1e-2 if gain == 1.0 else 2e-2), rel_out
+
+
+def test_clip_loop_vs_oracle_at_720p():
+    """Three recurrent frames of one 320x180 clip (BASELINE cfg2 frame size) through G.infer_clip against the CPU oracle's
+    restatement of main.py:173-219: warp of the previous 720p estimate, space-to-depth, concat and the frame kernel, chained
+    on the device.  U[0,0.25) LR pixels: every warp tap is a real gather."""
+    torch.set_num_threads(max(8, torch.get_num_threads()))
+    ref, G = _make(1.0, amode=FRAME)
+    r = torch.from_numpy(synth.clip_inputs(1, 3, 180, 320, seed=1234, hi=0.25))
+    want = O.infer_clip(ref, r)
+    got = G.infer_clip(r.cuda()).cpu()
+    assert got.shape == (1, 3, 3, 720, 1280)
+    per = [_psnr(got[:, t], want[:, t]) for t in range(3)]
+    d = (got - want).abs().max().item()
+    print(f"720p clip vs oracle: per-frame PSNR {[round(p, 1) for p in per]} dB, max|d| {d:.2e}")
+    assert min(per) >= 50.0, per
+    assert d <= 1e-2, d
+
+
 def test_loop_batch_and_nonsquare():
     torch.set_num_threads(8)
     ref, G = _make(1.7, nres=4)

@@ -64,18 +64,28 @@ def test_discriminator_inputs_vs_oracle():
         assert got.cpu()[:, 9:18, :16].abs().max().item() == 0.0
 
 
-def test_train_step_vs_oracle_and_golden(golden_dir):
+@pytest.mark.parametrize("fixture,crop,flags", [("train.npz", 32, {}), ("train_cfg5.npz", 64, {}),
+                                                ("train_pingpang.npz", 32, {"pingpang": True})],
+                         ids=["cfg4_shape", "cfg5_shape_fc192", "pingpang"])
+def test_train_step_vs_oracle_and_golden(golden_dir, fixture, crop, flags):
+    """One FRVSR_Train step against the CPU oracle (fp32 and bf16-operand) and against the golden step of the UNMODIFIED
+    reference (oracle/make_golden.py): at BASELINE cfg4's crop (32x32 LR -> D on 128x128, fc = 48), at cfg5's crop
+    (64x64 LR -> D on 256x256, fc = 192, colab/README.md:15-22) and with pingpang=True (19-frame forward + reversed
+    clip, ping-pong loss with gradient, flipped velocity field; code/train.py:56-62,153-156,275-285)."""
     from tecogan_b200 import train as T
-    torch.set_num_threads(8)
-    g = np.load(os.path.join(golden_dir, "train.npz"))
-    args = TO.default_train_args()
-    Gr, Dr, G, D = _nets(args)
+    torch.set_num_threads(max(8, torch.get_num_threads()))
+    g = np.load(os.path.join(golden_dir, fixture))
+    args = TO.default_train_args(crop_size=crop, **flags)
+    Gr, Dr, G, D = _nets(args, crop)
     b = int(g["batch"])
-    r_in = torch.from_numpy(synth.det_uniform((b, 10, 3, 32, 32), 51, 0.0, 1.0))
-    r_tg = torch.from_numpy(synth.det_uniform((b, 10, 3, 128, 128), 52, 0.0, 1.0))
+    hc = 4 * crop
+    sub = 16 if crop == 64 else 8
+    t_all = 19 if flags.get("pingpang") else 10
+    r_in = torch.from_numpy(synth.det_uniform((b, 10, 3, crop, crop), 51, 0.0, 1.0))
+    r_tg = torch.from_numpy(synth.det_uniform((b, 10, 3, hc, hc), 52, 0.0, 1.0))
     want = TO.train_step(Gr, Dr, _adam(Gr, args), _adam(Dr, args), r_in, r_tg, args, 0)
     # second oracle: the same step with bf16-rounded conv operands = the arithmetic the tensor-core path implements
-    Ge, De, _, _ = _nets(args)
+    Ge, De, _, _ = _nets(args, crop)
     O.emulate_bf16_operands(Ge)
     O.emulate_bf16_operands(De)
     TO.train_step(Ge, De, _adam(Ge, args), _adam(De, args), r_in, r_tg, args, 0)
@@ -95,10 +105,12 @@ def test_train_step_vs_oracle_and_golden(golden_dir):
     np.testing.assert_allclose([float(v) for v in out.update_list_avg[:n]], want["log_avg"], rtol=3e-2)
     assert abs(float(out.tb) - want["tb"]) <= 3e-2 * abs(want["tb"]) + 1e-3
     assert float(out.update_list_avg[n + 1]) == want["dt_ratio"]
-    # generator outputs [B,T,3,128,128], contiguous, within the bf16 bar of the fp32 oracle
-    assert out.gen_output.shape == (b, 10, 3, 128, 128) and out.gen_output.is_contiguous()
+    # generator outputs [B,T,3,4c,4c], contiguous, within the bf16 bar of the fp32 oracle and of the reference's own output
+    assert out.gen_output.shape == (b, t_all, 3, hc, hc) and out.gen_output.is_contiguous()
     d = (out.gen_output.detach().cpu() - want["gen_output"]).abs().max().item()
     assert d <= 1e-2, d
+    assert np.abs(out.gen_output.detach().cpu()[:, :, :, ::sub, ::sub].numpy() - g["gen_output_sub"]).max() <= 1e-2
+    assert np.abs(out.target.cpu()[:, :, ::sub, ::sub].numpy() - g["target_sub"]).max() <= 1e-3
     # the discriminator's real input is pure fp32 glue: <= 1e-5 (a few pixels where a 1-ulp difference of the up-scaled
     # velocity moves a bilinear tap may exceed it)
     dt = (out.target.cpu() - want["target"]).abs()
@@ -143,15 +155,62 @@ def test_second_step_runs_and_loss_moves():
     assert out.global_step == 5
 
 
-def test_rejects_unsupported_flags():
+def test_branches_the_reference_cannot_run_raise_like_the_reference():
+    """Dt_mergeDs=False and GAN_FLAG=False crash inside the reference's own TecoGAN (probed on CPU with the unmodified
+    code/train.py: RuntimeError "expected input ... to have 27 channels, but got 9" at :183-184, UnboundLocalError on
+    t_adversarial_loss at :293); the mirror raises the same exception types.  vgg_scaling > 0 (VGG19() cannot even be
+    constructed) selects the non-parity stand-in only when it is explicitly enabled."""
     from tecogan_b200 import train as T
-    args = TO.default_train_args(num_resblock=1, discrim_resblocks=1, discrim_channels=64, pingpang=True)
+    args = TO.default_train_args(num_resblock=1, discrim_resblocks=1, discrim_channels=64, Dt_mergeDs=False)
     _, _, G, D = _nets(args)
     x = torch.zeros(1, 10, 3, 32, 32, device="cuda")
     y = torch.zeros(1, 10, 3, 128, 128, device="cuda")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):
         T.FRVSR_Train(x, y, args, D, G, 0, 0.0, 0.0, _adam(G, args), _adam(D, args))
-    args.pingpang = False
+    args.Dt_mergeDs = True
+    with pytest.raises(UnboundLocalError):
+        T.TecoGAN(x, y, D, G, args, 0, 0.0, 0.0, _adam(G, args), _adam(D, args), GAN_FLAG=False)
     args.vgg_scaling = 0.2
     with pytest.raises(NotImplementedError):
         T.FRVSR_Train(x, y, args, D, G, 0, 0.0, 0.0, _adam(G, args), _adam(D, args))
+
+
+def test_ordinary_backward_after_a_train_step_returns_gradients():
+    """after a TecoGAN step the modules keep their flat gradient bucket; a later plain backward with
+    p.grad = None (optimizer.zero_grad(set_to_none=True)) must hand gradients to autograd, not add into the hidden bucket."""
+    from tecogan_b200 import train as T
+    args = TO.default_train_args(num_resblock=1, discrim_resblocks=1, discrim_channels=64)
+    _, _, G, D = _nets(args)
+    og, od = _adam(G, args), _adam(D, args)
+    r_in = torch.from_numpy(synth.det_uniform((1, 10, 3, 32, 32), 73, 0.0, 1.0)).cuda()
+    r_tg = torch.from_numpy(synth.det_uniform((1, 10, 3, 128, 128), 74, 0.0, 1.0)).cuda()
+    T.FRVSR_Train(r_in, r_tg, args, D, G, 0, 0.0, 0.0, og, od)
+    og.zero_grad(set_to_none=True)
+    od.zero_grad(set_to_none=True)
+    x = torch.from_numpy(synth.det_uniform((1, 51, 32, 32), 75, 0.0, 1.0)).cuda()
+    G(x).square().mean().backward()
+    assert all(p.grad is not None and p.grad.abs().sum().item() > 0 for p in G.parameters())
+    pr, _ = D(torch.from_numpy(synth.det_uniform((2, 27, 128, 128), 76, -1.0, 1.0)).cuda())
+    pr.sum().backward()
+    assert all(p.grad is not None for p in D.parameters())
+    assert D.fc.weight.grad.abs().sum().item() > 0
+
+
+def test_packed_weight_cache_follows_data_writes_after_invalidate():
+    """a write through ``p.data`` bumps no version counter; invalidate_packed() (called by load_state_dict and
+    broadcast_parameters) makes the next forward re-pack."""
+    args = TO.default_train_args(num_resblock=1, discrim_resblocks=1, discrim_channels=64)
+    _, _, G, D = _nets(args)
+    G.eval()
+    x = torch.from_numpy(synth.det_uniform((1, 51, 16, 16), 77, 0.0, 1.0)).cuda()
+    with torch.no_grad():
+        a = G(x).clone()
+        G.output.bias.data.add_(1.0)               # invisible to the (data_ptr, version) key
+        G.invalidate_packed()
+        b = G(x).clone()
+        sd = {k: v.clone() for k, v in G.state_dict().items()}
+        sd["output.bias"] -= 1.0
+        G.load_state_dict(sd)                      # invalidates by itself
+        c = G(x)
+    assert (b - a).abs().min().item() > 0.1
+    assert torch.equal(c, a)

@@ -84,23 +84,27 @@ def test_discriminator_vs_reference(golden_dir):
     np.testing.assert_allclose(D.block1[1].running_mean.numpy(), g["running_mean_block1"], rtol=0, atol=1e-6)
 
 
-def test_train_step_oracle_vs_reference(golden_dir):
-    """oracle/train_oracle.py against one step of the unmodified reference train.FRVSR_Train (tests/golden/train.npz):
+@pytest.mark.parametrize("fixture,crop,flags,sub", [("train.npz", 32, {}, 8), ("train_cfg5.npz", 64, {}, 16),
+                                                    ("train_pingpang.npz", 32, {"pingpang": True}, 8)],
+                         ids=["cfg4_shape", "cfg5_shape", "pingpang"])
+def test_train_step_oracle_vs_reference(golden_dir, fixture, crop, flags, sub):
+    """oracle/train_oracle.py against one step of the unmodified reference train.FRVSR_Train (tests/golden/train*.npz):
     every logged scalar, the EMA list, the generator outputs, the discriminator's real input, both nets' gradients
-    (per-tensor norm + projection fingerprint) and the Adam update."""
+    (per-tensor norm + projection fingerprint) and the Adam update — at BASELINE cfg4's crop (32), cfg5's crop (64, the
+    reference discriminator with fc = denselayer(192, 1) as colab/README.md:15-22 prescribes) and with pingpang=True."""
     from oracle import train_oracle as TO
-    g = _load(golden_dir, "train.npz")
+    g = _load(golden_dir, fixture)
     torch.set_num_threads(8)
-    args = TO.default_train_args()
+    args = TO.default_train_args(crop_size=crop, **flags)
     G = O.OracleGenerator(3, 16)
-    D = O.OracleDiscriminator(4, 128, 48)
+    D = O.OracleDiscriminator(4, 128, 48 * (crop // 32) ** 2)
     O.load_numpy_state(G, synth.fill_state_dict(G.state_dict(), seed=1, gain=1.0))
     O.load_numpy_state(D, synth.fill_state_dict(D.state_dict(), seed=2, gain=1.0))
     og = torch.optim.Adam(G.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps)
     od = torch.optim.Adam(D.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps)
     b = int(g["batch"])
-    r_in = torch.from_numpy(synth.det_uniform((b, 10, 3, 32, 32), 51, 0.0, 1.0))
-    r_tg = torch.from_numpy(synth.det_uniform((b, 10, 3, 128, 128), 52, 0.0, 1.0))
+    r_in = torch.from_numpy(synth.det_uniform((b, 10, 3, crop, crop), 51, 0.0, 1.0))
+    r_tg = torch.from_numpy(synth.det_uniform((b, 10, 3, 4 * crop, 4 * crop), 52, 0.0, 1.0))
     w0 = G.conv[0].weight.detach().clone()
     out = TO.train_step(G, D, og, od, r_in, r_tg, args, 0)
     assert list(out["log"].keys()) == [str(n) for n in g["names"]]
@@ -108,8 +112,8 @@ def test_train_step_oracle_vs_reference(golden_dir):
     np.testing.assert_allclose(out["log_avg"], g["update_list_avg"], rtol=2e-5)
     np.testing.assert_allclose([out["tb"], out["dt_ratio"], out["d_loss"], out["gen_loss"]],
                                [g["tb"], g["dt_ratio"], g["d_loss"], g["gen_loss"]], rtol=2e-5)
-    np.testing.assert_allclose(out["gen_output"][:, :, :, ::8, ::8].numpy(), g["gen_output_sub"], atol=2e-6)
-    np.testing.assert_allclose(out["target"][:, :, ::8, ::8].numpy(), g["target_sub"], atol=2e-6)
+    np.testing.assert_allclose(out["gen_output"][:, :, :, ::sub, ::sub].numpy(), g["gen_output_sub"], atol=2e-6)
+    np.testing.assert_allclose(out["target"][:, :, ::sub, ::sub].numpy(), g["target_sub"], atol=2e-6)
     for mod, key in ((G, "g_grad"), (D, "d_grad")):
         for i, (name, p) in enumerate(mod.named_parameters()):
             gr = p.grad.detach().double().flatten()
