@@ -112,9 +112,9 @@ def test_train_step_vs_oracle_and_golden(golden_dir, fixture, crop, flags):
     assert np.abs(out.gen_output.detach().cpu()[:, :, :, ::sub, ::sub].numpy() - g["gen_output_sub"]).max() <= 1e-2
     assert np.abs(out.target.cpu()[:, :, ::sub, ::sub].numpy() - g["target_sub"]).max() <= 1e-3
     # the discriminator's real input is pure fp32 glue: <= 1e-5 (a few pixels where a 1-ulp difference of the up-scaled
-    # velocity moves a bilinear tap may exceed it)
+    # velocity moves a bilinear tap may exceed it, SURVEY.md H4.2: 1e-4 of the pixels measured at 256x256, worst 2.8e-5)
     dt = (out.target.cpu() - want["target"]).abs()
-    assert (dt > 1e-5).float().mean().item() < 1e-4 and dt.max().item() <= 1e-3, (dt.max().item(), (dt > 1e-5).float().mean().item())
+    assert (dt > 1e-5).float().mean().item() < 3e-4 and dt.max().item() <= 1e-4, (dt.max().item(), (dt > 1e-5).float().mean().item())
     # gradients (left in .grad, unscaled by GradScaler.step) vs the oracles'.  The discriminator's gradient at random init
     # is chaotic under operand rounding (tests/test_gpu_discriminator.py::test_backward_vs_oracle): the bf16-operand
     # oracle itself sits at cosine 0.940 against the fp32 oracle on this step (measured on CPU), B200 at 0.939.
@@ -204,12 +204,12 @@ def test_packed_weight_cache_follows_data_writes_after_invalidate():
     G.eval()
     x = torch.from_numpy(synth.det_uniform((1, 51, 16, 16), 77, 0.0, 1.0)).cuda()
     with torch.no_grad():
+        sd = {k: v.clone() for k, v in G.state_dict().items()}
         a = G(x).clone()
         G.output.bias.data.add_(1.0)               # invisible to the (data_ptr, version) key
         G.invalidate_packed()
         b = G(x).clone()
-        sd = {k: v.clone() for k, v in G.state_dict().items()}
-        sd["output.bias"] -= 1.0
+        G.output.bias.data.copy_(sd["output.bias"])   # another invisible write, then the documented ways to re-sync:
         G.load_state_dict(sd)                      # invalidates by itself
         c = G(x)
     assert (b - a).abs().min().item() > 0.1
