@@ -14,8 +14,14 @@ One "step" = one batch of B independent 100-frame clips per GPU through the recu
   roofline   dominant kernel (tg::frame_kernel: all 41 tcgen05 conv layers of a frame) timed per launch with CUDA events
   train      second half of the metric ("train clips/s"): tecogan_b200.train.FRVSR_Train steps on cfg4 (N=1) and cfg5
              (global batch 32 split over the N ranks, gradient all-reduce inside the step), device-timed + e2e
+  cfg3       the same measurements on BASELINE configs[2] (960x540 -> 4K, 30-frame clips): frames/s, e2e, frame-kernel
+             roofline at 4K
+  lr_u01     `value` re-measured with the reference-faithful U[0,1) LR pixels (93 % of the warp taps out of bounds)
   cpu_baseline / --impl reference: the CPU oracle port (torch fp32 on the host cores) on a
-             bounded sample of the same workload.  Only these legs import oracle/.
+             bounded sample of the same workload (the SAME sample in both).
+  torch_gpu_baseline: the oracle port's modules moved to this GPU and run under torch.autocast (cuDNN / ATen kernels) -
+             "stock PyTorch on the same B200", the only GPU bar the reference offers (it ships no kernels).
+  Only the baseline legs import oracle/.
 """
 import argparse
 import json
@@ -36,6 +42,8 @@ FLOP_PER_LR_PIXEL_OUTCONV = 2 * 9 * 64 * 3 * 16
 TRAFFIC_BYTES_PER_LAUNCH = 2.522e9     # ncu --set full, final frame_kernel, 2 clips/launch: dram read 1.314 GB + write 1.208 GB (profiles/r01_frame_v10.ncu-rep)
 METRIC = "720p output frames/s (x4 VSR inference)"
 WORKLOAD = "cfg2: generator inference 320x180 -> 1280x720, 100-frame synthetic clips, sharded by clip"
+CPU_SAMPLE_FRAMES = 3                  # bounded sample of the clip for the CPU arms (cpu_baseline AND --impl reference)
+CPU_SAMPLE = f"{CPU_SAMPLE_FRAMES}-frame 320x180 clip (bounded sample of the 100-frame cfg2 clip), U[0,0.25) LR pixels"
 
 
 def parse():
@@ -51,6 +59,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (train clips/s)")
     ap.add_argument("--no-glue", action="store_true", help="skip the HBM roofline of the glue kernels (cfg3 sizes)")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the 4K (cfg3) inference leg")
+    ap.add_argument("--no-torch-gpu", action="store_true", help="skip the stock-PyTorch-on-this-GPU baseline leg")
+    ap.add_argument("--e2e-format", default="u8", choices=["f32", "f16", "u8"],
+                    help="what run_host ships to the host in the headline e2e (all three are reported)")
+    ap.add_argument("--lib", default=None, help="measurement only: load another build of libtecogan_b200.so (same-box A/B)")
     ap.add_argument("--train-steps", type=int, default=10)
     return ap.parse_args()
 
@@ -124,7 +137,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_frames = 2
+    n_frames = CPU_SAMPLE_FRAMES
     fps, step_s, cores = cpu_oracle_fps(n_frames, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
@@ -132,9 +145,9 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "arm": "reference CPU path (oracle port of models.py + main.py:173-219, "
                    "torch fp32 on the host cores)",
-                   "sample": f"{n_frames}-frame clip per step (bounded sample of the 100-frame clip)"},
+                   "sample": CPU_SAMPLE + " per step"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_frames} frames of a 320x180 clip per step, {args.steps} steps"},
+                         "sample": CPU_SAMPLE + f", {args.steps} steps"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -199,11 +212,10 @@ def run_train_leg(name, crop, global_batch, world, rank, dev, steps, warmup, bar
     D = models.discriminator(args).to(dev)
     parallel.broadcast_parameters(G)
     parallel.broadcast_parameters(D)
-    # main.py:239-243's optimizer; fused=True is torch's own single-kernel implementation of the same update, and the only
-    # one GradScaler.step() can drive without reading found_inf back to the host (TG_BENCH_FUSED_ADAM=0: the plain one)
-    fused = os.environ.get("TG_BENCH_FUSED_ADAM", "1") != "0"
-    og = torch.optim.Adam(G.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps, fused=fused)
-    od = torch.optim.Adam(D.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps, fused=fused)
+    # main.py:239-243's optimizers, built exactly as the reference builds them; tecogan_b200.train adopts them
+    # (tecogan_b200.optim.FlatAdam: repo kernels on the flat buckets) and captures the step in a CUDA graph when single-process
+    og = torch.optim.Adam(G.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps)
+    od = torch.optim.Adam(D.parameters(), args.learning_rate, betas=(args.beta, 0.999), eps=args.adameps)
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
     r_in = torch.rand((per, 10, 3, crop, crop), device=dev, generator=gen)
     r_tg = torch.rand((per, 10, 3, 4 * crop, 4 * crop), device=dev, generator=gen)
@@ -246,8 +258,9 @@ def run_train_leg(name, crop, global_batch, world, rank, dev, steps, warmup, bar
            "gpu_launches": int(launches),
            "step_tflops": flops / (dev_s / steps) / 1e12, "algorithmic_flops_per_step": flops,
            "losses_finite": bool(all(v == v and abs(v) != float("inf") for v in losses + host_losses)),
-           "optimizer": ("torch.optim.Adam(fused=True)" if fused else "torch.optim.Adam") +
-                        " + GradScaler (stock torch, as main.py:239-243 / code/train.py:335-342)"}
+           "optimizer": "torch.optim.Adam objects as main.py:239-243 builds them, stepped by tecogan_b200.optim.FlatAdam (fused flat-bucket "
+                        "Adam + GradScaler update + bf16 re-pack, repo kernels)" if T.FUSED_ADAM else "torch.optim.Adam + GradScaler (stock)",
+           "cuda_graph": bool(T.USE_CUDA_GRAPH and T.FUSED_ADAM and world == 1)}
     if with_cpu:
         cb = 4 if crop == 32 else 1
         cps, step_s, cores = cpu_oracle_train(crop, cb)
@@ -258,51 +271,69 @@ def run_train_leg(name, crop, global_batch, world, rank, dev, steps, warmup, bar
 
 
 # ------------------------------------------------------------------------------------- ours
-def run_ours(args):
-    import types
+def torch_gpu_fps(dev, n_frames, h, w, steps=3, warmup=1):
+    """"Stock PyTorch on the same B200": the oracle port's generator (plain nn.Conv2d / nn.ConvTranspose2d modules, the
+    reference's own layer stack) on this GPU under torch.autocast(fp16) - cuDNN / ATen kernels, exactly the arithmetic
+    the reference's GPU path runs (main.py:171-172) - through the reference's frame loop (main.py:173-219: F.grid_sample
+    with the .half() grid, deprocess, space-to-depth, cat).  Kinder to the baseline than the reference is to itself:
+    everything stays on the device (the reference bounces every frame through host memory, main.py:195,203,214)."""
     import torch
-    import torch.distributed as dist
+    import torch.nn.functional as F
+    from oracle import tecogan_oracle as O
+    torch.manual_seed(1)
+    G = O.OracleGenerator(3, 16).to(dev).eval()
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    r = torch.rand((1, n_frames, 3, h, w), device=dev, generator=gen) * 0.25
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    @torch.no_grad()
+    def clip():
+        with torch.autocast("cuda", dtype=torch.float16):
+            flow = F.interpolate(r[0, :-1] * 4.0, scale_factor=4, mode="bilinear", align_corners=False)[:, 0:2]   # main.py:186-189
+            x = torch.cat((r[:, 0], torch.zeros((1, 48, h, w), device=dev)), dim=1)                                # :191-193
+            prev = G(x).view(1, 3, 4 * h, 4 * w)                                                                   # :195-196
+            outs = [prev]
+            for i in range(n_frames - 1):                                                                          # :199
+                grid = flow[i].contiguous().view(1, 4 * h, 4 * w, 2)                                               # :200-201
+                wp = F.grid_sample(prev.float(), grid.half().float(), mode="bilinear", padding_mode="zeros", align_corners=False)  # :203
+                wp = (wp + 1) / 2                                                                                  # :206
+                x = torch.cat((r[:, i + 1], F.pixel_unshuffle(wp, 4)), dim=1)                                      # :207-213
+                prev = G(x)                                                                                        # :214
+                outs.append(prev)
+            return torch.stack(outs, dim=1)
 
-    from tecogan_b200 import _native as nt, models
+    for _ in range(warmup):
+        clip()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = clip()
+    e1.record()
+    torch.cuda.synchronize()
+    s = e0.elapsed_time(e1) * 1e-3
+    del G, out
+    torch.cuda.empty_cache()
+    return n_frames * steps / s, s / steps
+
+
+def inference_leg(G, dev, world, rank, B, frames, h, w, K, Wm, lr_hi, barrier, max_over_ranks, do_e2e, e2e_format, do_roof,
+                  traffic_per_launch, sampler=None):
+    """One inference configuration: B independent `frames`-frame h x w clips per GPU through the recurrent loop.
+    Returns (value, ms_per_step, launches, e2e dict, roofline dict, finite, clocks)."""
+    import ctypes
+    import torch
+    from tecogan_b200 import _native as nt
     from tecogan_b200.pipeline import ClipPipeline
     lib = nt.lib()
-
-    B, K, Wm = args.clips, args.steps, max(args.warmup, 3)
-    frames = args.frames
-    torch.manual_seed(1)                                   # reference default --rand_seed 1 (main.py:34)
-    G = models.generator(3, types.SimpleNamespace(num_resblock=16)).to(dev).eval()   # random init
-    pipe = ClipPipeline(G, B, frames, H, W, dev)
+    pipe = ClipPipeline(G, B, frames, h, w, dev)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    lr = torch.rand((B, frames, 3, H, W), device=dev, generator=gen) * 0.25
-    out = torch.empty((B, frames, 3, 4 * H, 4 * W), dtype=torch.float32, device=dev)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    sampler = ClockSampler(local)
-    # ---------------- device-resident throughput (value) ----------------
+    lr = torch.rand((B, frames, 3, h, w), device=dev, generator=gen) * lr_hi
+    out = torch.empty((B, frames, 3, 4 * h, 4 * w), dtype=torch.float32, device=dev)
     for _ in range(Wm):
         pipe.run_device(lr, out)
     barrier()
-    sampler.start()
+    if sampler:
+        sampler.start()
     launches0 = lib.tg_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -312,40 +343,52 @@ def run_ours(args):
     barrier()
     launches = lib.tg_launch_count() - launches0
     dev_s = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     value = world * B * frames * K / dev_s
     finite = bool(torch.isfinite(out[:, -1]).all().item())
+    del out
 
-    # ---------------- end to end with host buffers (e2e) ----------------
+    # ---------------- end to end with host buffers ----------------
     e2e = None
-    if not args.no_e2e:
-        lr_host = torch.empty((B, frames, 3, H, W), dtype=torch.float32).pin_memory()
+    if do_e2e:
+        dt = {"f32": torch.float32, "f16": torch.float16, "u8": torch.uint8}
+        lr_host = torch.empty((B, frames, 3, h, w), dtype=torch.float32).pin_memory()
         lr_host.copy_(lr.cpu())
-        out_host = torch.empty((frames, B, 3, 4 * H, 4 * W), dtype=torch.float32).pin_memory()
-        for _ in range(Wm):
-            pipe.run_host(lr_host, out_host)
-        barrier()
-        t0 = time.perf_counter()
-        e0.record()
-        for _ in range(K):
-            pipe.run_host(lr_host, out_host)               # returns with every frame in host memory
-        e1.record()
-        barrier()
-        host_s = max_over_ranks(max(e0.elapsed_time(e1) * 1e-3, 0.0))
-        wall_s = max_over_ranks(time.perf_counter() - t0)
-        bi, bo = pipe.bytes_per_run()
-        e2e = {"value": world * B * frames * K / max(host_s, wall_s), "unit": "frames/s",
-               "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
-               "api": "tecogan_b200.pipeline.ClipPipeline.run_host (pinned host in/out, D2H overlapped)",
-               "result_mean": float(out_host[-1].mean())}
-        del lr_host, out_host
+        res = {}
+        for fmt in ("f32", "f16", "u8"):
+            out_host = torch.empty(pipe._out_shape(dt[fmt]), dtype=dt[fmt]).pin_memory()
+            for _ in range(max(1, Wm - 1)):
+                pipe.run_host(lr_host, out_host, out_dtype=dt[fmt])
+            barrier()
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(K):
+                pipe.run_host(lr_host, out_host, out_dtype=dt[fmt])           # returns with every frame in host memory
+            e1.record()
+            barrier()
+            host_s = max_over_ranks(max(e0.elapsed_time(e1) * 1e-3, 0.0))
+            wall_s = max_over_ranks(time.perf_counter() - t0)
+            bi, bo = pipe.bytes_per_run(dt[fmt])
+            res[fmt] = {"value": world * B * frames * K / max(host_s, wall_s), "unit": "frames/s", "h2d_bytes_per_step": bi,
+                        "d2h_bytes_per_step": bo, "result_mean": float(out_host[-1].float().mean()) / (255.0 if fmt == "u8" else 1.0)}
+            del out_host
+        what = {"f32": "f32 planar frames (the parity default, bit-identical to generator.infer_clip)",
+                "f16": "fp16 planar frames (the f32 result rounded to fp16: what the reference's autocast GPU path emits, main.py:171-172)",
+                "u8": "uint8 NHWC frames ((x*255) truncated: exactly what the reference's save_as_gif makes of the clip before "
+                      "writing it, code/ops.py:234-237)"}
+        e2e = dict(res[e2e_format])
+        e2e["api"] = ("tecogan_b200.pipeline.ClipPipeline.run_host (pinned host LR in, every HR frame copied back to pinned host "
+                      "memory on a side stream while the next frame computes; copies inside the timed region)")
+        e2e["output_format"] = what[e2e_format]
+        e2e["other_formats"] = {k: {"value": v["value"], "d2h_bytes_per_step": v["d2h_bytes_per_step"], "output_format": what[k]}
+                                for k, v in res.items() if k != e2e_format}
+        del lr_host
 
     # ---------------- roofline of the dominant kernel, per-launch CUDA events ----------------
     roof = None
-    if rank == 0:
-        import ctypes
+    if do_roof and rank == 0:
         pf = min(frames, 20)
-        pipe_p = ClipPipeline(G, B, pf, H, W, dev)
+        pipe_p = ClipPipeline(G, B, pf, h, w, dev) if pf != frames else pipe
         lr_p = lr[:, :pf].contiguous()
         pipe_p.run_device(lr_p)
         torch.cuda.synchronize()
@@ -370,34 +413,104 @@ def run_ours(args):
         if fr:      # frame kernel: one launch = all 41 conv layers of one generator forward for B clips
             k_ms = sum(ms[i] for i in fr)
             k_n = len(fr)
-            flops = float(k_n) * B * FLOP_PER_LR_PIXEL * H * W
+            flops = float(k_n) * B * FLOP_PER_LR_PIXEL * h * w
             kname = "tg::frame_kernel (persistent tcgen05 implicit-GEMM generator forward, 1 launch/frame)"
         else:       # per-layer path: 40 conv_tc_kernel<64> launches per frame
             k_ms = sum(ms[i] for i in range(n) if ids[i] == 0)
             k_n = sum(1 for i in range(n) if ids[i] == 0)
-            flops = float(pf) * B * (FLOP_PER_LR_PIXEL - FLOP_PER_LR_PIXEL_OUTCONV) * H * W
+            flops = float(pf) * B * (FLOP_PER_LR_PIXEL - FLOP_PER_LR_PIXEL_OUTCONV) * h * w
             kname = "tg::conv_tc_kernel<64> (tcgen05 implicit-GEMM conv, 40 launches/frame)"
         achieved = flops / (k_ms * 1e-3) / 1e12
         roof = {"kernel": kname, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "peak_source": src,
-                "traffic": TRAFFIC_BYTES_PER_LAUNCH if (fr and B == 2) else None,
-                "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, one frame_kernel launch at "
-                                  "2 clips/launch (profiles/)" if (fr and B == 2 and TRAFFIC_BYTES_PER_LAUNCH) else None,
+                "traffic": traffic_per_launch if fr else None,
+                "traffic_source": ("ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one frame_kernel launch at this "
+                                   "configuration (profiles/)") if (fr and traffic_per_launch) else None,
                 "launches_timed": k_n, "avg_launch_us": k_ms * 1e3 / max(k_n, 1),
                 "algorithmic_flops_per_launch": flops / max(k_n, 1),
                 "kernel_share_of_step": k_ms / all_ms if all_ms else None}
-        del pipe_p
+    del pipe, lr
+    torch.cuda.empty_cache()
+    return value, dev_s / K * 1e3, int(launches), e2e, roof, finite, clocks
+
+
+def run_ours(args):
+    import types
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from tecogan_b200 import _native as nt, models
+    if args.lib:                                           # measurement only (same-box A/B of two builds)
+        nt.LIB_PATH = os.path.abspath(args.lib)
+    nt.lib()
+
+    B, K, Wm = args.clips, args.steps, max(args.warmup, 3)
+    frames = args.frames
+    torch.manual_seed(1)                                   # reference default --rand_seed 1 (main.py:34)
+    G = models.generator(3, types.SimpleNamespace(num_resblock=16)).to(dev).eval()   # random init
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- cfg2: the headline (value, e2e, roofline) ----------------
+    value, ms_step, launches, e2e, roof, finite, clocks = inference_leg(
+        G, dev, world, rank, B, frames, H, W, K, Wm, 0.25, barrier, max_over_ranks, not args.no_e2e, args.e2e_format, True,
+        TRAFFIC_BYTES_PER_LAUNCH if B == 2 else None, ClockSampler(local))
+
+    # ---------------- cfg2 with the reference-faithful LR distribution U[0,1) (value only) ----------------
+    v_u01, ms_u01, _, _, _, fin_u01, _ = inference_leg(G, dev, world, rank, B, min(frames, 30), H, W, max(2, K // 2), 3, 1.0, barrier,
+                                                       max_over_ranks, False, args.e2e_format, False, None)
+    lr_u01 = {"value": v_u01, "unit": "frames/s", "lr_dist": "U[0,1): the reference-faithful input (4*LR as the 'flow' puts 93 % of "
+              "the warp taps out of bounds -> zeros)", "frames_per_clip": min(frames, 30), "outputs_finite": fin_u01}
+
+    # ---------------- cfg3: 960x540 -> 4K, 30-frame clips ----------------
+    cfg3 = None
+    if not args.no_cfg3:
+        v3, ms3, l3, e3, r3, f3, _ = inference_leg(G, dev, world, rank, 1, 30, 540, 960, max(2, K // 2), 3, 0.25, barrier, max_over_ranks,
+                                                   not args.no_e2e, args.e2e_format, True, None)
+        cfg3 = {"workload": "cfg3: generator inference 960x540 -> 3840x2160 (4K), 30-frame synthetic clips, 1 clip per GPU per step",
+                "metric": "4K output frames/s (x4 VSR inference)", "value": v3, "unit": "frames/s", "ms_per_step": ms3,
+                "720p_equivalent_frames_per_s": v3 * 9.0, "gpu_launches": l3, "e2e": e3, "roofline": r3, "outputs_finite": f3,
+                "lr_dist": "U[0,0.25)"}
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, step_s, cores = cpu_oracle_fps(3, 1, 1)
+        fps, step_s, cores = cpu_oracle_fps(CPU_SAMPLE_FRAMES, 1, 1)
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": "one 3-frame 320x180 clip through oracle.infer_clip (torch CPU fp32)"}
+               "sample": CPU_SAMPLE + " through oracle.infer_clip (torch CPU fp32); the same sample as --impl reference"}
+
+    # ---------------- stock PyTorch (cuDNN, autocast fp16) on this GPU: the bar the reference's own GPU path sets ----------------
+    tgpu = None
+    if rank == 0 and world == 1 and not args.no_torch_gpu:
+        try:
+            fps2, step2 = torch_gpu_fps(dev, 10, H, W)
+            tgpu = {"value": fps2, "unit": "frames/s", "kind": "oracle-port modules on cuda:0 under torch.autocast(fp16), device-resident "
+                    "loop (no PCIe hops)", "sample": "one 10-frame 320x180 clip per step, 3 steps", "ms_per_frame": step2 / 10 * 1e3,
+                    "ours_over_this": value / world / fps2}
+        except Exception as e:                               # a baseline leg must never take the bench down
+            tgpu = {"unavailable": repr(e)[:200]}
 
     # ---------------- HBM roofline of the memory-bound glue kernels at cfg3 (4K) sizes ----------------
     glue = None
-    del pipe, out, lr
     torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_glue:
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
@@ -419,7 +532,7 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "clips_per_gpu_per_step": B, "frames_per_clip": frames, "lr_dist": "U[0,0.25) (all warp taps "
@@ -429,7 +542,7 @@ def run_ours(args):
                        "l2": "no explicit flush: every frame streams ~0.56 GB of activations per clip through the "
                              "126 MB L2, far larger than L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "outputs_finite": finite, "glue": glue, "train": train,
+            "torch_gpu_baseline": tgpu, "outputs_finite": finite, "lr_u01": lr_u01, "cfg3": cfg3, "glue": glue, "train": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -315,6 +315,28 @@ int tg_bn_apply(const float* x, const float* skip, float* y_f32, void* y_bf16, l
 int tg_bn_bwd(const void* g_out, const float* x, const float* act_out, void* dx, long long pixels, int c,
               const float* stats, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------ optimizer step on the flat buckets ---- */
+
+/* Fused multi-tensor Adam.  Replaces scaler.step(optimizer) / scaler.update() of code/train.py:337-338,
+ * 341-342 for the optimizers main.py:239-243 builds (torch.optim.Adam, amsgrad=False, weight_decay=0).  `params`,
+ * `grads`, `exp_avg`, `exp_avg_sq` are flat f32 buffers of n elements in the networks' flat parameter layout (16-byte
+ * aligned); lr, step, inv_scale, found_inf are DEVICE scalars (f32), so the launches are CUDA-graph capturable and a
+ * replayed graph follows StepLR / the loss scale.
+ *   tg_grad_check_finite: *found_inf = 1 if any gradient is inf / NaN, else 0 (GradScaler.unscale_'s check).
+ *   tg_adam_step        : g = grads * (*inv_scale, 1 if NULL), written back to grads when inv_scale != NULL (GradScaler.unscale_
+ *                         works in place); skipped entirely when found_inf != NULL and *found_inf != 0;
+ *                         t = *step + 1; exp_avg = b1*exp_avg + (1-b1)*g; exp_avg_sq = b2*exp_avg_sq + (1-b2)*g*g;
+ *                         params -= (*lr / (1 - b1^t)) * exp_avg / (sqrt(exp_avg_sq) / sqrt(1 - b2^t) + eps).
+ *   tg_scaler_update    : *step += 1 unless inf (step may be NULL); GradScaler.update(): on inf scale *= backoff_factor and
+ *                         growth_tracker = 0, else growth_tracker += 1 and every growth_interval clean steps
+ *                         scale *= growth_factor (scale / growth_tracker may both be NULL: plain optimizer without a scaler). */
+int tg_grad_check_finite(const float* grads, long long n, float* found_inf, void* stream);
+int tg_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, const float* lr,
+                 float beta1, float beta2, float eps, const float* step, const float* inv_scale, const float* found_inf,
+                 void* stream);
+int tg_scaler_update(float* scale, int* growth_tracker, const float* found_inf, float growth_factor, float backoff_factor,
+                     int growth_interval, float* step, void* stream);
+
 /* Workspace queries under the names SURVEY.md 8b lists (tg_workspace_bytes_<op>); the single-layer conv / glue entry
  * points need no workspace.  Same values as tg_gen_workspace_bytes / tg_gen_train_workspace_bytes / tg_disc_workspace_bytes. */
 size_t tg_workspace_bytes_gen_forward(int n, int h, int w);

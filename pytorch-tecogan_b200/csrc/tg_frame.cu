@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     bool grid_waited = false;
     int si_base = 0;
     Tick<kDbg> tk{0, stats != nullptr, true}, tall{0, stats != nullptr, true};
-    long long a_wempty = 0, a_dep = 0, a_aempty = 0, a_total = 0;
+    long long a_wempty = 0, a_dep = 0, a_aempty = 0, a_total = 0, a_issue = 0;
     tall.start();
     for (int it0 = blockIdx.x; it0 < P.total_items; it0 += 32 * G) {
       uint32_t l0, l1, l2, l3;
@@ -395,9 +395,12 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           tk.start();
           mbar_wait(bar_aempty + 8 * st, ph ^ 1);
           tk.stop(a_aempty);
+          tk.start();
           if (elect_one()) {
             if (!(dbg & 64)) fence_proxy_async_global();   // generic-proxy writes of other CTAs (acquired above) -> async-proxy read
-            if (kPair) {
+            if (kPair && (dbg & 1024) && tk.gate) {
+              mbar_expect_tx_cluster(lbar_afull + 8 * st, 0u);         // measurement: no A load in the selected segment
+            } else if (kPair) {
               mbar_expect_tx_cluster(lbar_afull + 8 * st, static_cast<uint32_t>(S.box_w * S.box_h) * 128u);
               tma_load_4d_pair(s_a + st * kAStride, &P.maps[S.map_a], lbar_afull + 8 * st, kc * 64, bx0, by0, n);
             } else {
@@ -406,6 +409,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
             }
           }
           __syncwarp();
+          tk.stop(a_issue);
           if (++st == kFrStages) { st = 0; ph ^= 1; }
         }
       }
@@ -413,8 +417,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     }
     tall.stop(a_total);
     if (stats && lane == 0) {
-      unsigned long long* o = stats + blockIdx.x * 16;
-      o[9] = a_wempty; o[10] = a_dep; o[11] = a_aempty; o[12] = a_total;
+      unsigned long long* o = stats + blockIdx.x * 32;
+      o[9] = a_wempty; o[10] = a_dep; o[11] = a_aempty; o[12] = a_total; o[22] = a_issue;
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA of a pair) ====================
@@ -425,7 +429,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     uint32_t ph = 0, gph = 0;
     int traced_si = -1;
     Tick<kDbg> tk{0, stats != nullptr, true}, tall{0, stats != nullptr, true};
-    long long a_cempty = 0, a_wfull = 0, a_afull = 0, a_total = 0;
+    long long a_cempty = 0, a_wfull = 0, a_afull = 0, a_total = 0, a_issue = 0;
     tall.start();
     // per-segment values live in registers (no shared-memory round trip on the issue path of every item)
     int seg_end = 0, m_wide = 0, m_kchunks = 1, tbl = 0;
@@ -467,10 +471,13 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         else mbar_wait(bar_afull + 8 * st, ph);
         tk.stop(a_afull);
         tc_fence_after();
+        tk.start();
         if (elect_one()) {
           const uint32_t a_base = s_a + st * kAStride;
           const uint32_t w_base = s_w + slot * kWSlotBytes;
-          if (wide) {
+          if ((dbg & 512) && tk.gate) {
+            // measurement: no MMAs in the selected segment (commits only)
+          } else if (wide) {
             // one MMA per (filter row, K=16 step): A = the box shifted by dy rows of 32 pixels (4096 B, so every
             // descriptor keeps the canonical 1024-byte group pitch), B = the row's three taps stacked along N.
             // Fully unrolled, descriptors advanced by immediates: for the N = 48 output conv the issue path, not
@@ -526,6 +533,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           }
         }
         __syncwarp();
+        tk.stop(a_issue);
         if (++st == kFrStages) { st = 0; ph ^= 1; }
       }
       g ^= 1;
@@ -533,8 +541,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     }
     tall.stop(a_total);
     if (stats && lane == 0) {
-      unsigned long long* o = stats + blockIdx.x * 16;
-      o[0] = a_cempty; o[1] = a_wfull; o[2] = a_afull; o[3] = a_total;
+      unsigned long long* o = stats + blockIdx.x * 32;
+      o[0] = a_cempty; o[1] = a_wfull; o[2] = a_afull; o[3] = a_total; o[20] = a_issue;
     }
     }
   } else if (kTwoSets && warp < 2 + kEpiWarps) {
@@ -554,7 +562,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     int si = 0, cur_si = -1;
     uint32_t gph = 0, pk = 0;
     Tick<kDbg> tk{0, stats != nullptr, true}, tall{0, stats != nullptr, true};
-    long long a_cfull = 0, a_body = 0, a_pub = 0, a_total = 0, a_tmem = 0;
+    long long a_cfull = 0, a_body = 0, a_pub = 0, a_total = 0, a_tmem = 0, a_hb = 0;
     tall.start();
     float nb0 = 0.f, nb1 = 0.f;                            // bias of segment nb_si, fetched one segment ahead
     int nb_si = -1;
@@ -624,16 +632,23 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
             const uint32_t col = static_cast<uint32_t>(half * 32 + pass * 16);
             uint32_t v[16], vb[16];
             uint64_t a2[8];
+            Tick<kDbg> t2{0, stats != nullptr, tk.gate};
+            t2.start();
             tmem_ld_32x16(tq + col, v);                    // P0: the left neighbour's value is needed
             tmem_ld_32x16(tq + 64 + col, vb);              // P1 (same round trip)
             tmem_ld_wait();
+            t2.stop(a_tmem);
 #pragma unroll
             for (int e = 0; e < 8; ++e)
               a2[e] = f2_add(f2_pack(__shfl_up_sync(0xFFFFFFFFu, v[2 * e], 1), __shfl_up_sync(0xFFFFFFFFu, v[2 * e + 1], 1)),
                              f2_pack(vb[2 * e], vb[2 * e + 1]));
+            t2.start();
             tmem_ld_32x16(tq + 128 + col, v);              // P2: the right neighbour's value
             tmem_ld_wait();
+            t2.stop(a_tmem);
+            t2.start();
             if (pass == 1) hand_back();
+            t2.stop(a_hb);
 #pragma unroll
             for (int e = 0; e < 8; ++e)
               a2[e] = f2_add(a2[e], f2_pack(__shfl_down_sync(0xFFFFFFFFu, v[2 * e], 1), __shfl_down_sync(0xFFFFFFFFu, v[2 * e + 1], 1)));
@@ -642,11 +657,16 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           }
         } else {
           uint32_t v0[4], v1[4], v2[4];                    // 3 output channels of each of the 3 partial sums
+          Tick<kDbg> t2{0, stats != nullptr, tk.gate};
+          t2.start();
           tmem_ld_32x4(tq, v0);
           tmem_ld_32x4(tq + 16, v1);
           tmem_ld_32x4(tq + 32, v2);
           tmem_ld_wait();
+          t2.stop(a_tmem);
+          t2.start();
           hand_back();
+          t2.stop(a_hb);
           // half 0: planes 0 and 1, half 1: plane 2
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
@@ -661,8 +681,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
               const size_t o = static_cast<size_t>(n) * S.out_nstride + opx + c * plane;
               const float y = 1.f / (1.f + expf(-z));
               if (S.out2) S.out2[static_cast<size_t>(n) * 3 * plane + opx + c * plane] = z;
-              if (S.out) store_network_output(S.out, c_mode, o, static_cast<size_t>(n) * (S.out_nstride / 3) + opx, c, y);
-              if (S.resid != nullptr) {                    // pixel-interleaved second copy (tg_glue.cu: gather3)
+              if (S.out && !(dbg & 128)) store_network_output(S.out, c_mode, o, static_cast<size_t>(n) * (S.out_nstride / 3) + opx, c, y);
+              if (S.resid != nullptr && !(dbg & 384)) {    // pixel-interleaved second copy (tg_glue.cu: gather3)
                 float* px = static_cast<float*>(const_cast<void*>(S.resid)) + ((static_cast<size_t>(n) * S.oh + wy) * S.ow + wx) * 4;
                 // the blue warp also writes the unused fourth component: every byte of the copy is written, so no
                 // sector is ever partially dirty (a partial sector costs a read-modify-write in ECC DRAM)
@@ -731,8 +751,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     }
     tall.stop(a_total);
     if (stats && warp == 2 && lane == 0) {
-      unsigned long long* o = stats + blockIdx.x * 16;
-      o[4] = a_cfull; o[5] = a_body; o[6] = a_pub; o[7] = a_total; o[8] = a_tmem;
+      unsigned long long* o = stats + blockIdx.x * 32;
+      o[4] = a_cfull; o[5] = a_body; o[6] = a_pub; o[7] = a_total; o[8] = a_tmem; o[17] = a_hb;
     }
   } else if (warp < 2 + kEpiWarps) {
     // ================================ epilogue (16 warps) ==================================
@@ -918,7 +938,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     }
     tall.stop(a_total);
     if (stats && warp == 2 && lane == 0) {
-      unsigned long long* o = stats + blockIdx.x * 16;
+      unsigned long long* o = stats + blockIdx.x * 32;
       o[4] = a_cfull; o[5] = a_body; o[6] = a_pub; o[7] = a_total; o[8] = a_tmem;
     }
   } else if (warp < 2 + kEpiWarps + kPubWarps) {
@@ -956,7 +976,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         }
       }
       if (stats && pw == 0) {
-        unsigned long long* o = stats + blockIdx.x * 16;
+        unsigned long long* o = stats + blockIdx.x * 32;
         o[13] = a_pfull; o[14] = a_red;
       }
     }
@@ -1254,7 +1274,7 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
   const int grid = items < max_ctas ? items : max_ctas;           // pair mode: items and max_ctas are even
   P.trace = (g_trace && g_trace_words >= static_cast<size_t>(nseg + 1) * grid) ? g_trace : nullptr;
   // optional stall accounting behind the trace: 16 words per CTA (see Tick)
-  P.stats = (P.trace && g_trace_words >= static_cast<size_t>(nseg + 1 + 16) * grid) ? g_trace + static_cast<size_t>(nseg + 1) * grid : nullptr;
+  P.stats = (P.trace && g_trace_words >= static_cast<size_t>(nseg + 1 + 32) * grid) ? g_trace + static_cast<size_t>(nseg + 1) * grid : nullptr;
 
   TG_CHECK_ARG(static_cast<size_t>(items) <= flag_capacity, "frame: %d items exceed the flag capacity %zu", items, flag_capacity);
   if (!flags_zeroed) TG_CUDA(cudaMemsetAsync(flags, 0, static_cast<size_t>(items) * sizeof(uint32_t), stream));

@@ -89,7 +89,9 @@ struct FrProgram {
   unsigned long long* trace;  // optional [nseg+1][grid] globaltimer stamps (tg_frame_set_trace), else null
   unsigned long long* stats;  // optional [grid][16] cycles per wait of every role (behind the trace buffer), else null
   int dbg;                    // measurement-only knobs (TG_FRAME_DBG): 1 no dependency wait, 2 no publish, 4 no acquire fence,
-                              //   8 issuer ignores accumulator-drained, 16 no bf16 epilogue stores, 32 cta-scope waits in the pair issuer
+                              //   8 issuer ignores accumulator-drained, 16 no bf16 epilogue stores, 32 cta-scope waits in the pair issuer,
+                              //   64 no proxy fence before the A loads, 128 no network-output stores, 256 no interleaved copy,
+                              //   512 / 1024: no MMAs / no A loads in segment stat_seg
   int pair;                   // 1: launched as CTA pairs (cta_group::2)
   int stat_seg;               // stall accounting restricted to this segment (TG_FRAME_STAT_SEG, -1 = all)
 };

@@ -100,6 +100,10 @@ SIGNATURES = {
     "tg_bn_apply": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int, _c_void_p, _c_int, _c_void_p]),
     "tg_bn_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                            _c_size_t, _c_void_p]),
+    "tg_grad_check_finite": (_c_int, [_c_void_p, _c_ll, _c_void_p, _c_void_p]),
+    "tg_adam_step": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_void_p, _c_float, _c_float, _c_float, _c_void_p,
+                              _c_void_p, _c_void_p, _c_void_p]),
+    "tg_scaler_update": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_float, _c_float, _c_int, _c_void_p, _c_void_p]),
     "tg_workspace_bytes_gen_forward": (_c_size_t, [_c_int, _c_int, _c_int]),
     "tg_workspace_bytes_gen_train": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),
     "tg_workspace_bytes_disc": (_c_size_t, [_c_int, _c_int, _c_int, _c_int, _c_int]),

@@ -145,6 +145,28 @@ class generator(nn.Module):
         self.invalidate_packed()
         return r
 
+    def _flat_source(self, params):
+        """the flat f32 parameter vector the pack kernels read: the bound flat buffer (tecogan_b200.optim.bind_flat_params:
+        the parameters ARE views of it, no copy) or a gathered copy."""
+        flat = getattr(self, "_flat_params", None)
+        if flat is not None and flat.data_ptr() == params[0].data_ptr() and flat.device == params[0].device:
+            return flat
+        return torch.cat([p.detach().reshape(-1).float() for p in params])
+
+    def repack_from_flat(self):
+        """Re-derive the packed bf16 weights after tecogan_b200.optim.FlatAdam updated the flat parameter buffer in place
+        (raw-pointer writes bump no tensor version: the caches keep their keys, their CONTENT is refreshed here).  Two
+        batched launches, graph-capturable, no gather copy."""
+        lib = _nt.lib()
+        params = self._param_list()
+        flat = self._flat_source(params)
+        nres = int(self.num)
+        st = _nt.stream_ptr(flat.device)
+        if self._packed is not None and self._packed_key is not None:
+            _nt.check(lib.tg_gen_pack(_nt.ptr(flat), nres, _nt.ptr(self._packed), st))
+        if getattr(self, "_packed_dgrad", None) is not None and getattr(self, "_packed_dgrad_key", None) is not None:
+            _nt.check(lib.tg_gen_pack_dgrad(_nt.ptr(flat), nres, _nt.ptr(self._packed_dgrad), st))
+
     def packed_weights(self):
         """bf16 MMA-ordered weight blocks + f32 biases; a derived cache, rebuilt whenever a
         parameter changed (optimizer step, load_state_dict) — tracked by tensor versions."""
@@ -156,7 +178,7 @@ class generator(nn.Module):
             if dev.type != "cuda":
                 raise RuntimeError("generator parameters must live on a CUDA device (call .cuda()); no CPU fallback")
             nres = int(self.num)
-            flat = torch.cat([p.detach().reshape(-1).float() for p in params])
+            flat = self._flat_source(params)
             assert flat.numel() == lib.tg_gen_param_count(nres), "parameter layout mismatch"
             if self._packed is None or self._packed.device != dev:
                 self._packed = torch.empty(lib.tg_gen_packed_bytes(nres), dtype=torch.uint8, device=dev)
@@ -171,8 +193,10 @@ class generator(nn.Module):
         if getattr(self, "_packed_dgrad", None) is None or key != getattr(self, "_packed_dgrad_key", None):
             lib = _nt.lib()
             nres = int(self.num)
-            flat = torch.cat([p.detach().reshape(-1).float() for p in params])
-            buf = torch.empty(lib.tg_gen_packed_dgrad_bytes(nres), dtype=torch.uint8, device=flat.device)
+            flat = self._flat_source(params)
+            buf = getattr(self, "_packed_dgrad", None)
+            if buf is None or buf.device != flat.device:
+                buf = torch.empty(lib.tg_gen_packed_dgrad_bytes(nres), dtype=torch.uint8, device=flat.device)
             _nt.check(lib.tg_gen_pack_dgrad(_nt.ptr(flat), nres, _nt.ptr(buf), _nt.stream_ptr()))
             self._packed_dgrad, self._packed_dgrad_key = buf, key
         return self._packed_dgrad
@@ -295,19 +319,37 @@ class discriminator(nn.Module):
             dev = params[0].device
             if dev.type != "cuda":
                 raise RuntimeError("discriminator parameters must live on a CUDA device (call .cuda()); no CPU fallback")
-            flat = torch.cat([p.detach().reshape(-1).float() for p in params])
+            bound = getattr(self, "_flat_params", None)
+            if bound is not None and bound.data_ptr() == params[0].data_ptr() and bound.device == dev:
+                flat = bound                        # the parameters ARE views of the flat buffer (tecogan_b200.optim)
+            else:
+                flat = torch.cat([p.detach().reshape(-1).float() for p in params])
             assert flat.numel() == lib.tg_disc_param_count(self.nb, self.ch, self.fc.in_features), "parameter layout mismatch"
-            packed = torch.empty(lib.tg_disc_packed_bytes(self.nb, self.ch), dtype=torch.uint8, device=dev)
+            packed = self._packed
+            if packed is None or packed.device != dev:
+                packed = torch.empty(lib.tg_disc_packed_bytes(self.nb, self.ch), dtype=torch.uint8, device=dev)
             _nt.check(lib.tg_disc_pack(_nt.ptr(flat), self.nb, self.ch, _nt.ptr(packed), _nt.stream_ptr()))
             self._flat, self._packed, self._key = flat, packed, key
         return self._flat, self._packed
+
+    def repack_from_flat(self):
+        """see generator.repack_from_flat: refresh the packed conv blocks after the flat parameters were updated in place."""
+        lib = _nt.lib()
+        if self._packed is None or self._key is None or self._flat is None:
+            return
+        st = _nt.stream_ptr(self._flat.device)
+        _nt.check(lib.tg_disc_pack(_nt.ptr(self._flat), self.nb, self.ch, _nt.ptr(self._packed), st))
+        if getattr(self, "_packed_dgrad", None) is not None and getattr(self, "_packed_dgrad_key", None) is not None:
+            _nt.check(lib.tg_disc_pack_dgrad(_nt.ptr(self._flat), self.nb, self.ch, _nt.ptr(self._packed_dgrad), st))
 
     def _dgrad_weights(self):
         """packed weights of the data-gradient convolutions (training only); rebuilt with the forward cache."""
         flat, _ = self._weights()
         if getattr(self, "_packed_dgrad_key", None) is None or self._packed_dgrad_key != self._key:
             lib = _nt.lib()
-            buf = torch.empty(lib.tg_disc_packed_dgrad_bytes(self.nb, self.ch), dtype=torch.uint8, device=flat.device)
+            buf = getattr(self, "_packed_dgrad", None)
+            if buf is None or buf.device != flat.device:
+                buf = torch.empty(lib.tg_disc_packed_dgrad_bytes(self.nb, self.ch), dtype=torch.uint8, device=flat.device)
             _nt.check(lib.tg_disc_pack_dgrad(_nt.ptr(flat), self.nb, self.ch, _nt.ptr(buf), _nt.stream_ptr()))
             self._packed_dgrad, self._packed_dgrad_key = buf, self._key
         return self._packed_dgrad

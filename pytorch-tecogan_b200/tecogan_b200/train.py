@@ -21,9 +21,21 @@ import collections
 
 import torch
 
+import os
+import warnings
+
 from . import _native as _nt
+from . import optim as _optim
 from . import parallel as _par
 from .models import *  # noqa: F401,F403  (reference: `from models import *`, code/train.py:1)
+
+# Fused flat-bucket Adam (tecogan_b200.optim) for the stock torch.optim.Adam objects main.py:239-243 builds, and CUDA-graph
+# capture of the whole step after GRAPH_WARMUP eager calls (single process; the gradient all-reduce of the data-parallel
+# path stays eager).  Both are on by default and fall back to the eager / stock-optimizer path when they do not apply;
+# TG_TRAIN_FUSED_ADAM=0 / TG_TRAIN_GRAPH=0 switch them off (A/B measurements).
+FUSED_ADAM = os.environ.get("TG_TRAIN_FUSED_ADAM", "1") != "0"
+USE_CUDA_GRAPH = os.environ.get("TG_TRAIN_GRAPH", "1") != "0"
+GRAPH_WARMUP = 2
 
 VGG_MEAN = [123.68, 116.78, 103.94]          # code/train.py:6
 identity = torch.nn.Identity()               # code/train.py:7
@@ -125,9 +137,15 @@ def _warp_loss(r_inputs):
     return torch.mean(torch.sum(torch.square(cur.reshape(b * (t - 1), 3, c, c) - s_warp), dim=[3]))
 
 
+def _dt_ratio_host(args, global_step):
+    """code/train.py:291-292 on the host (all inputs are host scalars)."""
+    return min(float(args.Dt_ratio_max), float(args.Dt_ratio_0) + float(args.Dt_ratio_add) * float(global_step))
+
+
 def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step, counter1, counter2, optimizer_g,
-            optimizer_d, GAN_FLAG=True):
-    """code/train.py:49-370."""
+            optimizer_d, GAN_FLAG=True, _dt_ratio_dev=None):
+    """code/train.py:49-370.  `_dt_ratio_dev` (internal): a device scalar holding Dt_ratio for this step, so that a captured
+    CUDA graph of this function follows Dt_ratio_add across replays."""
     if not GAN_FLAG:
         # code/train.py:293 reads t_adversarial_loss, which only the GAN_FLAG branch (:287-291) defines
         raise UnboundLocalError("TecoGAN: GAN_FLAG=False leaves t_adversarial_loss unbound (code/train.py:293 raises in "
@@ -184,8 +202,8 @@ def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step
     # terms are detached: the generator's gradient is the content loss's alone.
     t_adversarial_loss = torch.mean(-torch.log(tdiscrim_fake_output.detach() + args.EPS))
     d_adversarial_loss = torch.mean(-torch.log(tdiscrim_fake_output + args.EPS))
-    dt_ratio = torch.minimum(torch.tensor(float(args.Dt_ratio_max)),
-                             args.Dt_ratio_0 + args.Dt_ratio_add * torch.tensor(Global_step, dtype=torch.float32))
+    dt_ratio = torch.tensor(_dt_ratio_host(args, Global_step), dtype=torch.float32)          # :291-292 (a CPU tensor there too)
+    dt_mul = _dt_ratio_dev if _dt_ratio_dev is not None else float(dt_ratio)
     gen_loss = content_loss
     fnet_loss = content_loss
     if pploss is not None and args.pp_scaling > 0:         # :281-283, NOT detached: the generator also descends the ping-pong term
@@ -196,7 +214,7 @@ def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step
     update_list.append(t_adversarial_loss)
     update_list_name.append("t_adversarial_loss")
     if args.D_LAYERLOSS:
-        gen_loss += sum_layer_loss * float(dt_ratio)
+        gen_loss += sum_layer_loss * dt_mul
 
     # ---- discriminator loss (:303-322)
     t_discrim_fake_loss = torch.log(1 - tdiscrim_fake_output + args.EPS)
@@ -216,7 +234,7 @@ def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step
     k = vals.numel()
     idx = torch.arange(k, device=vals.device)
     expo = (idx[:, None] - idx[None, :]).clamp(min=0).float()
-    tri = torch.where(idx[:, None] >= idx[None, :], 0.99 * torch.pow(torch.tensor(0.01, device=vals.device), expo),
+    tri = torch.where(idx[:, None] >= idx[None, :], 0.99 * torch.pow(torch.full((), 0.01, device=vals.device), expo),
                       torch.zeros((), device=vals.device))
     update_list_avg = list(tri @ vals)
 
@@ -228,6 +246,8 @@ def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step
     # optimizer the whole step enqueues without the host ever waiting for the GPU.
     sc = _scaler()
     sync_g, sync_d = _par.GradSync(), _par.GradSync()
+    fa_g = _optim.FlatAdam.adopt(generator_F, optimizer_g) if FUSED_ADAM else None
+    fa_d = _optim.FlatAdam.adopt(discriminator_F, optimizer_d) if FUSED_ADAM else None
     optimizer_g.zero_grad()
     g_bucket = _par.zero_flat_grads(generator_F)
     one = torch.ones((), dtype=torch.float32, device=g_bucket.device)
@@ -239,13 +259,27 @@ def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step
     sc.scale(discrim_loss).backward()
     sync_d.start(d_bucket)
     sync_g.finish()
-    sc.step(optimizer_g)
-    sc.update()
-    sync_d.finish()
-    if scale0 is not None:
-        d_bucket.mul_(sc.scale(one) / scale0)              # exactly 1.0 unless update() just changed the scale
-    sc.step(optimizer_d)
-    sc.update()
+    if fa_g is not None and fa_d is not None:
+        # tecogan_b200.optim: inf/NaN check, Adam, GradScaler.update() and the bf16 re-pack as repo kernels on the flat
+        # buckets; lr / step / loss scale / found_inf are device scalars (nothing here reads the GPU back).  Both gradients
+        # were scaled by the loss scale BEFORE the first update(), so both are unscaled by 1 / that scale.
+        if not torch.cuda.is_current_stream_capturing():
+            fa_g.refresh_lr()
+            fa_d.refresh_lr()
+        inv0 = torch.reciprocal(scale0) if scale0 is not None else None
+        skw = dict(scale=sc._scale, growth_tracker=sc._growth_tracker, growth=sc.get_growth_factor(), backoff=sc.get_backoff_factor(),
+                   interval=sc.get_growth_interval()) if scale0 is not None else {}
+        fa_g.step_kernels(g_bucket, inv0, **skw)
+        sync_d.finish()
+        fa_d.step_kernels(d_bucket, inv0, **skw)
+    else:
+        sc.step(optimizer_g)
+        sc.update()
+        sync_d.finish()
+        if scale0 is not None:
+            d_bucket.mul_(sc.scale(one) / scale0)              # exactly 1.0 unless update() just changed the scale
+        sc.step(optimizer_d)
+        sc.update()
 
     update_list_avg += [tb, dt_ratio]
     update_list_name += ["t_balance", "Dst_ratio"]
@@ -257,8 +291,73 @@ def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step
                    d_loss=discrim_loss, gen_loss=gen_loss, fnet_loss=fnet_loss, tb=tb, target=real_in)
 
 
+class _GraphedStep:
+    """One captured CUDA graph of TecoGAN() for a fixed (networks, optimizers, batch shape, flags): the ~500 kernel
+    launches of a step (cfg4) become one graph launch.  Inputs are copied into static buffers, Dt_ratio and the two
+    learning rates are device scalars refreshed before every replay, everything else (weights, Adam moments, loss scale,
+    BatchNorm running statistics, step counters) lives in device memory the graph updates in place.  The returned
+    tensors are the graph's static outputs: valid until the next call (main.py consumes them immediately, :276-294)."""
+
+    def __init__(self, r_inputs, r_targets):
+        self.static_in = torch.empty_like(r_inputs)
+        self.static_tg = torch.empty_like(r_targets)
+        self.dt = torch.zeros((), dtype=torch.float32, device=r_inputs.device)
+        self.graph = None
+        self.out = None
+        self.calls = 0
+        self.failed = False
+
+    def run(self, r_inputs, r_targets, args, D, G, step, c1, c2, og, od):
+        self.static_in.copy_(r_inputs)
+        self.static_tg.copy_(r_targets)
+        self.dt.fill_(_dt_ratio_host(args, step + 1))
+        for net, opt in ((G, og), (D, od)):
+            _optim.FlatAdam.adopt(net, opt).refresh_lr()
+        if self.graph is None:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self.out = TecoGAN(self.static_in, self.static_tg, D, G, args, step, c1, c2, og, od, _dt_ratio_dev=self.dt)
+            self.graph = g
+        self.graph.replay()
+        out = self.out
+        n = len(out.update_list)
+        avg = list(out.update_list_avg[:n]) + [out.tb, torch.tensor(_dt_ratio_host(args, step + 1), dtype=torch.float32), c1, c2]
+        return out._replace(global_step=step + 1, update_list_avg=avg, learning_rate=args.learning_rate)
+
+
+_graphs = {}
+
+
+def _graph_key(r_inputs, r_targets, args, D, G, og, od):
+    flags = tuple((k, getattr(args, k, None)) for k in ("pingpang", "crop_dt", "Dt_mergeDs", "D_LAYERLOSS", "vgg_scaling", "pp_scaling",
+                                                         "ratio", "EPS", "RNN_N", "crop_size", "Dt_ratio_max", "Dt_ratio_0", "Dt_ratio_add"))
+    return (id(G), id(D), id(og), id(od), tuple(r_inputs.shape), tuple(r_targets.shape), r_inputs.device, flags)
+
+
 def FRVSR_Train(r_inputs, r_targets, args, discriminator_F, generator_F, step, counter1, counter2, optimizer_g,
                 optimizer_d):
-    """code/train.py:374-377"""
+    """code/train.py:374-377.  After GRAPH_WARMUP eager calls with the same networks / optimizers / shapes the step is
+    captured in a CUDA graph and replayed (single process, fused Adam adoptable, TG_TRAIN_GRAPH != 0)."""
+    if (USE_CUDA_GRAPH and FUSED_ADAM and _par.world_size() == 1 and isinstance(r_inputs, torch.Tensor) and r_inputs.is_cuda
+            and _optim.FlatAdam.adoptable(generator_F, optimizer_g) and _optim.FlatAdam.adoptable(discriminator_F, optimizer_d)):
+        key = _graph_key(r_inputs, r_targets, args, discriminator_F, generator_F, optimizer_g, optimizer_d)
+        gs = _graphs.get(key)
+        if gs is None:
+            if len(_graphs) > 8:
+                _graphs.clear()
+            gs = _graphs[key] = _GraphedStep(_nt.require_cuda_f32(r_inputs, "FRVSR_Train(r_inputs)"),
+                                             _nt.require_cuda_f32(r_targets, "FRVSR_Train(r_targets)"))
+        gs.calls += 1
+        if gs.calls > GRAPH_WARMUP and not gs.failed:
+            try:
+                return gs.run(r_inputs, r_targets, args, discriminator_F, generator_F, step, counter1, counter2, optimizer_g,
+                              optimizer_d)
+            except Exception as e:                      # capture is an optimisation: never lose the step over it
+                if gs.graph is not None:
+                    raise                               # a captured graph that fails on replay is a real error
+                gs.failed = True
+                warnings.warn(f"tecogan_b200.train: CUDA-graph capture of the training step failed ({e!r}); running eagerly")
+                torch.cuda.synchronize()
     return TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, step, counter1, counter2, optimizer_g,
                    optimizer_d)

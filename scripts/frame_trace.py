@@ -22,7 +22,7 @@ x0 = torch.rand(N, H, W, 64, device="cuda").to(torch.bfloat16)
 out = torch.empty(N, 3, 4 * H, 4 * W, device="cuda")
 G = 148
 NSEG = 44
-trace = torch.zeros((NSEG + 1 + 16) * G, dtype=torch.int64, device="cuda")
+trace = torch.zeros((NSEG + 1 + 32) * G, dtype=torch.int64, device="cuda")
 
 
 def run():
@@ -36,7 +36,7 @@ nt.check(lib.tg_frame_set_trace(nt.ptr(trace), trace.numel() * 8))
 run()
 torch.cuda.synchronize()
 nt.check(lib.tg_frame_set_trace(None, 0))
-stats = trace[(NSEG + 1) * G:].view(G, 16).cpu().double()
+stats = trace[(NSEG + 1) * G:].view(G, 32).cpu().double()
 t = trace[:(NSEG + 1) * G].view(NSEG + 1, G).cpu().double()
 t0 = t[t > 0].min()
 names = ["conv.0"] + [f"res{i // 2}.{'0' if i % 2 == 0 else '2'}" for i in range(32)] + ["convT64", "ct2.0 64@2x", "ct2.2 64@2x",
@@ -70,7 +70,8 @@ for s in range(NSEG + 1):
 lab = ["mma: wait acc drained", "mma: wait weights", "mma: wait A stage", "mma: loop total",
        "epi(w2): wait acc ready", "epi(w2): math+store (+ld if not wide bf16)", "epi(w2): publish handoff", "epi(w2): loop total", "epi(w2): tmem ld (wide bf16)",
        "prod: wait weight slot", "prod: wait dependencies", "prod: wait A stage free", "prod: loop total",
-       "pub: wait tile stored", "pub: release + arrive", "-"]
+       "pub: wait tile stored", "pub: release + arrive", "-", "-", "epi(w2): accumulator hand-back", "-", "-",
+       "mma: issue block (MMAs + commits)", "-", "prod: issue block (fence + expect_tx + TMA)"]
 for k, name in enumerate(lab):
     col = stats[:, k]
     col = col[col > 0]
