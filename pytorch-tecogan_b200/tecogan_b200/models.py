@@ -16,6 +16,21 @@ from .ops import *  # noqa: F401,F403  (reference star-import chain: code/models
 from .ops import conv2, conv2_tran, lrelu, batchnorm, denselayer
 
 
+def _grad_inputs(module, params):
+    """Autograd inputs that make a B200 forward node differentiable w.r.t. the module's parameters.
+
+    Plain use: the parameters themselves; the backward returns one gradient per parameter.
+    Flat-bucket use (tecogan_b200.parallel.bind_flat_grads: every p.grad IS a view of the module's flat gradient bucket, the
+    state tecogan_b200.train.TecoGAN sets up before its forward passes): ONE fresh scalar leaf.  The backward kernels add the
+    parameter gradients straight into the bucket and return nothing, so autograd never touches the parameters' cached
+    AccumulateGrad nodes - those remember the stream they were created on, and a node left over from an eager step on the
+    default stream would make the engine synchronise the default stream with a capturing stream and invalidate a CUDA-graph
+    capture of the step."""
+    if _par.bucket_bound(module, params):
+        return True, (torch.zeros((), dtype=torch.float32, device=params[0].device, requires_grad=True),)
+    return False, tuple(params)
+
+
 def residual_block(inputs, output_channel=64, stride=1):
     """code/models.py:54-58"""
     return nn.Sequential(conv2(inputs, 3, output_channel, stride, use_bias=True), nn.ReLU(),
@@ -28,7 +43,7 @@ class _GeneratorFn(torch.autograd.Function):
     (tg_gen_backward).  The input is detached in the reference (code/train.py:90,108): no input gradient."""
 
     @staticmethod
-    def forward(ctx, x, module, *params):
+    def forward(ctx, x, module, use_bucket, *params):
         lib = _nt.lib()
         x = x.detach().float().contiguous()
         n, _, h, w = x.shape
@@ -38,7 +53,7 @@ class _GeneratorFn(torch.autograd.Function):
         out = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=x.device)
         _nt.check(lib.tg_gen_forward_train(_nt.ptr(packed), nres, _nt.ptr(x), _nt.ptr(out), _nt.ptr(ws), ws.numel(), n, h, w,
                                            _nt.stream_ptr()))
-        ctx.module, ctx.ws, ctx.shape = module, ws, (n, h, w)
+        ctx.module, ctx.ws, ctx.shape, ctx.use_bucket = module, ws, (n, h, w), use_bucket
         ctx.packed_dgrad = module.packed_dgrad_weights()
         ctx.save_for_backward(out)
         ctx.mark_non_differentiable()
@@ -52,21 +67,24 @@ class _GeneratorFn(torch.autograd.Function):
         module = ctx.module
         nres = int(module.num)
         g = grad_out.float().contiguous()
-        return (None, None) + _gen_backward(module, ctx.packed_dgrad, g, out, ctx.ws, n, h, w)
+        return (None, None, None) + _gen_backward(module, ctx.packed_dgrad, g, out, ctx.ws, n, h, w, ctx.use_bucket)
 
 
-def _gen_backward(module, packed_dgrad, dout, out, ws, n, h, w):
-    """tg_gen_backward over n images; returns the per-parameter gradients, or Nones when the module has a flat gradient
-    bucket bound (tecogan_b200.parallel.bind_flat_grads: p.grad are views of the bucket, the kernels add in place)."""
+def _gen_backward(module, packed_dgrad, dout, out, ws, n, h, w, use_bucket):
+    """tg_gen_backward over n images; returns the per-parameter gradients, or a single None (for the anchor leaf of
+    _grad_inputs) when the forward ran in flat-bucket mode: p.grad are views of the bucket, the kernels add in place."""
     lib = _nt.lib()
     nres = int(module.num)
     params = module._param_list()
-    bucket = module._grad_bucket if _par.bucket_bound(module, params) else None
+    if use_bucket and not _par.bucket_bound(module, params):
+        raise RuntimeError("generator backward: the flat gradient bucket was unbound between forward and backward "
+                           "(p.grad re-assigned?); re-run the forward")
+    bucket = module._grad_bucket if use_bucket else None
     flat = bucket if bucket is not None else torch.zeros(lib.tg_gen_param_count(nres), dtype=torch.float32, device=out.device)
     _nt.check(lib.tg_gen_backward(_nt.ptr(packed_dgrad), nres, _nt.ptr(dout), _nt.ptr(out), _nt.ptr(flat), _nt.ptr(ws),
                                   ws.numel(), n, h, w, _nt.stream_ptr()))
     if bucket is not None:
-        return (None,) * len(params)
+        return (None,)
     grads, o = [], 0
     for p in params:
         grads.append(flat[o:o + p.numel()].view_as(p).to(p.dtype))
@@ -81,7 +99,7 @@ class _GeneratorClipFn(torch.autograd.Function):
     (code/train.py:90,108), so the frames are independent in the backward direction."""
 
     @staticmethod
-    def forward(ctx, lr, module, *params):
+    def forward(ctx, lr, module, use_bucket, *params):
         lib = _nt.lib()
         lr = _nt.require_cuda_f32(lr.detach(), "forward_clip_train(r_inputs)")
         b, t, c, h, w = lr.shape
@@ -91,7 +109,7 @@ class _GeneratorClipFn(torch.autograd.Function):
         out = torch.empty((t, b, 3, 4 * h, 4 * w), dtype=torch.float32, device=lr.device)
         _nt.check(lib.tg_gen_clip_forward_train(_nt.ptr(packed), nres, _nt.ptr(lr), _nt.ptr(out), _nt.ptr(ws), ws.numel(),
                                                 b, t, h, w, _nt.stream_ptr()))
-        ctx.module, ctx.ws, ctx.shape = module, ws, (b * t, h, w)
+        ctx.module, ctx.ws, ctx.shape, ctx.use_bucket = module, ws, (b * t, h, w), use_bucket
         ctx.packed_dgrad = module.packed_dgrad_weights()
         ctx.save_for_backward(out)
         return out
@@ -101,9 +119,9 @@ class _GeneratorClipFn(torch.autograd.Function):
         (out,) = ctx.saved_tensors
         n, h, w = ctx.shape
         g = grad_out.float().contiguous()
-        grads = _gen_backward(ctx.module, ctx.packed_dgrad, g, out, ctx.ws, n, h, w)
+        grads = _gen_backward(ctx.module, ctx.packed_dgrad, g, out, ctx.ws, n, h, w, ctx.use_bucket)
         ctx.ws = None
-        return (None, None) + grads
+        return (None, None, None) + grads
 
 
 class generator(nn.Module):
@@ -219,7 +237,8 @@ class generator(nn.Module):
                                           "code/train.py:90,108)")
             if return_logits:
                 raise RuntimeError("return_logits is an inference-only probe")
-            return _GeneratorFn.apply(x, self, *self._param_list())
+            use_bucket, leaves = _grad_inputs(self, self._param_list())
+            return _GeneratorFn.apply(x, self, use_bucket, *leaves)
         lib = _nt.lib()
         x = x.float().contiguous()
         n, _, h, w = x.shape
@@ -238,7 +257,8 @@ class generator(nn.Module):
         differentiable w.r.t. the parameters; ``.transpose(0, 1)`` gives the reference's [B,T,...] order)."""
         if r_inputs.dim() != 5 or r_inputs.shape[2] != 3:
             raise RuntimeError(f"forward_clip_train: expected [B,T,3,H,W], got {tuple(r_inputs.shape)}")
-        return _GeneratorClipFn.apply(r_inputs, self, *self._param_list())
+        use_bucket, leaves = _grad_inputs(self, self._param_list())
+        return _GeneratorClipFn.apply(r_inputs, self, use_bucket, *leaves)
 
     @torch.no_grad()
     def infer_clip(self, r_inputs):
@@ -386,7 +406,8 @@ class discriminator(nn.Module):
                                           "code/train.py:181,199)")
             if not self.training:
                 raise RuntimeError("discriminator: backward needs train-mode BatchNorm (the reference never leaves it)")
-            prob, *feats = _DiscriminatorFn.apply(x, self, *[p for _, p in self.named_parameters()])
+            use_bucket, leaves = _grad_inputs(self, [p for _, p in self.named_parameters()])
+            prob, *feats = _DiscriminatorFn.apply(x, self, use_bucket, *leaves)
             return prob, feats
         lib = _nt.lib()
         x = x.float().contiguous()
@@ -403,13 +424,13 @@ class _DiscriminatorFn(torch.autograd.Function):
     features are returned detached exactly as the reference consumes them (code/train.py:214)."""
 
     @staticmethod
-    def forward(ctx, x, module, *params):
+    def forward(ctx, x, module, use_bucket, *params):
         lib = _nt.lib()
         x = x.detach().float().contiguous()
         n, _, h, w = x.shape
         ws = torch.empty(lib.tg_disc_workspace_bytes(n, h, w, module.nb, module.ch), dtype=torch.uint8, device=x.device)
         prob, feats = module._run(x, ws)
-        ctx.module, ctx.ws, ctx.shape = module, ws, (n, h, w)
+        ctx.module, ctx.ws, ctx.shape, ctx.use_bucket = module, ws, (n, h, w), use_bucket
         ctx.flat, _ = module._weights()
         ctx.packed_dgrad = module._dgrad_weights()
         ctx.save_for_backward(prob)
@@ -423,7 +444,10 @@ class _DiscriminatorFn(torch.autograd.Function):
         n, h, w = ctx.shape
         module = ctx.module
         params = [p for _, p in module.named_parameters()]
-        bucket = module._grad_bucket if _par.bucket_bound(module, params) else None
+        if ctx.use_bucket and not _par.bucket_bound(module, params):
+            raise RuntimeError("discriminator backward: the flat gradient bucket was unbound between forward and backward "
+                               "(p.grad re-assigned?); re-run the forward")
+        bucket = module._grad_bucket if ctx.use_bucket else None
         flat_grad = bucket if bucket is not None else torch.zeros(ctx.flat.numel(), dtype=torch.float32, device=prob.device)
         g = dprob.float().contiguous()
         _nt.check(lib.tg_disc_backward(_nt.ptr(ctx.flat), _nt.ptr(ctx.packed_dgrad), module.nb, module.ch, module.fc.in_features,
@@ -431,12 +455,12 @@ class _DiscriminatorFn(torch.autograd.Function):
                                        _nt.stream_ptr()))
         ctx.ws = None
         if bucket is not None:          # gradients were accumulated in place into the bound flat bucket (p.grad are views)
-            return (None, None) + (None,) * len(params)
+            return (None, None, None, None)
         grads, o = [], 0
         for p in params:
             grads.append(flat_grad[o:o + p.numel()].view_as(p).to(p.dtype))
             o += p.numel()
-        return (None, None, *grads)
+        return (None, None, None, *grads)
 
 
 def f_net():

@@ -163,6 +163,11 @@ def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step
     hc = 4 * c
     learning_rate = args.learning_rate
 
+    # flat gradient buckets first: the forward nodes below then hand their parameter gradients to the bucket instead of
+    # autograd's per-parameter accumulators (tecogan_b200.models._grad_inputs)
+    _par.bind_flat_grads(generator_F)
+    _par.bind_flat_grads(discriminator_F)
+
     # ---- generator: all frames (:86-114)
     gen_tb = generator_F.forward_clip_train(r_inputs)                                      # [T,B,3,hc,hc]
     gen_outputs = gen_tb.transpose(0, 1)                                                   # [B,T,3,hc,hc] (view)
@@ -353,11 +358,13 @@ def FRVSR_Train(r_inputs, r_targets, args, discriminator_F, generator_F, step, c
             try:
                 return gs.run(r_inputs, r_targets, args, discriminator_F, generator_F, step, counter1, counter2, optimizer_g,
                               optimizer_d)
-            except Exception as e:                      # capture is an optimisation: never lose the step over it
+            except Exception as e:
                 if gs.graph is not None:
                     raise                               # a captured graph that fails on replay is a real error
+                # A capture that fails in capture_end leaves torch's capture bookkeeping (current stream, allocator pool, RNG
+                # state) half-open: continuing eagerly in this process is not safe.  Fail loudly with the way out.
                 gs.failed = True
-                warnings.warn(f"tecogan_b200.train: CUDA-graph capture of the training step failed ({e!r}); running eagerly")
-                torch.cuda.synchronize()
+                raise RuntimeError("tecogan_b200.train: CUDA-graph capture of the training step failed; set TG_TRAIN_GRAPH=0 "
+                                   "(or tecogan_b200.train.USE_CUDA_GRAPH = False) to run the step eagerly") from e
     return TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, step, counter1, counter2, optimizer_g,
                    optimizer_d)
