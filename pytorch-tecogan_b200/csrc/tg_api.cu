@@ -107,9 +107,9 @@ namespace tg {
 __device__ __forceinline__ void pack_weights_body(int kind, const float* __restrict__ w, const float* __restrict__ bias,
                                                   int cin, int cout, int cin_pad, int cout_pad, int nt,
                                                   __nv_bfloat16* __restrict__ dst, float* __restrict__ bias_dst) {
-  // conv taps in (ky,kx) raster order; transposed conv in (phase,tap) order, see launch_conv_tc
-  const int ct_ky[9] = {1, 1, 1, 2, 0, 2, 2, 0, 0};
-  const int ct_kx[9] = {1, 2, 0, 1, 1, 2, 0, 2, 0};
+  // conv taps in (ky,kx) raster order; transposed conv grouped by INPUT SHIFT, see tg_conv_tc.cuh (kCtKy / kCtKx)
+  const int ct_ky[9] = {1, 1, 2, 2, 1, 2, 0, 0, 0};     // == kCtKy / kCtKx (device-side copy)
+  const int ct_kx[9] = {1, 2, 2, 1, 0, 0, 2, 1, 0};
   const int kchunks = cin_pad / 64;
   const int ntap = (kind == kConv4x4s2 || kind == kPackConvT3x3s2Dgrad || kind == kPackConv4x4s2Dgrad) ? 16 : 9;
   const long long total = static_cast<long long>(ntap) * cin_pad * cout_pad;

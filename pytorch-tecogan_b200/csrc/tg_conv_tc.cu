@@ -463,11 +463,7 @@ int launch_conv_tc(int kind, int out_mode, const void* x, const void* packed_w, 
   // tap tables: (dy,dx) are offsets inside the staged box, in MMA issue order == packed block order
   static const int conv_dy[9] = {0, 0, 0, 1, 1, 1, 2, 2, 2};
   static const int conv_dx[9] = {0, 1, 2, 0, 1, 2, 0, 1, 2};
-  //                              phase:   00 | 01     | 10     | 11
-  static const int ct_dy[9] = {0, 0, 0, 0, 1, 0, 0, 1, 1};
-  static const int ct_dx[9] = {0, 0, 1, 0, 0, 0, 1, 0, 1};
-  static const int ct_acc[9] = {0, 1, 1, 2, 2, 3, 3, 3, 3};
-  static const int ct_first[9] = {1, 1, 0, 1, 0, 1, 0, 0, 0};
+  const int* ct_dy = kCtDy; const int* ct_dx = kCtDx; const int* ct_acc = kCtAcc; const int* ct_first = kCtFirst;
   for (int j = 0; j < p.ntaps; ++j) {
     int dy, dx;
     if (s2) { dy = j >> 1; dx = j & 1; }                    // kernel tap (2*dy + phase_y, 2*dx + phase_x)

@@ -22,6 +22,23 @@ enum TcPackKind { kPackConv3x3Dgrad = 3, kPackConvT3x3s2Dgrad = 4, kPackConv4x4s
 enum TcMask { kMaskNone = 0, kMaskRelu = 1, kMaskLrelu02 = 2 };   // backward of the activation that produced `mask`
 enum TcAct { kActNone = 0, kActRelu = 1, kActLrelu02 = 2 };   // LeakyReLU(0.2): code/ops.py:71-72
 
+// ConvTranspose2d(k3, s2, p1, op1) as four output phases (oy, ox) = (2y + py, 2x + px), accumulator a = 2*py + px.
+// The nine (phase, tap) products are ordered BY INPUT SHIFT (dy, dx) - the A view they read - so that the products of
+// one shift are consecutive weight blocks and can be issued as ONE N-stacked MMA into adjacent accumulators:
+//   j : 0    1    2    3  |  4    5  |  6    7  |  8
+//   k : k11  k12  k22  k21 | k10  k20 | k02  k01 | k00        (ky, kx of the ConvTranspose weight)
+//   a : 0    1    3    2  |  1    3  |  3    2  |  3          shift (0,0) | (0,1) | (1,0) | (1,1)
+// With the accumulators laid out [a0 | a1 | a3 | a2] the four shifts are MMAs of N = 256 / 128 / 128 / 64 onto column
+// offsets 0 / 64 / 128 / 128 (tg_frame.cu); the per-layer kernel issues the nine products one by one.  Per accumulator
+// the products are added in the same order in both kernels (bit-identical results).
+constexpr int kCtKy[9] = {1, 1, 2, 2, 1, 2, 0, 0, 0};
+constexpr int kCtKx[9] = {1, 2, 2, 1, 0, 0, 2, 1, 0};
+constexpr int kCtDy[9] = {0, 0, 0, 0, 0, 0, 1, 1, 1};
+constexpr int kCtDx[9] = {0, 0, 0, 0, 1, 1, 0, 0, 1};
+constexpr int kCtAcc[9] = {0, 1, 3, 2, 1, 3, 3, 2, 3};
+constexpr int kCtFirst[9] = {1, 1, 1, 1, 0, 0, 0, 0, 0};
+constexpr int kCtAccCol[4] = {0, 64, 192, 128};        // frame kernel: TMEM column of accumulator a ([a0 | a1 | a3 | a2])
+
 // One MMA group = one filter tap on one 64-channel K chunk: 4 x tcgen05.mma (K=16 each).
 struct TcTap {
   uint32_t a_off;   // byte offset of the (shifted) A view inside a stage

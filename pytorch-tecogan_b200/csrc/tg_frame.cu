@@ -70,15 +70,12 @@ static_assert(FrCfg<true>::kSmemBytes <= kFrSmemLimit && FrCfg<false>::kSmemByte
 constexpr int kGroupCols = 256;                       // TMEM columns per accumulator group (2 groups)
 constexpr uint32_t kItemDone = 128;                   // counter value of a published tile
 
-// tap tables: [kind][j] ; A view offset inside the staged box, accumulator, "first tap of accumulator"
-// [2]: 3x3 conv on the WIDE box, one view per tap (row pitch 32 pixels = 4096 B)
+// tap tables for the per-tap paths: [2]: 3x3 conv on the WIDE box, one view per tap (TG_FRAME_TAP=1; row pitch 32 pixels
+// = 4096 B); [0]: 3x3 conv on the tall box (TG_FRAME_WIDE=0).  The transposed conv is issued as four N-stacked shift groups.
 __constant__ uint32_t c_aoff[3][9] = {
     {0 * 128, 1 * 128, 2 * 128, 10 * 128, 11 * 128, 12 * 128, 20 * 128, 21 * 128, 22 * 128},
-    //  phase:   00 | 01        | 10         | 11
-    {0 * 128, 0 * 128, 1 * 128, 0 * 128, 10 * 128, 0 * 128, 1 * 128, 10 * 128, 11 * 128},
+    {0, 0, 0, 0, 0, 0, 0, 0, 0},
     {0 * 128, 1 * 128, 2 * 128, 32 * 128, 33 * 128, 34 * 128, 64 * 128, 65 * 128, 66 * 128}};
-__constant__ uint8_t c_acc[3][9] = {{0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 1, 1, 2, 2, 3, 3, 3, 3}, {0, 0, 0, 0, 0, 0, 0, 0, 0}};
-__constant__ uint8_t c_first[3][9] = {{1, 0, 0, 0, 0, 0, 0, 0, 0}, {1, 1, 0, 1, 0, 1, 0, 0, 0}, {1, 0, 0, 0, 0, 0, 0, 0, 0}};
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   uint32_t v;
@@ -364,12 +361,19 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
             if (elect_one()) {
               if (kPair) {
                 // this CTA's half of every N group: rows [rank * half, (rank + 1) * half) of the group's 2 * half rows
-                const uint32_t half = S.w_half_rows, box = S.w_box_rows;
-                mbar_expect_tx_cluster(lbar_wfull + 8 * slot, static_cast<uint32_t>(S.w_groups) * half * 128u);
-                for (uint32_t gi = 0; gi < static_cast<uint32_t>(S.w_groups); ++gi)
+                const uint32_t box = S.w_box_rows;
+                uint32_t dst_row = 0, src_row = 0;
+                for (int gi = 0; gi < S.w_groups; ++gi) dst_row += static_cast<uint32_t>(S.w_grp_half[gi]);
+                mbar_expect_tx_cluster(lbar_wfull + 8 * slot, dst_row * 128u);
+                dst_row = 0;
+                for (int gi = 0; gi < S.w_groups; ++gi) {
+                  const uint32_t half = static_cast<uint32_t>(S.w_grp_half[gi]);
                   for (uint32_t r0 = 0; r0 < half; r0 += box)
-                    tma_load_2d_pair(s_w + slot * kWSlotBytes + (gi * half + r0) * 128, &P.maps[S.w_map], lbar_wfull + 8 * slot, 0,
-                                     static_cast<int>(S.w_row0[kc] + gi * 2 * half + rank * half + r0));
+                    tma_load_2d_pair(s_w + slot * kWSlotBytes + (dst_row + r0) * 128, &P.maps[S.w_map], lbar_wfull + 8 * slot, 0,
+                                     static_cast<int>(S.w_row0[kc] + src_row + rank * half + r0));
+                  dst_row += half;
+                  src_row += 2 * half;
+                }
               } else {
                 mbar_expect_tx(bar_wfull + 8 * slot, S.w_rows * 128);
                 for (uint32_t r0 = 0; r0 < S.w_rows; r0 += kWBoxRows)
@@ -508,17 +512,37 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
                 else umma_bf16(d_base, ad + 2 * k, bd + 2 * k, idesc, (kc > 0 || j > 0 || k > 0) ? 1u : 0u);
               }
             }
-          } else {
-#pragma unroll 1
-            for (int j = 0; j < 9; ++j) {
-              const uint64_t ad = umma_desc_sw128(a_base + c_aoff[tbl][j], sbo);
-              const uint64_t bd = umma_desc_sw128(w_base + j * wtap_bytes, 1024);
-              const uint32_t d = d_base + c_acc[tbl][j] * kAccCols;
-              const uint32_t keep = (kc > 0 || !c_first[tbl][j]) ? 1u : 0u;
+          } else if (tbl == kConvT3x3s2) {
+            // Transposed conv: the nine (phase, tap) products grouped by input shift (tg_conv_tc.cuh: kCt*): four A views
+            // (shift (0,0), (0,1), (1,0), (1,1) inside the tall box) times the weight blocks of that shift stacked along N,
+            // N = 256 / 128 / 128 / 64, onto accumulator columns 0 / 64 / 128 / 128 ([a0 | a1 | a3 | a2]).  16 MMAs per K
+            // chunk instead of 36; per accumulator the products arrive in the per-layer kernel's order.
+            constexpr int M = kPair ? 256 : 128;
+            constexpr uint32_t kIdesc[4] = {umma_idesc_bf16(M, 256), umma_idesc_bf16(M, 128), umma_idesc_bf16(M, 128), umma_idesc_bf16(M, 64)};
+            constexpr uint32_t kAOff[4] = {0u, 1u * 128u, 10u * 128u, 11u * 128u};
+            constexpr uint32_t kDCol[4] = {0u, 64u, 128u, 128u};
+            constexpr uint32_t kBRow[4] = {0u, 256u, 384u, 512u};             // first weight row of the group (whole block)
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) {
+              const uint64_t ad = umma_desc_sw128(a_base + kAOff[gi], sbo);
+              const uint64_t bd = umma_desc_sw128(w_base + kBRow[gi] * (kPair ? 64u : 128u), 1024);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                if (kPair) umma_bf16_pair(d, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
-                else umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
+                const uint32_t acc = (gi > 0 || kc > 0 || k > 0) ? 1u : 0u;
+                if (kPair) umma_bf16_pair(d_base + kDCol[gi], ad + 2 * k, bd + 2 * k, kIdesc[gi], acc);
+                else umma_bf16(d_base + kDCol[gi], ad + 2 * k, bd + 2 * k, kIdesc[gi], acc);
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int j = 0; j < 9; ++j) {                        // 3x3 conv on the tall box (TG_FRAME_WIDE=0), one MMA group per tap
+              const uint64_t ad = umma_desc_sw128(a_base + c_aoff[tbl][j], sbo);
+              const uint64_t bd = umma_desc_sw128(w_base + j * wtap_bytes, 1024);
+              const uint32_t keep = (kc > 0 || j > 0) ? 1u : 0u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (kPair) umma_bf16_pair(d_base, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
+                else umma_bf16(d_base, ad + 2 * k, bd + 2 * k, idesc, (k > 0) ? 1u : keep);
               }
             }
           }
@@ -700,7 +724,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         const int n_acc = (c_kind == kConv3x3) ? 1 : 4;
         const int sc = (c_kind == kConv3x3) ? 1 : 2;
         for (int a = 0; a < n_acc; ++a) {
-          const uint32_t taddr = tq + static_cast<uint32_t>(a * kAccCols);
+          // accumulator a of a transposed conv sits at column kCtAccCol[a] = {0, 64, 192, 128} ([a0 | a1 | a3 | a2])
+          const uint32_t taddr = tq + static_cast<uint32_t>(n_acc == 1 ? 0 : (a == 0 ? 0 : (a == 1 ? 64 : (a == 2 ? 192 : 128))));
           const int oy = iy * sc + (a >> 1), ox = ix * sc + (a & 1);
           if (c_mode == kOutNHWCbf16) {
             const size_t off = static_cast<size_t>(n) * c_img_bytes + (static_cast<uint32_t>(oy) * c_row_bytes + static_cast<uint32_t>(ox) * c_px_bytes);
@@ -893,7 +918,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         const int n_acc = (c_kind == kConv3x3) ? 1 : 4;
         const int sc = (c_kind == kConv3x3) ? 1 : 2;
         for (int a = 0; a < n_acc; ++a) {
-          const uint32_t taddr = tq + static_cast<uint32_t>(a * kAccCols);
+          // accumulator a of a transposed conv sits at column kCtAccCol[a] = {0, 64, 192, 128} ([a0 | a1 | a3 | a2])
+          const uint32_t taddr = tq + static_cast<uint32_t>(n_acc == 1 ? 0 : (a == 0 ? 0 : (a == 1 ? 64 : (a == 2 ? 192 : 128))));
           const int oy = iy * sc + (a >> 1), ox = ix * sc + (a & 1);
           uint32_t v[16];
           tmem_ld_32x16(taddr + (c_mode == kOutNHWCbf16 ? part * 16 : 0), v);
@@ -1215,12 +1241,24 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
       S.map_a = 1 + li;
       S.kchunks = kchunks; S.kind = l.kind; S.nt = nt;
       S.w_rows = 9u * nt;
-      if (S.wide == 1) { S.w_groups = 3; S.w_half_rows = 3 * nt / 2; }   // one MMA N group per filter row: 3 taps x nt rows
-      else      { S.w_groups = 9; S.w_half_rows = nt / 2; }          // one per tap
-      S.w_box_rows = S.w_half_rows == 96 ? kWBoxRows : S.w_half_rows;
+      if (S.wide == 1) {                                              // one MMA N group per filter row: 3 taps x nt rows
+        S.w_groups = 3;
+        for (int gi = 0; gi < 3; ++gi) S.w_grp_half[gi] = 3 * nt / 2;
+        S.w_box_rows = (3 * nt / 2 == 96) ? kWBoxRows : 3 * nt / 2;   // 96 = 2 x 48-row boxes; the output conv: one 24-row box
+      } else if (l.kind == kConvT3x3s2) {                             // four shift groups of N = 256 / 128 / 128 / 64 (nt == 64)
+        TG_CHECK_ARG(nt == 64, "frame: the transposed conv needs 64-wide output chunks");
+        S.w_groups = 4;
+        S.w_grp_half[0] = 128; S.w_grp_half[1] = 64; S.w_grp_half[2] = 64; S.w_grp_half[3] = 32;
+        S.w_box_rows = 32;
+      } else {                                                        // one group per tap (measurement variants)
+        TG_CHECK_ARG(!pair || nt == 64, "frame: per-tap pair mode needs 64-wide chunks");
+        S.w_groups = 9;
+        for (int gi = 0; gi < 9; ++gi) S.w_grp_half[gi] = nt / 2;
+        S.w_box_rows = nt / 2;
+      }
       S.w_map = S.w_box_rows == kWBoxRows ? 0 : (S.w_box_rows == 32 ? kFrMapW32 : kFrMapW24);
       TG_CHECK_ARG(!pair || S.w_box_rows == kWBoxRows || S.w_box_rows == 32 || S.w_box_rows == 24,
-                   "frame: no pair-mode weight box for layer %d (%d rows per CTA)", li, S.w_half_rows);
+                   "frame: no pair-mode weight box for layer %d (%d-row boxes)", li, S.w_box_rows);
       for (int kc = 0; kc < kchunks; ++kc)
         S.w_row0[kc] = static_cast<uint32_t>(l.blob_off / 128) + static_cast<uint32_t>(c * kchunks + kc) * S.w_rows;
       S.out_mode = l.out_mode; S.relu = l.relu;

@@ -49,8 +49,9 @@ struct FrSeg {
   int nt;                     // UMMA N: 64, or 16 for the 3-channel output conv
   uint32_t w_row0[2];         // first 128-byte row of the weight block of K chunk 0/1 in the packed blob
   uint32_t w_rows;            // rows per weight block (9 taps * nt)
-  // pair mode: the block is w_groups MMA-N groups of 2 * w_half_rows rows; each CTA loads its half of every group
-  int w_groups, w_half_rows, w_box_rows, w_map;
+  // pair mode: the block is w_groups MMA-N groups; group g has 2 * w_grp_half[g] rows and each CTA loads its half of it
+  // (rows [rank * half, (rank + 1) * half) of the group) in boxes of w_box_rows rows through tensor map w_map
+  int w_groups, w_grp_half[9], w_box_rows, w_map;
   // epilogue
   int out_mode, relu, oh, ow, oc, ch0;   // ch0 = first output channel of this chunk
   long long out_nstride;
