@@ -45,14 +45,10 @@
 namespace tg {
 
 constexpr int kEpiWarps = 16;                          // 4 per TMEM lane quarter: 16 accumulator columns each
-// Epilogue organisation.  true: two SETS of 8 warps, set s drains accumulator group s, i.e. every other item, so two
-// items' epilogues are in flight at once (a warp = lane quarter x 32 columns, worked off as two 16-column passes with the
-// three partial sums loaded one after the other into the same registers).  false: all 16 warps on every item.
-#ifndef TG_FRAME_TWO_SETS
-#define TG_FRAME_TWO_SETS 1
-#endif
-constexpr bool kTwoSets = TG_FRAME_TWO_SETS != 0;
-constexpr int kSetWarps = kTwoSets ? kEpiWarps / 2 : kEpiWarps;   // arrivals per accumulator hand-back / publish
+// Epilogue organisation: two SETS of 8 warps, set s drains accumulator group s, i.e. every other item, so two items'
+// epilogues are in flight at once (a warp = lane quarter x 32 columns, worked off as two 16-column passes with the three
+// partial sums loaded one after the other into the same registers).  (All 16 warps on every item measured 8.5 % slower.)
+constexpr int kSetWarps = kEpiWarps / 2;              // arrivals per accumulator hand-back / publish
 constexpr int kPubWarps = 1;                          // (a second publisher WARP would be the 21st: 80 registers, spills - measured slower)
 constexpr int kFrThreads = 32 * (2 + kEpiWarps + kPubWarps + 1);   // producer, MMA, epilogue warps, publisher(s), dependency warp
 constexpr int kDepRing = 4;                            // dependency warp runs at most this many items ahead of the producer
@@ -569,7 +565,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       o[0] = a_cempty; o[1] = a_wfull; o[2] = a_afull; o[3] = a_total; o[20] = a_issue;
     }
     }
-  } else if (kTwoSets && warp < 2 + kEpiWarps) {
+  } else if (warp < 2 + kEpiWarps) {
     // ================================ epilogue, two sets of 8 warps =========================
     // Set s (warps 2+8s .. 9+8s) drains accumulator group s = the items k with (k & 1) == s of this CTA's sequence, so
     // the epilogue of item k+1 runs while item k's is still waiting on TMEM, shuffles or stores.  A warp owns one TMEM
@@ -691,28 +687,40 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
           t2.start();
           hand_back();
           t2.stop(a_hb);
-          // half 0: planes 0 and 1, half 1: plane 2
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int c = half == 0 ? k : 2;
-            if (half == 1 && k == 1) break;
-            const float l = __shfl_up_sync(0xFFFFFFFFu, __uint_as_float(c == 0 ? v0[0] : (c == 1 ? v0[1] : v0[2])), 1);
-            const float r2 = __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(c == 0 ? v2[0] : (c == 1 ? v2[1] : v2[2])), 1);
-            const float z = (l + __uint_as_float(c == 0 ? v1[0] : (c == 1 ? v1[1] : v1[2]))) + r2 + s_bias[c];
-            if (wvalid && c < S.oc) {
-              const size_t plane = static_cast<size_t>(S.oh) * S.ow;
-              const size_t opx = static_cast<size_t>(wy) * S.ow + wx;
-              const size_t o = static_cast<size_t>(n) * S.out_nstride + opx + c * plane;
-              const float y = 1.f / (1.f + expf(-z));
-              if (S.out2) S.out2[static_cast<size_t>(n) * 3 * plane + opx + c * plane] = z;
-              if (S.out && !(dbg & 128)) store_network_output(S.out, c_mode, o, static_cast<size_t>(n) * (S.out_nstride / 3) + opx, c, y);
-              if (S.resid != nullptr && !(dbg & 384)) {    // pixel-interleaved second copy (tg_glue.cu: gather3)
-                float* px = static_cast<float*>(const_cast<void*>(S.resid)) + ((static_cast<size_t>(n) * S.oh + wy) * S.ow + wx) * 4;
-                // the blue warp also writes the unused fourth component: every byte of the copy is written, so no
-                // sector is ever partially dirty (a partial sector costs a read-modify-write in ECC DRAM)
-                if (c == 2) *reinterpret_cast<float2*>(px + 2) = make_float2(y, 0.f);
-                else px[c] = y;
+          // half 0: planes 0 and 1, half 1: plane 2.  The two planes of a half-0 warp are independent chains (shuffles,
+          // exp, reciprocal) issued side by side; index arithmetic is done once per item.  The epilogue of this 3-channel
+          // layer is a latency chain, not a throughput problem: a set spent ~1500 cycles per item in it.
+          const int c0 = half == 0 ? 0 : 2;
+          const uint32_t p0 = half == 0 ? v0[0] : v0[2], q0 = half == 0 ? v1[0] : v1[2], r0 = half == 0 ? v2[0] : v2[2];
+          const float la = __shfl_up_sync(0xFFFFFFFFu, __uint_as_float(p0), 1), lb = __shfl_up_sync(0xFFFFFFFFu, __uint_as_float(v0[1]), 1);
+          const float ra = __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(r0), 1), rb = __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(v2[1]), 1);
+          const float za = (la + __uint_as_float(q0)) + ra + s_bias[c0];
+          const float zb = (lb + __uint_as_float(v1[1])) + rb + s_bias[1];
+          // sigmoid: ex2.approx + rcp.approx (relative error ~1e-6, far inside every output tolerance; the f16 / u8 forms
+          // are derived from this same value, so the compact formats stay bit-consistent with the f32 output)
+          const float ya = __fdividef(1.f, 1.f + __expf(-za));
+          const float yb = __fdividef(1.f, 1.f + __expf(-zb));
+          if (wvalid) {
+            const size_t plane = static_cast<size_t>(S.oh) * S.ow;
+            const size_t opx = static_cast<size_t>(static_cast<uint32_t>(wy) * static_cast<uint32_t>(S.ow) + static_cast<uint32_t>(wx));
+            const size_t obase = static_cast<size_t>(n) * S.out_nstride + opx;
+            const size_t pbase = static_cast<size_t>(n) * (S.out_nstride / 3) + opx;
+            float* px = S.resid != nullptr ? static_cast<float*>(const_cast<void*>(S.resid)) + (static_cast<size_t>(n) * plane + opx) * 4 : nullptr;
+            if (c0 < S.oc) {
+              if (S.out2) S.out2[static_cast<size_t>(n) * 3 * plane + opx + c0 * plane] = za;
+              if (S.out && !(dbg & 128)) store_network_output(S.out, c_mode, obase + c0 * plane, pbase, c0, ya);
+              // pixel-interleaved second copy (tg_glue.cu: gather3).  The blue warp also writes the unused fourth component:
+              // every byte of the copy is written, so no sector is ever partially dirty (a partial sector costs a
+              // read-modify-write in ECC DRAM)
+              if (px != nullptr && !(dbg & 384)) {
+                if (c0 == 2) *reinterpret_cast<float2*>(px + 2) = make_float2(ya, 0.f);
+                else px[0] = ya;
               }
+            }
+            if (half == 0 && 1 < S.oc) {
+              if (S.out2) S.out2[static_cast<size_t>(n) * 3 * plane + opx + plane] = zb;
+              if (S.out && !(dbg & 128)) store_network_output(S.out, c_mode, obase + plane, pbase, 1, yb);
+              if (px != nullptr && !(dbg & 384)) px[1] = yb;
             }
           }
         }
@@ -779,207 +787,19 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
       unsigned long long* o = stats + blockIdx.x * 32;
       o[4] = a_cfull; o[5] = a_body; o[6] = a_pub; o[7] = a_total; o[8] = a_tmem; o[17] = a_hb;
     }
-  } else if (warp < 2 + kEpiWarps) {
-    // ================================ epilogue (16 warps) ==================================
-    // warp = (TMEM lane quarter q, column part): 16 of the 64 accumulator columns of 32 pixels per item.  Sixteen
-    // narrow warps instead of eight wide ones: the per-item epilogue is a dependent chain (TMEM load -> shuffles ->
-    // bias/ReLU/residual -> pack -> store), its latency, not its instruction count, bounds the item rate.
-    const int q = warp & 3;                                // TMEM lane quarter of this warp
-    const int part = (warp - 2) >> 2;                      // which 16 of the 64 accumulator columns
-    const int m = q * 32 + lane;
-    const int pr = m >> 3, pc = m & 7;
-    float* s_bias = s_bias_all + (warp - 2) * 64;
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    int si = 0, cur_si = -1, g = 0;
-    uint32_t gph = 0;
-    // Publishing a tile: every epilogue warp arrives (lane 0, release.cta, after a __syncwarp) on a CTA-local mbarrier after its stores;
-    // the publisher warp then performs ONE gpu-scope release (MEMBAR.GPU + RED) for the whole tile, so the
-    // fence latency never stalls the epilogue.
-    uint32_t pk = 0;
-    Tick<kDbg> tk{0, stats != nullptr, true}, tall{0, stats != nullptr, true};
-    long long a_cfull = 0, a_body = 0, a_pub = 0, a_total = 0, a_tmem = 0;
-    tall.start();
-    float nb0 = 0.f, nb1 = 0.f;                            // bias of segment nb_si, fetched one segment ahead
-    int nb_si = -1;
-    // per-segment scalars live in registers: a shared-memory load per item sits on the item's critical path
-    // (measured: the compare waiting for segs[si].item_end was the second hottest instruction of the kernel)
-    int seg_end = 0, seg_begin = 0, seg_real = 0, c_tiles_x = 1, c_tiles_y = 1, c_h = 0, c_w = 0;
-    FastDiv c_fdx{0, 0}, c_fdy{0, 0};
-    uint32_t c_row_bytes = 0, c_px_bytes = 0, c_img_bytes = 0;
-    uint8_t* c_out = nullptr;
-    const uint8_t* c_res = nullptr;
-    int c_wide = 0, c_mode = 0, c_relu = 0, c_kind = 0;
-    for (int it = blockIdx.x; it < P.total_items; it += G) {
-      if (it >= seg_end) {
-        while (it >= segs[si].item_end) ++si;
-        const FrSegS& C = segs[si];
-        seg_end = C.item_end; seg_begin = C.item_begin; seg_real = C.items_real;
-        c_tiles_x = C.tiles_x; c_tiles_y = C.tiles_y; c_fdx = C.fd_tiles_x; c_fdy = C.fd_tiles_y;
-        c_h = C.h; c_w = C.w; c_wide = C.wide; c_mode = C.out_mode; c_relu = C.relu; c_kind = C.kind;
-        c_px_bytes = C.oc * 2u; c_row_bytes = C.ow * c_px_bytes; c_img_bytes = C.oh * c_row_bytes;   // < 4 GB (launch_frame)
-        c_out = static_cast<uint8_t*>(C.out) + C.ch0 * 2u + part * 32u;
-        c_res = C.resid ? static_cast<const uint8_t*>(C.resid) + C.ch0 * 2u + part * 32u : nullptr;
-      }
-      const FrSegS& S = segs[si];
-      if (si != cur_si) {                                  // warp-private bias copy of this segment
-        __syncwarp();
-        float b0 = nb0, b1 = nb1;
-        if (nb_si != si) {                                 // (first segment, or the CTA had no item in a segment)
-          b0 = lane < S.nt ? S.bias[lane] : 0.f;
-          b1 = lane + 32 < S.nt ? S.bias[lane + 32] : 0.f;
-        }
-        s_bias[lane] = b0;
-        s_bias[lane + 32] = b1;
-        __syncwarp();
-        cur_si = si;
-        if (si + 1 < P.nseg) {                             // in flight until the next segment starts
-          const FrSegS& N = segs[si + 1];
-          nb0 = lane < N.nt ? N.bias[lane] : 0.f;
-          nb1 = lane + 32 < N.nt ? N.bias[lane + 32] : 0.f;
-          nb_si = si + 1;
-        }
-      }
-      const uint32_t local = static_cast<uint32_t>(it - seg_begin);
-      const uint32_t r = fdiv(local, c_fdx);
-      const int tx = static_cast<int>(local - r * c_tiles_x);
-      const int n = static_cast<int>(fdiv(r, c_fdy));
-      const int ty = static_cast<int>(r) - n * c_tiles_y;
-      const bool real = local < static_cast<uint32_t>(seg_real);      // false: the padding item of a pair
-      tk.gate = stat_seg < 0 || si == stat_seg;
-      tk.start();
-      mbar_wait(bar_cfull + 8 * g, gph);
-      tk.stop(a_cfull);
-      tk.start();
-      tc_fence_after();
-      const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * kGroupCols);
-      if (c_wide == 1) {
-        // GEMM row = (tile row q, box column lane); columns [dx*nt + c] hold the partial sum of filter column dx
-        // evaluated AT this box pixel: out[x] = P0[x-1] + P1[x] + P2[x+1]  ->  lanes l-1, l, l+1 of this warp
-        const int wy = ty * kWideH + q, wx = tx * kWideW - 1 + lane;
-        const bool wvalid = real && (lane >= 1) && (lane <= kWideW) && (wy < c_h) && (wx < c_w);
-        if (c_mode == kOutNHWCbf16) {
-          uint32_t v0[16], v1[16], v2[16];
-          tmem_ld_32x16(tq + part * 16, v0);
-          tmem_ld_32x16(tq + 64 + part * 16, v1);
-          tmem_ld_32x16(tq + 128 + part * 16, v2);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) { if (kPair) mbar_arrive_cluster(lbar_cempty + 8 * g); else mbar_arrive(bar_cempty + 8 * g); }
-          tk.stop(a_tmem);
-          tk.start();
-          uint64_t a2[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {                        // (P0[x-1] + P1[x]) + P2[x+1], two channels per FADD2
-            const uint32_t l0 = __shfl_up_sync(0xFFFFFFFFu, v0[2 * e], 1), l1 = __shfl_up_sync(0xFFFFFFFFu, v0[2 * e + 1], 1);
-            const uint32_t r0 = __shfl_down_sync(0xFFFFFFFFu, v2[2 * e], 1), r1 = __shfl_down_sync(0xFFFFFFFFu, v2[2 * e + 1], 1);
-            a2[e] = f2_add(f2_add(f2_pack(l0, l1), f2_pack(v1[2 * e], v1[2 * e + 1])), f2_pack(r0, r1));
-          }
-          if (wvalid && !(dbg & 16)) {
-            // one 64-bit product per image, the rest in 32 bits (an image of a layer is < 4 GB: launch_frame checks)
-            const size_t off = static_cast<size_t>(n) * c_img_bytes + (static_cast<uint32_t>(wy) * c_row_bytes + static_cast<uint32_t>(wx) * c_px_bytes);
-            epi_store_bf16(a2, s_bias + part * 16, c_out + off, c_res ? c_res + off : nullptr, c_relu != 0);
-          }
-        } else {
-          uint32_t v0[4], v1[4], v2[4];                    // 3 output channels of each of the 3 partial sums
-          tmem_ld_32x4(tq, v0);
-          tmem_ld_32x4(tq + 16, v1);
-          tmem_ld_32x4(tq + 32, v2);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) { if (kPair) mbar_arrive_cluster(lbar_cempty + 8 * g); else mbar_arrive(bar_cempty + 8 * g); }
-          const int c = part < 3 ? part : 2;               // plane of this warp (part 3 idles)
-          const float l = __shfl_up_sync(0xFFFFFFFFu, __uint_as_float(c == 0 ? v0[0] : (c == 1 ? v0[1] : v0[2])), 1);
-          const float r2 = __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(c == 0 ? v2[0] : (c == 1 ? v2[1] : v2[2])), 1);
-          const float z = (l + __uint_as_float(c == 0 ? v1[0] : (c == 1 ? v1[1] : v1[2]))) + r2 + s_bias[c];
-          if (wvalid && part < 3 && part < S.oc) {
-            const size_t plane = static_cast<size_t>(S.oh) * S.ow;
-            const size_t opx = static_cast<size_t>(wy) * S.ow + wx;
-            const size_t o = static_cast<size_t>(n) * S.out_nstride + opx + c * plane;
-            const float y = 1.f / (1.f + expf(-z));
-            if (S.out2) S.out2[static_cast<size_t>(n) * 3 * plane + opx + c * plane] = z;
-            if (S.out) store_network_output(S.out, c_mode, o, static_cast<size_t>(n) * (S.out_nstride / 3) + opx, c, y);
-            // optional second copy, pixel-interleaved (float4 {R,G,B,-}, component `part` from this warp): the next
-            // frame's warp gathers three channels with one 16-byte load (tg_glue.cu: gather3)
-            if (S.resid != nullptr) {
-              float* px = static_cast<float*>(const_cast<void*>(S.resid)) + ((static_cast<size_t>(n) * S.oh + wy) * S.ow + wx) * 4;
-              if (c == 2) *reinterpret_cast<float2*>(px + 2) = make_float2(y, 0.f);
-              else px[c] = y;
-            }
-          }
-        }
-      } else {
-        // tall tile: GEMM row m = pixel (m / 8, m % 8); wide box with one view per tap: row = (tile row q, column lane),
-        // the view of tap dx starts dx pixels into the box row, so lane l IS output column l (30 valid)
-        const bool wtap = c_wide == 2;
-        const int iy = wtap ? ty * kWideH + q : ty * kTileH + pr, ix = wtap ? tx * kWideW + lane : tx * kTileW + pc;
-        const bool valid = real && (iy < c_h) && (ix < c_w) && (!wtap || lane < kWideW);
-        const int n_acc = (c_kind == kConv3x3) ? 1 : 4;
-        const int sc = (c_kind == kConv3x3) ? 1 : 2;
-        for (int a = 0; a < n_acc; ++a) {
-          // accumulator a of a transposed conv sits at column kCtAccCol[a] = {0, 64, 192, 128} ([a0 | a1 | a3 | a2])
-          const uint32_t taddr = tq + static_cast<uint32_t>(n_acc == 1 ? 0 : (a == 0 ? 0 : (a == 1 ? 64 : (a == 2 ? 192 : 128))));
-          const int oy = iy * sc + (a >> 1), ox = ix * sc + (a & 1);
-          uint32_t v[16];
-          tmem_ld_32x16(taddr + (c_mode == kOutNHWCbf16 ? part * 16 : 0), v);
-          tmem_ld_wait();
-          if (a == n_acc - 1) {                            // TMEM drained -> hand the group back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { if (kPair) mbar_arrive_cluster(lbar_cempty + 8 * g); else mbar_arrive(bar_cempty + 8 * g); }
-          }
-          if (c_mode == kOutNHWCbf16) {
-            if (valid) {
-              const size_t off = static_cast<size_t>(n) * c_img_bytes + (static_cast<uint32_t>(oy) * c_row_bytes + static_cast<uint32_t>(ox) * c_px_bytes);
-              uint64_t a2[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) a2[e] = f2_pack(v[2 * e], v[2 * e + 1]);
-              epi_store_bf16(a2, s_bias + part * 16, c_out + off, c_res ? c_res + off : nullptr, c_relu != 0);
-            }
-          } else if (valid && part < 3 && part < S.oc) {     // output conv, tall geometry: plane `part`
-            const size_t plane = static_cast<size_t>(S.oh) * S.ow;
-            const size_t o = static_cast<size_t>(n) * S.out_nstride + static_cast<size_t>(oy) * S.ow + ox + part * plane;
-            const float z = __uint_as_float(part == 0 ? v[0] : (part == 1 ? v[1] : v[2])) + s_bias[part];
-            if (S.out2) S.out2[o] = z;
-            static_cast<float*>(S.out)[o] = 1.f / (1.f + expf(-z));
-          }
-        }
-      }
-      tk.stop(a_body);
-      // the network output has no consumer inside the kernel: nothing to publish
-      if (c_mode == kOutNHWCbf16 && real && !(dbg & 2)) {
-        const uint32_t pg = pk & 1u, pph = (pk >> 1) & 1u;
-        tk.start();
-        __syncwarp();                                        // orders the 32 lanes' stores before lane 0's release
-        if (lane == 0) {
-          mbar_wait(bar_pempty + 8 * pg, pph ^ 1);           // publisher at most 2 tiles behind
-          mbar_arrive(bar_pfull + 8 * pg);
-        }
-        tk.stop(a_pub);
-        ++pk;
-      }
-      g ^= 1;
-      if (g == 0) gph ^= 1;
-    }
-    tall.stop(a_total);
-    if (stats && warp == 2 && lane == 0) {
-      unsigned long long* o = stats + blockIdx.x * 32;
-      o[4] = a_cfull; o[5] = a_body; o[6] = a_pub; o[7] = a_total; o[8] = a_tmem;
-    }
   } else if (warp < 2 + kEpiWarps + kPubWarps) {
     // ================================ publisher ============================================
     // A gpu-scope release (MEMBAR.GPU + RED) takes ~1300 cycles, more than an item's MMAs, so with two epilogue sets
     // two releases must be in flight: lanes 0 and 1 of this warp are two independent publishers (independent thread
     // scheduling lets one lane issue while the other sits in its fence), lane pw releasing the tiles of set pw.
     const int pw = lane;
-    if (pw < (kTwoSets ? 2 : 1)) {
+    if (pw < 2) {
       int si = 0;
       uint32_t pk = 0;
       Tick<kDbg> tk{0, stats != nullptr, true};
       long long a_pfull = 0, a_red = 0;
       int seg_end = 0, seg_pub_end = 0;                      // publish items [.., seg_pub_end) of the current segment
-      for (int it = blockIdx.x + (kTwoSets ? pw * G : 0); it < P.total_items; it += (kTwoSets ? 2 * G : G)) {
+      for (int it = blockIdx.x + pw * G; it < P.total_items; it += 2 * G) {
         if (it >= seg_end) {
           while (it >= segs[si].item_end) ++si;
           const FrSegS& C = segs[si];
@@ -988,9 +808,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         }
         tk.gate = stat_seg < 0 || si == stat_seg;
         if (it < seg_pub_end && !(dbg & 2)) {
-          // single epilogue set: two barriers used alternately; two sets: set pw has its own barrier pair
-          const uint32_t pg = kTwoSets ? static_cast<uint32_t>(pw) : (pk & 1u);
-          const uint32_t pph = kTwoSets ? (pk & 1u) : ((pk >> 1) & 1u);
+          const uint32_t pg = static_cast<uint32_t>(pw), pph = pk & 1u;   // set pw has its own barrier pair
           tk.start();
           mbar_wait(bar_pfull + 8 * pg, pph);                // all epilogue warps stored (acquire.cta)
           tk.stop(a_pfull);
