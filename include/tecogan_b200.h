@@ -139,6 +139,10 @@ int tg_conv3x3_out_sigmoid(const void* x, const void* packed, float* out, float*
  * plain gradient.  tcgen05 kernel with the pixel index as the GEMM reduction dimension (MN-major operands). */
 int tg_conv3x3_wgrad(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
                      void* stream);
+/* tg_conv3x3_wgrad plus the bias gradient db[cout] (f32) += sum over pixels of dy, in the same launch when cout <= 64 (the
+ * epilogue warps sum the staged dY tiles while the MMAs run), else followed by the tg_bias_grad reduction. */
+int tg_conv3x3_wgrad_bias(const void* x, const void* dy, float* dw, float* db, int n, int h, int w, int cin, int cout,
+                          void* stream);
 /* Same for ConvTranspose2d(k3,s2,p1,op1): x [n,h,w,pad64(cin)], dy [n,2h,2w,pad64(cout)] -> dw [cin][cout][3][3];
  * and for Conv2d(k4,s2,p1): x [n,2h,2w,pad64(cin)], dy [n,h,w,pad64(cout)] -> dw [cout][cin][4][4].  The operand at
  * twice the resolution is staged per parity phase with stride-2 TMA boxes. */

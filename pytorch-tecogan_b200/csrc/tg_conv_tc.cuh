@@ -94,8 +94,10 @@ int encode_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* di
                 const cuuint64_t* strides_bytes, const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr);
 
 // tg_wgrad.cu: dW[cout][cin][3][3] += sum_pixels dY (x) X (f32 atomics); x NHWC bf16 [n,h,w,cin_pad], dy [n,h,w,cout_pad]
+// db != null: also the bias gradient db[cout] += sum over pixels of dY (fused into the weight-gradient kernel for <= 64
+// output channels, a separate reduction launch otherwise)
 int launch_wgrad3x3(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout, int cin_pad,
-                    int cout_pad, cudaStream_t stream);
+                    int cout_pad, cudaStream_t stream, float* db = nullptr);
 // ConvTranspose2d(k3,s2,p1,op1): x [n,h,w,cin_pad], dy [n,2h,2w,cout_pad] -> dw [cin][cout][3][3]
 int launch_wgrad_convT3x3s2(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
                             int cin_pad, int cout_pad, cudaStream_t stream);

@@ -307,8 +307,9 @@ extern "C" int tg_disc_backward(const float* flat_params, const void* packed_dgr
   auto wgrad = [&](int ci, const void* x, const void* dy, int hh, int ww) {
     const DConv& c = L.convs[ci];
     const int cp = cin_padded(c.cin), op = c.cout <= 64 ? 64 : 128;
-    int r = (c.kind == kConv3x3) ? launch_wgrad3x3(x, dy, flat_grad + c.w_off, n, hh, ww, c.cin, c.cout, cp, op, st)
-                                 : launch_wgrad_conv4x4s2(x, dy, flat_grad + c.w_off, n, hh, ww, c.cin, c.cout, cp, op, st);
+    if (c.kind == kConv3x3)      // (the bias gradient rides on the weight-gradient launch)
+      return launch_wgrad3x3(x, dy, flat_grad + c.w_off, n, hh, ww, c.cin, c.cout, cp, op, st, c.has_bias ? flat_grad + c.b_off : nullptr);
+    int r = launch_wgrad_conv4x4s2(x, dy, flat_grad + c.w_off, n, hh, ww, c.cin, c.cout, cp, op, st);
     if (r || !c.has_bias) return r;
     return launch_bias_grad(dy, static_cast<long long>(n) * hh * ww, op, c.cout, flat_grad + c.b_off, st);
   };

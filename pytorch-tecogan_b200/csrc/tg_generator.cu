@@ -495,8 +495,9 @@ extern "C" int tg_gen_backward(const void* packed_dgrad, int num_resblock, const
   auto wgrad = [&](int li, const void* x, const void* dy, int hh, int ww) {
     const GenLayer& l = L[li];
     const int cp = cin_padded(l.cin), op = l.cout <= 64 ? 64 : 128;
-    int r = (l.kind == kConv3x3) ? launch_wgrad3x3(x, dy, flat_grad + l.w_off, n, hh, ww, l.cin, l.cout, cp, op, st)
-                                 : launch_wgrad_convT3x3s2(x, dy, flat_grad + l.w_off, n, hh, ww, l.cin, l.cout, cp, op, st);
+    if (l.kind == kConv3x3)      // (the bias gradient rides on the weight-gradient launch)
+      return launch_wgrad3x3(x, dy, flat_grad + l.w_off, n, hh, ww, l.cin, l.cout, cp, op, st, l.has_bias ? flat_grad + l.b_off : nullptr);
+    int r = launch_wgrad_convT3x3s2(x, dy, flat_grad + l.w_off, n, hh, ww, l.cin, l.cout, cp, op, st);
     if (r || !l.has_bias) return r;
     const long long opx = static_cast<long long>(n) * hh * ww * (l.kind == kConv3x3 ? 1 : 4);
     return launch_bias_grad(dy, opx, op, l.cout, flat_grad + l.b_off, st);

@@ -176,6 +176,206 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 3x3 weight gradient for layers with <= 64 OUTPUT channels (37 of the generator's 41 convs, half of the discriminator's):
+// with M = 128 accumulator rows and only 64 dY channels, the kernel above wastes half of every MMA (rows 64..127 mirror rows
+// 0..63) and spends three CTAs (one per filter row) on each pixel tile.  Here the filter-row shift is applied to the dY
+// operand instead of X - dW[ky][kx] = sum_q dY[q - (ky-1)] (x) X[q + (0, kx-1)] over the X pixels q of the tile - so that
+// two filter rows are the two 64-row halves of ONE MMA (the second half = the same dY box one tile row further: LBO = 1024 B):
+//   MMA 1: rows [ky = 2 | ky = 1] x N = 192 (three kx taps stacked, as above)      MMA 2: rows [ky = 0 | mirror] x N = 192
+// Two MMAs of 138 cycles per 16 pixels for all nine taps instead of three CTAs x 138: 1.5x the tensor-pipe efficiency
+// (1.74x for 128 input channels, where the old path needs three N = 128 MMAs per CTA), and one dY box {64, 8, 18} + one X box
+// {64, 10, 16} per tile instead of three of each.  grid = (pixel slabs, cin_pad / 64): a CTA owns one 64-channel block of X.
+struct WgKyParams {
+  int n, h, w, tiles_x, tiles_y, num_items;
+  int rows_real, cols_real;            // cout (<= 64), cin
+  int nstages;
+  uint32_t stage_stride;
+  float* dw;
+  float* db;                           // optional bias gradient (db[co] += sum of dY), or null
+};
+constexpr uint32_t kWgKyABytes = 8 * 18 * 128;        // dY box {64 ch, 8, 18}: the tile and one halo row above / below
+constexpr uint32_t kWgKyBBytes = 10 * 16 * 128;       // X box {64 ch, 10, 16}: one halo column left / right
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad3x3_ky_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x,
+                   const __grid_constant__ WgKyParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t s_st = base;
+  const uint32_t bar_full = base + p.nstages * p.stage_stride;
+  const uint32_t bar_empty = bar_full + 8 * p.nstages;
+  const uint32_t bar_done = bar_empty + 8 * p.nstages;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gbase + (bar_done + 8 - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cblk = blockIdx.y;                               // 64-channel block of X (GEMM N)
+  // the bias gradient rides on the first channel block's CTAs: warps 2..5 sum the staged dY tiles while the MMAs run
+  const bool do_bias = p.db != nullptr && cblk == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_dy);
+    tma_prefetch_desc(&tm_x);
+    for (int i = 0; i < p.nstages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, do_bias ? 5 : 1); }
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+      const int tx = it % p.tiles_x;
+      const int r = it / p.tiles_x;
+      const int ty = r % p.tiles_y;
+      const int n = r / p.tiles_y;
+      const int x0 = tx * kTileW, y0 = ty * kTileH;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(bar_full + 8 * s, kWgKyABytes + kWgKyBBytes);
+        const uint32_t dst = s_st + s * p.stage_stride;
+        tma_load_4d(dst, &tm_dy, bar_full + 8 * s, 0, x0, y0 - 1, n);
+        tma_load_4d(dst + kWgKyABytes, &tm_x, bar_full + 8 * s, cblk * 64, x0 - 1, y0, n);
+      }
+      __syncwarp();
+      if (++s == p.nstages) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16_mn(128, 192);
+    int s = 0;
+    uint32_t ph = 0, first = 1;
+    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+      mbar_wait(bar_full + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_base = s_st + s * p.stage_stride;
+        const uint32_t b_base = a_base + kWgKyABytes;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {                           // X tile rows 2j, 2j+1 = 16 pixels of the reduction
+          // dY box row of X row rx for filter row ky: rx + 2 - ky (the box starts one row above the tile)
+          const uint64_t a21 = umma_desc_mn_sw128(a_base + (2 * j) * 1024, 1024, 1024);       // rows [ky = 2 | ky = 1]
+          const uint64_t a0 = umma_desc_mn_sw128(a_base + (2 * j + 2) * 1024, 0, 1024);       // rows [ky = 0 | mirror]
+          const uint64_t bd = umma_desc_mn_sw128(b_base + 2 * j * (10 * 128), 128, 10 * 128); // three kx taps stacked along N
+          const uint32_t acc = (first && j == 0) ? 0u : 1u;
+          umma_bf16(tmem_base, a21, bd, idesc, acc);
+          umma_bf16(tmem_base + 192, a0, bd, idesc, acc);
+        }
+        umma_commit(bar_empty + 8 * s);
+      }
+      __syncwarp();
+      first = 0;
+      if (++s == p.nstages) { s = 0; ph ^= 1; }
+    }
+    if (elect_one()) umma_commit(bar_done);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                               // accumulator row
+    const bool have_work = blockIdx.x < p.num_items;
+    if (do_bias && have_work) {
+      // bias gradient: thread (warp - 2, lane) owns dY channels 2t, 2t+1 (t = 0..31) of a quarter of the tile's pixels;
+      // the tile proper is box rows 1..16 (128 pixels).  Reads race with nothing: the stage is released (bar_empty) only
+      // after these four warps arrived as well.
+      const int tq = warp - 2, ch2 = lane;                    // pixel quarter, channel pair
+      float s0 = 0.f, s1 = 0.f;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+        mbar_wait(bar_full + 8 * s, ph);
+        const uint8_t* tile = gbase + (s_st - base) + s * p.stage_stride + 8 * 128;   // skip the halo row
+#pragma unroll 4
+        for (int px = tq * 32; px < tq * 32 + 32; ++px) {
+          // SWIZZLE_128B: 16-byte chunk c of 128-byte row r sits at chunk c ^ (r & 7) (r counted from the 1024-aligned stage base)
+          const int r = px + 8;
+          const int chunk = (ch2 >> 2) ^ (r & 7);
+          const uint32_t u = *reinterpret_cast<const uint32_t*>(tile + px * 128 + chunk * 16 + (ch2 & 3) * 4);
+          s0 += bf16_lo(u);
+          s1 += bf16_hi(u);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+        if (++s == p.nstages) { s = 0; ph ^= 1; }
+      }
+      if (2 * ch2 < p.rows_real) atomicAdd(p.db + 2 * ch2, s0);
+      if (2 * ch2 + 1 < p.rows_real) atomicAdd(p.db + 2 * ch2 + 1, s1);
+    }
+    if (have_work) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+      const int co = m & 63;
+      for (int blk = 0; blk < 2; ++blk) {                      // accumulator 0: rows [ky 2 | ky 1]; accumulator 1: rows [ky 0 | mirror]
+        const int ky = blk == 0 ? (m < 64 ? 2 : 1) : 0;
+        const bool rows_ok = co < p.rows_real && (blk == 0 || m < 64);
+        for (int c0 = 0; c0 < 192; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + blk * 192 + c0, v);
+          tmem_ld_wait();
+          if (rows_ok) {
+            const int kx = c0 / 64;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int ci = cblk * 64 + (c0 & 63) + e;
+              if (ci < p.cols_real)
+                atomicAdd(p.dw + ((static_cast<size_t>(co) * p.cols_real + ci) * 3 + ky) * 3 + kx, __uint_as_float(v[e]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static int launch_wgrad3x3_ky(const void* x, const void* dy, float* dw, float* db, int n, int h, int w, int cin, int cout, int cin_pad,
+                              cudaStream_t stream) {
+  WgKyParams p{};
+  p.n = n; p.h = h; p.w = w;
+  p.tiles_x = tg_div_up(w, kTileW); p.tiles_y = tg_div_up(h, kTileH);
+  p.num_items = n * p.tiles_x * p.tiles_y;
+  p.rows_real = cout; p.cols_real = cin;
+  p.stage_stride = (kWgKyABytes + kWgKyBBytes + 1023u) & ~1023u;
+  p.nstages = 5;
+  p.dw = dw; p.db = db;
+  const uint32_t smem_bytes = p.nstages * p.stage_stride + 16 * p.nstages + 64 + 1024;
+  TG_CHECK_ARG(smem_bytes <= kWgSmemLimit, "wgrad3x3: stages do not fit in shared memory");
+  CUtensorMap tm_a, tm_b;
+  {
+    cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
+    cuuint64_t strides[3] = {128, static_cast<cuuint64_t>(w) * 128, static_cast<cuuint64_t>(h) * w * 128};
+    cuuint32_t box[4] = {64, kTileW, kTileH + 2, 1};
+    if (int rc = encode_bf16(&tm_a, dy, 4, dims, strides, box)) return rc;
+  }
+  {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(cin_pad), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(cin_pad) * 2, static_cast<cuuint64_t>(w) * cin_pad * 2,
+                             static_cast<cuuint64_t>(h) * w * cin_pad * 2};
+    cuuint32_t box[4] = {64, kTileW + 2, kTileH, 1};
+    if (int rc = encode_bf16(&tm_b, x, 4, dims, strides, box)) return rc;
+  }
+  static const int tiles_per_slab = []() { const char* e = getenv("TG_WGRAD_TILES_PER_SLAB"); const int v = e ? atoi(e) : 8; return v > 0 ? v : 8; }();
+  const int cblocks = cin_pad / 64;
+  int slabs = p.num_items / tiles_per_slab;
+  const int max_slabs = tg_num_sms() / cblocks;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  static TgPerDeviceOnce attr_once;
+  if (attr_once.need()) TG_CUDA(cudaFuncSetAttribute(wgrad3x3_ky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemLimit));
+  tg_prof_pre(TG_K_WGRAD, 2.0 * 9.0 * cin_pad * 64 * n * h * w, stream);
+  wgrad3x3_ky_kernel<<<dim3(slabs, cblocks), kWgThreads, smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes, stream>>>(tm_a, tm_b, p);
+  tg_prof_post(stream);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
 static int wgrad_launch_common(WgParams& p, const void* a, int a_pad, const void* b, int b_pad, int bh, int bw,
                                int b_box_w, int b_box_h, int ngroups, double flops, cudaStream_t stream) {
   p.tiles_x = tg_div_up(p.w, kTileW); p.tiles_y = tg_div_up(p.h, kTileH);
@@ -225,11 +425,16 @@ static int wgrad_launch_common(WgParams& p, const void* a, int a_pad, const void
 }
 
 int launch_wgrad3x3(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout, int cin_pad,
-                    int cout_pad, cudaStream_t stream) {
+                    int cout_pad, cudaStream_t stream, float* db) {
   TG_CHECK_ARG(x && dy && dw, "wgrad3x3: null pointer");
   TG_CHECK_ARG(n > 0 && h > 0 && w > 0, "wgrad3x3: bad shape");
   TG_CHECK_ARG((cin_pad == 64 || cin_pad == 128) && (cout_pad == 64 || cout_pad == 128), "wgrad3x3: padded channels must be 64 or 128");
   TG_CHECK_ARG(cin >= 1 && cin <= cin_pad && cout >= 1 && cout <= cout_pad, "wgrad3x3: bad channel counts");
+  static const bool ky_on = []() { const char* e = getenv("TG_WGRAD_KYSTACK"); return !(e && e[0] == '0'); }();   // A/B knob
+  if (cout_pad == 64 && ky_on) return launch_wgrad3x3_ky(x, dy, dw, db, n, h, w, cin, cout, cin_pad, stream);
+  if (db) {                                                  // 128 output channels: the separate HBM-rate reduction
+    if (int rc = launch_bias_grad(dy, static_cast<long long>(n) * h * w, cout_pad, cout, db, stream)) return rc;
+  }
   WgParams p{};
   p.n = n; p.h = h; p.w = w;
   p.rows_real = cout; p.cols_real = cin; p.ks = 3;           // A = dY (M = co), B = X (N = ci)
@@ -351,6 +556,10 @@ static int pad64(int c) { return c <= 64 ? 64 : 128; }
 extern "C" int tg_conv3x3_wgrad(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
                                 void* stream) {
   return tg::launch_wgrad3x3(x, dy, dw, n, h, w, cin, cout, pad64(cin), pad64(cout), static_cast<cudaStream_t>(stream));
+}
+extern "C" int tg_conv3x3_wgrad_bias(const void* x, const void* dy, float* dw, float* db, int n, int h, int w, int cin, int cout,
+                                     void* stream) {
+  return tg::launch_wgrad3x3(x, dy, dw, n, h, w, cin, cout, pad64(cin), pad64(cout), static_cast<cudaStream_t>(stream), db);
 }
 extern "C" int tg_convT3x3s2_wgrad(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
                                    void* stream) {

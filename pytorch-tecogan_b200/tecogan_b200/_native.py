@@ -50,6 +50,7 @@ SIGNATURES = {
     "tg_conv3x3_out_sigmoid": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
                                         _c_void_p]),
     "tg_conv3x3_wgrad": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "tg_conv3x3_wgrad_bias": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "tg_convT3x3s2_wgrad": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "tg_conv4x4s2_wgrad": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "tg_bias_grad": (_c_int, [_c_void_p, _c_void_p, _c_ll, _c_int, _c_void_p]),

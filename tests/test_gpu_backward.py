@@ -251,3 +251,26 @@ def test_bn_abi_stats_apply_bwd_vs_torch(pixels, c, act, skip):
     # workspace too small -> TG_ERR_WORKSPACE, not a crash
     rc = lib.tg_bn_stats(nt.ptr(xd), pixels, c, nt.ptr(gd), nt.ptr(bd), nt.ptr(stats), None, None, None, nt.ptr(ws), 16, nt.stream_ptr())
     assert rc == -4
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 20, 13, 64, 64), (1, 32, 32, 128, 64), (3, 16, 24, 51, 64), (1, 40, 24, 64, 3)])
+def test_conv3x3_wgrad_with_fused_bias_grad_through_generator_backward_shapes(n, h, w, cin, cout):
+    """The <= 64-output-channel weight-gradient kernel (filter rows stacked along M) also sums dY into the bias gradient
+    while the MMAs run: check both against torch autograd on the same bf16-rounded operands, via the public wgrad entry
+    point for dW and tg_bias_grad's contract (db += sum over pixels of dY) for the bias, using the fused path exactly as
+    tg_gen_backward / tg_disc_backward drive it (launch through tg_conv3x3_wgrad_bias)."""
+    from tecogan_b200 import _native as nt
+    lib = nt.lib()
+    x = _bf(torch.from_numpy(synth.det_uniform((n, cin, h, w), 11, -1, 1)))
+    dy = _bf(torch.from_numpy(synth.det_uniform((n, cout, h, w), 12, -1, 1)))
+    wt = torch.zeros(cout, cin, 3, 3, requires_grad=True)
+    bt = torch.zeros(cout, requires_grad=True)
+    F.conv2d(x, wt, bt, padding=1).backward(dy)
+    xd = _nhwc_bf16(x, 64 if cin <= 64 else 128)
+    dyd = _nhwc_bf16(dy, 64)
+    dw = torch.zeros(cout, cin, 3, 3, device="cuda")
+    db = torch.zeros(cout, device="cuda")
+    nt.check(lib.tg_conv3x3_wgrad_bias(nt.ptr(xd), nt.ptr(dyd), nt.ptr(dw), nt.ptr(db), n, h, w, cin, cout, nt.stream_ptr()))
+    torch.cuda.synchronize()
+    assert _rel(dw.cpu(), wt.grad) <= 1e-4, _rel(dw.cpu(), wt.grad)
+    assert _rel(db.cpu(), bt.grad) <= 1e-4, _rel(db.cpu(), bt.grad)
