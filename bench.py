@@ -260,7 +260,7 @@ def run_train_leg(name, crop, global_batch, world, rank, dev, steps, warmup, bar
            "losses_finite": bool(all(v == v and abs(v) != float("inf") for v in losses + host_losses)),
            "optimizer": "torch.optim.Adam objects as main.py:239-243 builds them, stepped by tecogan_b200.optim.FlatAdam (fused flat-bucket "
                         "Adam + GradScaler update + bf16 re-pack, repo kernels)" if T.FUSED_ADAM else "torch.optim.Adam + GradScaler (stock)",
-           "cuda_graph": bool(T.USE_CUDA_GRAPH and T.FUSED_ADAM and world == 1)}
+           "cuda_graph": bool(T.USE_CUDA_GRAPH and T.FUSED_ADAM and (world == 1 or T.GRAPH_WITH_NCCL))}
     if with_cpu:
         cb = 4 if crop == 32 else 1
         cps, step_s, cores = cpu_oracle_train(crop, cb)

@@ -30,11 +30,11 @@ from . import parallel as _par
 from .models import *  # noqa: F401,F403  (reference: `from models import *`, code/train.py:1)
 
 # Fused flat-bucket Adam (tecogan_b200.optim) for the stock torch.optim.Adam objects main.py:239-243 builds, and CUDA-graph
-# capture of the whole step after GRAPH_WARMUP eager calls (single process; the gradient all-reduce of the data-parallel
-# path stays eager).  Both are on by default and fall back to the eager / stock-optimizer path when they do not apply;
+# capture of the whole step after GRAPH_WARMUP eager calls (data-parallel: the two NCCL all-reduces are captured with it).  Both are on by default and fall back to the eager / stock-optimizer path when they do not apply;
 # TG_TRAIN_FUSED_ADAM=0 / TG_TRAIN_GRAPH=0 switch them off (A/B measurements).
 FUSED_ADAM = os.environ.get("TG_TRAIN_FUSED_ADAM", "1") != "0"
 USE_CUDA_GRAPH = os.environ.get("TG_TRAIN_GRAPH", "1") != "0"
+GRAPH_WITH_NCCL = os.environ.get("TG_TRAIN_GRAPH_NCCL", "1") != "0"      # capture the data-parallel step (all-reduces included)
 GRAPH_WARMUP = 2
 
 VGG_MEAN = [123.68, 116.78, 103.94]          # code/train.py:6
@@ -321,7 +321,11 @@ class _GraphedStep:
         if self.graph is None:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
-            with torch.cuda.graph(g):
+            # data-parallel: the two gradient all-reduces are captured with the step (NCCL enqueues on its own stream, joined
+            # to the capture by events); NCCL's watchdog thread polls events concurrently, which only the thread-local
+            # capture mode tolerates
+            mode = "thread_local" if _par.world_size() > 1 else "global"
+            with torch.cuda.graph(g, capture_error_mode=mode):
                 self.out = TecoGAN(self.static_in, self.static_tg, D, G, args, step, c1, c2, og, od, _dt_ratio_dev=self.dt)
             self.graph = g
         self.graph.replay()
@@ -344,7 +348,7 @@ def FRVSR_Train(r_inputs, r_targets, args, discriminator_F, generator_F, step, c
                 optimizer_d):
     """code/train.py:374-377.  After GRAPH_WARMUP eager calls with the same networks / optimizers / shapes the step is
     captured in a CUDA graph and replayed (single process, fused Adam adoptable, TG_TRAIN_GRAPH != 0)."""
-    if (USE_CUDA_GRAPH and FUSED_ADAM and _par.world_size() == 1 and isinstance(r_inputs, torch.Tensor) and r_inputs.is_cuda
+    if (USE_CUDA_GRAPH and FUSED_ADAM and (_par.world_size() == 1 or GRAPH_WITH_NCCL) and isinstance(r_inputs, torch.Tensor) and r_inputs.is_cuda
             and _optim.FlatAdam.adoptable(generator_F, optimizer_g) and _optim.FlatAdam.adoptable(discriminator_F, optimizer_d)):
         key = _graph_key(r_inputs, r_targets, args, discriminator_F, generator_F, optimizer_g, optimizer_d)
         gs = _graphs.get(key)
