@@ -30,11 +30,14 @@ from . import parallel as _par
 from .models import *  # noqa: F401,F403  (reference: `from models import *`, code/train.py:1)
 
 # Fused flat-bucket Adam (tecogan_b200.optim) for the stock torch.optim.Adam objects main.py:239-243 builds, and CUDA-graph
-# capture of the whole step after GRAPH_WARMUP eager calls (data-parallel: the two NCCL all-reduces are captured with it).  Both are on by default and fall back to the eager / stock-optimizer path when they do not apply;
+# capture of the whole step after GRAPH_WARMUP eager calls (single process; the data-parallel step stays eager by default).  Both are on by default and fall back to the eager / stock-optimizer path when they do not apply;
 # TG_TRAIN_FUSED_ADAM=0 / TG_TRAIN_GRAPH=0 switch them off (A/B measurements).
 FUSED_ADAM = os.environ.get("TG_TRAIN_FUSED_ADAM", "1") != "0"
 USE_CUDA_GRAPH = os.environ.get("TG_TRAIN_GRAPH", "1") != "0"
-GRAPH_WITH_NCCL = os.environ.get("TG_TRAIN_GRAPH_NCCL", "1") != "0"      # capture the data-parallel step (all-reduces included)
+# Capturing the data-parallel step (the two NCCL all-reduces inside the graph) is EXPERIMENTAL and off: on a 2-GPU box the
+# captured steps ran, but torch.distributed's process-group teardown hung afterwards (profiles/r02_summary.md).  Opt in with
+# TG_TRAIN_GRAPH_NCCL=1; by default the data-parallel step runs eagerly (fused Adam still applies).
+GRAPH_WITH_NCCL = os.environ.get("TG_TRAIN_GRAPH_NCCL", "0") == "1"
 GRAPH_WARMUP = 2
 
 VGG_MEAN = [123.68, 116.78, 103.94]          # code/train.py:6

