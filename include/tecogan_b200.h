@@ -286,6 +286,14 @@ int tg_disc_forward(const float* flat_params, const void* packed, int nb, int ch
                     float* prob, float* const* feats, void* const* bn_running, int training,
                     void* workspace, size_t workspace_bytes, int n, int h, int w, void* stream);
 
+/* The same forward for `groups` (1 or 2) independent passes in ONE batch: x holds the groups back to back ([groups * n/groups,
+ * 27, h, w]; the real and the fake triplets of code/train.py:181,199), every convolution runs once over all n samples, and
+ * BatchNorm uses SEPARATE batch statistics per group and applies the running-statistics updates in group order — bit for
+ * bit what two consecutive tg_disc_forward calls produce, in half the launches.  tg_disc_backward_groups is its backward. */
+int tg_disc_forward_groups(const float* flat_params, const void* packed, int nb, int ch, int fc_in, const float* x,
+                           float* prob, float* const* feats, void* const* bn_running, int training, void* workspace,
+                           size_t workspace_bytes, int n, int groups, int h, int w, void* stream);
+
 /* discriminator backward (code/train.py:340, scaler.scale(discrim_loss).backward()).  The reference detaches the
  * discriminator's inputs (code/train.py:181,199) and the layer features (code/train.py:214), so the gradient enters
  * through prob only and no input gradient is produced.
@@ -298,6 +306,9 @@ int tg_disc_pack_dgrad(const float* flat_params, int nb, int ch, void* packed_dg
 int tg_disc_backward(const float* flat_params, const void* packed_dgrad, int nb, int ch, int fc_in,
                      const float* dprob, const float* prob, float* flat_grad, void* workspace,
                      size_t workspace_bytes, int n, int h, int w, void* stream);
+int tg_disc_backward_groups(const float* flat_params, const void* packed_dgrad, int nb, int ch, int fc_in,
+                            const float* dprob, const float* prob, float* flat_grad, void* workspace,
+                            size_t workspace_bytes, int n, int groups, int h, int w, void* stream);
 
 /* ------------------------------------------------------------ BatchNorm building blocks ---- */
 

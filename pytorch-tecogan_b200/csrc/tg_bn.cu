@@ -8,6 +8,7 @@ namespace tg {
 
 constexpr int kBnThreads = 256;
 constexpr int kBnMaxBlocks = 296;   // two per SM: enough loads in flight to stream at HBM rate, short serial tail
+constexpr int kBnMaxGroups = 2;     // independent BatchNorm batches inside one launch (the real and the fake pass)
 
 // ---------------------------------------------------------------------------------------------
 // Batch statistics of x [P pixels][C] f32 (raw conv outputs are kept in f32: normalisation amplifies rounding).  Every block reduces a strided slice of the pixels to
@@ -16,11 +17,18 @@ constexpr int kBnMaxBlocks = 296;   // two per SM: enough loads in flight to str
 // normalise+affine, and applies the running-statistics update of nn.BatchNorm2d (momentum 0.1,
 // unbiased variance).  The ticket is reset for the next use.
 // ---------------------------------------------------------------------------------------------
+// Groups (gridDim.y): the discriminator's real and fake forward passes (code/train.py:181,199) run as ONE batch of 2n
+// samples through every kernel; BatchNorm statistics stay per pass: group g = samples [g*n, (g+1)*n), its own partials
+// and stats block (stats + g*512).  The LAST block of all groups finalizes the groups in order 0, 1, ..., so the running
+// statistics receive the two momentum updates in the order two separate forward calls would apply them.
 __global__ void __launch_bounds__(kBnThreads)
 bn_stats_nhwc_kernel(const float* __restrict__ x, long long pixels, int c, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, float momentum, float* __restrict__ partial,
                      unsigned int* __restrict__ ticket, float* __restrict__ stats, float* running_mean,
                      float* running_var, long long* num_batches_tracked) {
+  x += static_cast<long long>(blockIdx.y) * pixels * c;
+  float* const partial_all = partial;
+  partial += static_cast<size_t>(blockIdx.y) * kBnMaxBlocks * 128 * 2;
   __shared__ float s_sum[kBnThreads][9];      // +1 padding
   __shared__ float s_sq[kBnThreads][9];
   __shared__ bool s_last;
@@ -51,33 +59,37 @@ bn_stats_nhwc_kernel(const float* __restrict__ x, long long pixels, int c, const
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1);
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   if (threadIdx.x < c) {
-    double a = 0.0, b = 0.0;
-    for (unsigned int k = 0; k < gridDim.x; ++k) {
-      a += static_cast<double>(__ldcg(partial + (static_cast<size_t>(k) * c + threadIdx.x) * 2 + 0));
-      b += static_cast<double>(__ldcg(partial + (static_cast<size_t>(k) * c + threadIdx.x) * 2 + 1));
-    }
-    const double mean = a / static_cast<double>(pixels);
-    double var = b / static_cast<double>(pixels) - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float ga = gamma[threadIdx.x] * rstd;
-    stats[threadIdx.x * 4 + 0] = static_cast<float>(mean);
-    stats[threadIdx.x * 4 + 1] = rstd;
-    stats[threadIdx.x * 4 + 2] = ga;
-    stats[threadIdx.x * 4 + 3] = beta[threadIdx.x] - static_cast<float>(mean) * ga;
-    if (running_mean) {
-      const double unbiased = pixels > 1 ? var * static_cast<double>(pixels) / static_cast<double>(pixels - 1) : var;
-      running_mean[threadIdx.x] = (1.f - momentum) * running_mean[threadIdx.x] + momentum * static_cast<float>(mean);
-      running_var[threadIdx.x] = (1.f - momentum) * running_var[threadIdx.x] + momentum * static_cast<float>(unbiased);
+    for (unsigned int g = 0; g < gridDim.y; ++g) {
+      const float* pg = partial_all + static_cast<size_t>(g) * kBnMaxBlocks * 128 * 2;
+      float* sg = stats + g * 512;
+      double a = 0.0, b = 0.0;
+      for (unsigned int k = 0; k < gridDim.x; ++k) {
+        a += static_cast<double>(__ldcg(pg + (static_cast<size_t>(k) * c + threadIdx.x) * 2 + 0));
+        b += static_cast<double>(__ldcg(pg + (static_cast<size_t>(k) * c + threadIdx.x) * 2 + 1));
+      }
+      const double mean = a / static_cast<double>(pixels);
+      double var = b / static_cast<double>(pixels) - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      const float ga = gamma[threadIdx.x] * rstd;
+      sg[threadIdx.x * 4 + 0] = static_cast<float>(mean);
+      sg[threadIdx.x * 4 + 1] = rstd;
+      sg[threadIdx.x * 4 + 2] = ga;
+      sg[threadIdx.x * 4 + 3] = beta[threadIdx.x] - static_cast<float>(mean) * ga;
+      if (running_mean) {
+        const double unbiased = pixels > 1 ? var * static_cast<double>(pixels) / static_cast<double>(pixels - 1) : var;
+        running_mean[threadIdx.x] = (1.f - momentum) * running_mean[threadIdx.x] + momentum * static_cast<float>(mean);
+        running_var[threadIdx.x] = (1.f - momentum) * running_var[threadIdx.x] + momentum * static_cast<float>(unbiased);
+      }
     }
   }
   if (threadIdx.x == 0) {
-    if (num_batches_tracked) *num_batches_tracked += 1;
+    if (num_batches_tracked) *num_batches_tracked += gridDim.y;
     *ticket = 0u;
   }
 }
@@ -102,6 +114,14 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_apply_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ skip, float* __restrict__ y32,
                      __nv_bfloat16* __restrict__ y16, long long pixels, int c, const float* __restrict__ stats, int act) {
   __shared__ float s_a[128], s_b[128];
+  {                                                           // group blockIdx.y: its slice of every tensor, its stats block
+    const long long goff = static_cast<long long>(blockIdx.y) * pixels * c;
+    x += goff;
+    if (skip) skip += goff;
+    if (y32) y32 += goff;
+    if (y16) y16 += goff;
+    stats += blockIdx.y * 512;
+  }
   for (int i = threadIdx.x; i < c; i += blockDim.x) { s_a[i] = stats[i * 4 + 2]; s_b[i] = stats[i * 4 + 3]; }
   __syncthreads();
   const int groups = c / 4;
@@ -151,13 +171,19 @@ nhwc_f32_to_nchw_f32_kernel(const float* __restrict__ in, float* __restrict__ ou
 // Saves y (post-LeakyReLU, the fc input) and {mean, rstd, a, b} for the backward pass.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-disc_head_kernel(const float* __restrict__ r, int n, int hw, const float* __restrict__ gamma, const float* __restrict__ beta,
+disc_head_kernel(const float* r, int n, int hw, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, float momentum, int training, float* running_mean, float* running_var,
                  long long* num_batches_tracked, const float* __restrict__ fc_w, const float* __restrict__ fc_b,
-                 float* __restrict__ y, float* __restrict__ stats, float* __restrict__ logit, float* __restrict__ prob) {
+                 float* y, float* stats, float* logit, float* prob, int ngroups) {
   __shared__ double s_red[2][256];
   __shared__ float s_ab[3][2];
   const int per = n * hw;
+  // groups (gridDim.x is 1; the group loop is serial so that the running statistics see the passes in order)
+  const float* const r_all = r; float* const y_all = y; float* const stats_all = stats; float* const logit_all = logit; float* const prob_all = prob;
+  for (int grp = 0; grp < ngroups; ++grp) {
+  r = r_all + static_cast<size_t>(grp) * n * 3 * hw; y = y_all + static_cast<size_t>(grp) * n * 3 * hw;
+  stats = stats_all + grp * 512; logit = logit_all ? logit_all + grp * n : nullptr; prob = prob_all + grp * n;
+  __syncthreads();
   for (int ch = 0; ch < 3; ++ch) {
     double a = 0.0, b = 0.0;
     if (training) {
@@ -214,6 +240,7 @@ disc_head_kernel(const float* __restrict__ r, int n, int hw, const float* __rest
       prob[s] = 1.f / (1.f + expf(-z));
     }
   }
+  }   // groups
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -230,6 +257,14 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g_out, const float* __res
   __shared__ float s_sum[kBnThreads][9];
   __shared__ float s_sq[kBnThreads][9];
   __shared__ bool s_last;
+  {                                                           // group blockIdx.y (see bn_stats_nhwc_kernel)
+    const long long goff = static_cast<long long>(blockIdx.y) * pixels * c;
+    g_out += goff; x += goff;
+    if (act) act += goff;
+    stats += blockIdx.y * 512;
+  }
+  float* const partial_all = partial;
+  partial += static_cast<size_t>(blockIdx.y) * kBnMaxBlocks * 128 * 2;
   const int groups = c / 8;
   const int pix_per_iter = kBnThreads / groups;
   const int gi = threadIdx.x % groups, pl = threadIdx.x / groups;
@@ -269,20 +304,23 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g_out, const float* __res
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1);
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   if (threadIdx.x < c) {
-    double a = 0.0, b = 0.0;
-    for (unsigned int k = 0; k < gridDim.x; ++k) {
-      a += static_cast<double>(__ldcg(partial + (static_cast<size_t>(k) * c + threadIdx.x) * 2 + 0));
-      b += static_cast<double>(__ldcg(partial + (static_cast<size_t>(k) * c + threadIdx.x) * 2 + 1));
+    for (unsigned int g = 0; g < gridDim.y; ++g) {
+      const float* pg = partial_all + static_cast<size_t>(g) * kBnMaxBlocks * 128 * 2;
+      double a = 0.0, b = 0.0;
+      for (unsigned int k = 0; k < gridDim.x; ++k) {
+        a += static_cast<double>(__ldcg(pg + (static_cast<size_t>(k) * c + threadIdx.x) * 2 + 0));
+        b += static_cast<double>(__ldcg(pg + (static_cast<size_t>(k) * c + threadIdx.x) * 2 + 1));
+      }
+      dbeta[threadIdx.x] += static_cast<float>(a);
+      dgamma[threadIdx.x] += static_cast<float>(b);
+      red[g * 256 + threadIdx.x * 2 + 0] = static_cast<float>(a / static_cast<double>(pixels));
+      red[g * 256 + threadIdx.x * 2 + 1] = static_cast<float>(b / static_cast<double>(pixels));
     }
-    dbeta[threadIdx.x] += static_cast<float>(a);
-    dgamma[threadIdx.x] += static_cast<float>(b);
-    red[threadIdx.x * 2 + 0] = static_cast<float>(a / static_cast<double>(pixels));
-    red[threadIdx.x * 2 + 1] = static_cast<float>(b / static_cast<double>(pixels));
   }
   if (threadIdx.x == 0) *ticket = 0u;
 }
@@ -292,6 +330,13 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g_out, const float* __rest
                     __nv_bfloat16* __restrict__ dx, long long pixels, int c, const float* __restrict__ stats,
                     const float* __restrict__ red) {
   __shared__ float s_mean[128], s_rstd[128], s_a[128], s_m1[128], s_m2[128];
+  {
+    const long long goff = static_cast<long long>(blockIdx.y) * pixels * c;
+    g_out += goff; x += goff; dx += goff;
+    if (act) act += goff;
+    stats += blockIdx.y * 512;
+    red += blockIdx.y * 256;
+  }
   for (int i = threadIdx.x; i < c; i += blockDim.x) {
     s_mean[i] = stats[i * 4 + 0]; s_rstd[i] = stats[i * 4 + 1]; s_a[i] = stats[i * 4 + 2];
     s_m1[i] = red[i * 2 + 0]; s_m2[i] = red[i * 2 + 1];
@@ -325,13 +370,18 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g_out, const float* __rest
 // Backward of the discriminator head (disc_head_kernel), one block: dprob -> sigmoid -> fc -> LeakyReLU -> BatchNorm(3).
 // Writes d(raw block5 conv output) as NHWC bf16 [n][hw][64] (3 real channels) and ADDS the fc / BN parameter gradients.
 __global__ void __launch_bounds__(256)
-disc_head_bwd_kernel(const float* __restrict__ dprob, const float* __restrict__ prob, const float* __restrict__ y,
-                     const float* __restrict__ r, int n, int hw, const float* __restrict__ stats,
+disc_head_bwd_kernel(const float* dprob, const float* prob, const float* y, const float* r, int n, int hw, const float* stats,
                      const float* __restrict__ fc_w, float* d_fc_w, float* d_fc_b, float* dgamma, float* dbeta,
-                     float* __restrict__ dlogit, __nv_bfloat16* __restrict__ dr) {
+                     float* dlogit, __nv_bfloat16* dr, int ngroups) {
   __shared__ double s_red[2][256];
   __shared__ float s_m[3][2];
   const int feat = 3 * hw, per = n * hw;
+  const float* const dprob_all = dprob; const float* const prob_all = prob; const float* const y_all = y; const float* const r_all = r;
+  const float* const stats_all = stats; float* const dlogit_all = dlogit; __nv_bfloat16* const dr_all = dr;
+  for (int grp = 0; grp < ngroups; ++grp) {
+  dprob = dprob_all + grp * n; prob = prob_all + grp * n; y = y_all + static_cast<size_t>(grp) * n * feat; r = r_all + static_cast<size_t>(grp) * n * feat;
+  stats = stats_all + grp * 512; dlogit = dlogit_all + grp * n; dr = dr_all + static_cast<size_t>(grp) * per * 64;
+  __syncthreads();
   for (int s = threadIdx.x; s < n; s += blockDim.x) dlogit[s] = dprob[s] * prob[s] * (1.f - prob[s]);
   __syncthreads();
   for (int k = threadIdx.x; k < feat; k += blockDim.x) {           // fc weight gradient
@@ -382,27 +432,29 @@ disc_head_bwd_kernel(const float* __restrict__ dprob, const float* __restrict__ 
 #pragma unroll
     for (int k = 1; k < 8; ++k) dst[k] = make_uint4(0u, 0u, 0u, 0u);
   }
+  }   // groups
 }
 
 // ------------------------------------------------------------------------------------ launchers
 int bn_stats_launch(const void* x, long long pixels, int c, const float* gamma, const float* beta, float* partial,
                     unsigned int* ticket, float* stats, float* running_mean, float* running_var,
-                    long long* nbt, cudaStream_t st) {
+                    long long* nbt, cudaStream_t st, int groups) {
   TG_CHECK_ARG(c == 64 || c == 128, "bn_stats: channels must be 64 or 128 (got %d)", c);
   TG_CHECK_ARG(pixels >= 1, "bn_stats: empty batch");
+  TG_CHECK_ARG(groups >= 1 && groups <= kBnMaxGroups, "bn: groups must be 1..%d", kBnMaxGroups);
   const int pix_per_iter = kBnThreads / (c / 8);
   long long blocks = (pixels + pix_per_iter * 4 - 1) / (pix_per_iter * 4);
   if (blocks > kBnMaxBlocks) blocks = kBnMaxBlocks;
   if (blocks < 1) blocks = 1;
-  tg_prof_pre(TG_K_GLUE, 4.0 * pixels * c, st);
-  bn_stats_nhwc_kernel<<<static_cast<int>(blocks), kBnThreads, 0, st>>>(
+  tg_prof_pre(TG_K_GLUE, 4.0 * pixels * c * groups, st);
+  bn_stats_nhwc_kernel<<<dim3(static_cast<int>(blocks), groups), kBnThreads, 0, st>>>(
       static_cast<const float*>(x), pixels, c, gamma, beta, 1e-3f, 0.1f, partial, ticket, stats, running_mean,
       running_var, nbt);
   tg_prof_post(st);
   TG_CUDA(cudaGetLastError());
   return TG_OK;
 }
-size_t bn_partial_floats() { return static_cast<size_t>(kBnMaxBlocks) * 128 * 2; }
+size_t bn_partial_floats() { return static_cast<size_t>(kBnMaxGroups) * kBnMaxBlocks * 128 * 2; }
 
 int bn_fold_running_launch(int c, const float* gamma, const float* beta, const float* running_mean,
                            const float* running_var, float* stats, cudaStream_t st) {
@@ -412,14 +464,15 @@ int bn_fold_running_launch(int c, const float* gamma, const float* beta, const f
 }
 
 int bn_apply_launch(const void* x, const void* skip, void* y32, void* y16, long long pixels, int c, const float* stats,
-                    int act, cudaStream_t st) {
+                    int act, cudaStream_t st, int groups) {
   TG_CHECK_ARG(c == 64 || c == 128, "bn_apply: channels must be 64 or 128 (got %d)", c);
+  TG_CHECK_ARG(groups >= 1 && groups <= kBnMaxGroups, "bn: groups must be 1..%d", kBnMaxGroups);
   const long long total = pixels * (c / 4);
   long long blocks = (total + kBnThreads - 1) / kBnThreads;
   const long long cap = static_cast<long long>(tg_num_sms()) * 8;
   if (blocks > cap) blocks = cap;
-  tg_prof_pre(TG_K_GLUE, (skip ? 14.0 : 10.0) * pixels * c, st);
-  bn_apply_nhwc_kernel<<<static_cast<int>(blocks), kBnThreads, 0, st>>>(
+  tg_prof_pre(TG_K_GLUE, (skip ? 14.0 : 10.0) * pixels * c * groups, st);
+  bn_apply_nhwc_kernel<<<dim3(static_cast<int>(blocks), groups), kBnThreads, 0, st>>>(
       static_cast<const float*>(x), static_cast<const float*>(skip), static_cast<float*>(y32),
       static_cast<__nv_bfloat16*>(y16), pixels, c, stats, act);
   tg_prof_post(st);
@@ -441,24 +494,25 @@ int nhwc_to_nchw_f32_launch(const void* in, float* out, int n, int c, long long 
 
 int disc_head_launch(const float* r, int n, int hw, const float* gamma, const float* beta, int training,
                      float* running_mean, float* running_var, long long* nbt, const float* fc_w, const float* fc_b,
-                     float* y, float* stats, float* logit, float* prob, cudaStream_t st) {
-  tg_prof_pre(TG_K_GLUE, 8.0 * n * 3 * hw, st);
+                     float* y, float* stats, float* logit, float* prob, cudaStream_t st, int groups) {
+  tg_prof_pre(TG_K_GLUE, 8.0 * n * 3 * hw * groups, st);
   disc_head_kernel<<<1, 256, 0, st>>>(r, n, hw, gamma, beta, 1e-3f, 0.1f, training, running_mean, running_var, nbt, fc_w,
-                                      fc_b, y, stats, logit, prob);
+                                      fc_b, y, stats, logit, prob, groups);
   tg_prof_post(st);
   TG_CUDA(cudaGetLastError());
   return TG_OK;
 }
 
 int bn_bwd_launch(const void* g_out, const void* x, const void* act, void* dx, long long pixels, int c, const float* stats,
-                  float* partial, unsigned int* ticket, float* red, float* dgamma, float* dbeta, cudaStream_t st) {
+                  float* partial, unsigned int* ticket, float* red, float* dgamma, float* dbeta, cudaStream_t st, int groups) {
   TG_CHECK_ARG(c == 64 || c == 128, "bn_bwd: channels must be 64 or 128 (got %d)", c);
+  TG_CHECK_ARG(groups >= 1 && groups <= kBnMaxGroups, "bn: groups must be 1..%d", kBnMaxGroups);
   const int pix_per_iter = kBnThreads / (c / 8);
   long long blocks = (pixels + pix_per_iter * 4 - 1) / (pix_per_iter * 4);
   if (blocks > kBnMaxBlocks) blocks = kBnMaxBlocks;
   if (blocks < 1) blocks = 1;
-  tg_prof_pre(TG_K_GLUE, (act ? 10.0 : 6.0) * pixels * c, st);
-  bn_bwd_reduce_kernel<<<static_cast<int>(blocks), kBnThreads, 0, st>>>(
+  tg_prof_pre(TG_K_GLUE, (act ? 10.0 : 6.0) * pixels * c * groups, st);
+  bn_bwd_reduce_kernel<<<dim3(static_cast<int>(blocks), groups), kBnThreads, 0, st>>>(
       static_cast<const __nv_bfloat16*>(g_out), static_cast<const float*>(x), static_cast<const float*>(act), pixels, c, stats,
       partial, ticket, red, dgamma, dbeta);
   tg_prof_post(st);
@@ -467,8 +521,8 @@ int bn_bwd_launch(const void* g_out, const void* x, const void* act, void* dx, l
   long long ab = (total + kBnThreads - 1) / kBnThreads;
   const long long cap = static_cast<long long>(tg_num_sms()) * 8;
   if (ab > cap) ab = cap;
-  tg_prof_pre(TG_K_GLUE, (act ? 12.0 : 8.0) * pixels * c, st);
-  bn_bwd_apply_kernel<<<static_cast<int>(ab), kBnThreads, 0, st>>>(
+  tg_prof_pre(TG_K_GLUE, (act ? 12.0 : 8.0) * pixels * c * groups, st);
+  bn_bwd_apply_kernel<<<dim3(static_cast<int>(ab), groups), kBnThreads, 0, st>>>(
       static_cast<const __nv_bfloat16*>(g_out), static_cast<const float*>(x), static_cast<const float*>(act),
       static_cast<__nv_bfloat16*>(dx), pixels, c, stats, red);
   tg_prof_post(st);
@@ -478,10 +532,10 @@ int bn_bwd_launch(const void* g_out, const void* x, const void* act, void* dx, l
 
 int disc_head_bwd_launch(const float* dprob, const float* prob, const float* y, const float* r, int n, int hw,
                          const float* stats, const float* fc_w, float* d_fc_w, float* d_fc_b, float* dgamma, float* dbeta,
-                         float* dlogit, void* dr, cudaStream_t st) {
-  tg_prof_pre(TG_K_GLUE, 16.0 * n * 3 * hw, st);
+                         float* dlogit, void* dr, cudaStream_t st, int groups) {
+  tg_prof_pre(TG_K_GLUE, 16.0 * n * 3 * hw * groups, st);
   disc_head_bwd_kernel<<<1, 256, 0, st>>>(dprob, prob, y, r, n, hw, stats, fc_w, d_fc_w, d_fc_b, dgamma, dbeta, dlogit,
-                                          static_cast<__nv_bfloat16*>(dr));
+                                          static_cast<__nv_bfloat16*>(dr), groups);
   tg_prof_post(st);
   TG_CUDA(cudaGetLastError());
   return TG_OK;
@@ -499,7 +553,7 @@ BnWs bn_ws() {
   w.partial = 0;
   w.ticket = (bn_partial_floats() * 4 + 255) & ~static_cast<size_t>(255);
   w.red = w.ticket + 256;
-  w.total = w.red + 2 * 128 * 4;
+  w.total = w.red + kBnMaxGroups * 2 * 128 * 4;
   return w;
 }
 int bn_check_ws(const char* who, const void* ws, size_t bytes) {

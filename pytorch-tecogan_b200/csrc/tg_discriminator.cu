@@ -59,6 +59,8 @@ static DLayout disc_layout(int nb, int ch, int fc_in) {
 static inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
 // Workspace: every activation of the forward pass is kept (the backward pass reads them).
+constexpr size_t kStatStride = 2 * 128 * 4;     // floats of one BatchNorm layer's statistics: [group (<= 2)][128][4]
+
 struct DWorkspace {
   size_t x_in, a0;                    // packed input, conv.0 output
   // per BN layer: raw conv output (f32), BN(+act/skip) output as f32 (residual stream, features) and as bf16
@@ -92,7 +94,7 @@ static DWorkspace disc_ws(int n, int h, int w, int nb, int ch) {
   const size_t p5 = px >> 10;
   ws.r5 = take(p5 * 3 * 4);
   ws.y5 = take(p5 * 3 * 4);
-  ws.stats = take(static_cast<size_t>(5 + 3 * nb) * 128 * 4 * 4);
+  ws.stats = take(static_cast<size_t>(5 + 3 * nb) * kStatStride * 4);
   ws.partial = take(bn_partial_floats() * 4);
   ws.tickets = take(256);
   ws.logit = take(static_cast<size_t>(n) * 4);
@@ -101,7 +103,7 @@ static DWorkspace disc_ws(int n, int h, int w, int nb, int ch) {
   ws.d_a0 = take(px * 64 * 2);
   ws.d_r5 = take(p5 * 64 * 2);
   ws.d_logit = take(static_cast<size_t>(n) * 4);
-  ws.red = take(2 * 128 * 4);
+  ws.red = take(2 * 2 * 128 * 4);
   ws.total = o;
   return ws;
 }
@@ -145,7 +147,15 @@ extern "C" size_t tg_workspace_bytes_disc(int n, int h, int w, int nb, int ch) {
 extern "C" int tg_disc_forward(const float* flat_params, const void* packed, int nb, int ch, int fc_in, const float* x,
                                float* prob, float* const* feats, void* const* bn_running, int training,
                                void* workspace, size_t workspace_bytes, int n, int h, int w, void* stream) {
+  return tg_disc_forward_groups(flat_params, packed, nb, ch, fc_in, x, prob, feats, bn_running, training, workspace,
+                                workspace_bytes, n, 1, h, w, stream);
+}
+
+extern "C" int tg_disc_forward_groups(const float* flat_params, const void* packed, int nb, int ch, int fc_in, const float* x,
+                                      float* prob, float* const* feats, void* const* bn_running, int training,
+                                      void* workspace, size_t workspace_bytes, int n, int groups, int h, int w, void* stream) {
   TG_CHECK_ARG(flat_params && packed && x && prob && workspace, "disc_forward: null pointer");
+  TG_CHECK_ARG(groups >= 1 && groups <= 2 && n % groups == 0, "disc_forward: n = %d samples do not split into %d groups", n, groups);
   if (int rc = check_cfg(nb, ch)) return rc;
   TG_CHECK_ARG(n >= 1 && h >= 32 && w >= 32 && (h % 32) == 0 && (w % 32) == 0,
                "disc_forward: input must be [n,27,h,w] with h, w multiples of 32 (got %dx%d)", h, w);
@@ -180,17 +190,19 @@ extern "C" int tg_disc_forward(const float* flat_params, const void* packed, int
   // BatchNorm (+ LeakyReLU or + skip) of the raw conv output of BN layer `bi`
   auto bn = [&](const void* raw, const void* skip, void* out32, void* out16, long long pixels, int act) {
     const DBn& b = L.bns[bi];
-    float* stats = stats_all + static_cast<size_t>(bi) * 128 * 4;
+    float* stats = stats_all + static_cast<size_t>(bi) * kStatStride;
     float* rm = bn_running ? static_cast<float*>(bn_running[3 * bi + 0]) : nullptr;
     float* rv = bn_running ? static_cast<float*>(bn_running[3 * bi + 1]) : nullptr;
     long long* nbt = bn_running ? static_cast<long long*>(bn_running[3 * bi + 2]) : nullptr;
-    int rc;
-    if (training) rc = bn_stats_launch(raw, pixels, b.c, flat_params + b.g_off, flat_params + b.b_off, partial, tickets, stats,
-                                       rm, rv, nbt, st);
-    else rc = bn_fold_running_launch(b.c, flat_params + b.g_off, flat_params + b.b_off, rm, rv, stats, st);
+    int rc = TG_OK;
+    // `pixels` is the whole batch; the statistics are per group (= per forward pass of the reference)
+    if (training) rc = bn_stats_launch(raw, pixels / groups, b.c, flat_params + b.g_off, flat_params + b.b_off, partial, tickets, stats,
+                                       rm, rv, nbt, st, groups);
+    else for (int g = 0; g < groups && !rc; ++g)
+      rc = bn_fold_running_launch(b.c, flat_params + b.g_off, flat_params + b.b_off, rm, rv, stats + g * 512, st);
     if (rc) return rc;
     ++bi;
-    return bn_apply_launch(raw, skip, out32, out16, pixels, b.c, stats, act, st);
+    return bn_apply_launch(raw, skip, out32, out16, pixels / groups, b.c, stats, act, st, groups);
   };
 
   int rc;
@@ -229,10 +241,10 @@ extern "C" int tg_disc_forward(const float* flat_params, const void* packed, int
     float* rm = bn_running ? static_cast<float*>(bn_running[3 * bi + 0]) : nullptr;
     float* rv = bn_running ? static_cast<float*>(bn_running[3 * bi + 1]) : nullptr;
     long long* nbt = bn_running ? static_cast<long long*>(bn_running[3 * bi + 2]) : nullptr;
-    rc = disc_head_launch(reinterpret_cast<const float*>(wsp + ws.r5), n, hh * ww, flat_params + b.g_off, flat_params + b.b_off,
+    rc = disc_head_launch(reinterpret_cast<const float*>(wsp + ws.r5), n / groups, hh * ww, flat_params + b.g_off, flat_params + b.b_off,
                           training, rm, rv, nbt, flat_params + L.fc_w, flat_params + L.fc_b,
-                          reinterpret_cast<float*>(wsp + ws.y5), stats_all + static_cast<size_t>(bi) * 128 * 4,
-                          reinterpret_cast<float*>(wsp + ws.logit), prob, st);
+                          reinterpret_cast<float*>(wsp + ws.y5), stats_all + static_cast<size_t>(bi) * kStatStride,
+                          reinterpret_cast<float*>(wsp + ws.logit), prob, st, groups);
   }
   return rc;
 }
@@ -282,7 +294,15 @@ extern "C" int tg_disc_pack_dgrad(const float* flat_params, int nb, int ch, void
 extern "C" int tg_disc_backward(const float* flat_params, const void* packed_dgrad, int nb, int ch, int fc_in,
                                 const float* dprob, const float* prob, float* flat_grad, void* workspace,
                                 size_t workspace_bytes, int n, int h, int w, void* stream) {
+  return tg_disc_backward_groups(flat_params, packed_dgrad, nb, ch, fc_in, dprob, prob, flat_grad, workspace, workspace_bytes, n, 1,
+                                 h, w, stream);
+}
+
+extern "C" int tg_disc_backward_groups(const float* flat_params, const void* packed_dgrad, int nb, int ch, int fc_in,
+                                       const float* dprob, const float* prob, float* flat_grad, void* workspace,
+                                       size_t workspace_bytes, int n, int groups, int h, int w, void* stream) {
   TG_CHECK_ARG(flat_params && packed_dgrad && dprob && prob && flat_grad && workspace, "disc_backward: null pointer");
+  TG_CHECK_ARG(groups >= 1 && groups <= 2 && n % groups == 0, "disc_backward: n = %d samples do not split into %d groups", n, groups);
   if (int rc = check_cfg(nb, ch)) return rc;
   TG_CHECK_ARG(n >= 1 && h >= 32 && w >= 32 && (h % 32) == 0 && (w % 32) == 0, "disc_backward: bad shape");
   TG_CHECK_ARG(fc_in == 3 * (h / 32) * (w / 32), "disc_backward: fc in-features do not match the input size");
@@ -322,8 +342,8 @@ extern "C" int tg_disc_backward(const float* flat_params, const void* packed_dgr
   };
   auto bn_bwd = [&](int bi, const void* g_out, const void* raw, const void* act, void* dx, long long pixels) {
     const DBn& b = L.bns[bi];
-    return bn_bwd_launch(g_out, raw, act, dx, pixels, b.c, stats_all + static_cast<size_t>(bi) * 128 * 4, partial, tickets, red,
-                         flat_grad + b.g_off, flat_grad + b.b_off, st);
+    return bn_bwd_launch(g_out, raw, act, dx, pixels / groups, b.c, stats_all + static_cast<size_t>(bi) * kStatStride, partial, tickets, red,
+                         flat_grad + b.g_off, flat_grad + b.b_off, st, groups);
   };
 
   const int n_conv = static_cast<int>(L.convs.size()), n_bn = static_cast<int>(L.bns.size());
@@ -331,10 +351,10 @@ extern "C" int tg_disc_backward(const float* flat_params, const void* packed_dgr
   {
     const DBn& b = L.bns[n_bn - 1];
     const int hw5 = (h / 32) * (w / 32);
-    rc = disc_head_bwd_launch(dprob, prob, reinterpret_cast<const float*>(wsp + ws.y5), reinterpret_cast<const float*>(wsp + ws.r5), n,
-                              hw5, stats_all + static_cast<size_t>(n_bn - 1) * 128 * 4, flat_params + L.fc_w, flat_grad + L.fc_w,
-                              flat_grad + L.fc_b, flat_grad + b.g_off, flat_grad + b.b_off,
-                              reinterpret_cast<float*>(wsp + ws.d_logit), B(ws.d_r5), st);
+    rc = disc_head_bwd_launch(dprob, prob, reinterpret_cast<const float*>(wsp + ws.y5), reinterpret_cast<const float*>(wsp + ws.r5),
+                              n / groups, hw5, stats_all + static_cast<size_t>(n_bn - 1) * kStatStride, flat_params + L.fc_w,
+                              flat_grad + L.fc_w, flat_grad + L.fc_b, flat_grad + b.g_off, flat_grad + b.b_off,
+                              reinterpret_cast<float*>(wsp + ws.d_logit), B(ws.d_r5), st, groups);
     if (rc) return rc;
   }
   // walk the forward structure backwards.  Indices at the END of the forward pass:

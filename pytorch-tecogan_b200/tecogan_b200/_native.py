@@ -91,6 +91,10 @@ SIGNATURES = {
     "tg_disc_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int, _c_int]),
     "tg_disc_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                  _c_int, _c_void_p, _c_size_t, _c_int, _c_int, _c_int, _c_void_p]),
+    "tg_disc_forward_groups": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                        _c_int, _c_void_p, _c_size_t, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "tg_disc_backward_groups": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                         _c_size_t, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "tg_disc_packed_dgrad_bytes": (_c_size_t, [_c_int, _c_int]),
     "tg_disc_pack_dgrad": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
     "tg_disc_backward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,

@@ -374,8 +374,9 @@ class discriminator(nn.Module):
             self._packed_dgrad, self._packed_dgrad_key = buf, self._key
         return self._packed_dgrad
 
-    def _run(self, x, ws):
-        """one tg_disc_forward launch sequence into workspace `ws`; returns (prob, feats)."""
+    def _run(self, x, ws, groups=1):
+        """one tg_disc_forward launch sequence into workspace `ws`; returns (prob, feats).  groups = 2: x holds two
+        independent passes back to back (BatchNorm statistics per pass)."""
         import ctypes
         lib = _nt.lib()
         n, _, h, w = x.shape
@@ -390,12 +391,27 @@ class discriminator(nn.Module):
             run[3 * i + 0] = m.running_mean.data_ptr()
             run[3 * i + 1] = m.running_var.data_ptr()
             run[3 * i + 2] = m.num_batches_tracked.data_ptr()
-        _nt.check(lib.tg_disc_forward(_nt.ptr(flat), _nt.ptr(packed), self.nb, self.ch, self.fc.in_features, _nt.ptr(x),
-                                      _nt.ptr(prob), feat_ptrs, run, 1 if self.training else 0, _nt.ptr(ws),
-                                      ws.numel(), n, h, w, _nt.stream_ptr()))
+        _nt.check(lib.tg_disc_forward_groups(_nt.ptr(flat), _nt.ptr(packed), self.nb, self.ch, self.fc.in_features, _nt.ptr(x),
+                                             _nt.ptr(prob), feat_ptrs, run, 1 if self.training else 0, _nt.ptr(ws),
+                                             ws.numel(), n, int(groups), h, w, _nt.stream_ptr()))
         return prob, feats
 
+    def forward_pair(self, x_real, x_fake):
+        """``(self(x_real), self(x_fake))`` — the two discriminator passes of a training step (code/train.py:181,199) — as ONE
+        batch: every convolution / weight-gradient kernel runs once over both halves, BatchNorm keeps separate batch
+        statistics per half and updates the running statistics in call order (real, then fake), so the results are those
+        of two consecutive calls at half the launches.  Returns ((prob_real, feats_real), (prob_fake, feats_fake))."""
+        if x_real.shape != x_fake.shape:
+            raise RuntimeError("discriminator.forward_pair: the two inputs must have the same shape")
+        n = x_real.shape[0]
+        prob, feats = self._forward_groups(torch.cat((x_real, x_fake), dim=0), 2)
+        return (prob[:n], [f[:n] for f in feats]), (prob[n:], [f[n:] for f in feats])
+
     def forward(self, x):
+        prob, feats = self._forward_groups(x, 1)
+        return prob, feats
+
+    def _forward_groups(self, x, groups):
         if not x.is_cuda:
             raise RuntimeError("discriminator.forward: input must be a CUDA tensor (no CPU fallback)")
         if x.dim() != 4 or x.shape[1] != 27:
@@ -407,7 +423,7 @@ class discriminator(nn.Module):
             if not self.training:
                 raise RuntimeError("discriminator: backward needs train-mode BatchNorm (the reference never leaves it)")
             use_bucket, leaves = _grad_inputs(self, [p for _, p in self.named_parameters()])
-            prob, *feats = _DiscriminatorFn.apply(x, self, use_bucket, *leaves)
+            prob, *feats = _DiscriminatorFn.apply(x, self, use_bucket, groups, *leaves)
             return prob, feats
         lib = _nt.lib()
         x = x.float().contiguous()
@@ -415,7 +431,7 @@ class discriminator(nn.Module):
         need = lib.tg_disc_workspace_bytes(n, h, w, self.nb, self.ch)
         if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
             self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
-        return self._run(x, self._ws)
+        return self._run(x, self._ws, groups)
 
 
 class _DiscriminatorFn(torch.autograd.Function):
@@ -424,13 +440,13 @@ class _DiscriminatorFn(torch.autograd.Function):
     features are returned detached exactly as the reference consumes them (code/train.py:214)."""
 
     @staticmethod
-    def forward(ctx, x, module, use_bucket, *params):
+    def forward(ctx, x, module, use_bucket, groups, *params):
         lib = _nt.lib()
         x = x.detach().float().contiguous()
         n, _, h, w = x.shape
         ws = torch.empty(lib.tg_disc_workspace_bytes(n, h, w, module.nb, module.ch), dtype=torch.uint8, device=x.device)
-        prob, feats = module._run(x, ws)
-        ctx.module, ctx.ws, ctx.shape, ctx.use_bucket = module, ws, (n, h, w), use_bucket
+        prob, feats = module._run(x, ws, groups)
+        ctx.module, ctx.ws, ctx.shape, ctx.use_bucket, ctx.groups = module, ws, (n, h, w), use_bucket, groups
         ctx.flat, _ = module._weights()
         ctx.packed_dgrad = module._dgrad_weights()
         ctx.save_for_backward(prob)
@@ -450,17 +466,17 @@ class _DiscriminatorFn(torch.autograd.Function):
         bucket = module._grad_bucket if ctx.use_bucket else None
         flat_grad = bucket if bucket is not None else torch.zeros(ctx.flat.numel(), dtype=torch.float32, device=prob.device)
         g = dprob.float().contiguous()
-        _nt.check(lib.tg_disc_backward(_nt.ptr(ctx.flat), _nt.ptr(ctx.packed_dgrad), module.nb, module.ch, module.fc.in_features,
-                                       _nt.ptr(g), _nt.ptr(prob), _nt.ptr(flat_grad), _nt.ptr(ctx.ws), ctx.ws.numel(), n, h, w,
-                                       _nt.stream_ptr()))
+        _nt.check(lib.tg_disc_backward_groups(_nt.ptr(ctx.flat), _nt.ptr(ctx.packed_dgrad), module.nb, module.ch, module.fc.in_features,
+                                              _nt.ptr(g), _nt.ptr(prob), _nt.ptr(flat_grad), _nt.ptr(ctx.ws), ctx.ws.numel(), n,
+                                              int(ctx.groups), h, w, _nt.stream_ptr()))
         ctx.ws = None
         if bucket is not None:          # gradients were accumulated in place into the bound flat bucket (p.grad are views)
-            return (None, None, None, None)
+            return (None, None, None, None, None)
         grads, o = [], 0
         for p in params:
             grads.append(flat_grad[o:o + p.numel()].view_as(p).to(p.dtype))
             o += p.numel()
-        return (None, None, None, *grads)
+        return (None, None, None, None, *grads)
 
 
 def f_net():

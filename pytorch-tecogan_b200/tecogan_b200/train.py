@@ -39,6 +39,7 @@ USE_CUDA_GRAPH = os.environ.get("TG_TRAIN_GRAPH", "1") != "0"
 # TG_TRAIN_GRAPH_NCCL=1; by default the data-parallel step runs eagerly (fused Adam still applies).
 GRAPH_WITH_NCCL = os.environ.get("TG_TRAIN_GRAPH_NCCL", "0") == "1"
 GRAPH_WARMUP = 2
+PAIR_DISCRIMINATOR_PASSES = os.environ.get("TG_TRAIN_PAIR_D", "1") != "0"   # real + fake discriminator pass as one batch
 
 VGG_MEAN = [123.68, 116.78, 103.94]          # code/train.py:6
 identity = torch.nn.Identity()               # code/train.py:7
@@ -178,8 +179,13 @@ def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step
 
     # ---- discriminator on real / fake triplets (:130-199)
     real_in, fake_in = discriminator_inputs(r_inputs, r_targets, gen_tb, args)
-    tdiscrim_real_output, real_layers = discriminator_F(real_in)                           # :181
-    tdiscrim_fake_output, fake_layers = discriminator_F(fake_in)                           # :199 (input detached)
+    if PAIR_DISCRIMINATOR_PASSES and hasattr(discriminator_F, "forward_pair"):
+        # :181 and :199 (input detached) as one batch: same results as two calls (BatchNorm statistics per pass, running
+        # statistics updated real first), half the launches
+        (tdiscrim_real_output, real_layers), (tdiscrim_fake_output, fake_layers) = discriminator_F.forward_pair(real_in, fake_in)
+    else:
+        tdiscrim_real_output, real_layers = discriminator_F(real_in)                       # :181
+        tdiscrim_fake_output, fake_layers = discriminator_F(fake_in)                       # :199 (input detached)
 
     # ---- layer losses (:203-232), detached on both sides
     sum_layer_loss = 0

@@ -295,3 +295,34 @@ def test_backward_needs_no_input_grad_and_accumulates():
     p.sum().backward()                    # autograd accumulates into .grad
     for a, q in zip(g1, D.parameters()):
         assert torch.allclose(q.grad, 2 * a, rtol=2e-2, atol=1e-6 + 2e-2 * a.abs().max().item())
+
+
+@pytest.mark.parametrize("nb,ch,n,crop", [(2, 128, 3, 32), (1, 64, 2, 64)])
+def test_forward_pair_equals_two_calls(nb, ch, n, crop):
+    """discriminator.forward_pair(real, fake) - both passes of a training step as ONE batch with per-pass BatchNorm
+    statistics - against two consecutive forward calls on an identical copy: probabilities, all feature maps, running
+    statistics (two momentum updates, real first) and, after the same loss, every parameter gradient."""
+    _, D1 = _make(nb, ch, crop, seed=5)
+    _, D2 = _make(nb, ch, crop, seed=5)
+    real = torch.from_numpy(synth.det_uniform((n, 27, 4 * crop, 4 * crop), 61, -1.0, 1.0)).cuda()
+    fake = torch.from_numpy(synth.det_uniform((n, 27, 4 * crop, 4 * crop), 62, -1.0, 1.0)).cuda()
+    eps = 1e-12
+    pr1, fr1 = D1(real)
+    pf1, ff1 = D1(fake)
+    (pr2, fr2), (pf2, ff2) = D2.forward_pair(real, fake)
+    # same kernels on the same data: the convolutions see a batch of 2n instead of n (tile -> CTA assignment differs, the
+    # per-output arithmetic does not), BatchNorm partial sums are grouped differently -> equal to rounding
+    assert torch.allclose(pr1, pr2, atol=1e-5) and torch.allclose(pf1, pf2, atol=1e-5)
+    for a, b in zip(fr1 + ff1, fr2 + ff2):
+        assert a.shape == b.shape
+        assert (a - b).abs().max().item() <= 2e-3 * max(1.0, b.abs().max().item())
+    for m1, m2 in zip(D1._bn_modules(), D2._bn_modules()):
+        assert int(m1.num_batches_tracked) == int(m2.num_batches_tracked) == 2
+        assert torch.allclose(m1.running_mean, m2.running_mean, atol=1e-5)
+        assert torch.allclose(m1.running_var, m2.running_var, rtol=1e-4, atol=1e-6)
+    torch.mean(-(torch.log(1 - pf1 + eps) + torch.log(pr1 + eps))).backward()
+    torch.mean(-(torch.log(1 - pf2 + eps) + torch.log(pr2 + eps))).backward()
+    g1 = torch.cat([p.grad.flatten() for p in D1.parameters()]).double()
+    g2 = torch.cat([p.grad.flatten() for p in D2.parameters()]).double()
+    cos = float(g1 @ g2 / (g1.norm() * g2.norm()))
+    assert cos >= 0.9995 and abs(float(g1.norm() / g2.norm()) - 1.0) <= 1e-2, (cos, float(g1.norm() / g2.norm()))
