@@ -309,24 +309,36 @@ wgrad3x3_ky_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_const
     if (have_work) {
       mbar_wait(bar_done, 0);
       tc_fence_after();
+      // The CTA's result is, for every output channel co, the CONTIGUOUS run dW[co][cblk*64 .. +64][3][3] (576 floats).  An
+      // accumulator row holds it strided (column = kx*64 + ci, row block = ky), so a direct atomicAdd per element scatters
+      // every warp instruction over 9-10 cache lines; small layers then spend more time in their atomics than in their
+      // MMAs.  Instead the rows are transposed through shared memory (the pipeline stages are idle once bar_done fired;
+      // row pitch 577 floats: conflict-free for lanes = rows) and added with coalesced atomics: one line per instruction.
+      float* stg = reinterpret_cast<float*>(gbase + (s_st - base));
+      constexpr int kLd = 577;
       const int co = m & 63;
       for (int blk = 0; blk < 2; ++blk) {                      // accumulator 0: rows [ky 2 | ky 1]; accumulator 1: rows [ky 0 | mirror]
         const int ky = blk == 0 ? (m < 64 ? 2 : 1) : 0;
-        const bool rows_ok = co < p.rows_real && (blk == 0 || m < 64);
+        const bool rows_ok = blk == 0 || m < 64;
         for (int c0 = 0; c0 < 192; c0 += 32) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + blk * 192 + c0, v);
           tmem_ld_wait();
           if (rows_ok) {
             const int kx = c0 / 64;
+            float* dst = stg + co * kLd + ((c0 & 63) * 9 + ky * 3 + kx);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int ci = cblk * 64 + (c0 & 63) + e;
-              if (ci < p.cols_real)
-                atomicAdd(p.dw + ((static_cast<size_t>(co) * p.cols_real + ci) * 3 + ky) * 3 + kx, __uint_as_float(v[e]));
-            }
+            for (int e = 0; e < 32; ++e) dst[e * 9] = __uint_as_float(v[e]);
           }
         }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");           // the four epilogue warps (warps 2..5)
+      const int ci_valid = min(64, p.cols_real - cblk * 64);
+      const int ncols = ci_valid > 0 ? ci_valid * 9 : 0;
+      for (int row = warp - 2; row < p.rows_real; row += 4) {
+        float* g = p.dw + (static_cast<size_t>(row) * p.cols_real + cblk * 64) * 9;
+        const float* srow = stg + row * kLd;
+        for (int j = lane; j < ncols; j += 32) atomicAdd(g + j, srow[j]);
       }
     }
   }
