@@ -26,6 +26,7 @@ import warnings
 
 from . import _native as _nt
 from . import optim as _optim
+from . import perceptual as _perceptual
 from . import parallel as _par
 from .models import *  # noqa: F401,F403  (reference: `from models import *`, code/train.py:1)
 
@@ -74,8 +75,10 @@ class EMA(torch.nn.Module):
 
 def VGG19_slim(input, reuse, deep_list=None, norm_flag=True):
     """code/train.py:30-45 cannot run in the reference (VGG19() lacks its required arguments, torch.min(...) + float;
-    SURVEY.md 8c) and vgg_scaling defaults to -0.002 (main.py:98), so the branch is never taken."""
-    raise NotImplementedError("the reference's VGG perceptual branch is unrunnable (SURVEY.md 8c); vgg_scaling must stay <= 0")
+    SURVEY.md 8c) and vgg_scaling defaults to -0.002 (main.py:98), so the branch is never taken.  With the labelled,
+    non-parity stand-in enabled (tecogan_b200.perceptual.ENABLED) TecoGAN uses that instead; otherwise this raises."""
+    raise NotImplementedError("the reference's VGG perceptual branch is unrunnable (SURVEY.md 8c); keep vgg_scaling <= 0 or enable "
+                              "the labelled non-parity stand-in (tecogan_b200.perceptual.ENABLED = True)")
 
 
 Network = collections.namedtuple('Network', 'gen_output, learning_rate, update_list, update_list_name, update_list_avg, '
@@ -88,7 +91,7 @@ def _check_args(args, r_inputs):
         # have 27 channels" in the reference's own conv (code/models.py:102); same exception type here
         raise RuntimeError("TecoGAN: Dt_mergeDs=False feeds a 9-channel input to the 27-channel discriminator "
                            "(code/train.py:183-184 raises in the reference as well)")
-    if float(getattr(args, "vgg_scaling", -1.0)) > 0.0:
+    if float(getattr(args, "vgg_scaling", -1.0)) > 0.0 and not _perceptual.ENABLED:
         VGG19_slim(None, None)
     if r_inputs.dim() != 5 or r_inputs.shape[2] != 3 or r_inputs.shape[3] != r_inputs.shape[4]:
         raise RuntimeError(f"TecoGAN: r_inputs must be [B,T,3,crop,crop], got {tuple(r_inputs.shape)}")
@@ -205,6 +208,13 @@ def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step
     update_list_name.append("l2_content_loss")
     update_list.append(_warp_loss(r_inputs))
     update_list_name.append("l2_warp_loss")
+    if float(getattr(args, "vgg_scaling", -1.0)) > 0.0:                                    # :124-127,253-273 -> the labelled stand-in
+        bt = b * t
+        vgg_loss, vgg_layers = _perceptual.get(r_inputs.device).loss(gen_outputs.reshape(bt, 3, hc, hc), r_targets.reshape(bt, 3, hc, hc))
+        update_list += list(vgg_layers) + [vgg_loss]
+        update_list_name += ["vgg_loss_%d" % (i + 2) for i in range(len(vgg_layers))] + ["vgg_all"]
+    else:
+        vgg_loss = None
     pploss = None
     if pingpang:                                                                           # :275-285
         pploss = torch.mean(torch.abs(gen_outputs[:, 0:rnn_n - 1] - torch.flip(gen_outputs, dims=[1])[:, :rnn_n - 1]))
@@ -220,6 +230,8 @@ def TecoGAN(r_inputs, r_targets, discriminator_F, generator_F, args, Global_step
     dt_mul = _dt_ratio_dev if _dt_ratio_dev is not None else float(dt_ratio)
     gen_loss = content_loss
     fnet_loss = content_loss
+    if vgg_loss is not None:                               # :267-268 (with gradient to the generator)
+        gen_loss += args.vgg_scaling * vgg_loss
     if pploss is not None and args.pp_scaling > 0:         # :281-283, NOT detached: the generator also descends the ping-pong term
         gen_loss += pploss * args.pp_scaling
         fnet_loss += pploss * args.pp_scaling
