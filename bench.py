@@ -198,7 +198,7 @@ def cpu_oracle_train(crop, b):
     return b / dt, dt, torch.get_num_threads()
 
 
-def run_train_leg(name, crop, global_batch, world, rank, dev, steps, warmup, barrier, max_over_ranks, with_cpu):
+def run_train_leg(name, crop, global_batch, world, rank, dev, steps, warmup, barrier, max_over_ranks, with_cpu, perceptual=False):
     """One training configuration: `steps` calls of tecogan_b200.train.FRVSR_Train (the reference's train entry point,
     code/train.py:374-377) on this rank's share of the global batch; gradients all-reduced inside the step when
     world > 1.  Returns the JSON sub-object (rank 0) or None."""
@@ -206,6 +206,14 @@ def run_train_leg(name, crop, global_batch, world, rank, dev, steps, warmup, bar
     from tecogan_b200 import _native as nt, models, parallel, train as T
     lib = nt.lib()
     args = train_args(crop)
+    saved_graph = T.USE_CUDA_GRAPH
+    if perceptual:
+        # BASELINE configs[3] wording ("random-init VGG19 perceptual loss"): the reference's VGG branch cannot run,
+        # so this variant times OUR labelled, non-parity stand-in (tecogan_b200.perceptual); eager (no graph capture)
+        from tecogan_b200 import perceptual as PS
+        PS.ENABLED = True
+        args.vgg_scaling = 0.2
+        T.USE_CUDA_GRAPH = False
     per = global_batch // world
     torch.manual_seed(1)                                   # identical replicas on every rank
     G = models.generator(3, args).to(dev)
@@ -244,6 +252,9 @@ def run_train_leg(name, crop, global_batch, world, rank, dev, steps, warmup, bar
         host_losses = (float(out.gen_loss), float(out.d_loss))          # D2H read of the step's result
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    if perceptual:
+        PS.ENABLED = False
+        T.USE_CUDA_GRAPH = saved_graph
     if rank != 0:
         return None
     flops = train_step_flops(global_batch, 10, crop)
@@ -260,7 +271,11 @@ def run_train_leg(name, crop, global_batch, world, rank, dev, steps, warmup, bar
            "losses_finite": bool(all(v == v and abs(v) != float("inf") for v in losses + host_losses)),
            "optimizer": "torch.optim.Adam objects as main.py:239-243 builds them, stepped by tecogan_b200.optim.FlatAdam (fused flat-bucket "
                         "Adam + GradScaler update + bf16 re-pack, repo kernels)" if T.FUSED_ADAM else "torch.optim.Adam + GradScaler (stock)",
-           "cuda_graph": bool(T.USE_CUDA_GRAPH and T.FUSED_ADAM and (world == 1 or T.GRAPH_WITH_NCCL))}
+           "cuda_graph": bool(T.USE_CUDA_GRAPH and T.FUSED_ADAM and (world == 1 or T.GRAPH_WITH_NCCL)) and not perceptual}
+    if perceptual:
+        res["perceptual_loss"] = ("NON-PARITY stand-in (tecogan_b200.perceptual): random-init VGG19-to-conv4_4 on the conv core, features "
+                                  "conv2_2/3_4/4_4, cosine loss, vgg_scaling 0.2; the reference's VGG branch is unrunnable (SURVEY.md 8c). "
+                                  "step_tflops counts the generator + discriminator work only")
     if with_cpu:
         cb = 4 if crop == 32 else 1
         cps, step_s, cores = cpu_oracle_train(crop, cb)
@@ -526,6 +541,9 @@ def run_ours(args):
         if world == 1:
             train["cfg4"] = run_train_leg("cfg4: training step, batch 4 x 10 frames of 32x32 LR crops, single B200", 32, 4,
                                           world, rank, dev, args.train_steps, 3, barrier, max_over_ranks, with_cpu)
+            train["cfg4_perceptual_standin"] = run_train_leg(
+                "cfg4 + perceptual-loss stand-in (non-parity): batch 4 x 10 frames of 32x32 LR crops, single B200", 32, 4, world, rank, dev,
+                max(3, args.train_steps // 2), 3, barrier, max_over_ranks, False, perceptual=True)
         train["cfg5"] = run_train_leg("cfg5: data-parallel training, global batch 32 x 10 frames of 64x64 LR crops", 64, 32,
                                       world, rank, dev, max(3, args.train_steps // 2), 3, barrier, max_over_ranks, with_cpu)
 

@@ -113,7 +113,9 @@ class PerceptualStandIn:
                     L = _Layer()
                     L.cin, L.cout, L.group, L.index = cin, cout, gi, li
                     L.weight, L.bias = wgt, bias                          # f32 originals (tests re-run the network with torch)
-                    L.cin_blocks, L.needs_dx = _blocks(cin), True
+                    if cin < 64:                                          # the RGB layer: explicit zero weights for the 61 padding
+                        wgt = F.pad(wgt, (0, 0, 0, 0, 0, 64 - cin))       # channels (the data-gradient packing needs >= 64 outputs)
+                    L.cin_blocks, L.needs_dx = _blocks(wgt.shape[1]), True
                     L.packed, L.packed_dgrad = [], []
                     for co0, con in _blocks(cout):
                         row, rowd = [], []
