@@ -2,8 +2,6 @@
 // warp, bilinear x4 upscale, and the fused producer of the generator input.
 // All kernels are pure streaming / gather kernels: coalesced 128-bit accesses on the contiguous
 // side, shared-memory staging where the two sides disagree, grid-stride over whole rows.
-#include <stdlib.h>
-
 #include "tg_frame.cuh"
 
 namespace tg {
@@ -218,111 +216,6 @@ warp4_kernel(const float* __restrict__ img, const float4* __restrict__ grid, flo
       v.x = gather(plane, w, t[0]); v.y = gather(plane, w, t[1]); v.z = gather(plane, w, t[2]); v.w = gather(plane, w, t[3]);
       *reinterpret_cast<float4*>(out + (b * c + ch) * plane_o + pix) = v;
     }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Tile-staged backward warp.  A motion-like sampling field maps an output tile onto a source window barely larger than
-// the tile, so instead of 12 predicated 4-byte global gathers per pixel (ncu: 9.9 L1 sectors per pixel, l1tex-bound at
-// 0.44 of HBM) a CTA computes the bounding box of its taps, copies that window of every channel into shared memory with
-// coalesced row loads, and gathers from there.  One CTA = 32 x 64 output pixels, 8 per thread (two rows of four).
-// When the window does not fit (random / scattered fields - e.g. the reference's pixel-intensity "flow") the CTA falls
-// back to the per-pixel global gather; both paths use identical taps, weights and summation order (bit-identical).
-// ---------------------------------------------------------------------------------------------
-constexpr int kWtH = 32, kWtW = 64, kWtThreads = 256;
-constexpr int kWtMaxBox = 5120;                                  // source pixels staged per channel (3 channels: 60 KB)
-constexpr int kWtMaxC = 3;
-
-__device__ __forceinline__ float gather_smem(const float* __restrict__ win, int bw, int bx0, int by0, const Taps& t) {
-  const float* p = win + (t.y0 - by0) * bw + (t.x0 - bx0);
-  float acc = 0.f;
-  if (t.ok_nw) acc += p[0] * t.wnw;
-  if (t.ok_ne) acc += p[1] * t.wne;
-  if (t.ok_sw) acc += p[bw] * t.wsw;
-  if (t.ok_se) acc += p[bw + 1] * t.wse;
-  return acc;
-}
-
-__global__ void __launch_bounds__(kWtThreads)
-warp_tile_kernel(const float* __restrict__ img, const float4* __restrict__ grid, float* __restrict__ out, int n, int c, int h,
-                 int w, int ho, int wo, int tiles_x, int tiles_y) {
-  extern __shared__ float s_win[];                              // [c][box_h * box_w]
-  __shared__ int s_box[4];                                      // min x, max x, min y, max y of the in-image taps
-  const int tid = threadIdx.x, lane = tid & 31;
-  const long long plane_o = static_cast<long long>(ho) * wo;
-  const long long plane_i = static_cast<long long>(h) * w;
-  const int ntiles = n * tiles_x * tiles_y;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int tx = tile % tiles_x;
-    const int r = tile / tiles_x;
-    const int ty = r % tiles_y;
-    const int b = r / tiles_y;
-    if (tid == 0) { s_box[0] = w; s_box[1] = -1; s_box[2] = h; s_box[3] = -1; }
-    __syncthreads();
-    // thread -> 4 consecutive pixels of rows (tid / 16) and (tid / 16) + 16
-    const int px0 = tx * kWtW + (tid & 15) * 4;
-    Taps t[2][4];
-    bool live[2];
-    int mnx = w, mxx = -1, mny = h, mxy = -1;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int py = ty * kWtH + (tid >> 4) + 16 * k;
-      live[k] = py < ho && px0 < wo;                            // (wo % 4 == 0: a group of four never straddles the edge)
-      if (live[k]) {
-        const long long gi = (static_cast<long long>(b) * plane_o + static_cast<long long>(py) * wo + px0) / 2;   // float4 = 2 grid points
-        const float4 g0 = __ldg(grid + gi), g1 = __ldg(grid + gi + 1);
-        t[k][0] = make_taps(round_fp16(g0.x), round_fp16(g0.y), h, w);
-        t[k][1] = make_taps(round_fp16(g0.z), round_fp16(g0.w), h, w);
-        t[k][2] = make_taps(round_fp16(g1.x), round_fp16(g1.y), h, w);
-        t[k][3] = make_taps(round_fp16(g1.z), round_fp16(g1.w), h, w);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const Taps& q = t[k][j];
-          if (q.ok_nw || q.ok_ne || q.ok_sw || q.ok_se) {       // clamp the 2x2 footprint to the image
-            mnx = min(mnx, max(q.x0, 0)); mxx = max(mxx, min(q.x0 + 1, w - 1));
-            mny = min(mny, max(q.y0, 0)); mxy = max(mxy, min(q.y0 + 1, h - 1));
-          }
-        }
-      }
-    }
-    mnx = __reduce_min_sync(0xFFFFFFFFu, mnx); mxx = __reduce_max_sync(0xFFFFFFFFu, mxx);
-    mny = __reduce_min_sync(0xFFFFFFFFu, mny); mxy = __reduce_max_sync(0xFFFFFFFFu, mxy);
-    if (lane == 0) { atomicMin(&s_box[0], mnx); atomicMax(&s_box[1], mxx); atomicMin(&s_box[2], mny); atomicMax(&s_box[3], mxy); }
-    __syncthreads();
-    const int bx0 = s_box[0], by0 = s_box[2];
-    const int bw = s_box[1] - bx0 + 1, bh = s_box[3] - by0 + 1;
-    const bool empty = s_box[1] < 0;                            // every tap of the tile is out of the image: zeros
-    const bool staged = !empty && bw > 0 && bh > 0 && bw * bh <= kWtMaxBox;
-    if (staged) {
-      // coalesced copy of the window: warp w takes rows w, w + 8, ... of every channel
-      for (int ch = 0; ch < c; ++ch) {
-        const float* src = img + (static_cast<long long>(b) * c + ch) * plane_i + static_cast<long long>(by0) * w + bx0;
-        float* dst = s_win + ch * (bw * bh);
-        for (int row = tid >> 5; row < bh; row += kWtThreads / 32)
-          for (int col = lane; col < bw; col += 32) dst[row * bw + col] = __ldg(src + static_cast<long long>(row) * w + col);
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (!live[k]) continue;
-      const int py = ty * kWtH + (tid >> 4) + 16 * k;
-      for (int ch = 0; ch < c; ++ch) {
-        float4 v;
-        if (staged) {
-          const float* win = s_win + ch * (bw * bh);
-          v.x = gather_smem(win, bw, bx0, by0, t[k][0]); v.y = gather_smem(win, bw, bx0, by0, t[k][1]);
-          v.z = gather_smem(win, bw, bx0, by0, t[k][2]); v.w = gather_smem(win, bw, bx0, by0, t[k][3]);
-        } else if (empty) {
-          v = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          const float* plane = img + (static_cast<long long>(b) * c + ch) * plane_i;
-          v.x = gather(plane, w, t[k][0]); v.y = gather(plane, w, t[k][1]); v.z = gather(plane, w, t[k][2]); v.w = gather(plane, w, t[k][3]);
-        }
-        *reinterpret_cast<float4*>(out + (static_cast<long long>(b) * c + ch) * plane_o + static_cast<long long>(py) * wo + px0) = v;
-      }
-    }
-    __syncthreads();                                            // s_win / s_box are reused by the next tile
   }
 }
 
@@ -574,18 +467,7 @@ extern "C" int tg_warp_bilinear(const float* img, const float* grid, float* out,
   const long long work = static_cast<long long>(n) * ho * wo;
   if (work == 0) return TG_OK;
   tg_prof_pre(TG_K_GLUE, (8.0 * c + 4.0) * n * ho * wo, static_cast<cudaStream_t>(stream));   // f32 img in/out + fp16 grid
-  static const bool tile_on = []() { const char* e = getenv("TG_WARP_TILE"); return !(e && e[0] == '0'); }();   // A/B knob
-  const bool vec_ok = (wo & 3) == 0 && ((reinterpret_cast<uintptr_t>(grid) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-  if (vec_ok && tile_on && c <= kWtMaxC && wo >= kWtW && ho >= 8) {
-    const int tiles_x = tg_div_up(wo, kWtW), tiles_y = tg_div_up(ho, kWtH);
-    const long long ntiles = static_cast<long long>(n) * tiles_x * tiles_y;
-    const size_t smem = static_cast<size_t>(c) * kWtMaxBox * sizeof(float);
-    static TgPerDeviceOnce attr_once;
-    if (attr_once.need()) TG_CUDA(cudaFuncSetAttribute(warp_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWtMaxC * kWtMaxBox * 4));
-    const long long cap = static_cast<long long>(tg_num_sms()) * 3;
-    warp_tile_kernel<<<static_cast<int>(ntiles < cap ? ntiles : cap), kWtThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        img, reinterpret_cast<const float4*>(grid), out, n, c, h, w, ho, wo, tiles_x, tiles_y);
-  } else if (vec_ok)
+  if ((wo & 3) == 0 && ((reinterpret_cast<uintptr_t>(grid) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
     warp4_kernel<<<grid_for(work / 4, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         img, reinterpret_cast<const float4*>(grid), out, n, c, h, w, ho, wo);
   else

@@ -141,11 +141,10 @@ def _motion_grid(n, ho, wo, amp_px, seed):
 
 @pytest.mark.parametrize("n,c,h,w,kind", [(2, 3, 96, 128, "motion"), (1, 3, 100, 200, "motion_edges"), (1, 3, 64, 64, "random"),
                                           (2, 2, 72, 132, "mixed"), (1, 3, 40, 68, "all_out")])
-def test_tile_staged_warp_vs_oracle(n, c, h, w, kind):
-    """The tile-staged warp kernel (source window of a 32x64 output tile copied to shared memory when it fits, the
-    per-pixel global gather when it does not) against the numpy oracle and torch.grid_sample: <= 1e-5 (BASELINE.json
-    north_star) on a motion-like field (staged path), a field that pushes taps across every image edge, a random field
-    (fallback path), a half-and-half field (both paths in one launch) and a field that leaves the image entirely."""
+def test_warp_on_motion_and_mixed_fields_vs_oracle(n, c, h, w, kind):
+    """The warp kernel against the numpy oracle and torch.grid_sample, <= 1e-5 (BASELINE.json north_star), on the kinds of
+    sampling field it meets: a motion-like field (identity +- 2 px), one that pushes taps across every image edge, a
+    random field, a half-and-half field and one that leaves the image entirely (zeros padding)."""
     from tecogan_b200 import ops
     img = synth.det_uniform((n, c, h, w), 21, -1, 1)
     if kind == "motion":
