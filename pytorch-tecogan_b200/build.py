@@ -35,15 +35,19 @@ def up_to_date():
     return all(os.path.getmtime(p) <= t for p in deps())
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant / defines: measurement builds (same-box A/B through `bench.py --lib`): libtecogan_b200.<variant>.so compiled
+    with extra -D flags next to the product library; never loaded by the package itself."""
+    target = OUT if not variant else os.path.join(HERE, f"libtecogan_b200.{variant}.so")
+    if not variant and not force and up_to_date():
         return OUT
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build" if not variant else f"build_{variant}")
+    os.makedirs(bdir, exist_ok=True)
     for src in sources():
-        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [NVCC] + FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False
@@ -54,10 +58,13 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libtecogan_b200 (see output above)")
-    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [NVCC, "-shared", "-o", target] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
-    return OUT
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    # python build.py [--force] [--verbose] [--variant NAME -DFOO=1 ...]
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=var,
+                defines=[a[2:] for a in sys.argv if a.startswith("-D")]))

@@ -84,8 +84,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// TG_MBAR_HINT_NS > 0: suspend-time hint of try_wait (the thread sleeps in hardware until the phase completes or the hint
+// expires, instead of the short system default) - fewer polls on the shared-memory pipe the epilogue's stores share.
+#ifndef TG_MBAR_HINT_NS
+#define TG_MBAR_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if TG_MBAR_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(static_cast<uint32_t>(TG_MBAR_HINT_NS))
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -93,6 +107,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // Bounded wait: a pipeline bug must surface as a trapped kernel (CUDA error), never as a hung
@@ -256,11 +271,19 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
+#if TG_MBAR_HINT_NS > 0
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(static_cast<uint32_t>(TG_MBAR_HINT_NS))
+      : "memory");
+#else
       "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {

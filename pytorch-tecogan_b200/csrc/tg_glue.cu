@@ -219,6 +219,84 @@ warp4_kernel(const float* __restrict__ img, const float4* __restrict__ grid, flo
   }
 }
 
+// Branch-free form of the same four-pixel kernel for three planes and 32-bit plane indices (every frame this path sees):
+// an out-of-range tap keeps a clamped, valid address and gets weight 0 instead of a predicate, the image index is
+// blockIdx.y (no 64-bit division per thread) and the plane loop is unrolled.  The kernel is bound by issued instructions,
+// not by L1 sectors or DRAM (profiles/r02_summary.md): this halves them.  Same products in the same order as gather().
+struct TapsB {
+  int o_nw, o_ne, o_sw, o_se;
+  float wnw, wne, wsw, wse;
+};
+__device__ __forceinline__ TapsB make_taps_b(float gx, float gy, int h, int w) {
+  TapsB t;
+  const float ix = ((gx + 1.f) * w - 1.f) / 2.f;
+  const float iy = ((gy + 1.f) * h - 1.f) / 2.f;
+  const float fx = floorf(ix), fy = floorf(iy);
+  const float ax = ix - fx, ay = iy - fy;
+  const float bx = (fx + 1.f) - ix, by = (fy + 1.f) - iy;
+  const float cx = fminf(fmaxf(fx, -2.f), static_cast<float>(w) + 1.f);
+  const float cy = fminf(fmaxf(fy, -2.f), static_cast<float>(h) + 1.f);
+  const int x0 = static_cast<int>(cx), y0 = static_cast<int>(cy);
+  const bool finite = (fx == fx) && (fy == fy);
+  const bool xl = static_cast<unsigned>(x0) < static_cast<unsigned>(w), xr = static_cast<unsigned>(x0 + 1) < static_cast<unsigned>(w);
+  const bool yt = finite && static_cast<unsigned>(y0) < static_cast<unsigned>(h);
+  const bool yb = finite && static_cast<unsigned>(y0 + 1) < static_cast<unsigned>(h);
+  t.wnw = (xl && yt) ? bx * by : 0.f; t.wne = (xr && yt) ? ax * by : 0.f;
+  t.wsw = (xl && yb) ? bx * ay : 0.f; t.wse = (xr && yb) ? ax * ay : 0.f;
+  const int xa = min(max(x0, 0), w - 1), xb = min(max(x0 + 1, 0), w - 1);
+  const int ra = min(max(y0, 0), h - 1) * w, rb = min(max(y0 + 1, 0), h - 1) * w;
+  t.o_nw = ra + xa; t.o_ne = ra + xb; t.o_sw = rb + xa; t.o_se = rb + xb;
+  return t;
+}
+__device__ __forceinline__ float gather_b(const float* __restrict__ plane, const TapsB& t) {
+  float acc = __ldg(plane + t.o_nw) * t.wnw;
+  acc = fmaf(__ldg(plane + t.o_ne), t.wne, acc);
+  acc = fmaf(__ldg(plane + t.o_sw), t.wsw, acc);
+  acc = fmaf(__ldg(plane + t.o_se), t.wse, acc);
+  return acc;
+}
+// A warp owns kWarpPx * 32 consecutive pixels; its k-th instruction handles pixels k*32 + lane, so every tap load of a
+// smooth field and every store touches one or two 128-byte lines (four CONSECUTIVE pixels per thread made each load a
+// 16-byte-strided access: 3.3 L1 wavefronts per request, the L1 data pipe at 85 % - profiles/r02_summary.md).
+#ifndef TG_WARP_PX
+#define TG_WARP_PX 4
+#endif
+#ifndef TG_WARP_MINB
+#define TG_WARP_MINB 1
+#endif
+constexpr int kWarpPx = TG_WARP_PX;
+__global__ void __launch_bounds__(256, TG_WARP_MINB)
+warp4c3_kernel(const float* __restrict__ img, const float2* __restrict__ grid, float* __restrict__ out, int h, int w, int ho,
+               int wo) {
+  const int plane_i = h * w, plane_o = ho * wo, chunks = (plane_o + 32 * kWarpPx - 1) / (32 * kWarpPx);
+  const float* src = img + static_cast<long long>(blockIdx.y) * 3 * plane_i;
+  float* dst = out + static_cast<long long>(blockIdx.y) * 3 * plane_o;
+  const float2* g = grid + static_cast<long long>(blockIdx.y) * plane_o;
+  const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+  for (int ck = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ck < chunks; ck += warps) {
+    const int p0 = ck * (32 * kWarpPx) + lane;
+    TapsB t[kWarpPx];
+#pragma unroll
+    for (int k = 0; k < kWarpPx; ++k) {
+      const float2 gk = __ldg(g + min(p0 + 32 * k, plane_o - 1));
+      t[k] = make_taps_b(round_fp16(gk.x), round_fp16(gk.y), h, w);
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float* plane = src + ch * plane_i;
+      // keep the plane base in a vector register pair: each tap address is then ONE IMAD.WIDE (offset * 4 + base); with the
+      // (CTA-uniform) base in uniform registers the compiler emits a LEA / LEA.HI pair per tap instead
+      asm volatile("" : "+l"(plane));
+      float v[kWarpPx];
+#pragma unroll
+      for (int k = 0; k < kWarpPx; ++k) v[k] = gather_b(plane, t[k]);
+#pragma unroll
+      for (int k = 0; k < kWarpPx; ++k)
+        if (p0 + 32 * k < plane_o) dst[ch * plane_o + p0 + 32 * k] = v[k];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Fused producer of the spatio-temporal discriminator's input (reference code/train.py:139-198, Dt_mergeDs=True):
 // out[s, 0:9]   = before9[s]                                  the three target frames of triplet s        (:175)
@@ -301,11 +379,42 @@ __device__ __forceinline__ void gather3(const float4* __restrict__ img, int w, c
   if (t.ok_se) { const float4 a = __ldg(p + w + 1); v[0] += a.x * t.wse; v[1] += a.y * t.wse; v[2] += a.z * t.wse; }
 }
 
+// Branch-free forms for the per-pixel loop below (it is bound by issued instructions): 16-byte taps at clamped addresses
+// with zeroed weights (make_taps_b), and the two flow components of one pixel - columns col, col + 1 of one row of the
+// x4-upscaled plane - sharing the row part of up4_sample (same arithmetic per value).
+__device__ __forceinline__ void gather3_b(const float4* __restrict__ img, const TapsB& t, float (&v)[3]) {
+  const float4 a = __ldg(img + t.o_nw), b = __ldg(img + t.o_ne), c = __ldg(img + t.o_sw), d = __ldg(img + t.o_se);
+  v[0] = a.x * t.wnw; v[1] = a.y * t.wnw; v[2] = a.z * t.wnw;
+  v[0] = fmaf(b.x, t.wne, v[0]); v[1] = fmaf(b.y, t.wne, v[1]); v[2] = fmaf(b.z, t.wne, v[2]);
+  v[0] = fmaf(c.x, t.wsw, v[0]); v[1] = fmaf(c.y, t.wsw, v[1]); v[2] = fmaf(c.z, t.wsw, v[2]);
+  v[0] = fmaf(d.x, t.wse, v[0]); v[1] = fmaf(d.y, t.wse, v[1]); v[2] = fmaf(d.z, t.wse, v[2]);
+}
+__device__ __forceinline__ void up4_pair(const float* __restrict__ plane, int h, int w, int row, int col, float pre, float& u0,
+                                         float& u1) {
+  float sy = (row + 0.5f) * 0.25f - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  const int y0 = min(static_cast<int>(sy), h - 1), y1 = min(y0 + 1, h - 1);
+  const float ly1 = sy - y0, ly0 = 1.f - ly1;
+  const float* r0 = plane + y0 * w;
+  const float* r1 = plane + y1 * w;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    float sx = (col + k + 0.5f) * 0.25f - 0.5f;
+    sx = sx < 0.f ? 0.f : sx;
+    const int x0 = min(static_cast<int>(sx), w - 1), x1 = min(x0 + 1, w - 1);
+    const float lx1 = sx - x0, lx0 = 1.f - lx1;
+    const float p00 = __ldg(r0 + x0) * pre, p01 = __ldg(r0 + x1) * pre;
+    const float p10 = __ldg(r1 + x0) * pre, p11 = __ldg(r1 + x1) * pre;
+    const float u = ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11);
+    if (k == 0) u0 = u; else u1 = u;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 fused_input_kernel(const float* __restrict__ lr_t, const float* __restrict__ lr_prev,
                    const float* __restrict__ prev_hr, const float4* __restrict__ prev_rgbx,
                    __nv_bfloat16* __restrict__ x, int n, int h, int w,
-                   long long lr_bs, long long hr_bs, uint32_t* __restrict__ zero, size_t zero_count) {
+                   long long lr_bs, long long hr_bs, uint32_t* __restrict__ zero, size_t zero_count, FastDiv fd_wo) {
   __shared__ __align__(16) __nv_bfloat16 tile[kFT * kFT][64];
   // clear the frame kernel's per-item completion counters (this kernel runs between two frame kernels)
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < zero_count;
@@ -313,7 +422,7 @@ fused_input_kernel(const float* __restrict__ lr_t, const float* __restrict__ lr_
     zero[i] = 0u;
   const int tiles_x = (w + kFT - 1) / kFT, tiles_y = (h + kFT - 1) / kFT;
   const int ho = 4 * h, wo = 4 * w;
-  const long long hw_o = static_cast<long long>(ho) * wo;
+  const uint32_t hw_o = static_cast<uint32_t>(ho) * static_cast<uint32_t>(wo);     // 2 * hw_o < 2^31 (host-checked)
   const int ntiles = n * tiles_x * tiles_y;
   for (int tIdx = blockIdx.x; tIdx < ntiles; tIdx += gridDim.x) {
     const int tx = tIdx % tiles_x;
@@ -334,26 +443,29 @@ fused_input_kernel(const float* __restrict__ lr_t, const float* __restrict__ lr_
       }
     }
     // channels 3..50: space_to_depth(deprocess(warp(prev_hr)))
+    const float* flow = lr_prev != nullptr ? lr_prev + b * lr_bs : nullptr;
+    const float4* rgbx = prev_rgbx != nullptr ? prev_rgbx + static_cast<long long>(b) * hw_o : nullptr;
     for (int i = threadIdx.x; i < (4 * kFT) * (4 * kFT); i += blockDim.x) {
       const int hy = i / (4 * kFT), hx = i % (4 * kFT);
       const int oy = 4 * ly0 + hy, ox = 4 * lx0 + hx;
       float v[3] = {0.f, 0.f, 0.f};
       if (prev_hr != nullptr && oy < ho && ox < wo) {
-        // grid element (oy,ox,:) = two consecutive floats of the [2,Ho,Wo] planar flow buffer
-        const long long f = (static_cast<long long>(oy) * wo + ox) * 2;
-        const int plane = static_cast<int>(f / hw_o);
-        const long long rem = f - plane * hw_o;
-        const int row = static_cast<int>(rem / wo), col = static_cast<int>(rem % wo);
-        const float* fl = lr_prev + b * lr_bs + static_cast<long long>(plane) * h * w;
-        const float gx = round_fp16(up4_sample(fl, h, w, row, col, 4.f));
-        const float gy = round_fp16(up4_sample(fl, h, w, row, col + 1, 4.f));
-        const Taps t = make_taps(gx, gy, ho, wo);
-        if (prev_rgbx != nullptr) {
-          gather3(prev_rgbx + b * hw_o, wo, t, v);
+        // grid element (oy,ox,:) = two consecutive floats of the [2,Ho,Wo] planar flow buffer (wo is even: same row)
+        const uint32_t f = (static_cast<uint32_t>(oy) * static_cast<uint32_t>(wo) + static_cast<uint32_t>(ox)) * 2u;
+        const uint32_t plane = f >= hw_o ? 1u : 0u;
+        const uint32_t rem = f - plane * hw_o;
+        const uint32_t row = fdiv(rem, fd_wo), col = rem - row * static_cast<uint32_t>(wo);
+        float gx, gy;
+        up4_pair(flow + plane * static_cast<uint32_t>(h * w), h, w, static_cast<int>(row), static_cast<int>(col), 4.f, gx, gy);
+        gx = round_fp16(gx); gy = round_fp16(gy);
+        if (rgbx != nullptr) {
+          const TapsB t = make_taps_b(gx, gy, ho, wo);
+          gather3_b(rgbx, t, v);
         } else {
+          const Taps t = make_taps(gx, gy, ho, wo);
           const float* img = prev_hr + b * hr_bs;
 #pragma unroll
-          for (int ch = 0; ch < 3; ++ch) v[ch] = gather(img + ch * hw_o, wo, t);
+          for (int ch = 0; ch < 3; ++ch) v[ch] = gather(img + ch * static_cast<long long>(hw_o), wo, t);
         }
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) v[ch] = (v[ch] + 1.f) / 2.f;
@@ -467,7 +579,16 @@ extern "C" int tg_warp_bilinear(const float* img, const float* grid, float* out,
   const long long work = static_cast<long long>(n) * ho * wo;
   if (work == 0) return TG_OK;
   tg_prof_pre(TG_K_GLUE, (8.0 * c + 4.0) * n * ho * wo, static_cast<cudaStream_t>(stream));   // f32 img in/out + fp16 grid
-  if ((wo & 3) == 0 && ((reinterpret_cast<uintptr_t>(grid) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+  static const bool branch_free = []() { const char* e = getenv("TG_WARP_BRANCHFREE"); return !(e && e[0] == '0'); }();   // A/B knob
+  const bool vec4 = (wo & 3) == 0 && ((reinterpret_cast<uintptr_t>(grid) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (branch_free && c == 3 && n <= 65535 && 3LL * h * w < (1LL << 31) && 3LL * ho * wo < (1LL << 31) - 1024) {
+    const int chunks = (ho * wo + 32 * kWarpPx - 1) / (32 * kWarpPx);   // one warp per chunk, 8 warps per CTA
+    int bx = (chunks + 7) / 8;
+    const int cap = (tg_num_sms() * 16 + n - 1) / n;          // ~16 CTAs per SM over all images
+    if (bx > cap) bx = cap;
+    warp4c3_kernel<<<dim3(bx, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, reinterpret_cast<const float2*>(grid), out, h, w,
+                                                                              ho, wo);
+  } else if (vec4)
     warp4_kernel<<<grid_for(work / 4, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         img, reinterpret_cast<const float4*>(grid), out, n, c, h, w, ho, wo);
   else
@@ -500,6 +621,7 @@ int tg::fused_input_launch(const float* lr_t, const float* lr_prev, const float*
   TG_CHECK_ARG(lr_t && x_nhwc, "fused_warp_s2d_concat: null pointer");
   TG_CHECK_ARG(n >= 1 && h >= 1 && w >= 1, "fused_warp_s2d_concat: bad shape");
   TG_CHECK_ARG((reinterpret_cast<uintptr_t>(x_nhwc) & 15) == 0, "fused_warp_s2d_concat: x must be 16-byte aligned");
+  TG_CHECK_ARG(32LL * h * w < (1LL << 31), "fused_warp_s2d_concat: frame too large for 32-bit pixel indices (%d x %d)", h, w);
   if (!lr_prev || !prev_hr) { lr_prev = nullptr; prev_hr = nullptr; }
   const int tiles = n * tg_div_up(w, kFT) * tg_div_up(h, kFT);
   int blocks = tiles < tg_num_sms() * 8 ? tiles : tg_num_sms() * 8;
@@ -509,7 +631,7 @@ int tg::fused_input_launch(const float* lr_t, const float* lr_prev, const float*
   if (!prev_hr) prev_rgbx = nullptr;
   fused_input_kernel<<<blocks, 256, 0, stream>>>(lr_t, lr_prev, prev_hr, static_cast<const float4*>(prev_rgbx),
                                                  static_cast<__nv_bfloat16*>(x_nhwc), n, h, w, lr_batch_stride, hr_batch_stride,
-                                                 zero, zero_count);
+                                                 zero, zero_count, make_fastdiv(static_cast<uint32_t>(4 * w)));
   tg_prof_post(stream);
   TG_CUDA(cudaGetLastError());
   return TG_OK;

@@ -332,6 +332,7 @@ class _GraphedStep:
         self.out = None
         self.calls = 0
         self.failed = False
+        self.kernels = 0                # repo-kernel launches recorded in the graph (tg_launch_count over the capture)
 
     def run(self, r_inputs, r_targets, args, D, G, step, c1, c2, og, od):
         self.static_in.copy_(r_inputs)
@@ -346,9 +347,14 @@ class _GraphedStep:
             # to the capture by events); NCCL's watchdog thread polls events concurrently, which only the thread-local
             # capture mode tolerates
             mode = "thread_local" if _par.world_size() > 1 else "global"
+            k0 = _nt.lib().tg_launch_count()
             with torch.cuda.graph(g, capture_error_mode=mode):
                 self.out = TecoGAN(self.static_in, self.static_tg, D, G, args, step, c1, c2, og, od, _dt_ratio_dev=self.dt)
+            self.kernels = int(_nt.lib().tg_launch_count() - k0)
             self.graph = g
+        else:
+            global replayed_launches
+            replayed_launches += self.kernels   # (the capturing call's kernels were counted by tg_launch_count itself)
         self.graph.replay()
         out = self.out
         n = len(out.update_list)
@@ -357,6 +363,7 @@ class _GraphedStep:
 
 
 _graphs = {}
+replayed_launches = 0                   # repo kernels executed through graph replays (bench.py's gpu_launches adds this)
 
 
 def _graph_key(r_inputs, r_targets, args, D, G, og, od):

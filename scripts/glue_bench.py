@@ -16,6 +16,8 @@ sys.path.insert(0, os.path.join(ROOT, "pytorch-tecogan_b200"))
 
 def measure(n=2, h=540, w=960, iters=10, dev=None):
     from tecogan_b200 import _native as nt
+    if os.environ.get("TG_GLUE_LIB"):                         # measurement only: another build of the library (same-box A/B)
+        nt.LIB_PATH = os.path.abspath(os.environ["TG_GLUE_LIB"])
     lib = nt.lib()
     dev = dev or torch.device("cuda", torch.cuda.current_device())
     ho, wo = 4 * h, 4 * w
@@ -26,11 +28,19 @@ def measure(n=2, h=540, w=960, iters=10, dev=None):
     lr = torch.rand((n, 3, h, w), device=dev, generator=g) * 0.25
     lr_prev = torch.rand((n, 3, h, w), device=dev, generator=g) * 0.25       # flow in [0,1): every warp tap in bounds
     grid = (torch.rand((n, ho, wo, 2), device=dev, generator=g) * 2 - 1) * 0.98         # every pixel samples a random place
-    # a motion-like field: the identity sampling grid plus a displacement of up to +-2 pixels
+    # a jittered field: the identity sampling grid plus an INDEPENDENT displacement of up to +-2 pixels per pixel (neighbouring
+    # pixels sample up to five different rows: harsher than any real flow, kept for continuity with round 1)
     ys = ((torch.arange(ho, device=dev, dtype=torch.float32) + 0.5) * 2 / ho - 1).view(1, ho, 1).expand(n, ho, wo)
     xs = ((torch.arange(wo, device=dev, dtype=torch.float32) + 0.5) * 2 / wo - 1).view(1, 1, wo).expand(n, ho, wo)
     smooth = torch.stack((xs, ys), dim=-1) + (torch.rand((n, ho, wo, 2), device=dev, generator=g) - 0.5) * (8.0 / wo)
     smooth = smooth.contiguous()
+    # what upscale_four(flow) hands the reference's warp (code/train.py:94-101): a spatially smooth displacement (here up
+    # to +-2 pixels, varying over ~100-pixel periods), so neighbouring pixels sample neighbouring taps
+    yy = torch.arange(ho, device=dev, dtype=torch.float32).view(1, ho, 1)
+    xx = torch.arange(wo, device=dev, dtype=torch.float32).view(1, 1, wo)
+    dxs = 2.0 * torch.sin(yy * (6.2831853 / 97.0)) * torch.cos(xx * (6.2831853 / 131.0))
+    dys = 2.0 * torch.cos(yy * (6.2831853 / 113.0)) * torch.sin(xx * (6.2831853 / 89.0))
+    flowlike = torch.stack((xs + dxs * (2.0 / wo), ys + dys * (2.0 / ho)), dim=-1).contiguous()
     depth = torch.empty((n, 48, h, w), device=dev)
     x_in = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=dev)
     st = nt.stream_ptr()
@@ -54,6 +64,7 @@ def measure(n=2, h=540, w=960, iters=10, dev=None):
         "reference_fill_f32 (write only)": (4.0 * big.numel() / hr_px, lambda: big.zero_()),
         "space_to_depth": (24.0, lambda: nt.check(lib.tg_space_to_depth(nt.ptr(hr), nt.ptr(depth), n, 3, h, w, 4, st))),
         "depth_to_space": (24.0, lambda: nt.check(lib.tg_depth_to_space(nt.ptr(depth), nt.ptr(hr2), n, 3, h, w, 4, st))),
+        "warp_bilinear_smooth_field": (28.0, lambda: nt.check(lib.tg_warp_bilinear(nt.ptr(hr), nt.ptr(flowlike), nt.ptr(hr2), n, 3, ho, wo, ho, wo, st))),
         "warp_bilinear_motion_field": (28.0, lambda: nt.check(lib.tg_warp_bilinear(nt.ptr(hr), nt.ptr(smooth), nt.ptr(hr2), n, 3, ho, wo, ho, wo, st))),
         "warp_bilinear_random_field": (28.0, lambda: nt.check(lib.tg_warp_bilinear(nt.ptr(hr), nt.ptr(grid), nt.ptr(hr2), n, 3, ho, wo, ho, wo, st))),
         "upscale4_bilinear": (12.75, lambda: nt.check(lib.tg_upscale4_bilinear(nt.ptr(lr), nt.ptr(hr2), n, 3, h, w, 4.0, st))),

@@ -43,7 +43,8 @@ def test_committed_bench_lines_keep_the_contract():
     slowdown reason."""
     import glob
     paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_v10*.json")) +
-                   glob.glob(os.path.join(ROOT, "profiles", "r01_bench_v9.json")) + glob.glob(os.path.join(ROOT, "profiles", "r01_bench_v8.json")))
+                   glob.glob(os.path.join(ROOT, "profiles", "r01_bench_v9.json")) + glob.glob(os.path.join(ROOT, "profiles", "r01_bench_v8.json")) +
+                   glob.glob(os.path.join(ROOT, "profiles", "r02_bench_v*.json")))
     assert paths
     for path in paths:
         d = json.loads(open(path).read().strip().splitlines()[-1])
