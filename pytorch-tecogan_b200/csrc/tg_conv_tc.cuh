@@ -98,6 +98,10 @@ int encode_bf16(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* di
 // output channels, a separate reduction launch otherwise)
 int launch_wgrad3x3(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout, int cin_pad,
                     int cout_pad, cudaStream_t stream, float* db = nullptr);
+// nlayers consecutive same-shape layers (cout <= 64) in one launch: X / dY blocks of n images each back to back, gradients
+// dw_stride / db_stride floats apart (db may be null)
+int launch_wgrad3x3_batched(const void* x, const void* dy, float* dw, float* db, int nlayers, long long dw_stride, long long db_stride,
+                            int n, int h, int w, int cin, int cout, int cin_pad, cudaStream_t stream);
 // ConvTranspose2d(k3,s2,p1,op1): x [n,h,w,cin_pad], dy [n,2h,2w,cout_pad] -> dw [cin][cout][3][3]
 int launch_wgrad_convT3x3s2(const void* x, const void* dy, float* dw, int n, int h, int w, int cin, int cout,
                             int cin_pad, int cout_pad, cudaStream_t stream);

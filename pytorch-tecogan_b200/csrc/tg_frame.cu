@@ -131,7 +131,7 @@ __device__ __forceinline__ uint32_t f2_to_bf16x2(uint64_t v) {
 // store, NHWC).  ReLU commutes with the rounding to bf16, so it is one bf16x2 max per pair; a layer has a ReLU or a
 // residual, never both (launch_frame checks).
 __device__ __forceinline__ void epi_store_bf16(uint64_t (&a)[8], const float* bias16, uint8_t* dst, const uint8_t* res,
-                                               bool relu) {
+                                               bool relu, const uint8_t* msk = nullptr) {
   const uint64_t* b2 = reinterpret_cast<const uint64_t*>(bias16);
 #pragma unroll
   for (int e = 0; e < 8; ++e) a[e] = f2_add(a[e], b2[e]);
@@ -149,6 +149,15 @@ __device__ __forceinline__ void epi_store_bf16(uint64_t (&a)[8], const float* bi
       o[e] = f2_to_bf16x2(a[e]);
       if (relu) asm("max.bf16x2 %0, %1, %2;" : "=r"(o[e]) : "r"(o[e]), "r"(0u));
     }
+  }
+  if (msk) {
+    // backward of the ReLU that produced the saved activation `msk` (same layout as the output): the gradient passes where
+    // the activation is non-zero (tg_conv_tc.cu: kMaskRelu).  The activation belongs to an earlier launch: plain L2 load.
+    uint32_t mv[8];
+    ld_global_cg_v8(msk, mv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      o[e] &= ((mv[e] & 0x7FFFu) ? 0xFFFFu : 0u) | ((mv[e] & 0x7FFF0000u) ? 0xFFFF0000u : 0u);
   }
   st_global_v8(dst, o);
 }
@@ -228,7 +237,8 @@ __device__ __forceinline__ void decode_batch(const FrProgram& P, int it0, int la
 }
 
 // kDbg: the measurement build (TG_FRAME_DBG knobs, segment trace, stall accounting); the production build has none of it.
-template <bool kPair, bool kDbg>
+// kMask: the data-gradient build (tg_gen_backward): bf16 layers may carry a ReLU mask (FrLayer::mask) applied after the residual.
+template <bool kPair, bool kDbg, bool kMask = false>
 __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_constant__ FrProgram P) {
   const int dbg = kDbg ? P.dbg : 0;
   unsigned long long* const trace = kDbg ? P.trace : nullptr;
@@ -591,6 +601,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     uint32_t c_row_bytes = 0, c_px_bytes = 0, c_img_bytes = 0;
     uint8_t* c_out = nullptr;
     const uint8_t* c_res = nullptr;
+    const uint8_t* c_msk = nullptr;
     int c_wide = 0, c_mode = 0, c_relu = 0, c_kind = 0;
     const uint32_t bar_cf = bar_cfull + 8 * set, bar_pf = bar_pfull + 8 * set, bar_pe = bar_pempty + 8 * set;
     const uint32_t bar_ce = lbar_cempty + 8 * set, bar_ce_local = bar_cempty + 8 * set;
@@ -609,6 +620,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         c_px_bytes = C.oc * 2u; c_row_bytes = C.ow * c_px_bytes; c_img_bytes = C.oh * c_row_bytes;   // < 4 GB (launch_frame)
         c_out = static_cast<uint8_t*>(C.out) + C.ch0 * 2u + half * 64u;
         c_res = C.resid ? static_cast<const uint8_t*>(C.resid) + C.ch0 * 2u + half * 64u : nullptr;
+        // (bf16 layers have no f32 logits copy: out2 carries the ReLU mask of the data-gradient build)
+        c_msk = (kMask && C.out2 && C.out_mode == kOutNHWCbf16) ? reinterpret_cast<const uint8_t*>(C.out2) + C.ch0 * 2u + half * 64u : nullptr;
       }
       const FrSegS& S = segs[si];
       if (si != cur_si) {                                  // warp-private bias copy of this segment
@@ -673,7 +686,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
             for (int e = 0; e < 8; ++e)
               a2[e] = f2_add(a2[e], f2_pack(__shfl_down_sync(0xFFFFFFFFu, v[2 * e], 1), __shfl_down_sync(0xFFFFFFFFu, v[2 * e + 1], 1)));
             if (wvalid && !(dbg & 16))
-              epi_store_bf16(a2, s_bias + col, c_out + off + pass * 32u, c_res ? c_res + off + pass * 32u : nullptr, c_relu != 0);
+              epi_store_bf16(a2, s_bias + col, c_out + off + pass * 32u, c_res ? c_res + off + pass * 32u : nullptr, c_relu != 0,
+                             (kMask && c_msk) ? c_msk + off + pass * 32u : nullptr);
           }
         } else {
           uint32_t v0[4], v1[4], v2[4];                    // 3 output channels of each of the 3 partial sums
@@ -748,7 +762,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
                 uint64_t a2[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) a2[e] = f2_pack(v[2 * e], v[2 * e + 1]);
-                epi_store_bf16(a2, s_bias + col, c_out + off + pass * 32u, c_res ? c_res + off + pass * 32u : nullptr, c_relu != 0);
+                epi_store_bf16(a2, s_bias + col, c_out + off + pass * 32u, c_res ? c_res + off + pass * 32u : nullptr, c_relu != 0,
+                               (kMask && c_msk) ? c_msk + off + pass * 32u : nullptr);
               }
             }
           } else {                                           // output conv on the tall geometry (TG_FRAME_WIDE=0)
@@ -940,6 +955,8 @@ static const FrDev& frame_device() {
   ok &= cudaFuncSetAttribute(frame_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<true>::kSmemBytes) == cudaSuccess;
   ok &= cudaFuncSetAttribute(frame_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<false>::kSmemBytes) == cudaSuccess;
   ok &= cudaFuncSetAttribute(frame_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<true>::kSmemBytes) == cudaSuccess;
+  ok &= cudaFuncSetAttribute(frame_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<false>::kSmemBytes) == cudaSuccess;
+  ok &= cudaFuncSetAttribute(frame_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrCfg<true>::kSmemBytes) == cudaSuccess;
   if (!ok) { cudaGetLastError(); return d; }
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_kernel<false, false>, kFrThreads, FrCfg<false>::kSmemBytes) == cudaSuccess)
@@ -1011,6 +1028,7 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
     }
   }
   int nseg = 0, items = 0;
+  bool any_mask = false;
   int first_seg[kFrMaxMaps], nchunks[kFrMaxMaps];
   double flops = 0.0;
   for (int li = 0; li < nlayers; ++li) {
@@ -1019,6 +1037,8 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
     TG_CHECK_ARG(l.cout_pad == 16 || l.cout_pad == 64 || l.cout_pad == 128, "frame: cout_pad must be 16/64/128");
     TG_CHECK_ARG((l.blob_off % 128) == 0, "frame: packed blob offsets must be 128-byte aligned");
     TG_CHECK_ARG(!(l.relu && l.resid), "frame: layer %d has both a ReLU and a residual", li);
+    TG_CHECK_ARG(!l.mask || (l.out_mode == kOutNHWCbf16 && !l.relu && !l.out2), "frame: layer %d: a ReLU mask goes with a plain bf16 output", li);
+    any_mask |= l.mask != nullptr;
     TG_CHECK_ARG(l.w < 32768 && l.h < 32768 && n < (1 << 23), "frame: layer size out of range");
     TG_CHECK_ARG(4.0 * l.h * l.w * l.cout_pad * 2 < 4294967296.0, "frame: one image of layer %d exceeds 4 GB", li);
     {
@@ -1085,7 +1105,7 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
       S.oc = net_out ? 3 : l.cout_pad;
       S.ch0 = c * 64;
       S.out_nstride = l.out_nstride > 0 ? l.out_nstride : static_cast<long long>(S.oc) * S.oh * S.ow;
-      S.out = l.out; S.out2 = l.out2;
+      S.out = l.out; S.out2 = l.mask ? static_cast<float*>(const_cast<void*>(l.mask)) : l.out2;
       S.resid = net_out ? l.out_rgbx : l.resid;
       TG_CHECK_ARG(l.out_rgbx == nullptr || (net_out && wide && l.cout_pad == 16),
                    "frame: the interleaved copy exists for the wide output conv only");
@@ -1148,7 +1168,10 @@ int launch_frame(const FrLayer* layers, int nlayers, const void* packed, size_t 
   cfg.numAttrs = pair ? 2 : 1;
   tg_prof_pre(TG_K_FRAME, flops, stream);
   const bool measure = P.dbg != 0 || P.trace != nullptr;
-  if (pair) {
+  if (any_mask) {                                                  // data-gradient chain (no measurement build of it)
+    if (pair) TG_CUDA(cudaLaunchKernelEx(&cfg, frame_kernel<true, false, true>, P));
+    else TG_CUDA(cudaLaunchKernelEx(&cfg, frame_kernel<false, false, true>, P));
+  } else if (pair) {
     if (measure) TG_CUDA(cudaLaunchKernelEx(&cfg, frame_kernel<true, true>, P));
     else TG_CUDA(cudaLaunchKernelEx(&cfg, frame_kernel<true, false>, P));
   } else {

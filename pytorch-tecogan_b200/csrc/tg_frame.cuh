@@ -76,7 +76,7 @@ struct FrSegS {
   FastDiv fd_tiles_x, fd_tiles_y;
   long long out_nstride;
   void* out;
-  float* out2;
+  float* out2;                // network-output layers: optional f32 logits; bf16 layers: the optional ReLU mask (FrLayer::mask)
   const void* resid;          // output conv: the optional interleaved float4 copy (FrLayer::out_rgbx) instead
   const float* bias;
 };
@@ -106,6 +106,8 @@ struct FrLayer {              // host-side description of one conv layer of the 
   size_t blob_off;            // byte offset of the layer's packed blob
   long long out_nstride;
   void* out_rgbx;             // output conv only (optional): second copy of the result as float4 {R,G,B,0} per pixel
+  const void* mask;           // bf16 layers only (optional): saved post-ReLU activation with the output's layout; the result is
+                              //   zeroed where it is zero (ReLU backward, applied after the residual) - tg_gen_backward
 };
 
 size_t frame_flag_count(const FrLayer* layers, int nlayers, int n);

@@ -314,9 +314,12 @@ namespace tg {
 
 struct GenTrainWs {
   size_t x_in;
-  std::vector<size_t> net, t;          // net[0..nres] (64ch @1x), t[0..nres-1] = relu(conv1)
+  std::vector<size_t> net, t;          // net[0..nres] (64ch @1x), t[0..nres-1] = relu(conv1): each family one contiguous block
   size_t b0, b1, b2, c0, c1, d, e;     // upsampling stack activations
-  size_t g_z, g_e, g_d, g_c1, g_c0, g_b[2], g_net[2], g_t;   // gradient buffers
+  // gradient buffers, one per tensor (the data-gradient chain runs as persistent multi-layer launches and the weight
+  // gradients read them afterwards): g_net[0..nres], g_t[0..nres-1] contiguous like net / t
+  size_t g_z, g_e, g_d, g_c1, g_c0, g_b[3];
+  std::vector<size_t> g_net, g_t;
   size_t flags, flag_count, total;
 };
 static GenTrainWs gen_train_ws(int n, int h, int w, int nres) {
@@ -324,18 +327,24 @@ static GenTrainWs gen_train_ws(int n, int h, int w, int nres) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align256(bytes); return r; };
   const size_t px = static_cast<size_t>(n) * h * w;
+  auto family = [&](std::vector<size_t>& v, int count) {    // `count` blocks of px * 128 bytes back to back (no padding between)
+    const size_t base = take(px * 128 * static_cast<size_t>(count > 0 ? count : 1));
+    for (int i = 0; i < count; ++i) v.push_back(base + i * px * 128);
+  };
   ws.x_in = take(px * 128);
-  for (int i = 0; i <= nres; ++i) ws.net.push_back(take(px * 128));
-  for (int i = 0; i < nres; ++i) ws.t.push_back(take(px * 128));
+  family(ws.net, nres + 1);
+  family(ws.t, nres);
   ws.b0 = take(px * 4 * 128); ws.b1 = take(px * 4 * 128); ws.b2 = take(px * 4 * 128);
   ws.c0 = take(px * 4 * 256); ws.c1 = take(px * 4 * 256);
   ws.d = take(px * 16 * 256); ws.e = take(px * 16 * 128);
   ws.g_z = take(px * 16 * 128); ws.g_e = take(px * 16 * 128); ws.g_d = take(px * 16 * 256);
   ws.g_c1 = take(px * 4 * 256); ws.g_c0 = take(px * 4 * 256);
-  ws.g_b[0] = take(px * 4 * 128); ws.g_b[1] = take(px * 4 * 128);
-  ws.g_net[0] = take(px * 128); ws.g_net[1] = take(px * 128); ws.g_t = take(px * 128);
+  ws.g_b[0] = take(px * 4 * 128); ws.g_b[1] = take(px * 4 * 128); ws.g_b[2] = take(px * 4 * 128);
+  family(ws.g_net, nres + 1);
+  family(ws.g_t, nres);
   auto tiles = [&](int s) { return static_cast<size_t>(n) * frame_tiles_max(h * s, w * s); };
-  ws.flag_count = static_cast<size_t>(2 * nres + 2) * tiles(1) + 8 * tiles(2) + 2 * tiles(4) + 2 * nres + 16;   // + pair padding
+  // forward: 2 nres + 2 segments @1x, 8 @2x, 2 @4x; the backward chains need fewer @1x / @2x and 3 @4x (+ pair padding)
+  ws.flag_count = static_cast<size_t>(2 * nres + 2) * tiles(1) + 8 * tiles(2) + 3 * tiles(4) + 2 * nres + 16;
   ws.flags = take(ws.flag_count * 4);
   ws.total = o;
   return ws;
@@ -519,50 +528,89 @@ extern "C" int tg_gen_backward(const void* packed_dgrad, int num_resblock, const
   auto B = [&](size_t off) { return static_cast<void*>(wsp + off); };
   const int iOut = 2 * nres + 8, iCt6 = iOut - 1, iCt4 = iOut - 2, iC32 = iOut - 3, iC30 = iOut - 4, iC22 = iOut - 5,
             iC20 = iOut - 6, iCt0 = iOut - 7;
-
-  // final sigmoid
-  if ((rc = sigmoid_bwd_pack_launch(dout, out, B(ws.g_z), n, 16LL * h * w, 48LL * h * w, 48LL * h * w, st))) return rc;
-  // output conv 64 -> 3
-  if ((rc = wgrad(iOut, B(ws.e), B(ws.g_z), 4 * h, 4 * w))) return rc;
-  if ((rc = dgrad(iOut, B(ws.g_z), nullptr, B(ws.e), B(ws.g_e), 4 * h, 4 * w))) return rc;
-  // conv_trans.6: 128 -> 64 @4x
-  if ((rc = wgrad(iCt6, B(ws.d), B(ws.g_e), 4 * h, 4 * w))) return rc;
-  if ((rc = dgrad(iCt6, B(ws.g_e), nullptr, B(ws.d), B(ws.g_d), 4 * h, 4 * w))) return rc;
-  // conv_trans.4: ConvT 128 -> 128, 2x -> 4x
-  if ((rc = wgrad(iCt4, B(ws.c1), B(ws.g_d), 2 * h, 2 * w))) return rc;
-  if ((rc = dgrad(iCt4, B(ws.g_d), nullptr, nullptr, B(ws.g_c1), 2 * h, 2 * w))) return rc;
-  // conv_trans.3.2: 128 -> 128 (no bias, no activation after it)
-  if ((rc = wgrad(iC32, B(ws.c0), B(ws.g_c1), 2 * h, 2 * w))) return rc;
-  if ((rc = dgrad(iC32, B(ws.g_c1), nullptr, B(ws.c0), B(ws.g_c0), 2 * h, 2 * w))) return rc;
-  // conv_trans.3.0: 64 -> 128 + ReLU
-  if ((rc = wgrad(iC30, B(ws.b2), B(ws.g_c0), 2 * h, 2 * w))) return rc;
-  if ((rc = dgrad(iC30, B(ws.g_c0), nullptr, nullptr, B(ws.g_b[0]), 2 * h, 2 * w))) return rc;       // b2 has no activation
-  // conv_trans.2.2: 64 -> 64 (no bias)
-  if ((rc = wgrad(iC22, B(ws.b1), B(ws.g_b[0]), 2 * h, 2 * w))) return rc;
-  if ((rc = dgrad(iC22, B(ws.g_b[0]), nullptr, B(ws.b1), B(ws.g_b[1]), 2 * h, 2 * w))) return rc;
-  // conv_trans.2.0: 64 -> 64 + ReLU
-  if ((rc = wgrad(iC20, B(ws.b0), B(ws.g_b[1]), 2 * h, 2 * w))) return rc;
-  if ((rc = dgrad(iC20, B(ws.g_b[1]), nullptr, B(ws.b0), B(ws.g_b[0]), 2 * h, 2 * w))) return rc;
-  // conv_trans.0: ConvT 64 -> 64, 1x -> 2x
-  if ((rc = wgrad(iCt0, B(ws.net[nres]), B(ws.g_b[0]), h, w))) return rc;
-  int cur = 0;
-  if ((rc = dgrad(iCt0, B(ws.g_b[0]), nullptr, nullptr, B(ws.g_net[cur]), h, w))) return rc;
-  // residual trunk, last block first: net[k+1] = conv2(t[k]) + net[k], t[k] = relu(conv1(net[k]) + b)
-  for (int k = nres - 1; k >= 0; --k) {
-    const int i1 = 1 + 2 * k, i2 = 2 + 2 * k;
-    if ((rc = wgrad(i2, B(ws.t[k]), B(ws.g_net[cur]), h, w))) return rc;
-    if ((rc = dgrad(i2, B(ws.g_net[cur]), nullptr, B(ws.t[k]), B(ws.g_t), h, w))) return rc;
-    if ((rc = wgrad(i1, B(ws.net[k]), B(ws.g_t), h, w))) return rc;
-    // d net[k] = dgrad(conv1) + d net[k+1]; net[0] = relu(conv.0) -> masked
-    if ((rc = dgrad(i1, B(ws.g_t), B(ws.g_net[cur]), k == 0 ? B(ws.net[0]) : nullptr, B(ws.g_net[cur ^ 1]), h, w))) return rc;
-    cur ^= 1;
-  }
   if (nres == 0) {
     // no trunk: the ConvT data gradient still has to pass conv.0's ReLU; reuse the mask path of a copy-free dgrad is not
     // possible, so this configuration is rejected (the reference default is 16 blocks)
     tg_set_error("gen_backward: num_resblock == 0 is not supported");
     return TG_ERR_BAD_ARG;
   }
+  // TG_GEN_BWD_FRAME=0: one conv_tc launch per data gradient and one weight-gradient launch per layer (A/B, fallback)
+  static const bool chain_on = []() { const char* e = getenv("TG_GEN_BWD_FRAME"); return !(e && e[0] == '0'); }();
+  size_t dgrad_bytes = 0;
+  gen_dgrad_offsets(L, &dgrad_bytes);
+  // A run of 3x3 data gradients as ONE persistent launch of the frame kernel's data-gradient build (tg_frame.cu, kMask): the
+  // layers are chained by tile counters instead of kernel boundaries.  chain[i] = {layer, dy, resid, mask, dx, scale of (h, w)}
+  struct Link { int li; size_t dy, resid, mask, dx; int s; bool has_resid, has_mask; };
+  auto run_chain = [&](const std::vector<Link>& chain) {
+    if (!chain_on) {
+      for (const Link& c : chain)
+        if ((rc = dgrad(c.li, B(c.dy), c.has_resid ? B(c.resid) : nullptr, c.has_mask ? B(c.mask) : nullptr, B(c.dx), c.s * h, c.s * w))) return rc;
+      return TG_OK;
+    }
+    std::vector<FrLayer> P;
+    for (const Link& c : chain) {
+      const GenLayer& l = L[c.li];
+      FrLayer f{};
+      f.kind = kConv3x3; f.cin_pad = l.cout <= 64 ? 64 : 128; f.cout_pad = cin_padded(l.cin);
+      f.out_mode = kOutNHWCbf16; f.relu = 0; f.h = c.s * h; f.w = c.s * w;
+      f.in = B(c.dy); f.out = B(c.dx); f.resid = c.has_resid ? B(c.resid) : nullptr; f.mask = c.has_mask ? B(c.mask) : nullptr;
+      f.blob_off = doff[c.li];
+      P.push_back(f);
+    }
+    const size_t nflags = frame_flag_count(P.data(), static_cast<int>(P.size()), n);
+    if (nflags > ws.flag_count) {
+      tg_set_error("gen_backward: internal flag capacity (%zu > %zu)", nflags, ws.flag_count);
+      return TG_ERR_WORKSPACE;
+    }
+    return launch_frame(P.data(), static_cast<int>(P.size()), pd, dgrad_bytes, n, reinterpret_cast<uint32_t*>(wsp + ws.flags),
+                        ws.flag_count, false, st);
+  };
+
+  // final sigmoid
+  if ((rc = sigmoid_bwd_pack_launch(dout, out, B(ws.g_z), n, 16LL * h * w, 48LL * h * w, 48LL * h * w, st))) return rc;
+  // output conv 64 -> 3 and conv_trans.6 (128 -> 64) @4x
+  if ((rc = run_chain({{iOut, ws.g_z, 0, ws.e, ws.g_e, 4, false, true}, {iCt6, ws.g_e, 0, ws.d, ws.g_d, 4, false, true}}))) return rc;
+  if ((rc = wgrad(iOut, B(ws.e), B(ws.g_z), 4 * h, 4 * w))) return rc;
+  if ((rc = wgrad(iCt6, B(ws.d), B(ws.g_e), 4 * h, 4 * w))) return rc;
+  // conv_trans.4: ConvT 128 -> 128, 2x -> 4x
+  if ((rc = wgrad(iCt4, B(ws.c1), B(ws.g_d), 2 * h, 2 * w))) return rc;
+  if ((rc = dgrad(iCt4, B(ws.g_d), nullptr, nullptr, B(ws.g_c1), 2 * h, 2 * w))) return rc;
+  // conv_trans.3.2 (128 -> 128, no bias), .3.0 (64 -> 128 + ReLU; its input b2 has no activation), .2.2 (64 -> 64, no bias),
+  // .2.0 (64 -> 64 + ReLU) @2x
+  if ((rc = run_chain({{iC32, ws.g_c1, 0, ws.c0, ws.g_c0, 2, false, true}, {iC30, ws.g_c0, 0, 0, ws.g_b[0], 2, false, false},
+                       {iC22, ws.g_b[0], 0, ws.b1, ws.g_b[1], 2, false, true}, {iC20, ws.g_b[1], 0, ws.b0, ws.g_b[2], 2, false, true}}))) return rc;
+  if ((rc = wgrad(iC32, B(ws.c0), B(ws.g_c1), 2 * h, 2 * w))) return rc;
+  if ((rc = wgrad(iC30, B(ws.b2), B(ws.g_c0), 2 * h, 2 * w))) return rc;
+  if ((rc = wgrad(iC22, B(ws.b1), B(ws.g_b[0]), 2 * h, 2 * w))) return rc;
+  if ((rc = wgrad(iC20, B(ws.b0), B(ws.g_b[1]), 2 * h, 2 * w))) return rc;
+  // conv_trans.0: ConvT 64 -> 64, 1x -> 2x
+  if ((rc = wgrad(iCt0, B(ws.net[nres]), B(ws.g_b[2]), h, w))) return rc;
+  if ((rc = dgrad(iCt0, B(ws.g_b[2]), nullptr, nullptr, B(ws.g_net[nres]), h, w))) return rc;
+  // residual trunk, last block first: net[k+1] = conv2(t[k]) + net[k], t[k] = relu(conv1(net[k]) + b):
+  //   d t[k] = dgrad(conv2)(d net[k+1]) masked by t[k];  d net[k] = dgrad(conv1)(d t[k]) + d net[k+1]  (net[0] = relu(conv.0): masked)
+  {
+    std::vector<Link> trunk;
+    for (int k = nres - 1; k >= 0; --k) {
+      trunk.push_back({2 + 2 * k, ws.g_net[k + 1], 0, ws.t[k], ws.g_t[k], 1, false, true});
+      trunk.push_back({1 + 2 * k, ws.g_t[k], ws.g_net[k + 1], ws.net[0], ws.g_net[k], 1, true, k == 0});
+    }
+    if ((rc = run_chain(trunk))) return rc;
+  }
+  // the trunk's weight gradients: the 16 conv1 layers (x = net[k], dy = d t[k], with bias) and the 16 conv2 layers (x = t[k],
+  // dy = d net[k+1]) as two batched launches
+  if (chain_on && nres >= 2) {
+    const long long wstride = static_cast<long long>(L[3].w_off) - static_cast<long long>(L[1].w_off);
+    if ((rc = launch_wgrad3x3_batched(B(ws.net[0]), B(ws.g_t[0]), flat_grad + L[1].w_off, flat_grad + L[1].b_off, nres, wstride, wstride,
+                                      n, h, w, 64, 64, 64, st))) return rc;
+    if ((rc = launch_wgrad3x3_batched(B(ws.t[0]), B(ws.g_net[1]), flat_grad + L[2].w_off, nullptr, nres, wstride, 0, n, h, w, 64, 64, 64, st)))
+      return rc;
+  } else {
+    for (int k = nres - 1; k >= 0; --k) {
+      if ((rc = wgrad(2 + 2 * k, B(ws.t[k]), B(ws.g_net[k + 1]), h, w))) return rc;
+      if ((rc = wgrad(1 + 2 * k, B(ws.net[k]), B(ws.g_t[k]), h, w))) return rc;
+    }
+  }
+  const int cur = 0;
   // conv.0: 51 -> 64 + ReLU (its input is detached: no data gradient)
   (void)px1;
   return wgrad(0, B(ws.x_in), B(ws.g_net[cur]), h, w);

@@ -193,6 +193,9 @@ struct WgKyParams {
   uint32_t stage_stride;
   float* dw;
   float* db;                           // optional bias gradient (db[co] += sum of dY), or null
+  // batched form (launch_wgrad3x3_ky_batched): blockIdx.z = layer; the layers' X / dY tensors are consecutive blocks of n
+  // images each (image index layer * n + i of one tensor map), their gradients dw_stride / db_stride floats apart
+  long long dw_stride, db_stride;
 };
 constexpr uint32_t kWgKyABytes = 8 * 18 * 128;        // dY box {64 ch, 8, 18}: the tile and one halo row above / below
 constexpr uint32_t kWgKyBBytes = 10 * 16 * 128;       // X box {64 ch, 10, 16}: one halo column left / right
@@ -212,8 +215,11 @@ wgrad3x3_ky_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cblk = blockIdx.y;                               // 64-channel block of X (GEMM N)
+  const int layer = blockIdx.z, n_base = layer * p.n;        // batched launch: this CTA's layer (0 otherwise)
+  float* const dw = p.dw + layer * p.dw_stride;
+  float* const db = p.db ? p.db + layer * p.db_stride : nullptr;
   // the bias gradient rides on the first channel block's CTAs: warps 2..5 sum the staged dY tiles while the MMAs run
-  const bool do_bias = p.db != nullptr && cblk == 0;
+  const bool do_bias = db != nullptr && cblk == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_dy);
@@ -241,8 +247,8 @@ wgrad3x3_ky_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_const
       if (elect_one()) {
         mbar_expect_tx(bar_full + 8 * s, kWgKyABytes + kWgKyBBytes);
         const uint32_t dst = s_st + s * p.stage_stride;
-        tma_load_4d(dst, &tm_dy, bar_full + 8 * s, 0, x0, y0 - 1, n);
-        tma_load_4d(dst + kWgKyABytes, &tm_x, bar_full + 8 * s, cblk * 64, x0 - 1, y0, n);
+        tma_load_4d(dst, &tm_dy, bar_full + 8 * s, 0, x0, y0 - 1, n_base + n);
+        tma_load_4d(dst + kWgKyABytes, &tm_x, bar_full + 8 * s, cblk * 64, x0 - 1, y0, n_base + n);
       }
       __syncwarp();
       if (++s == p.nstages) { s = 0; ph ^= 1; }
@@ -303,8 +309,8 @@ wgrad3x3_ky_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_const
         if (lane == 0) mbar_arrive(bar_empty + 8 * s);
         if (++s == p.nstages) { s = 0; ph ^= 1; }
       }
-      if (2 * ch2 < p.rows_real) atomicAdd(p.db + 2 * ch2, s0);
-      if (2 * ch2 + 1 < p.rows_real) atomicAdd(p.db + 2 * ch2 + 1, s1);
+      if (2 * ch2 < p.rows_real) atomicAdd(db + 2 * ch2, s0);
+      if (2 * ch2 + 1 < p.rows_real) atomicAdd(db + 2 * ch2 + 1, s1);
     }
     if (have_work) {
       mbar_wait(bar_done, 0);
@@ -336,7 +342,7 @@ wgrad3x3_ky_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_const
       const int ci_valid = min(64, p.cols_real - cblk * 64);
       const int ncols = ci_valid > 0 ? ci_valid * 9 : 0;
       for (int row = warp - 2; row < p.rows_real; row += 4) {
-        float* g = p.dw + (static_cast<size_t>(row) * p.cols_real + cblk * 64) * 9;
+        float* g = dw + (static_cast<size_t>(row) * p.cols_real + cblk * 64) * 9;
         const float* srow = stg + row * kLd;
         for (int j = lane; j < ncols; j += 32) atomicAdd(g + j, srow[j]);
       }
@@ -348,26 +354,28 @@ wgrad3x3_ky_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_const
 }
 
 static int launch_wgrad3x3_ky(const void* x, const void* dy, float* dw, float* db, int n, int h, int w, int cin, int cout, int cin_pad,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, int nlayers = 1, long long dw_stride = 0, long long db_stride = 0) {
   WgKyParams p{};
   p.n = n; p.h = h; p.w = w;
   p.tiles_x = tg_div_up(w, kTileW); p.tiles_y = tg_div_up(h, kTileH);
-  p.num_items = n * p.tiles_x * p.tiles_y;
+  p.num_items = n * p.tiles_x * p.tiles_y;                   // per layer
   p.rows_real = cout; p.cols_real = cin;
   p.stage_stride = (kWgKyABytes + kWgKyBBytes + 1023u) & ~1023u;
   p.nstages = 5;
   p.dw = dw; p.db = db;
+  p.dw_stride = dw_stride; p.db_stride = db_stride;
   const uint32_t smem_bytes = p.nstages * p.stage_stride + 16 * p.nstages + 64 + 1024;
   TG_CHECK_ARG(smem_bytes <= kWgSmemLimit, "wgrad3x3: stages do not fit in shared memory");
+  const cuuint64_t images = static_cast<cuuint64_t>(n) * nlayers;
   CUtensorMap tm_a, tm_b;
   {
-    cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
+    cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), images};
     cuuint64_t strides[3] = {128, static_cast<cuuint64_t>(w) * 128, static_cast<cuuint64_t>(h) * w * 128};
     cuuint32_t box[4] = {64, kTileW, kTileH + 2, 1};
     if (int rc = encode_bf16(&tm_a, dy, 4, dims, strides, box)) return rc;
   }
   {
-    cuuint64_t dims[4] = {static_cast<cuuint64_t>(cin_pad), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(cin_pad), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), images};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(cin_pad) * 2, static_cast<cuuint64_t>(w) * cin_pad * 2,
                              static_cast<cuuint64_t>(h) * w * cin_pad * 2};
     cuuint32_t box[4] = {64, kTileW + 2, kTileH, 1};
@@ -376,16 +384,31 @@ static int launch_wgrad3x3_ky(const void* x, const void* dy, float* dw, float* d
   static const int tiles_per_slab = []() { const char* e = getenv("TG_WGRAD_TILES_PER_SLAB"); const int v = e ? atoi(e) : 8; return v > 0 ? v : 8; }();
   const int cblocks = cin_pad / 64;
   int slabs = p.num_items / tiles_per_slab;
-  const int max_slabs = tg_num_sms() / cblocks;
+  // a batch of layers shares the machine: SMs / (layers x channel blocks) slabs per layer (every CTA ends with rows x taps x
+  // cols atomics, so few big slabs per layer beat many small ones)
+  int max_slabs = tg_num_sms() / (cblocks * nlayers);
+  if (max_slabs < 1) max_slabs = 1;
   if (slabs > max_slabs) slabs = max_slabs;
   if (slabs < 1) slabs = 1;
   static TgPerDeviceOnce attr_once;
   if (attr_once.need()) TG_CUDA(cudaFuncSetAttribute(wgrad3x3_ky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemLimit));
-  tg_prof_pre(TG_K_WGRAD, 2.0 * 9.0 * cin_pad * 64 * n * h * w, stream);
-  wgrad3x3_ky_kernel<<<dim3(slabs, cblocks), kWgThreads, smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes, stream>>>(tm_a, tm_b, p);
+  tg_prof_pre(TG_K_WGRAD, 2.0 * 9.0 * cin_pad * 64 * n * h * w * nlayers, stream);
+  wgrad3x3_ky_kernel<<<dim3(slabs, cblocks, nlayers), kWgThreads, smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes, stream>>>(tm_a, tm_b, p);
   tg_prof_post(stream);
   TG_CUDA(cudaGetLastError());
   return TG_OK;
+}
+
+// nlayers same-shape 3x3 layers (<= 64 output channels) in ONE launch: layer l reads X at x + l * (n*h*w*cin_pad) elements and
+// dY at dy + l * (n*h*w*64), and adds into dw + l * dw_stride (and db + l * db_stride).  The residual trunk's 2 x 16 weight
+// gradients are two such launches instead of 32: at small crops a per-layer launch is mostly its final atomics and its tail.
+int launch_wgrad3x3_batched(const void* x, const void* dy, float* dw, float* db, int nlayers, long long dw_stride, long long db_stride,
+                            int n, int h, int w, int cin, int cout, int cin_pad, cudaStream_t stream) {
+  TG_CHECK_ARG(x && dy && dw && nlayers >= 1, "wgrad3x3_batched: null pointer / no layers");
+  TG_CHECK_ARG(n > 0 && h > 0 && w > 0 && static_cast<long long>(n) * nlayers < (1LL << 31), "wgrad3x3_batched: bad shape");
+  TG_CHECK_ARG((cin_pad == 64 || cin_pad == 128) && cin >= 1 && cin <= cin_pad && cout >= 1 && cout <= 64, "wgrad3x3_batched: bad channel counts");
+  TG_CHECK_ARG(nlayers <= 65535, "wgrad3x3_batched: too many layers");
+  return launch_wgrad3x3_ky(x, dy, dw, db, n, h, w, cin, cout, cin_pad, stream, nlayers, dw_stride, db_stride);
 }
 
 static int wgrad_launch_common(WgParams& p, const void* a, int a_pad, const void* b, int b_pad, int bh, int bw,
