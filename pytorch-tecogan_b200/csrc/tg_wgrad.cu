@@ -196,6 +196,7 @@ struct WgKyParams {
   // batched form (launch_wgrad3x3_ky_batched): blockIdx.z = layer; the layers' X / dY tensors are consecutive blocks of n
   // images each (image index layer * n + i of one tensor map), their gradients dw_stride / db_stride floats apart
   long long dw_stride, db_stride;
+  int co_blocks;                       // 64-row blocks of dY channels (cout_pad / 64): blockIdx.z = layer * co_blocks + block
 };
 constexpr uint32_t kWgKyABytes = 8 * 18 * 128;        // dY box {64 ch, 8, 18}: the tile and one halo row above / below
 constexpr uint32_t kWgKyBBytes = 10 * 16 * 128;       // X box {64 ch, 10, 16}: one halo column left / right
@@ -215,9 +216,11 @@ wgrad3x3_ky_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cblk = blockIdx.y;                               // 64-channel block of X (GEMM N)
-  const int layer = blockIdx.z, n_base = layer * p.n;        // batched launch: this CTA's layer (0 otherwise)
-  float* const dw = p.dw + layer * p.dw_stride;
-  float* const db = p.db ? p.db + layer * p.db_stride : nullptr;
+  const int layer = blockIdx.z / p.co_blocks, coblk = blockIdx.z - layer * p.co_blocks;   // batched launch: this CTA's layer
+  const int n_base = layer * p.n;
+  const int rows_real = min(64, p.rows_real - coblk * 64);   // output channels of this CTA's 64-row block of dY
+  float* const dw = p.dw + layer * p.dw_stride + static_cast<size_t>(coblk) * 64 * p.cols_real * 9;
+  float* const db = p.db ? p.db + layer * p.db_stride + coblk * 64 : nullptr;
   // the bias gradient rides on the first channel block's CTAs: warps 2..5 sum the staged dY tiles while the MMAs run
   const bool do_bias = db != nullptr && cblk == 0;
 
@@ -247,7 +250,7 @@ wgrad3x3_ky_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_const
       if (elect_one()) {
         mbar_expect_tx(bar_full + 8 * s, kWgKyABytes + kWgKyBBytes);
         const uint32_t dst = s_st + s * p.stage_stride;
-        tma_load_4d(dst, &tm_dy, bar_full + 8 * s, 0, x0, y0 - 1, n_base + n);
+        tma_load_4d(dst, &tm_dy, bar_full + 8 * s, coblk * 64, x0, y0 - 1, n_base + n);
         tma_load_4d(dst + kWgKyABytes, &tm_x, bar_full + 8 * s, cblk * 64, x0 - 1, y0, n_base + n);
       }
       __syncwarp();
@@ -309,8 +312,8 @@ wgrad3x3_ky_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_const
         if (lane == 0) mbar_arrive(bar_empty + 8 * s);
         if (++s == p.nstages) { s = 0; ph ^= 1; }
       }
-      if (2 * ch2 < p.rows_real) atomicAdd(db + 2 * ch2, s0);
-      if (2 * ch2 + 1 < p.rows_real) atomicAdd(db + 2 * ch2 + 1, s1);
+      if (2 * ch2 < rows_real) atomicAdd(db + 2 * ch2, s0);
+      if (2 * ch2 + 1 < rows_real) atomicAdd(db + 2 * ch2 + 1, s1);
     }
     if (have_work) {
       mbar_wait(bar_done, 0);
@@ -341,7 +344,7 @@ wgrad3x3_ky_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_const
       asm volatile("bar.sync 1, 128;" ::: "memory");           // the four epilogue warps (warps 2..5)
       const int ci_valid = min(64, p.cols_real - cblk * 64);
       const int ncols = ci_valid > 0 ? ci_valid * 9 : 0;
-      for (int row = warp - 2; row < p.rows_real; row += 4) {
+      for (int row = warp - 2; row < rows_real; row += 4) {
         float* g = dw + (static_cast<size_t>(row) * p.cols_real + cblk * 64) * 9;
         const float* srow = stg + row * kLd;
         for (int j = lane; j < ncols; j += 32) atomicAdd(g + j, srow[j]);
@@ -354,7 +357,7 @@ wgrad3x3_ky_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_const
 }
 
 static int launch_wgrad3x3_ky(const void* x, const void* dy, float* dw, float* db, int n, int h, int w, int cin, int cout, int cin_pad,
-                              cudaStream_t stream, int nlayers = 1, long long dw_stride = 0, long long db_stride = 0) {
+                              cudaStream_t stream, int nlayers = 1, long long dw_stride = 0, long long db_stride = 0, int cout_pad = 64) {
   WgKyParams p{};
   p.n = n; p.h = h; p.w = w;
   p.tiles_x = tg_div_up(w, kTileW); p.tiles_y = tg_div_up(h, kTileH);
@@ -364,13 +367,15 @@ static int launch_wgrad3x3_ky(const void* x, const void* dy, float* dw, float* d
   p.nstages = 5;
   p.dw = dw; p.db = db;
   p.dw_stride = dw_stride; p.db_stride = db_stride;
+  p.co_blocks = cout_pad / 64;
   const uint32_t smem_bytes = p.nstages * p.stage_stride + 16 * p.nstages + 64 + 1024;
   TG_CHECK_ARG(smem_bytes <= kWgSmemLimit, "wgrad3x3: stages do not fit in shared memory");
   const cuuint64_t images = static_cast<cuuint64_t>(n) * nlayers;
   CUtensorMap tm_a, tm_b;
   {
-    cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), images};
-    cuuint64_t strides[3] = {128, static_cast<cuuint64_t>(w) * 128, static_cast<cuuint64_t>(h) * w * 128};
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(cout_pad), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), images};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(cout_pad) * 2, static_cast<cuuint64_t>(w) * cout_pad * 2,
+                             static_cast<cuuint64_t>(h) * w * cout_pad * 2};
     cuuint32_t box[4] = {64, kTileW, kTileH + 2, 1};
     if (int rc = encode_bf16(&tm_a, dy, 4, dims, strides, box)) return rc;
   }
@@ -386,14 +391,14 @@ static int launch_wgrad3x3_ky(const void* x, const void* dy, float* dw, float* d
   int slabs = p.num_items / tiles_per_slab;
   // a batch of layers shares the machine: SMs / (layers x channel blocks) slabs per layer (every CTA ends with rows x taps x
   // cols atomics, so few big slabs per layer beat many small ones)
-  int max_slabs = tg_num_sms() / (cblocks * nlayers);
+  int max_slabs = tg_num_sms() / (cblocks * nlayers * p.co_blocks);
   if (max_slabs < 1) max_slabs = 1;
   if (slabs > max_slabs) slabs = max_slabs;
   if (slabs < 1) slabs = 1;
   static TgPerDeviceOnce attr_once;
   if (attr_once.need()) TG_CUDA(cudaFuncSetAttribute(wgrad3x3_ky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemLimit));
-  tg_prof_pre(TG_K_WGRAD, 2.0 * 9.0 * cin_pad * 64 * n * h * w * nlayers, stream);
-  wgrad3x3_ky_kernel<<<dim3(slabs, cblocks, nlayers), kWgThreads, smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes, stream>>>(tm_a, tm_b, p);
+  tg_prof_pre(TG_K_WGRAD, 2.0 * 9.0 * cin_pad * cout_pad * n * h * w * nlayers, stream);
+  wgrad3x3_ky_kernel<<<dim3(slabs, cblocks, nlayers * p.co_blocks), kWgThreads, smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes, stream>>>(tm_a, tm_b, p);
   tg_prof_post(stream);
   TG_CUDA(cudaGetLastError());
   return TG_OK;
@@ -466,7 +471,9 @@ int launch_wgrad3x3(const void* x, const void* dy, float* dw, int n, int h, int 
   TG_CHECK_ARG((cin_pad == 64 || cin_pad == 128) && (cout_pad == 64 || cout_pad == 128), "wgrad3x3: padded channels must be 64 or 128");
   TG_CHECK_ARG(cin >= 1 && cin <= cin_pad && cout >= 1 && cout <= cout_pad, "wgrad3x3: bad channel counts");
   static const bool ky_on = []() { const char* e = getenv("TG_WGRAD_KYSTACK"); return !(e && e[0] == '0'); }();   // A/B knob
-  if (cout_pad == 64 && ky_on) return launch_wgrad3x3_ky(x, dy, dw, db, n, h, w, cin, cout, cin_pad, stream);
+  // (128 output channels: two 64-row blocks of dY, each its own CTAs - TG_WGRAD_KY128=0 keeps them on the generic kernel)
+  static const bool ky128_on = []() { const char* e = getenv("TG_WGRAD_KY128"); return !(e && e[0] == '0'); }();
+  if (ky_on && (cout_pad == 64 || ky128_on)) return launch_wgrad3x3_ky(x, dy, dw, db, n, h, w, cin, cout, cin_pad, stream, 1, 0, 0, cout_pad);
   if (db) {                                                  // 128 output channels: the separate HBM-rate reduction
     if (int rc = launch_bias_grad(dy, static_cast<long long>(n) * h * w, cout_pad, cout, db, stream)) return rc;
   }
