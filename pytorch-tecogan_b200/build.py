@@ -28,19 +28,33 @@ def deps():
     return d
 
 
-def up_to_date():
-    if not os.path.exists(OUT):
+def source_digest(defines=()):
+    """sha256 over the contents of every source / header the library is built from (+ flags): file times do not survive a
+    copy to another box or a `git stash`, contents do."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in sorted(deps()):
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(FLAGS + list(defines)).encode())
+    return h.hexdigest()
+
+
+def up_to_date(target=OUT, defines=()):
+    stamp = target + ".srchash"
+    if not (os.path.exists(target) and os.path.exists(stamp)):
         return False
-    t = os.path.getmtime(OUT)
-    return all(os.path.getmtime(p) <= t for p in deps())
+    with open(stamp) as f:
+        return f.read().strip() == source_digest(defines)
 
 
 def build(force=False, verbose=False, variant=None, defines=()):
     """variant / defines: measurement builds (same-box A/B through `bench.py --lib`): libtecogan_b200.<variant>.so compiled
     with extra -D flags next to the product library; never loaded by the package itself."""
     target = OUT if not variant else os.path.join(HERE, f"libtecogan_b200.{variant}.so")
-    if not variant and not force and up_to_date():
-        return OUT
+    if not force and up_to_date(target, defines):
+        return target
     objs = []
     procs = []
     bdir = os.path.join(HERE, "build" if not variant else f"build_{variant}")
@@ -60,6 +74,8 @@ def build(force=False, verbose=False, variant=None, defines=()):
         raise RuntimeError("nvcc failed building libtecogan_b200 (see output above)")
     cmd = [NVCC, "-shared", "-o", target] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
+    with open(target + ".srchash", "w") as f:
+        f.write(source_digest(defines) + "\n")
     return target
 
 
