@@ -256,6 +256,19 @@ def run_train_leg(name, crop, global_batch, world, rank, dev, steps, warmup, bar
     if perceptual:
         PS.ENABLED = False
         T.USE_CUDA_GRAPH = saved_graph
+    # exposed all-reduce time: the same steps with the two gradient all-reduces skipped (replicas diverge: measurement only)
+    nocomm_s = None
+    if world > 1:
+        parallel.SKIP_ALLREDUCE = True
+        T.FRVSR_Train(r_in, r_tg, args, D, G, warmup + 2 * steps, 0.0, 0.0, og, od)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            T.FRVSR_Train(r_in, r_tg, args, D, G, warmup + 2 * steps + 1 + i, 0.0, 0.0, og, od)
+        e1.record()
+        barrier()
+        nocomm_s = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+        parallel.SKIP_ALLREDUCE = False
     if rank != 0:
         return None
     flops = train_step_flops(global_batch, 10, crop)
@@ -272,7 +285,12 @@ def run_train_leg(name, crop, global_batch, world, rank, dev, steps, warmup, bar
            "losses_finite": bool(all(v == v and abs(v) != float("inf") for v in losses + host_losses)),
            "optimizer": "torch.optim.Adam objects as main.py:239-243 builds them, stepped by tecogan_b200.optim.FlatAdam (fused flat-bucket "
                         "Adam + GradScaler update + bf16 re-pack, repo kernels)" if T.FUSED_ADAM else "torch.optim.Adam + GradScaler (stock)",
-           "cuda_graph": bool(T.USE_CUDA_GRAPH and T.FUSED_ADAM and (world == 1 or T.GRAPH_WITH_NCCL)) and not perceptual}
+           "cuda_graph": bool(T.USE_CUDA_GRAPH and T.FUSED_ADAM and (world == 1 or T.GRAPH_DATA_PARALLEL)) and not perceptual}
+    if nocomm_s is not None:
+        res["allreduce"] = {"bytes_per_step": int(sum(p.numel() for p in G.parameters()) + sum(p.numel() for p in D.parameters())) * 4,
+                            "ms_per_step_without_allreduce": nocomm_s / steps * 1e3,
+                            "exposed_ms_per_step": (dev_s - nocomm_s) / steps * 1e3,
+                            "how": "the same steps timed again with both gradient all-reduces skipped (tecogan_b200.parallel.SKIP_ALLREDUCE)"}
     if perceptual:
         res["perceptual_loss"] = ("NON-PARITY stand-in (tecogan_b200.perceptual): random-init VGG19-to-conv4_4 on the conv core, features "
                                   "conv2_2/3_4/4_4, cosine loss, vgg_scaling 0.2; the reference's VGG branch is unrunnable (SURVEY.md 8c). "

@@ -42,33 +42,105 @@ def unbind_flat_grads(module):
             p.grad = None
 
 
+# measurement only (bench.py: exposed all-reduce time = step time with - step time without): skip the collective, the
+# replicas then diverge
+SKIP_ALLREDUCE = False
+
+
 def world_size():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class GraphSegments:
+    """A training step captured as a SEQUENCE of CUDA graphs with the NCCL calls between them left eager
+    (tecogan_b200.train): ``eager(fn)`` is called at every collective / wait.  While a capture is running it closes the
+    current graph, runs ``fn`` on the capturing stream, remembers it, and opens the next graph in the same memory pool;
+    ``replay()`` then alternates graph replays and the remembered calls.  Outside a capture ``eager`` just calls ``fn``.
+    (Capturing the collectives INSIDE one graph worked but hung torch.distributed's teardown - DESIGN.md section 6.)"""
+
+    def __init__(self):
+        self.ops = []                   # torch.cuda.CUDAGraph | callable, in execution order
+        self.capturing = False
+        self._graph = None
+        self._pool = None
+        self._mode = "thread_local"     # NCCL's watchdog thread polls events concurrently
+
+    def begin(self):
+        self.capturing = True
+        self._open()
+
+    def _open(self):
+        g = torch.cuda.CUDAGraph()
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()      # one private memory pool for all segments of the step
+        g.capture_begin(pool=self._pool, capture_error_mode=self._mode)
+        self._graph = g
+
+    def _close(self):
+        self._graph.capture_end()
+        self.ops.append(self._graph)
+        self._graph = None
+
+    def eager(self, fn):
+        if not self.capturing:
+            return fn()
+        self._close()
+        r = fn()
+        self.ops.append(fn)
+        self._open()
+        return r
+
+    def end(self):
+        self._close()
+        self.capturing = False
+
+    def replay(self):
+        for op in self.ops:
+            if isinstance(op, torch.cuda.CUDAGraph):
+                op.replay()
+            else:
+                op()
+
+
+_segments = None                        # the GraphSegments of the step being captured / None (set by tecogan_b200.train)
+
+
+def _eager(fn):
+    return _segments.eager(fn) if _segments is not None else fn()
 
 
 class GradSync:
     """Asynchronous mean all-reduce of one flat bucket.  ``start`` enqueues the collective behind the kernels already on
     the current stream (NCCL runs it on its own stream: later kernels of the current stream overlap it); ``finish``
-    makes the current stream wait for it and applies the 1/world scaling."""
+    makes the current stream wait for it and applies the 1/world scaling.  Both NCCL-facing calls go through the step's
+    GraphSegments (when one is capturing) so that they stay outside the CUDA graphs."""
 
     def __init__(self, group=None):
         self.group = group
         self.work = None
-        self.bucket = None
+        self.bucket = None              # kept after finish(): a captured step replays _start / _wait on the same bucket
+        self.active = False
+
+    def _start(self):
+        self.work = dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _wait(self):
+        self.work.wait()
+        self.work = None
 
     def start(self, bucket):
-        if world_size() == 1:
+        if world_size() == 1 or SKIP_ALLREDUCE:
             return
         self.bucket = bucket
-        self.work = dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.active = True
+        _eager(self._start)
 
     def finish(self):
-        if self.work is None:
+        if not self.active:
             return
-        self.work.wait()
+        _eager(self._wait)
         self.bucket.mul_(1.0 / dist.get_world_size(self.group))
-        self.work = None
-        self.bucket = None
+        self.active = False
 
 
 def shard_batch(t, rank=None, world=None):

@@ -31,14 +31,14 @@ from . import parallel as _par
 from .models import *  # noqa: F401,F403  (reference: `from models import *`, code/train.py:1)
 
 # Fused flat-bucket Adam (tecogan_b200.optim) for the stock torch.optim.Adam objects main.py:239-243 builds, and CUDA-graph
-# capture of the whole step after GRAPH_WARMUP eager calls (single process; the data-parallel step stays eager by default).  Both are on by default and fall back to the eager / stock-optimizer path when they do not apply;
-# TG_TRAIN_FUSED_ADAM=0 / TG_TRAIN_GRAPH=0 switch them off (A/B measurements).
+# capture of the whole step after GRAPH_WARMUP eager calls.  Both are on by default and fall back to the eager /
+# stock-optimizer path when they do not apply; TG_TRAIN_FUSED_ADAM=0 / TG_TRAIN_GRAPH=0 switch them off (A/B measurements).
 FUSED_ADAM = os.environ.get("TG_TRAIN_FUSED_ADAM", "1") != "0"
 USE_CUDA_GRAPH = os.environ.get("TG_TRAIN_GRAPH", "1") != "0"
-# Capturing the data-parallel step (the two NCCL all-reduces inside the graph) is EXPERIMENTAL and off: on a 2-GPU box the
-# captured steps ran, but torch.distributed's process-group teardown hung afterwards (profiles/r02_summary.md).  Opt in with
-# TG_TRAIN_GRAPH_NCCL=1; by default the data-parallel step runs eagerly (fused Adam still applies).
-GRAPH_WITH_NCCL = os.environ.get("TG_TRAIN_GRAPH_NCCL", "0") == "1"
+# The data-parallel step is captured as a SEQUENCE of graphs with the NCCL calls (two all-reduce launches, two waits) left
+# eager between them (tecogan_b200.parallel.GraphSegments).  Capturing the collectives inside one graph also ran, but
+# torch.distributed's process-group teardown then hung on a 2-GPU box.  TG_TRAIN_GRAPH_DP=0: eager step.
+GRAPH_DATA_PARALLEL = os.environ.get("TG_TRAIN_GRAPH_DP", "1") != "0"
 GRAPH_WARMUP = 2
 PAIR_DISCRIMINATOR_PASSES = os.environ.get("TG_TRAIN_PAIR_D", "1") != "0"   # real + fake discriminator pass as one batch
 
@@ -341,17 +341,29 @@ class _GraphedStep:
         for net, opt in ((G, og), (D, od)):
             _optim.FlatAdam.adopt(net, opt).refresh_lr()
         if self.graph is None:
-            g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
-            # data-parallel: the two gradient all-reduces are captured with the step (NCCL enqueues on its own stream, joined
-            # to the capture by events); NCCL's watchdog thread polls events concurrently, which only the thread-local
-            # capture mode tolerates
-            mode = "thread_local" if _par.world_size() > 1 else "global"
             k0 = _nt.lib().tg_launch_count()
-            with torch.cuda.graph(g, capture_error_mode=mode):
-                self.out = TecoGAN(self.static_in, self.static_tg, D, G, args, step, c1, c2, og, od, _dt_ratio_dev=self.dt)
+            if _par.world_size() > 1:
+                # data-parallel: graph segments with the NCCL calls eager between them, captured on a side stream
+                seg = _par.GraphSegments()
+                side = torch.cuda.Stream(device=self.static_in.device)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    _par._segments = seg
+                    seg.begin()
+                    try:
+                        self.out = TecoGAN(self.static_in, self.static_tg, D, G, args, step, c1, c2, og, od, _dt_ratio_dev=self.dt)
+                    finally:
+                        _par._segments = None
+                    seg.end()
+                torch.cuda.current_stream().wait_stream(side)
+                self.graph = seg
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="global"):
+                    self.out = TecoGAN(self.static_in, self.static_tg, D, G, args, step, c1, c2, og, od, _dt_ratio_dev=self.dt)
+                self.graph = g
             self.kernels = int(_nt.lib().tg_launch_count() - k0)
-            self.graph = g
         else:
             global replayed_launches
             replayed_launches += self.kernels   # (the capturing call's kernels were counted by tg_launch_count itself)
@@ -376,7 +388,7 @@ def FRVSR_Train(r_inputs, r_targets, args, discriminator_F, generator_F, step, c
                 optimizer_d):
     """code/train.py:374-377.  After GRAPH_WARMUP eager calls with the same networks / optimizers / shapes the step is
     captured in a CUDA graph and replayed (single process, fused Adam adoptable, TG_TRAIN_GRAPH != 0)."""
-    if (USE_CUDA_GRAPH and FUSED_ADAM and (_par.world_size() == 1 or GRAPH_WITH_NCCL) and isinstance(r_inputs, torch.Tensor) and r_inputs.is_cuda
+    if (USE_CUDA_GRAPH and FUSED_ADAM and (_par.world_size() == 1 or GRAPH_DATA_PARALLEL) and isinstance(r_inputs, torch.Tensor) and r_inputs.is_cuda
             and _optim.FlatAdam.adoptable(generator_F, optimizer_g) and _optim.FlatAdam.adoptable(discriminator_F, optimizer_d)):
         key = _graph_key(r_inputs, r_targets, args, discriminator_F, generator_F, optimizer_g, optimizer_d)
         gs = _graphs.get(key)

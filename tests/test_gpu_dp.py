@@ -77,8 +77,9 @@ def _worker(rank, world, port, q):
             dist.all_gather(ps, p)
             res.append(float((ps[0] - ps[1]).abs().max()))
         res.append(float(out.gen_loss))
-        # (C) four more steps on the same objects (the fused flat-bucket Adam + loss-scale bookkeeping on every rank; eager:
-        # graph capture of the NCCL step is opt-in): the replicas must stay bit-identical and the losses finite
+        # (C) four more steps on the same objects (the fused flat-bucket Adam + loss-scale bookkeeping on every rank; from the
+        # third call on the step replays as graph segments with the NCCL calls eager between them): the replicas must stay
+        # bit-identical and the losses finite
         for i in range(1, 5):
             out = T.FRVSR_Train(r_in, r_tg, args, D, G, i, 0.0, 0.0, og, od)
         torch.cuda.synchronize()
@@ -92,6 +93,10 @@ def _worker(rank, world, port, q):
         res.append((gs is not None and gs.graph is not None, spread, float(out.gen_loss.detach()), float(out.d_loss.detach())))
         dist.barrier()
         q.put((rank, res))
+    except BaseException as e:                               # the parent must not wait out its queue timeout on a dead worker
+        import traceback
+        q.put((rank, "worker failed: " + "".join(traceback.format_exception(type(e), e, e.__traceback__))[-3000:]))
+        os._exit(1)                                          # (a failed capture leaves NCCL / the allocator in no state to tear down)
     finally:
         dist.destroy_process_group()
 
@@ -106,7 +111,14 @@ def test_dp_step_two_gpus():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=600) for _ in range(world))
+    res = dict(q.get(timeout=150) for _ in range(world))
+    failed = {r: v for r, v in res.items() if isinstance(v, str)}
+    if failed:
+        for p in procs:
+            p.join(10)
+            if p.is_alive():
+                p.kill()
+        pytest.fail("\n".join(f"rank {r}: {v}" for r, v in failed.items()))
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
@@ -114,6 +126,7 @@ def test_dp_step_two_gpus():
         captured, spread, gl, dl = graphed
         print(f"rank {rank}: graphed data-parallel steps: captured={captured} replica spread {spread:.1e} gen_loss {gl:.4f} d_loss {dl:.4f}")
         assert spread == 0.0 and gl == gl and dl == dl
+        assert captured, "the data-parallel step was not captured as graph segments"
         print(f"rank {rank}: G grad rel err {g_rel:.2e}, G param spread {g_par:.1e}, D grad rel err {d_rel:.2e}, "
               f"D param spread {d_par:.1e}, gen_loss {loss:.4f}")
         # f32 atomics reorder the wgrad sums run to run: 1e-4 of the peak gradient is the noise floor
