@@ -498,7 +498,6 @@ extern "C" int tg_gen_backward(const void* packed_dgrad, int num_resblock, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* wsp = static_cast<uint8_t*>(workspace);
   const uint8_t* pd = static_cast<const uint8_t*>(packed_dgrad);
-  const long long px1 = static_cast<long long>(n) * h * w;
   int rc;
   // weight / bias gradient of layer li given its input x and output gradient dy (sizes of the layer's INPUT)
   auto wgrad = [&](int li, const void* x, const void* dy, int hh, int ww) {
@@ -610,8 +609,6 @@ extern "C" int tg_gen_backward(const void* packed_dgrad, int num_resblock, const
       if ((rc = wgrad(1 + 2 * k, B(ws.net[k]), B(ws.g_t[k]), h, w))) return rc;
     }
   }
-  const int cur = 0;
   // conv.0: 51 -> 64 + ReLU (its input is detached: no data gradient)
-  (void)px1;
-  return wgrad(0, B(ws.x_in), B(ws.g_net[cur]), h, w);
+  return wgrad(0, B(ws.x_in), B(ws.g_net[0]), h, w);
 }
