@@ -340,6 +340,9 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
     uint32_t ph = 0, dk = 0;
     bool grid_waited = false;
     int si_base = 0;
+    int p_si = -1, p_kch = 1;
+    uint32_t p_box_bytes = 0;
+    const CUtensorMap* p_map = &P.maps[0];
     Tick<kDbg> tk{0, stats != nullptr, true}, tall{0, stats != nullptr, true};
     long long a_wempty = 0, a_dep = 0, a_aempty = 0, a_total = 0, a_issue = 0;
     tall.start();
@@ -356,7 +359,13 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
         tk.gate = stat_seg < 0 || si == stat_seg;
         const int bx0 = static_cast<int>(static_cast<int16_t>(b1 & 0xFFFFu)), by0 = static_cast<int>(b1) >> 16;
         const FrSeg& S = P.segs[si];
-        for (int kc = 0; kc < S.kchunks; ++kc) {
+        if (si != p_si) {                                    // per-segment values in registers: the item path of this strictly
+          p_si = si;                                         // serial role reads no kernel-parameter memory
+          p_kch = S.kchunks;
+          p_box_bytes = static_cast<uint32_t>(S.box_w * S.box_h) * 128u;
+          p_map = &P.maps[S.map_a];
+        }
+        for (int kc = 0; kc < p_kch; ++kc) {
           bool is_load;
           uint32_t nth;
           const int slot = ws.use(si * 2 + kc, &is_load, &nth);
@@ -411,11 +420,11 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
             if (kPair && (dbg & 1024) && tk.gate) {
               mbar_expect_tx_cluster(lbar_afull + 8 * st, 0u);         // measurement: no A load in the selected segment
             } else if (kPair) {
-              mbar_expect_tx_cluster(lbar_afull + 8 * st, static_cast<uint32_t>(S.box_w * S.box_h) * 128u);
-              tma_load_4d_pair(s_a + st * kAStride, &P.maps[S.map_a], lbar_afull + 8 * st, kc * 64, bx0, by0, n);
+              mbar_expect_tx_cluster(lbar_afull + 8 * st, p_box_bytes);
+              tma_load_4d_pair(s_a + st * kAStride, p_map, lbar_afull + 8 * st, kc * 64, bx0, by0, n);
             } else {
-              mbar_expect_tx(bar_afull + 8 * st, static_cast<uint32_t>(S.box_w * S.box_h) * 128u);
-              tma_load_4d(s_a + st * kAStride, &P.maps[S.map_a], bar_afull + 8 * st, kc * 64, bx0, by0, n);
+              mbar_expect_tx(bar_afull + 8 * st, p_box_bytes);
+              tma_load_4d(s_a + st * kAStride, p_map, bar_afull + 8 * st, kc * 64, bx0, by0, n);
             }
           }
           __syncwarp();

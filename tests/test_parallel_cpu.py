@@ -88,6 +88,46 @@ def test_single_process_is_a_no_op():
     assert m.weight.grad is None
 
 
+def test_graph_segments_sequence_the_eager_calls_between_graphs(monkeypatch):
+    """GraphSegments (the data-parallel step as graph segments with the NCCL calls eager between them): outside a capture
+    eager() just calls; during a capture every eager() closes the running segment, runs and records the call, opens the
+    next one in the same pool; replay() alternates them in order.  (The CUDA capture itself: tests/test_gpu_dp.py.)"""
+    from tecogan_b200 import parallel as P
+    log = []
+
+    class FakeGraph:
+        n = 0
+
+        def __init__(self):
+            FakeGraph.n += 1
+            self.id = FakeGraph.n
+
+        def capture_begin(self, pool=None, capture_error_mode=None):
+            log.append(("begin", self.id, pool, capture_error_mode))
+
+        def capture_end(self):
+            log.append(("end", self.id))
+
+        def replay(self):
+            log.append(("replay", self.id))
+
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", FakeGraph)
+    monkeypatch.setattr(torch.cuda, "graph_pool_handle", lambda: "pool0")
+    seg = P.GraphSegments()
+    assert seg.eager(lambda: 7) == 7 and log == []          # not capturing: a plain call
+    seg.begin()
+    assert seg.eager(lambda: log.append("allreduce G") or "w") == "w"
+    seg.eager(lambda: log.append("wait G"))
+    seg.end()
+    assert log == [("begin", 1, "pool0", "thread_local"), ("end", 1), "allreduce G", ("begin", 2, "pool0", "thread_local"),
+                   ("end", 2), "wait G", ("begin", 3, "pool0", "thread_local"), ("end", 3)]
+    del log[:]
+    seg.replay()
+    assert log == [("replay", 1), "allreduce G", ("replay", 2), "wait G", ("replay", 3)]
+    # GradSync routes its NCCL-facing calls through the step's segments only when one is installed
+    assert P._segments is None and P._eager(lambda: 3) == 3
+
+
 def test_train_mirror_interface():
     """the reference-facing surface of tecogan_b200.train (code/train.py): names, signature, namedtuple fields."""
     import inspect
