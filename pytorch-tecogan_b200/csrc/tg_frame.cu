@@ -421,6 +421,13 @@ __global__ void __launch_bounds__(kFrThreads, 1) frame_kernel(const __grid_const
               mbar_expect_tx_cluster(lbar_afull + 8 * st, 0u);         // measurement: no A load in the selected segment
             } else if (kPair) {
               mbar_expect_tx_cluster(lbar_afull + 8 * st, p_box_bytes);
+#ifdef TG_EXP_OUT_SAMEBOX
+              // measurement build: every activation load of the segments selected by the mask reads the SAME box (always an L2
+              // hit) - is the segment waiting for HBM?  bit 0: output conv (nt 16), bit 1: 128-input-channel layers
+              if (((TG_EXP_OUT_SAMEBOX & 1) && S.nt == 16) || ((TG_EXP_OUT_SAMEBOX & 2) && S.kchunks == 2))
+                tma_load_4d_pair(s_a + st * kAStride, p_map, lbar_afull + 8 * st, kc * 64, -1, -1, 0);
+              else
+#endif
               tma_load_4d_pair(s_a + st * kAStride, p_map, lbar_afull + 8 * st, kc * 64, bx0, by0, n);
             } else {
               mbar_expect_tx(bar_afull + 8 * st, p_box_bytes);
