@@ -12,6 +12,8 @@ One "step" = one batch of B independent 100-frame clips per GPU through the recu
   e2e        frames/s through ClipPipeline.run_host: pinned host LR in, every HR frame copied
              back to pinned host memory, copies inside the timed region
   roofline   dominant kernel (tg::frame_kernel: all 41 tcgen05 conv layers of a frame) timed per launch with CUDA events
+             INSIDE the long step (one more full step right after the K timed ones, same clock / power state) against the
+             sustained bf16 peak; roofline.burst = a 20-frame run timed alone against the burst peak
   train      second half of the metric ("train clips/s"): tecogan_b200.train.FRVSR_Train steps on cfg4 (N=1) and cfg5
              (global batch 32 split over the N ranks, gradient all-reduce inside the step), device-timed + e2e
   cfg3       the same measurements on BASELINE configs[2] (960x540 -> 4K, 30-frame clips): frames/s, e2e, frame-kernel
