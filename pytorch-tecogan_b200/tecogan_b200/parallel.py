@@ -122,14 +122,16 @@ class GradSync:
         self.active = False
 
     def _start(self):
-        self.work = dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        # (SKIP_ALLREDUCE is read at call time: a captured step replays this method)
+        self.work = None if SKIP_ALLREDUCE else dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def _wait(self):
-        self.work.wait()
-        self.work = None
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
 
     def start(self, bucket):
-        if world_size() == 1 or SKIP_ALLREDUCE:
+        if world_size() == 1 or (SKIP_ALLREDUCE and _segments is None):
             return
         self.bucket = bucket
         self.active = True
