@@ -31,6 +31,27 @@ def _declared_symbols():
     return syms
 
 
+def test_build_is_up_to_date_by_content_not_by_file_time(built_lib, tmp_path):
+    """The in-tree library carries a hash of the sources it was built from: file times do not survive the copy to a GPU
+    box (a stale .so once ran two measurements), contents do."""
+    import importlib.util
+    import shutil
+    spec = importlib.util.spec_from_file_location("tg_build2", os.path.join(ROOT, "pytorch-tecogan_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.up_to_date()                                   # right after build()
+    os.utime(os.path.join(ROOT, "include", "tecogan_b200.h"))   # a newer file time alone does not invalidate it
+    assert mod.up_to_date()
+    # another set of flags (a measurement variant) or a missing / foreign stamp is never "up to date"
+    assert not mod.up_to_date(built_lib, defines=("TG_SOMETHING=1",))
+    fake = str(tmp_path / "libtecogan_b200.so")
+    shutil.copy(built_lib, fake)
+    assert not mod.up_to_date(fake)
+    with open(fake + ".srchash", "w") as f:
+        f.write("0" * 64 + "\n")
+    assert not mod.up_to_date(fake)
+
+
 def test_library_exports_every_declared_symbol(built_lib):
     lib = ctypes.CDLL(built_lib)
     declared = _declared_symbols()
