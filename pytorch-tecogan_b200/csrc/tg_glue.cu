@@ -493,19 +493,22 @@ fused_input_kernel(const float* __restrict__ lr_t, const float* __restrict__ lr_
 __global__ void __launch_bounds__(256)
 pack_nhwc64_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int n, int c,
                    long long hw) {
-  __shared__ __align__(16) __nv_bfloat16 tile[32][64 + 8];
-  const long long groups = (hw + 31) / 32;
+  // 128 pixels per iteration: c x 128 coalesced plane loads in flight per CTA (32 pixels per iteration left the kernel
+  // latency-bound at 2.4 TB/s), transposed through shared memory, written as whole 128-byte pixels
+  constexpr int kPx = 128;
+  __shared__ __align__(16) __nv_bfloat16 tile[kPx][64 + 8];
+  const long long groups = (hw + kPx - 1) / kPx;
   for (long long gi = blockIdx.x; gi < groups * n; gi += gridDim.x) {
     const long long b = gi / groups;
-    const long long p0 = (gi % groups) * 32;
-    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
-      const int ch = i >> 5, px = i & 31;
+    const long long p0 = (gi % groups) * kPx;
+    for (int i = threadIdx.x; i < 64 * kPx; i += blockDim.x) {
+      const int ch = i / kPx, px = i % kPx;
       float v = 0.f;
       if (ch < c && p0 + px < hw) v = __ldg(in + (b * c + ch) * hw + p0 + px);
       tile[px][ch] = __float2bfloat16_rn(v);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * 8; i += blockDim.x) {
+    for (int i = threadIdx.x; i < kPx * 8; i += blockDim.x) {
       const int px = i >> 3, ck = i & 7;
       if (p0 + px < hw) {
         const uint4 vv = *reinterpret_cast<const uint4*>(&tile[px][ck * 8]);
@@ -648,7 +651,7 @@ extern "C" int tg_pack_nchw_to_nhwc64(const float* in, void* out, int n, int c, 
   TG_CHECK_ARG(in && out, "pack_nchw_to_nhwc64: null pointer");
   TG_CHECK_ARG(n >= 1 && c >= 1 && c <= 64 && h >= 1 && w >= 1, "pack_nchw_to_nhwc64: bad shape (c must be <= 64)");
   const long long hw = static_cast<long long>(h) * w;
-  const long long groups = (hw + 31) / 32 * n;
+  const long long groups = (hw + 127) / 128 * n;             // 128 pixels per CTA iteration (pack_nhwc64_kernel)
   const long long cap = static_cast<long long>(tg_num_sms()) * 8;
   tg_prof_pre(TG_K_GLUE, (4.0 * c + 128.0) * n * hw, static_cast<cudaStream_t>(stream));
   pack_nhwc64_kernel<<<static_cast<int>(groups < cap ? groups : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -666,20 +669,34 @@ namespace tg {
 __global__ void __launch_bounds__(256)
 sigmoid_bwd_pack_kernel(const float* __restrict__ dout, const float* __restrict__ out, __nv_bfloat16* __restrict__ dz,
                         int n, long long hw, long long dout_nstride, long long out_nstride) {
+  // A warp owns 32 consecutive pixels: every lane computes ITS pixel's three gradients (coalesced plane loads), then the
+  // warp writes the 32 x 128-byte rows four pixels per instruction, eight lanes per pixel (whole 128-byte lines; one
+  // 16-byte store per lane at a 128-byte stride wrote half sectors and ran at 2 TB/s).
   const long long total = static_cast<long long>(n) * hw;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long b = i / hw, px = i - b * hw;
-    float g[3];
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long w0 = ((blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5) * 32; w0 < total; w0 += warps * 32) {
+    const long long i = w0 + lane;
+    uint32_t lo = 0u, hi = 0u;
+    if (i < total) {
+      const long long b = i / hw, px = i - b * hw;
+      float g[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float y = __ldg(out + b * out_nstride + c * hw + px);
-      g[c] = __ldg(dout + b * dout_nstride + c * hw + px) * y * (1.f - y);
+      for (int c = 0; c < 3; ++c) {
+        const float y = __ldg(out + b * out_nstride + c * hw + px);
+        g[c] = __ldg(dout + b * dout_nstride + c * hw + px) * y * (1.f - y);
+      }
+      lo = pack_bf16x2(g[0], g[1]);
+      hi = pack_bf16x2(g[2], 0.f);
     }
-    uint4* dst = reinterpret_cast<uint4*>(dz + i * 64);
-    dst[0] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], 0.f), 0u, 0u);
 #pragma unroll
-    for (int k = 1; k < 8; ++k) dst[k] = make_uint4(0u, 0u, 0u, 0u);
+    for (int k = 0; k < 8; ++k) {
+      const int src = k * 4 + (lane >> 3);                     // pixel of this lane's 16-byte chunk in round k
+      const uint32_t a = __shfl_sync(0xFFFFFFFFu, lo, src), b2 = __shfl_sync(0xFFFFFFFFu, hi, src);
+      const long long p = w0 + src;
+      if (p < total)
+        reinterpret_cast<uint4*>(dz + p * 64)[lane & 7] = (lane & 7) == 0 ? make_uint4(a, b2, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    }
   }
 }
 
