@@ -9,6 +9,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "pytorch-tecogan_b200"))
 import bench  # noqa: E402
+from tecogan_b200 import _native as _nt  # noqa: E402
+if os.environ.get("TG_LIB"):                               # measurement only: another build of the library (same-box A/B)
+    _nt.LIB_PATH = os.path.abspath(os.environ["TG_LIB"])
 from tecogan_b200 import models, train as T  # noqa: E402
 
 cfg5 = os.environ.get("TG_CFG", "4") == "5"
