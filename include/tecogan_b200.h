@@ -78,7 +78,10 @@ int tg_depth_to_space(const void* in, void* out, int n, int c, int h_in, int w_i
                       void* stream);
 /* F.grid_sample(img, grid.half()) bilinear / zeros / align_corners=False.
  * img [n,c,h,w] f32, grid [n,ho,wo,2] f32 (rounded to fp16 inside, as the reference does),
- * out [n,c,ho,wo] f32.  Replaces main.py:203, code/train.py:81,98,165,187. */
+ * out [n,c,ho,wo] f32.  Replaces main.py:203, code/train.py:81,98,165,187.
+ * Three-plane inputs take a branch-free path: an out-of-range tap keeps a clamped (valid) address and weight 0, so the
+ * result equals grid_sample's zero padding for FINITE images (frames are finite; an Inf / NaN border pixel would leak into
+ * samples outside the image, where grid_sample returns 0). */
 int tg_warp_bilinear(const float* img, const float* grid, float* out, int n, int c, int h, int w,
                      int ho, int wo, void* stream);
 /* nn.Upsample(scale_factor=4, mode="bilinear") (align_corners=False); out = up4(in * pre_scale).
